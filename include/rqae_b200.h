@@ -1,0 +1,116 @@
+/*
+ * rqae_b200 -- C ABI of the B200 (sm_100a) implementation of the RQAE residual-quantization
+ * hot path.  Plain C: device pointers, sizes and a CUDA stream handle; no torch types.
+ *
+ * The reference (harish-kamath/rqae) is pure Python and has no FFI of its own; its boundary for
+ * this path is the Python surface of `rqae.model.RQAE` (rqae/model.py).  Each entry point below
+ * names the reference method it replaces.  `rqae_b200/model.py` is the reference-side binding
+ * (ctypes), and INTEGRATION.md shows the three-line change a maintainer of the reference makes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an RQAE_E* code; rqae_strerror() names it.
+ *     No exception or signal crosses the ABI.  Asynchronous CUDA errors surface at the caller's
+ *     next synchronisation, as with any kernel launch.
+ *   - all `const float*` / `void*` data arguments are DEVICE pointers unless the name ends in
+ *     `_host`.  The library never allocates or frees caller-visible memory; it borrows the
+ *     pointers for the duration of the launch.
+ *   - `stream` is a cudaStream_t passed as void* (0 = the legacy default stream).  Kernels are
+ *     enqueued on it and the call returns without synchronising, so the functions can be called
+ *     from inside a framework forward hook (rqae/model.py:276-289 runs mid-forward).
+ *   - code tensors: `code_dtype` 0 = int16, 1 = int32, 2 = int64 (the reference returns int64,
+ *     rqae/model.py:226; scripts/1_create_activations.py:184-186 stores int32).
+ */
+#ifndef RQAE_B200_H
+#define RQAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQAE_OK 0
+#define RQAE_EINVAL 1      /* bad argument (null pointer, non-positive size, unknown dtype) */
+#define RQAE_EUNSUPPORTED 2 /* shape outside the compiled instantiations (codebook_dim != 4, dim > 3584) */
+#define RQAE_ECUDA 3       /* a CUDA runtime call failed; see rqae_last_cuda_error() */
+#define RQAE_ENODEVICE 4   /* no sm_100 device / kernels not loadable on the current device */
+#define RQAE_ESIZE 5       /* caller's buffer is smaller than required */
+
+#define RQAE_CODE_I16 0
+#define RQAE_CODE_I32 1
+#define RQAE_CODE_I64 2
+
+/* Library / build identification ("rqae_b200 <version> sm_100a"). */
+const char* rqae_version(void);
+const char* rqae_strerror(int code);
+/* cudaGetErrorString of the last failing CUDA call made by this library on this thread. */
+const char* rqae_last_cuda_error(void);
+
+/* Bytes of the packed weight buffer for a model with `nq` quantizer layers, hidden size `dim`,
+ * `codebook_dim` (must be 4) and `K` codebook rows.  Returns 0 for unsupported shapes. */
+size_t rqae_packed_bytes(int nq, int dim, int codebook_dim, int K);
+
+/* Pack the weights of all layers into the streaming layout the kernels read.
+ * Replaces nothing in the reference: it is the load-time step that follows
+ * RQAE.load_state_dict (rqae/model.py:89-96).  Inputs are the reference parameters stacked
+ * over layers, in the reference's own layouts:
+ *   w_in  [nq][cd][dim]   layers.{l}.0.weight      b_in  [nq][cd]   layers.{l}.0.bias
+ *   w_out [nq][dim][cd]   layers.{l}.1.weight      b_out [nq][dim]  layers.{l}.1.bias
+ *   codebook [nq][K][cd] (codebook_shared = 0) or [1][K][cd] (= 1: fsq / round_fsq, where
+ *   every layer holds the same table, rqae/model.py:63-72).
+ * In shared mode bit-identical duplicate rows are removed from the search table (the lowest
+ * original index is kept, which is what torch.argmax returns on ties). */
+int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                      const float* codebook, int codebook_shared, int nq, int dim, int codebook_dim,
+                      int K, void* packed, size_t packed_bytes, void* stream);
+
+/* RQAE.forward (rqae/model.py:199-230), eval / temperature-0 semantics, all `nq_run` =
+ * min(max_layers, nq) layers fused into one persistent kernel.
+ *   x       [n_tokens][dim] fp32
+ *   codes   [n_tokens][code_stride] of code_dtype, written for layers 0..nq_run-1 (nullable)
+ *   q_out   [n_tokens][dim] fp32 reconstruction (nullable: "encode", codes only)
+ *   teacher nullable int32 [n_tokens][nq_run]: codes that drive the residual recurrence while
+ *           `codes` still receives this implementation's own per-layer argmax (parity testing)
+ *   z_out   nullable fp32 [n_tokens][nq_run][4]: the in-projection values (parity testing)
+ * `codebook` is the same device pointer that was given to rqae_pack_weights. */
+int rqae_forward_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run,
+                     int dim, int codebook_dim, int K, const float* x, int64_t n_tokens, void* codes,
+                     int code_dtype, int64_t code_stride, float* q_out, const int32_t* teacher,
+                     float* z_out, void* stream);
+
+/* RQAE.decode / decode_from_codebook_values (rqae/model.py:232-252): sum over the selected layers,
+ * in ascending order, of W_out[l] c_l + b_out[l], with the reference's fp32 arithmetic
+ * (o = fma(c3,w3,fma(c2,w2,fma(c1,w1,c0*w0))) + b; q = o_first, then q += o).
+ *   codes       [n_tokens][code_stride] of code_dtype, or NULL when `cv` is given
+ *   cv          nullable fp32 [n_tokens][nq][4] codebook values (decode_from_codebook_values)
+ *   codebook0   [K][4] layer-0 table (the reference indexes codebook[0] for every layer)
+ *   layer_mask  nullable uint8 [nq], DEVICE: 1 = include layer (the `layers=` filter)
+ *   nq_codes    number of layers present in `codes` / `cv` (layers >= nq_codes are skipped) */
+int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_codes, int dim,
+                    int codebook_dim, int K, const void* codes, int code_dtype, int64_t code_stride,
+                    const float* cv, const uint8_t* layer_mask, int64_t n_tokens, float* q_out,
+                    void* stream);
+
+/* Host-buffer front end of rqae_forward_f32 (the end-to-end path bench.py times as `e2e`):
+ * x_host / codes_host / q_host are HOST pointers (pinned for full speed).  The call stages
+ * chunks of `chunk_tokens` tokens through internal device buffers on three internal streams
+ * (H2D, compute, D2H double-buffered) and returns after the last D2H copy has completed. */
+int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq,
+                          int nq_run, int dim, int codebook_dim, int K, const float* x_host,
+                          int64_t n_tokens, void* codes_host, int code_dtype, float* q_host,
+                          int64_t chunk_tokens);
+
+/* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
+ * sustained packed-FFMA2 / scalar-FFMA rate of the FP32 pipe, in FLOP per call; time it with
+ * CUDA events on `stream`. */
+int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, float* sink, void* stream);
+
+/* Number of kernels this library has launched on this thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t rqae_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQAE_B200_H */

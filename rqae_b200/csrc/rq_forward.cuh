@@ -1,0 +1,373 @@
+// Fused RQAE forward / encode kernel for sm_100a (B200).
+//
+// Replaces the per-layer op sequence of rqae/model.py:199-230 (reference, harish-kamath/rqae):
+// F.linear(D->4), L2-normalise, [T,4]x[4,K] cos-sim matmul, argmax, gather, straight-through
+// add/sub, F.linear(4->D), residual subtract, reconstruction add -- ~13 launches per layer,
+// 1024 layers -- by ONE persistent kernel in which the residual never leaves registers.
+//
+// CTA = 384 threads, one CTA per SM (the register file is the capacity that matters):
+//   warps 0-3   compute group A : TG tokens, residual r[TG][D] in registers (D split over 128 threads)
+//   warps 4-7   compute group B : TG other tokens; runs half a layer out of phase with A so that
+//                                 one group's argmax latency is hidden behind the other's FMA work
+//   warps 8-10  quantizer       : cross-warp sum of the in-projection partials, cos-sim argmax over
+//                                 the de-duplicated codebook (lowest original index wins ties, NaN
+//                                 -> index 0 as torch.argmax), straight-through value, code output
+//   warp  11    producer        : one lane streaming weight chunks L2 -> shared memory with bulk TMA
+//                                 (cp.async.bulk + mbarrier complete_tx) through an NSLOT-deep ring
+// Registers are re-split with setmaxnreg: compute warpgroups grow, the helper warpgroup shrinks.
+//
+// One *pass* of a compute group over stage s (see rq_layout.h) does, per owned element d and per
+// token pair, with packed FFMA2 (two tokens per instruction, each half IEEE fp32 round-to-nearest):
+//     o   = fma(w_out[d][3], c'3, fma(w_out[d][2], c'2, fma(w_out[d][1], c'1, fma(w_out[d][0], c'0, b_out[d]))))
+//     r_d = r_d - o                                  (model.py:221-223)
+//     acc[k] = fma(w_in[k][d], r_d, acc[k]), k<4     (model.py:211, partial over the thread's elements)
+// then reduces acc over the warp with a shuffle butterfly and hands 4 per-warp partials per (token, k)
+// to the quantizer warps through shared memory.  Summation order is fixed (thread-sequential over j,
+// lane tree with strides 16,8,4,2,1, warps 0..3 sequentially, then + b_in), so results do not depend on
+// the tile a token lands in, on the grid size or on timing.  The reconstruction is emitted as
+// q = x - r_final (one extra read of x) instead of a second register-resident accumulator.
+#pragma once
+#include "rq_common.cuh"
+#include "rq_layout.h"
+
+namespace rq {
+
+struct FwdParams {
+  const unsigned char* packed;  // packed buffer (rq_layout.h)
+  unsigned long long off_bin, off_cbt, off_map, off_stage;
+  const float* codebook;        // original codebook, device: [nq][K][4] or [1][K][4]
+  int cb_shared;                // 1: one table for all layers (fsq / round_fsq)
+  int K;
+  int nq_run;                   // layers to run = min(max_layers, nq)
+  int D;
+  const float* x;               // [n_tokens][D]
+  long long n_tokens;
+  void* codes;                  // [n_tokens][code_stride] of code_dtype (nullable)
+  int code_dtype;               // 0: int16, 1: int32, 2: int64
+  long long code_stride;        // elements between consecutive tokens
+  float* q_out;                 // [n_tokens][D] (nullable -> encode only)
+  const int* teacher;           // nullable: [n_tokens][nq_run] codes that drive the recurrence
+  float* z_out;                 // nullable debug: [n_tokens][nq_run][4] in-projection values
+};
+
+constexpr int kComputeWarps = 8;
+constexpr int kQuantWarps = 3;
+constexpr int kThreads = 384;
+constexpr int kCodeBuf = 16;  // layers buffered per token before a 128-byte code store
+
+template <int E, int EC, int CH, int NSLOT, int TG>
+struct FwdCfg {
+  static constexpr int NP = TG / 2;              // token pairs per group
+  static constexpr int JC = E / CH;              // elements per thread per chunk
+  static constexpr int NB = JC / EC;             // register blocks per chunk
+  static constexpr int CHUNK_BYTES = JC * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
+  static constexpr int OFF_WIN = JC * RQ_GROUP_THREADS * 16;
+  static constexpr int OFF_BO = JC * RQ_GROUP_THREADS * 32;
+  static_assert(E % CH == 0 && JC % EC == 0 && TG % 2 == 0 && TG <= 8, "bad shape");
+  // shared memory carve-up (bytes)
+  static constexpr int SM_RING = 0;
+  static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[1024]
+  static constexpr int SM_MAP = SM_CBT + RQ_MAX_SMEM_CODEBOOK * 16;         // uint16[1024]
+  static constexpr int SM_PART = SM_MAP + RQ_MAX_SMEM_CODEBOOK * 2;         // float[2][4][32]
+  static constexpr int SM_CPR = SM_PART + 2 * 4 * 32 * 4;                   // u64[2][NP][4]
+  static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
+  static constexpr int SM_BAR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // mbarriers
+  static constexpr int N_BAR = 2 * NSLOT + 4;
+  static constexpr int SM_TOTAL = SM_BAR + N_BAR * 8;
+  static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// lane L ends with the sum over the 32 lanes of logical value L (see file header for the order)
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; i++) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+    }
+  }
+  return v[0];
+}
+
+template <int E, int EC, int CH, int NSLOT, int TG, int REG_COMPUTE = 232, int REG_HELPER = 48>
+__global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams p) {
+  static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= 65536, "register file budget");
+  using C = FwdCfg<E, EC, CH, NSLOT, TG>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);
+  uint64_t* full = bars;                  // [NSLOT] producer -> compute
+  uint64_t* empty = bars + NSLOT;         // [NSLOT] compute -> producer (8 warp arrivals)
+  uint64_t* part_full = bars + 2 * NSLOT; // [2] compute group -> quantizer (4 warp arrivals)
+  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (3 warp arrivals)
+
+  // work split: a unit is TG consecutive tokens; CTA b handles unit pairs b, b+grid, ...
+  const long long n_units = (p.n_tokens + TG - 1) / TG;
+  const long long n_pairs = (n_units + 1) / 2;
+  const long long my_iters = (n_pairs > (long long)blockIdx.x) ? (n_pairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kComputeWarps); }
+    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], kQuantWarps); }
+    mbar_fence_init();
+  }
+  // search table -> shared memory (shared-codebook mode with a table that fits)
+  const RqHeader* hdr = reinterpret_cast<const RqHeader*>(p.packed);
+  const int kd_pad = p.cb_shared ? hdr->kd_pad : 0;
+  const bool cb_in_smem = p.cb_shared && kd_pad <= RQ_MAX_SMEM_CODEBOOK;
+  if (cb_in_smem) {
+    const float4* src = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
+    const unsigned short* msrc = reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+    float4* dst = reinterpret_cast<float4*>(smem + C::SM_CBT);
+    unsigned short* mdst = reinterpret_cast<unsigned short*>(smem + C::SM_MAP);
+    for (int i = threadIdx.x; i < kd_pad; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
+  }
+  __syncthreads();
+
+  if (warp < kComputeWarps) {
+    // =============================== compute groups ===============================
+    reg_inc<REG_COMPUTE>();
+    const int g = warp >> 2;
+    const int wg = warp & 3;                 // warp within group
+    const int tg = threadIdx.x & 127;        // thread within group
+    const uint32_t ring = smem_u32(smem + C::SM_RING);
+    const uint32_t cpr = smem_u32(smem + C::SM_CPR) + g * (4 * 4 * 8);
+    const uint32_t part = smem_u32(smem + C::SM_PART) + (g * 4 + wg) * 32 * 4 + lane * 4;
+    const u64 neg1 = pack2(-1.0f, -1.0f);
+    uint32_t slot = 0, full_par = 0, cr_par = 0;
+
+    for (long long it = 0; it < my_iters; ++it) {
+      const long long unit = 2 * ((long long)blockIdx.x + it * gridDim.x) + g;
+      const long long tok0 = unit * TG;
+      // ---- load the unit's activations into registers (zeros outside [0,n_tokens) x [0,D)) ----
+      u64 r2[C::NP][E];
+#pragma unroll
+      for (int pi = 0; pi < C::NP; pi++) {
+        const long long ta = tok0 + 2 * pi, tb = ta + 1;
+        const float* xa = p.x + ta * (long long)p.D;
+        const float* xb = p.x + tb * (long long)p.D;
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+          const int d = j * RQ_GROUP_THREADS + tg;
+          const float a = (ta < p.n_tokens && d < p.D) ? __ldcs(xa + d) : 0.0f;
+          const float b = (tb < p.n_tokens && d < p.D) ? __ldcs(xb + d) : 0.0f;
+          r2[pi][j] = pack2(a, b);
+        }
+      }
+
+      // Pass 0 has no code to project out yet: stage 0 carries W_out = b_out = 0 and the group zeroes
+      // its c' slots, so o = fma(0, 0, 0) = 0 and r is unchanged.  The quantizer warps cannot touch the
+      // slots again before this group's pass-0 partials arrive, hence a group-local barrier suffices.
+      if (tg < 32) sts32(cpr + tg * 4, 0.0f);
+      named_bar_sync(1 + g, RQ_GROUP_THREADS);
+
+      for (int l = 0; l <= p.nq_run; ++l) {
+        u64 acc[C::NP][4];
+#pragma unroll
+        for (int pi = 0; pi < C::NP; pi++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) acc[pi][k] = 0ull;
+        if (l > 0) { mbar_wait(&c_ready[g], cr_par); cr_par ^= 1; }
+
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          mbar_wait(&full[slot], full_par);
+          const uint32_t sb = ring + slot * C::CHUNK_BYTES + tg * 16;
+#pragma unroll
+          for (int nb = 0; nb < C::NB; nb++) {
+            float4 wo[EC], wi[EC];
+            float bo[EC];
+#pragma unroll
+            for (int e = 0; e < EC; e++) {
+              const int jj = nb * EC + e;
+              wo[e] = lds128(sb + jj * (RQ_GROUP_THREADS * 16));
+              wi[e] = lds128(sb + C::OFF_WIN + jj * (RQ_GROUP_THREADS * 16));
+              bo[e] = lds32(sb + C::OFF_BO - tg * 12 + jj * (RQ_GROUP_THREADS * 4));
+            }
+#pragma unroll
+            for (int pi = 0; pi < C::NP; pi++) {
+              u64 c0, c1, c2, c3;
+              lds128_u64(cpr + pi * 32, c0, c1);
+              lds128_u64(cpr + pi * 32 + 16, c2, c3);
+#pragma unroll
+              for (int e = 0; e < EC; e++) {
+                const int j = c * C::JC + nb * EC + e;
+                u64 o = fma2(pack2(wo[e].x, wo[e].x), c0, pack2(bo[e], bo[e]));
+                o = fma2(pack2(wo[e].y, wo[e].y), c1, o);
+                o = fma2(pack2(wo[e].z, wo[e].z), c2, o);
+                o = fma2(pack2(wo[e].w, wo[e].w), c3, o);
+                const u64 r = fma2(o, neg1, r2[pi][j]);
+                r2[pi][j] = r;
+                acc[pi][0] = fma2(pack2(wi[e].x, wi[e].x), r, acc[pi][0]);
+                acc[pi][1] = fma2(pack2(wi[e].y, wi[e].y), r, acc[pi][1]);
+                acc[pi][2] = fma2(pack2(wi[e].z, wi[e].z), r, acc[pi][2]);
+                acc[pi][3] = fma2(pack2(wi[e].w, wi[e].w), r, acc[pi][3]);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+          if (++slot == NSLOT) { slot = 0; full_par ^= 1; }
+        }
+
+        if (l < p.nq_run) {
+          // logical value index = token * 4 + k, token = 2*pair + half
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = 0.0f;
+#pragma unroll
+          for (int pi = 0; pi < C::NP; pi++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) unpack2(acc[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
+          const float s = butterfly32(v, lane);
+          sts32(part, s);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&part_full[g]);
+        }
+      }
+
+      // ---- reconstruction q = x - r_final ----
+      if (p.q_out != nullptr) {
+#pragma unroll
+        for (int pi = 0; pi < C::NP; pi++) {
+          const long long ta = tok0 + 2 * pi, tb = ta + 1;
+#pragma unroll
+          for (int j = 0; j < E; j++) {
+            const int d = j * RQ_GROUP_THREADS + tg;
+            float ra, rb;
+            unpack2(r2[pi][j], ra, rb);
+            if (d < p.D) {
+              if (ta < p.n_tokens) __stcs(p.q_out + ta * (long long)p.D + d, __fsub_rn(__ldcs(p.x + ta * (long long)p.D + d), ra));
+              if (tb < p.n_tokens) __stcs(p.q_out + tb * (long long)p.D + d, __fsub_rn(__ldcs(p.x + tb * (long long)p.D + d), rb));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    reg_dec<REG_HELPER>();
+    if (warp == kComputeWarps + kQuantWarps) {
+      // =============================== weight producer ===============================
+      if (lane == 0) {
+        const unsigned char* stages = p.packed + p.off_stage;
+        const uint32_t ring = smem_u32(smem + C::SM_RING);
+        const uint64_t pol = l2_policy_evict_last();
+        uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on parity 1
+        for (long long it = 0; it < my_iters; ++it) {
+          for (int l = 0; l <= p.nq_run; ++l) {
+            const unsigned char* src = stages + (size_t)l * (CH * (size_t)C::CHUNK_BYTES);
+            for (int c = 0; c < CH; c++) {
+              mbar_wait(&empty[slot], par);
+              mbar_arrive_expect_tx(&full[slot], C::CHUNK_BYTES);
+              tma_bulk_g2s_hint(ring + slot * C::CHUNK_BYTES, src + (size_t)c * C::CHUNK_BYTES, C::CHUNK_BYTES,
+                                &full[slot], pol);
+              if (++slot == NSLOT) { slot = 0; par ^= 1; }
+            }
+          }
+        }
+      }
+    } else {
+      // =============================== quantizer warps ===============================
+      const int hw = warp - kComputeWarps;
+      const float4* cb_s = cb_in_smem ? reinterpret_cast<const float4*>(smem + C::SM_CBT)
+                                      : reinterpret_cast<const float4*>(p.packed + p.off_cbt);
+      const unsigned short* map_s = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
+                                               : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+      const uint32_t codes_s = smem_u32(smem + C::SM_CODES);
+      const uint32_t part0 = smem_u32(smem + C::SM_PART);
+      const uint32_t cpr0 = smem_u32(smem + C::SM_CPR);
+      const int n_rows = p.cb_shared ? kd_pad : p.K;
+      uint32_t pf_bits = 0;  // bit g = parity of part_full[g]
+      for (long long it = 0; it < my_iters; ++it) {
+        const long long pair_tok0 = 2 * ((long long)blockIdx.x + it * gridDim.x) * TG;  // first token of group 0
+#pragma unroll 1
+        for (int l = 0; l < p.nq_run; ++l) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
+          const float4* cb_l = p.cb_shared ? cb_s : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
+#pragma unroll 1
+          for (int g = 0; g < 2; g++) {
+            mbar_wait(&part_full[g], (pf_bits >> g) & 1u);
+            pf_bits ^= 1u << g;
+#pragma unroll 1
+            for (int tok = hw; tok < TG; tok += kQuantWarps) {
+              // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
+              const uint32_t pa = part0 + (g * 4 * 32 + tok * 4) * 4;
+              const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
+              const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
+              const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
+              const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
+              const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
+              // x / x.norm()  (model.py:188): sqrt(((z0^2 + z1^2) + z2^2) + z3^2), IEEE divide
+              const float nrm = __fsqrt_rn(__fadd_rn(
+                  __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
+              const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
+              // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
+              float bv = -INFINITY;
+              int bk = 0x7fffffff;
+#pragma unroll 2
+              for (int k = lane; k < n_rows; k += 32) {
+                const float4 cw = cb_l[k];
+                const float v = __fmaf_rn(n3, cw.w, __fmaf_rn(n2, cw.z, __fmaf_rn(n1, cw.y, __fmul_rn(n0, cw.x))));
+                if (k == lane || v > bv) { bv = v; bk = k; }
+              }
+#pragma unroll
+              for (int s = 16; s >= 1; s >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, s);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, s);
+                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+              }
+              // a NaN row (z == 0, inf or NaN input) compares false everywhere: lane 0 still holds row 0,
+              // which is what torch.argmax returns for an all-NaN row
+              bk = __shfl_sync(0xffffffffu, bk, 0);
+              const int code = p.cb_shared ? (int)map_s[bk] : bk;
+              const long long token = pair_tok0 + g * TG + tok;
+              if (p.z_out != nullptr && lane == 0 && token < p.n_tokens)
+                reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
+              float4 cw;
+              if (p.teacher != nullptr) {
+                const int tc = (token < p.n_tokens) ? p.teacher[token * p.nq_run + l] : 0;
+                cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
+              } else {
+                cw = cb_l[bk];
+              }
+              // straight-through value c' = z + (c - z)  (model.py:218-220)
+              if (lane < 4) {
+                const float zc = lane == 0 ? z0 : lane == 1 ? z1 : lane == 2 ? z2 : z3;
+                const float cc = lane == 0 ? cw.x : lane == 1 ? cw.y : lane == 2 ? cw.z : cw.w;
+                sts32(cpr0 + g * 128 + (tok >> 1) * 32 + lane * 8 + (tok & 1) * 4, __fadd_rn(zc, __fsub_rn(cc, zc)));
+              }
+              if (lane == 0)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + ((g * 8 + tok) * kCodeBuf + (l & (kCodeBuf - 1))) * 2),
+                             "h"((unsigned short)code)
+                             : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c_ready[g]);
+            // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
+            if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
+              const int l0 = l & ~(kCodeBuf - 1);
+              for (int tok = hw; tok < TG; tok += kQuantWarps) {
+                const long long token = pair_tok0 + g * TG + tok;
+                if (lane <= l - l0 && token < p.n_tokens) {
+                  unsigned short cval;
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cval) : "r"(codes_s + ((g * 8 + tok) * kCodeBuf + lane) * 2));
+                  const long long off = token * p.code_stride + l0 + lane;
+                  if (p.code_dtype == 2) reinterpret_cast<long long*>(p.codes)[off] = (long long)cval;
+                  else if (p.code_dtype == 1) reinterpret_cast<int*>(p.codes)[off] = (int)cval;
+                  else reinterpret_cast<short*>(p.codes)[off] = (short)cval;
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace rq

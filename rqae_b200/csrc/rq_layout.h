@@ -1,0 +1,76 @@
+// Packed weight layout shared by the host C-ABI and the kernels ("Data layout").
+//
+// The reference keeps 2*nq separate nn.Linear modules (rqae/model.py:29-36).  The kernels
+// stream them as nq+1 *stages*; stage s holds exactly what one pass of the fused loop needs:
+//     W_out[s-1] rows + b_out[s-1]   (out-projection of the code chosen at layer s-1)
+//     W_in[s] columns                (in-projection of layer s)
+// with zeros for W_out[-1], b_out[-1] and W_in[nq].  A stage is cut into CH chunks, one
+// bulk-TMA copy each.  A compute group has 128 threads; thread t owns elements
+// d = j*128 + t (j < E) of the D axis, so inside a chunk (JC = E/CH values of j):
+//     [ float4 w_out4 [JC][128] | float4 w_in4 [JC][128] | float b_out [JC][128] ]
+// and a warp's 128-bit shared loads are 512 contiguous bytes (conflict free).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#define RQ_GROUP_THREADS 128
+#define RQ_BYTES_PER_ELEM 36 /* float4 + float4 + float */
+#define RQ_HDR_BYTES 256
+#define RQ_MAX_SMEM_CODEBOOK 1024 /* rows of the search table kept in shared memory */
+
+struct RqShape {
+  int E;     /* elements per thread: D_pad = 128 * E */
+  int EC;    /* register block (elements per inner block) */
+  int CH;    /* chunks per stage */
+  int NSLOT; /* ring slots */
+  int TG;    /* tokens per group */
+};
+
+/* Supported instantiations, smallest first. Returns 0 on success. */
+static inline int rq_pick_shape(int D, struct RqShape* s) {
+  static const struct RqShape table[] = {
+      {2, 2, 1, 4, 8},    /* D <=  256 */
+      {6, 3, 1, 4, 8},    /* D <=  768 */
+      {12, 3, 2, 6, 8},   /* D <= 1536 */
+      {18, 3, 3, 7, 8},   /* D <= 2304  (Gemma-2-2B) */
+      {28, 2, 7, 11, 6},  /* D <= 3584  (Gemma-2-9B) */
+  };
+  for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
+    if (D <= table[i].E * RQ_GROUP_THREADS) {
+      *s = table[i];
+      return 0;
+    }
+  }
+  return 1;
+}
+
+struct RqLayout {
+  size_t off_bin;    /* float4[nq+1]          in-projection biases                    */
+  size_t off_cbt;    /* float4[KT]            de-duplicated search table (shared mode) */
+  size_t off_map;    /* uint16[KT]            search row -> lowest original index      */
+  size_t off_stage;  /* (nq+1) stages                                                  */
+  size_t stage_bytes;
+  size_t chunk_bytes;
+  size_t total;
+  int KT; /* K rounded up to a multiple of 32 */
+};
+
+static inline size_t rq_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLayout* L) {
+  L->KT = (K + 31) / 32 * 32;
+  L->off_bin = RQ_HDR_BYTES;
+  L->off_cbt = rq_align_up(L->off_bin + (size_t)(nq + 1) * 16, 256);
+  L->off_map = rq_align_up(L->off_cbt + (size_t)L->KT * 16, 256);
+  L->off_stage = rq_align_up(L->off_map + (size_t)L->KT * 2, 1024);
+  L->stage_bytes = (size_t)s->E * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
+  L->chunk_bytes = L->stage_bytes / s->CH;
+  L->total = L->off_stage + (size_t)(nq + 1) * L->stage_bytes;
+}
+
+/* Device-resident header at offset 0 of the packed buffer. */
+struct RqHeader {
+  int kd_pad;    /* rows in the search table (multiple of 32), written by the pack kernel */
+  int kd;        /* distinct rows */
+  int reserved[62];
+};

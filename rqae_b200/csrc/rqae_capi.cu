@@ -1,0 +1,363 @@
+// C ABI of librqae_b200.so (declared in include/rqae_b200.h): weight packing, kernel selection and
+// launch.  Host logic only; the kernels live in rq_forward.cuh / rq_decode.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/rqae_b200.h"
+#include "rq_decode.cuh"
+#include "rq_forward.cuh"
+#include "rq_layout.h"
+
+namespace {
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+thread_local int64_t g_launches = 0;
+
+#define RQ_CUDA(call)                    \
+  do {                                   \
+    cudaError_t e__ = (call);            \
+    if (e__ != cudaSuccess) {            \
+      g_last_cuda = e__;                 \
+      return RQAE_ECUDA;                 \
+    }                                    \
+  } while (0)
+
+int device_sm_count(int* sms) {
+  int dev = 0;
+  RQ_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  RQ_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return RQAE_ENODEVICE;
+  RQ_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return RQAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_stages_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                   const float* __restrict__ w_out, const float* __restrict__ b_out, int nq, int D,
+                                   int E, int CH, unsigned char* __restrict__ packed, size_t off_bin,
+                                   size_t off_stage, size_t stage_bytes) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_stage = (long long)E * RQ_GROUP_THREADS;
+  const long long total = (long long)(nq + 1) * per_stage;
+  if (gid < nq + 1) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gid < nq) b = make_float4(b_in[gid * 4 + 0], b_in[gid * 4 + 1], b_in[gid * 4 + 2], b_in[gid * 4 + 3]);
+    reinterpret_cast<float4*>(packed + off_bin)[gid] = b;
+  }
+  if (gid >= total) return;
+  const int s = (int)(gid / per_stage);
+  const int rem = (int)(gid % per_stage);
+  const int j = rem / RQ_GROUP_THREADS, t = rem % RQ_GROUP_THREADS;
+  const int JC = E / CH;
+  const int c = j / JC, jj = j % JC;
+  const int d = j * RQ_GROUP_THREADS + t;
+  unsigned char* chunk = packed + off_stage + (size_t)s * stage_bytes + (size_t)c * (stage_bytes / CH);
+  float4 wo = make_float4(0.f, 0.f, 0.f, 0.f), wi = wo;
+  float bo = 0.f;
+  if (d < D) {
+    if (s >= 1) {
+      const float* w = w_out + ((size_t)(s - 1) * D + d) * 4;
+      wo = make_float4(w[0], w[1], w[2], w[3]);
+      bo = b_out[(size_t)(s - 1) * D + d];
+    }
+    if (s < nq) {
+      const float* w = w_in + (size_t)s * 4 * D + d;
+      wi = make_float4(w[0], w[(size_t)D], w[2 * (size_t)D], w[3 * (size_t)D]);
+    }
+  }
+  const size_t e = (size_t)jj * RQ_GROUP_THREADS + t;
+  reinterpret_cast<float4*>(chunk)[e] = wo;
+  reinterpret_cast<float4*>(chunk + (size_t)JC * RQ_GROUP_THREADS * 16)[e] = wi;
+  reinterpret_cast<float*>(chunk + (size_t)JC * RQ_GROUP_THREADS * 32)[e] = bo;
+}
+
+// Search table for the shared-codebook mode: drop rows that are value-identical to an earlier row
+// (torch.argmax returns the first maximum, so a later duplicate can never be selected), keep the
+// original index of every surviving row, pad to a multiple of 32 with copies of row 0 (a copy ties
+// with row 0 and loses on the index).  Single block; runs once per weight load.
+__global__ void pack_codebook_kernel(const float* __restrict__ cb, int K, int KT, unsigned char* __restrict__ packed,
+                                     size_t off_cbt, size_t off_map) {
+  extern __shared__ unsigned char keep[];
+  const float4* rows = reinterpret_cast<const float4*>(cb);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float4 a = rows[k];
+    bool dup = false;
+    for (int j = 0; j < k && !dup; j++) {
+      const float4 b = rows[j];
+      dup = (a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w);
+    }
+    keep[k] = dup ? 0 : 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4* out = reinterpret_cast<float4*>(packed + off_cbt);
+    unsigned short* map = reinterpret_cast<unsigned short*>(packed + off_map);
+    int n = 0;
+    for (int k = 0; k < K; k++)
+      if (keep[k]) { out[n] = rows[k]; map[n] = (unsigned short)k; n++; }
+    const int kd = n;
+    const int kd_pad = (kd + 31) / 32 * 32;
+    for (; n < kd_pad && n < KT; n++) { out[n] = out[0]; map[n] = map[0]; }
+    RqHeader* h = reinterpret_cast<RqHeader*>(packed);
+    h->kd = kd;
+    h->kd_pad = kd_pad;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32-pipe probes (roofline denominators measured by bench.py)
+// ---------------------------------------------------------------------------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(512, 1) fp32_probe_kernel(int iters, float* sink) {
+  using namespace rq;
+  const float s = 1.0f + 1e-7f * (float)(threadIdx.x & 7), t = 1e-9f * (float)threadIdx.x;
+  if (PACKED) {
+    u64 a[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) a[i] = pack2((float)i, (float)(i + 1));
+    const u64 ss = pack2(s, s), tt = pack2(t, t);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) a[i] = fma2(a[i], ss, tt);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { float lo, hi; unpack2(a[i], lo, hi); acc += lo + hi; }
+    if (acc == 12345.678f) sink[0] = acc;
+  } else {
+    float a[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) a[i] = (float)i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int i = 0; i < 24; i++) a[i] = __fmaf_rn(a[i], s, t);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc += a[i];
+    if (acc == 12345.678f) sink[0] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward launch
+// ---------------------------------------------------------------------------------------------
+template <int E, int EC, int CH, int NSLOT, int TG>
+int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+  using C = rq::FwdCfg<E, EC, CH, NSLOT, TG>;
+  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL); });
+  RQ_CUDA(attr_err);
+  const long long n_units = (prm.n_tokens + TG - 1) / TG;
+  const long long n_pairs = (n_units + 1) / 2;
+  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  kern<<<grid, rq::kThreads, C::SM_TOTAL, st>>>(prm);
+  g_launches++;
+  RQ_CUDA(cudaGetLastError());
+  return RQAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rqae_version(void) { return "rqae_b200 0.1.0 sm_100a"; }
+
+const char* rqae_strerror(int code) {
+  switch (code) {
+    case RQAE_OK: return "ok";
+    case RQAE_EINVAL: return "invalid argument";
+    case RQAE_EUNSUPPORTED: return "unsupported shape (codebook_dim must be 4, dim <= 3584, K <= 65535)";
+    case RQAE_ECUDA: return "CUDA runtime error";
+    case RQAE_ENODEVICE: return "current device is not an sm_100 (B200) GPU";
+    case RQAE_ESIZE: return "buffer too small";
+    default: return "unknown error";
+  }
+}
+
+const char* rqae_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+int64_t rqae_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+size_t rqae_packed_bytes(int nq, int dim, int codebook_dim, int K) {
+  RqShape s;
+  if (nq <= 0 || dim <= 0 || codebook_dim != 4 || K <= 0 || K > 65535 || rq_pick_shape(dim, &s)) return 0;
+  RqLayout L;
+  rq_layout(nq, K, &s, &L);
+  return L.total;
+}
+
+int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                      const float* codebook, int codebook_shared, int nq, int dim, int codebook_dim, int K,
+                      void* packed, size_t packed_bytes, void* stream) {
+  if (!w_in || !b_in || !w_out || !b_out || !codebook || !packed || nq <= 0 || dim <= 0 || K <= 0) return RQAE_EINVAL;
+  RqShape s;
+  if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
+  RqLayout L;
+  rq_layout(nq, K, &s, &L);
+  if (packed_bytes < L.total) return RQAE_ESIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* pk = (unsigned char*)packed;
+  RQ_CUDA(cudaMemsetAsync(pk, 0, RQ_HDR_BYTES, st));
+  const long long total = (long long)(nq + 1) * s.E * RQ_GROUP_THREADS;
+  pack_stages_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_in, b_in, w_out, b_out, nq, dim, s.E, s.CH, pk,
+                                                                      L.off_bin, L.off_stage, L.stage_bytes);
+  g_launches++;
+  RQ_CUDA(cudaGetLastError());
+  if (codebook_shared) {
+    pack_codebook_kernel<<<1, 1024, (size_t)K, st>>>(codebook, K, L.KT, pk, L.off_cbt, L.off_map);
+    g_launches++;
+    RQ_CUDA(cudaGetLastError());
+  }
+  return RQAE_OK;
+}
+
+int rqae_forward_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                     int codebook_dim, int K, const float* x, int64_t n_tokens, void* codes, int code_dtype,
+                     int64_t code_stride, float* q_out, const int32_t* teacher, float* z_out, void* stream) {
+  if (!packed || !codebook || nq <= 0 || nq_run <= 0 || nq_run > nq || dim <= 0 || K <= 0 || n_tokens < 0) return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2 || (codes && code_stride < nq_run)) return RQAE_EINVAL;
+  if (n_tokens > 0 && !x) return RQAE_EINVAL;
+  RqShape s;
+  if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
+  if (n_tokens == 0) return RQAE_OK;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  RqLayout L;
+  rq_layout(nq, K, &s, &L);
+  rq::FwdParams prm;
+  prm.packed = (const unsigned char*)packed;
+  prm.off_bin = L.off_bin; prm.off_cbt = L.off_cbt; prm.off_map = L.off_map; prm.off_stage = L.off_stage;
+  prm.codebook = codebook; prm.cb_shared = codebook_shared ? 1 : 0; prm.K = K; prm.nq_run = nq_run; prm.D = dim;
+  prm.x = x; prm.n_tokens = n_tokens; prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride;
+  prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (s.E) {
+    case 2: return launch_forward<2, 2, 1, 4, 8>(prm, sms, st);
+    case 6: return launch_forward<6, 3, 1, 4, 8>(prm, sms, st);
+    case 12: return launch_forward<12, 3, 2, 6, 8>(prm, sms, st);
+    case 18: return launch_forward<18, 3, 3, 7, 8>(prm, sms, st);
+    case 28: return launch_forward<28, 2, 7, 11, 6>(prm, sms, st);
+    default: return RQAE_EUNSUPPORTED;
+  }
+}
+
+int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_codes, int dim, int codebook_dim, int K,
+                    const void* codes, int code_dtype, int64_t code_stride, const float* cv,
+                    const uint8_t* layer_mask, int64_t n_tokens, float* q_out, void* stream) {
+  if (!packed || !q_out || nq <= 0 || nq_codes < 0 || nq_codes > nq || dim <= 0 || K <= 0 || n_tokens < 0) return RQAE_EINVAL;
+  if (!codes && !cv) return RQAE_EINVAL;
+  if (codes && (!codebook0 || code_dtype < 0 || code_dtype > 2 || code_stride < nq_codes)) return RQAE_EINVAL;
+  RqShape s;
+  if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
+  if (n_tokens == 0) return RQAE_OK;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  RqLayout L;
+  rq_layout(nq, K, &s, &L);
+  rq::DecParams prm;
+  prm.packed = (const unsigned char*)packed;
+  prm.off_stage = L.off_stage; prm.stage_bytes = L.stage_bytes;
+  prm.codebook0 = codebook0; prm.K = K; prm.nq_codes = nq_codes; prm.D = dim; prm.E = s.E; prm.CH = s.CH;
+  prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride; prm.cv = cv;
+  prm.layer_mask = layer_mask; prm.n_tokens = n_tokens; prm.q_out = q_out;
+  rc = rq::launch_decode(prm, sms, (cudaStream_t)stream);
+  if (rc == 0) g_launches++;
+  if (rc == RQAE_ECUDA) g_last_cuda = cudaGetLastError();
+  return rc;
+}
+
+int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, float* sink, void* stream) {
+  if (iters <= 0 || !sink) return RQAE_EINVAL;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  const int grid = sms * 2, block = 512;
+  if (packed_f32x2) fp32_probe_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+  else fp32_probe_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+  g_launches++;
+  RQ_CUDA(cudaGetLastError());
+  if (flops_per_launch) *flops_per_launch = (double)grid * block * (double)iters * 8.0 * 24.0 * 2.0;
+  return RQAE_OK;
+}
+
+int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                          int codebook_dim, int K, const float* x_host, int64_t n_tokens, void* codes_host,
+                          int code_dtype, float* q_host, int64_t chunk_tokens) {
+  if (!packed || !codebook || !x_host || n_tokens < 0 || chunk_tokens <= 0 || code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
+  if (nq_run <= 0 || nq_run > nq) return RQAE_EINVAL;
+  if (n_tokens == 0) return RQAE_OK;
+  const size_t csz = code_dtype == 2 ? 8 : (code_dtype == 1 ? 4 : 2);
+  if (chunk_tokens > n_tokens) chunk_tokens = n_tokens;
+  cudaStream_t s_in, s_cmp, s_out;
+  RQ_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  RQ_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+  RQ_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  float* dx[2] = {nullptr, nullptr};
+  float* dq[2] = {nullptr, nullptr};
+  void* dc[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+  int rc = RQAE_OK;
+  auto fail = [&](cudaError_t e) { g_last_cuda = e; rc = RQAE_ECUDA; };
+  for (int b = 0; b < 2 && rc == 0; b++) {
+    cudaError_t e;
+    if ((e = cudaMalloc(&dx[b], (size_t)chunk_tokens * dim * 4)) != cudaSuccess) fail(e);
+    if (rc == 0 && q_host && (e = cudaMalloc(&dq[b], (size_t)chunk_tokens * dim * 4)) != cudaSuccess) fail(e);
+    if (rc == 0 && codes_host && (e = cudaMalloc(&dc[b], (size_t)chunk_tokens * nq_run * csz)) != cudaSuccess) fail(e);
+    cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_cmp[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming);
+  }
+  int64_t n_chunks = (n_tokens + chunk_tokens - 1) / chunk_tokens;
+  for (int64_t c = 0; c < n_chunks && rc == 0; c++) {
+    const int b = (int)(c & 1);
+    const int64_t t0 = c * chunk_tokens;
+    const int64_t nt = (n_tokens - t0 < chunk_tokens) ? (n_tokens - t0) : chunk_tokens;
+    // buffer b is free once the D2H copies of chunk c-2 are done
+    if (c >= 2) cudaStreamWaitEvent(s_in, ev_out[b], 0);
+    cudaError_t e = cudaMemcpyAsync(dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, s_in);
+    if (e != cudaSuccess) { fail(e); break; }
+    cudaEventRecord(ev_in[b], s_in);
+    cudaStreamWaitEvent(s_cmp, ev_in[b], 0);
+    if (c >= 2) cudaStreamWaitEvent(s_cmp, ev_out[b], 0);
+    rc = rqae_forward_f32(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, dx[b], nt, dc[b],
+                          code_dtype, nq_run, dq[b], nullptr, nullptr, (void*)s_cmp);
+    if (rc) break;
+    cudaEventRecord(ev_cmp[b], s_cmp);
+    cudaStreamWaitEvent(s_out, ev_cmp[b], 0);
+    if (codes_host)
+      cudaMemcpyAsync((char*)codes_host + (size_t)t0 * nq_run * csz, dc[b], (size_t)nt * nq_run * csz, cudaMemcpyDeviceToHost, s_out);
+    if (q_host) cudaMemcpyAsync(q_host + (size_t)t0 * dim, dq[b], (size_t)nt * dim * 4, cudaMemcpyDeviceToHost, s_out);
+    cudaEventRecord(ev_out[b], s_out);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+  if (rc == 0 && e1 != cudaSuccess) fail(e1);
+  if (rc == 0 && e2 != cudaSuccess) fail(e2);
+  if (rc == 0 && e3 != cudaSuccess) fail(e3);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(dx[b]); cudaFree(dq[b]); cudaFree(dc[b]);
+    cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_cmp[b]); cudaEventDestroy(ev_out[b]);
+  }
+  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
+  return rc;
+}
+
+}  // extern "C"

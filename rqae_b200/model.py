@@ -1,0 +1,420 @@
+"""``RQAE`` -- host-side mirror of ``rqae.model.RQAE`` (harish-kamath/rqae, rqae/model.py) whose
+hot path runs in the sm_100a kernels of ``librqae_b200.so``.
+
+What is kept exactly as in the reference (so that ``rqae/llm.py`` hooks, ``rqae/feature.py`` and
+``scripts/1_create_activations.py`` / ``scripts/3_make_rqae_features.py`` work unchanged):
+
+* constructor signature and defaults, RNG consumption order of the random init (model.py:18-73);
+* parameter / buffer names and shapes: ``layers.{l}.0.{weight,bias}``, ``layers.{l}.1.{weight,bias}``,
+  ``codebook``, ``codebook_counts`` -- ``load_state_dict(strict=True)`` from the published
+  safetensors works (model.py:89-96);
+* ``forward(x, max_layers, temperature) -> (quantized_out fp32, indices int64)`` (model.py:199-230),
+  ``decode`` / ``decode_from_codebook_values`` / ``indices_to_codebook_values`` (model.py:232-252),
+  ``hook(**kwargs) -> hook_fn(module, input, output)`` (model.py:254-291), the derived tables
+  ``codebook_sims / subfeatures / subfeature_sims / layer_norms`` (model.py:133-178).
+
+What is new: ``encode(x, max_layers, out_dtype)`` (codes only), ``forward_host`` (host buffers in,
+host buffers out, copies pipelined inside the C library).
+
+The module holds no compute of its own: ``forward`` packs the weights once per weight version into
+the streaming layout (``rqae_pack_weights``) and launches ONE fused kernel on the current CUDA stream
+without synchronising.  CPU tensors are rejected -- there is deliberately no fallback path.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+_FSQ = ("fsq", "round_fsq")
+
+
+def _fsq_grid(codebook_size: int, codebook_dim: int, normalise: bool) -> torch.Tensor:
+    """linspace(-1, 1, cbs)^cd, first coordinate slowest (itertools.product order), rows divided by
+    their float64 norm for round_fsq with the zero row left untouched, then cast to fp32
+    (model.py:63-72).  sqrt and divide are correctly rounded in float64 both here and in numpy, so
+    the table is bit-identical to the reference's."""
+    axis = torch.linspace(-1, 1, codebook_size, dtype=torch.float64)
+    grid = torch.cartesian_prod(*([axis] * codebook_dim)).reshape(-1, codebook_dim)
+    if normalise:
+        n = grid.pow(2).sum(-1, keepdim=True).sqrt()
+        grid = grid / torch.where(n == 0, torch.ones_like(n), n)
+    return grid.to(torch.float32)
+
+
+class RQAE(nn.Module):
+    PRETRAINED = {
+        "google/gemma-2-2b": "harish-kamath/rqae/gemma-2-2b",
+        "rqae-rqae-round_fsq-cbd4-cbs5-nq1024": "harish-kamath/rqae/gemma-2-2b",
+    }
+
+    def __init__(self, dim: int = 2304, codebook_dim: int = 4, codebook_size: int = 5,
+                 num_quantizers: int = 1024, quantization_method: str = "round_fsq", name: str = "", **kwargs):
+        super().__init__()
+        # Same module creation order as the reference so that torch.manual_seed(s); RQAE(...) yields the
+        # same random weights (model.py:29-36): per layer Linear(dim, cd) then Linear(cd, dim).
+        self.layers = nn.ModuleList(
+            nn.ModuleList([nn.Linear(dim, codebook_dim), nn.Linear(codebook_dim, dim)])
+            for _ in range(num_quantizers))
+        rows = codebook_size ** codebook_dim if quantization_method in _FSQ else codebook_size
+        self.codebook = nn.Parameter(torch.randn(num_quantizers, rows, codebook_dim))
+        self.register_buffer("codebook_counts", torch.zeros(num_quantizers, rows), persistent=True)
+        self.dim = dim
+        self.quantization_method = quantization_method
+        self.num_quantizers = num_quantizers
+        self.codebook_dim = codebook_dim
+        self.codebook_size = codebook_size
+        self.name = name
+        if quantization_method in _FSQ:
+            with torch.no_grad():
+                self.codebook.copy_(_fsq_grid(codebook_size, codebook_dim, quantization_method == "round_fsq"))
+            self.codebook.requires_grad = False
+        else:
+            self.normalize_codebooks()
+        self._packed = None          # (key, packed uint8 tensor, shared flag, search codebook tensor)
+        self._static_weights = False
+
+    # ------------------------------------------------------------------ loading (model.py:75-99)
+    @classmethod
+    def from_pretrained(cls, model_name: str):
+        from huggingface_hub import hf_hub_download
+        from safetensors import safe_open
+
+        model_name = cls.PRETRAINED.get(model_name, model_name)
+        username, reponame, *rest = model_name.split("/")
+        folder = "/".join(rest)
+        model_path = hf_hub_download(f"{username}/{reponame}", os.path.join(folder, "model.safetensors"))
+        config_path = hf_hub_download(f"{username}/{reponame}", os.path.join(folder, "config.json"))
+        with open(config_path, "r") as f:
+            params = json.load(f)
+        name = (f"rqae-{reponame}-{params['quantization_method']}-cbd{params['codebook_dim']}"
+                f"-cbs{params['codebook_size']}-nq{params['num_quantizers']}")
+        model = cls(**params, name=name)
+        if model_path.endswith(".safetensors"):
+            with safe_open(model_path, framework="pt") as f:
+                state = {k: f.get_tensor(k) for k in f.keys()}
+            model.load_state_dict(state, strict=True)
+        elif model_path.endswith(".pt"):
+            model.load_state_dict(torch.load(model_path, weights_only=True))
+        else:
+            raise ValueError(f"Unknown file extension for {model_path}")
+        return model
+
+    def update_codebook_counts(self, indices):
+        """Codebook-usage EMA of the reference is disabled there (unconditional return, model.py:101-104)."""
+        return
+
+    def normalize_codebooks(self):
+        """model.py:126-131: learned codebooks are re-normalised in place; fsq tables are left alone."""
+        if self.quantization_method in _FSQ:
+            return
+        with torch.no_grad():
+            self.codebook.copy_(self.codebook / self.codebook.norm(dim=-1, keepdim=True))
+
+    # ------------------------------------------------------------------ packed weights
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        for k in ("_codebook_sims", "_subfeatures", "_subfeature_sims", "_layer_norms"):
+            self.__dict__.pop(k, None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def repack(self):
+        """Drop the packed copy of the weights (call after editing parameters through ``.data``)."""
+        self._packed = None
+
+    def freeze_packed(self, flag: bool = True):
+        """Skip the per-call weight-version check (saves ~0.3 ms of Python per call when the weights
+        are known not to change, e.g. inside an inference hook)."""
+        self._static_weights = bool(flag)
+
+    def _weights_key(self):
+        w = self.layers[0][0].weight
+        key = [w.device, w.data_ptr(), self.codebook.data_ptr()]
+        if not self._static_weights:
+            try:
+                key.append(sum(p._version for p in self.parameters()))
+            except RuntimeError:  # inference tensors carry no version counter
+                pass
+        return tuple(key)
+
+    def _ensure_packed(self):
+        key = self._weights_key()
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed
+        dev = self.layers[0][0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("rqae_b200.RQAE computes on CUDA (sm_100a) only; move the module with .to('cuda'). "
+                               "There is no CPU fallback.")
+        if self.layers[0][0].weight.dtype != torch.float32:
+            raise RuntimeError("rqae_b200.RQAE kernels are fp32 (the reference's compute dtype); call .float()")
+        lib = _lib.load()
+        nq, D, cd = self.num_quantizers, self.dim, self.codebook_dim
+        K = self.codebook.shape[1]
+        nbytes = lib.rqae_packed_bytes(nq, D, cd, K)
+        if nbytes == 0:
+            raise NotImplementedError(
+                f"rqae_b200 kernels support codebook_dim == 4, dim <= 3584 and <= 65535 codebook rows "
+                f"(got codebook_dim={cd}, dim={D}, rows={K})")
+        with torch.no_grad():
+            w_in = torch.stack([l[0].weight for l in self.layers]).contiguous()
+            b_in = torch.stack([l[0].bias for l in self.layers]).contiguous()
+            w_out = torch.stack([l[1].weight for l in self.layers]).contiguous()
+            b_out = torch.stack([l[1].bias for l in self.layers]).contiguous()
+            cb = self.codebook.detach()
+            # The reference indexes codebook[layer] in forward; the single-table fast path is valid only
+            # when every layer holds the same table (always true for fsq / round_fsq as constructed).
+            shared = self.quantization_method in _FSQ and bool((cb == cb[:1]).all().item())
+            cb_arg = cb[:1].contiguous() if shared else cb.contiguous()
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            with torch.cuda.device(dev):
+                rc = lib.rqae_pack_weights(w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr(),
+                                           cb_arg.data_ptr(), int(shared), nq, D, cd, K, packed.data_ptr(), nbytes,
+                                           stream)
+            _lib.check(rc, "rqae_pack_weights")
+            for t in (w_in, b_in, w_out, b_out):
+                t.record_stream(torch.cuda.current_stream(dev))
+        self._packed = (key, packed, shared, cb_arg)
+        return self._packed
+
+    # ------------------------------------------------------------------ hot path
+    def _learned_tables(self, nq_run: int) -> torch.Tensor:
+        """Reference quirk (model.py:126-131,196): ``quantize`` re-normalises the whole codebook parameter
+        in place before EVERY layer, so layer l sees a table normalised l+1 times since the call began and
+        the parameter ends up normalised nq_run times.  Reproduced here (iteration stops early once the
+        normalisation reaches its fixed point) and the per-layer tables are handed to the kernel."""
+        with torch.no_grad():
+            cur = self.codebook.detach()
+            tables = torch.empty_like(cur)
+            done = 0
+            for l in range(nq_run):
+                nxt = cur / cur.norm(dim=-1, keepdim=True)
+                tables[l] = nxt[l]
+                done = l + 1
+                fixed = bool((nxt == cur).all().item())
+                cur = nxt
+                if fixed:
+                    break
+            if done < nq_run:
+                tables[done:nq_run] = cur[done:nq_run]
+            if nq_run < tables.shape[0]:
+                tables[nq_run:] = cur[nq_run:]
+            self.codebook.copy_(cur)
+        return tables.contiguous()
+
+    def _run_forward(self, x: torch.Tensor, max_layers, temperature: float, want_q: bool, out_dtype: torch.dtype,
+                     teacher: Optional[torch.Tensor] = None, want_z: bool = False):
+        if self.training and temperature >= 1e-7:
+            raise NotImplementedError("gumbel-softmax sampling (training with temperature >= 1e-7, model.py:180-185) "
+                                      "is not part of the inference hot path")
+        if not x.is_cuda:
+            raise RuntimeError("rqae_b200.RQAE.forward needs a CUDA tensor; there is no CPU fallback")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 activations (the reference hook calls .float() first), got {x.dtype}")
+        if x.shape[-1] != self.dim:
+            raise RuntimeError(f"last dimension must be {self.dim}, got {tuple(x.shape)}")
+        nq_run = int(min(max_layers, self.num_quantizers))
+        if nq_run <= 0:
+            raise RuntimeError("max_layers must be >= 1 (the reference fails on an empty index list, model.py:226)")
+        _, packed, shared, cb_arg = self._ensure_packed()
+        if not shared and self.quantization_method not in _FSQ:
+            cb_arg = self._learned_tables(nq_run)
+        lib = _lib.load()
+        xc = x.detach().contiguous()
+        lead = xc.shape[:-1]
+        n = xc.numel() // self.dim
+        dev = xc.device
+        codes = torch.empty(*lead, nq_run, dtype=out_dtype, device=dev)
+        q = torch.empty_like(xc) if want_q else None
+        z = torch.empty(*lead, nq_run, 4, dtype=torch.float32, device=dev) if want_z else None
+        tch = None
+        if teacher is not None:
+            tch = teacher.to(device=dev, dtype=torch.int32).contiguous()
+            assert tch.shape == codes.shape
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = lib.rqae_forward_f32(
+                    packed.data_ptr(), cb_arg.data_ptr(), int(shared), self.num_quantizers, nq_run, self.dim,
+                    self.codebook_dim, self.codebook.shape[1], xc.data_ptr(), n, codes.data_ptr(),
+                    _lib.CODE_DTYPE[str(out_dtype).split(".")[-1]], nq_run,
+                    0 if q is None else q.data_ptr(), 0 if tch is None else tch.data_ptr(),
+                    0 if z is None else z.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "rqae_forward_f32")
+        return q, codes, z
+
+    def forward(self, x, max_layers: int = float("inf"), temperature=0.0):
+        """model.py:199-230.  Returns (quantized_out (B,S,D) fp32, indices (B,S,nq') int64)."""
+        q, codes, _ = self._run_forward(x, max_layers, temperature, True, torch.int64)
+        self.update_codebook_counts(codes)
+        return q, codes
+
+    def encode(self, x, max_layers: int = float("inf"), out_dtype: torch.dtype = torch.int64):
+        """Codes only (forward without the reconstruction write).  ``out_dtype`` may be int16 / int32 / int64;
+        every code is < codebook rows <= 65535."""
+        _, codes, _ = self._run_forward(x, max_layers, 0.0, False, out_dtype)
+        return codes
+
+    def indices_to_codebook_values(self, indices):
+        """model.py:232-234 -- always the layer-0 table."""
+        return self.codebook[0][indices]
+
+    def _layer_mask(self, layers, nq_codes: int, dev):
+        if layers is None:
+            return None, nq_codes > 0
+        mask = torch.zeros(max(nq_codes, 1), dtype=torch.uint8)
+        any_sel = False
+        for l in range(nq_codes):
+            if l in layers:
+                mask[l] = 1
+                any_sel = True
+        return mask.to(dev), any_sel
+
+    def _run_decode(self, codes: Optional[torch.Tensor], cv: Optional[torch.Tensor], layers):
+        src = codes if codes is not None else cv
+        if not src.is_cuda:
+            raise RuntimeError("rqae_b200.RQAE.decode needs CUDA tensors; there is no CPU fallback")
+        _, packed, _, _ = self._ensure_packed()
+        lib = _lib.load()
+        dev = src.device
+        if codes is not None:
+            if codes.dtype not in (torch.int16, torch.int32, torch.int64):
+                codes = codes.to(torch.int64)
+            codes = codes.contiguous()
+            lead, nq_codes = codes.shape[:-1], codes.shape[-1]
+            code_dtype = _lib.CODE_DTYPE[str(codes.dtype).split(".")[-1]]
+        else:
+            if cv.shape[-1] != self.codebook_dim:
+                raise RuntimeError("codebook values must have last dimension codebook_dim")
+            cv = cv.detach().to(torch.float32).contiguous()
+            lead, nq_codes = cv.shape[:-2], cv.shape[-2]
+            code_dtype = 0
+        nq_codes = min(nq_codes, self.num_quantizers)
+        mask, any_sel = self._layer_mask(layers, nq_codes, dev)
+        if not any_sel:
+            return None  # the reference returns its initial `quantized = None` (model.py:238,248)
+        n = int(math.prod(lead)) if len(lead) else 1
+        q = torch.empty(*lead, self.dim, dtype=torch.float32, device=dev)
+        cb0 = self.codebook.detach()[0].contiguous()
+        if n > 0:
+            stride = (codes.shape[-1] if codes is not None else 0)
+            if cv is not None and cv.shape[-2] != nq_codes:
+                cv = cv[..., :nq_codes, :].contiguous()
+            with torch.cuda.device(dev):
+                rc = lib.rqae_decode_f32(
+                    packed.data_ptr(), cb0.data_ptr(), self.num_quantizers, nq_codes, self.dim, self.codebook_dim,
+                    self.codebook.shape[1], 0 if codes is None else codes.data_ptr(), code_dtype, stride,
+                    0 if cv is None else cv.data_ptr(), 0 if mask is None else mask.data_ptr(), n, q.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "rqae_decode_f32")
+        return q
+
+    def decode_from_codebook_values(self, codebook_values, layers=None):
+        """model.py:236-248."""
+        return self._run_decode(None, codebook_values, layers)
+
+    def decode(self, indices, layers=None):
+        """model.py:250-252: gather from codebook[0] + sum of the selected layers' out-projections, fused
+        (the (B,S,nq,4) intermediate of the reference is never materialised)."""
+        return self._run_decode(indices, None, layers)
+
+    def forward_host(self, x_host: torch.Tensor, max_layers=float("inf"), want_q: bool = True,
+                     out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 65536, device=None):
+        """End-to-end variant for host-resident activations: ``x_host`` is a CPU tensor (pinned for full
+        copy speed); codes and reconstruction come back in (pinned) CPU tensors.  H2D copy, kernel and D2H
+        copies of consecutive chunks overlap inside ``rqae_forward_host_f32``."""
+        if x_host.is_cuda or x_host.dtype != torch.float32:
+            raise RuntimeError("forward_host expects a float32 CPU tensor")
+        nq_run = int(min(max_layers, self.num_quantizers))
+        _, packed, shared, cb_arg = self._ensure_packed()
+        if not shared and self.quantization_method not in _FSQ:
+            cb_arg = self._learned_tables(nq_run)
+        dev = packed.device
+        xc = x_host.contiguous()
+        lead = xc.shape[:-1]
+        n = xc.numel() // self.dim
+        pin = torch.cuda.is_available()
+        codes = torch.empty(*lead, nq_run, dtype=out_dtype, pin_memory=pin)
+        q = torch.empty(*lead, self.dim, dtype=torch.float32, pin_memory=pin) if want_q else None
+        torch.cuda.current_stream(dev).synchronize()  # packed weights are produced on the current stream
+        with torch.cuda.device(dev):
+            rc = _lib.load().rqae_forward_host_f32(
+                packed.data_ptr(), cb_arg.data_ptr(), int(shared), self.num_quantizers, nq_run, self.dim,
+                self.codebook_dim, self.codebook.shape[1], xc.data_ptr(), n, codes.data_ptr(),
+                _lib.CODE_DTYPE[str(out_dtype).split(".")[-1]], 0 if q is None else q.data_ptr(), int(chunk_tokens))
+        _lib.check(rc, "rqae_forward_host_f32")
+        return q, codes
+
+    # ------------------------------------------------------------------ hook (model.py:254-291)
+    def hook(self, **kwargs) -> Callable:
+        if "llm" in kwargs:
+            llm = kwargs.pop("llm")
+            assert hasattr(llm, "norm") and hasattr(llm, "denorm"), "RQAE hook requires norm and denorm from LLM"
+            return self.hook(norm=llm.norm, denorm=llm.denorm, **kwargs)
+        store = kwargs.get("store", lambda name, value: None)
+        skip_bos = kwargs.get("skip_bos", True)
+        replace = kwargs.get("replace", True)
+        if "norm" not in kwargs:
+            raise ValueError("RQAE hook requires norm from LLM")
+        if "denorm" not in kwargs:
+            raise ValueError("RQAE hook requires denorm from LLM")
+        norm, denorm = kwargs["norm"], kwargs["denorm"]
+
+        def hook_fn(module, input, output):
+            hs = output[0].float()                      # (B, S, dim)
+            store("original", hs.detach().clone())
+            rms_hs = norm(hs)
+            store("normed", rms_hs.detach().clone())
+            q_out, indices = self(rms_hs)               # one fused kernel on the current stream, no sync
+            store("quantized", q_out.detach().clone())
+            store("indices", indices.detach().clone())
+            q_out = denorm(q_out, hs)
+            if skip_bos:
+                q_out[:, 0] = hs[:, 0]
+            store("new", q_out.detach().clone())
+            if replace:
+                output[0].data.copy_(q_out)
+
+        return hook_fn
+
+    # ------------------------------------------------------------------ derived tables (model.py:133-178)
+    @property
+    def codebook_sims(self):
+        if "_codebook_sims" not in self.__dict__:
+            if self.quantization_method != "round_fsq":
+                raise ValueError("Codebook sims only supported for round_fsq for now")
+            cb = F.normalize(self.codebook.data.detach().clone()[0], dim=-1)
+            self.__dict__["_codebook_sims"] = (cb @ cb.T).to(torch.float16)
+        return self.__dict__["_codebook_sims"]
+
+    @property
+    def subfeatures(self):
+        if "_subfeatures" not in self.__dict__:
+            self.__dict__["_subfeatures"] = torch.stack(
+                [self.layers[l][1](self.codebook[l]) for l in range(self.num_quantizers)])
+        return self.__dict__["_subfeatures"]  # (num_quantizers, rows, dim)
+
+    @property
+    def subfeature_sims(self):
+        if "_subfeature_sims" not in self.__dict__:
+            n = F.normalize(self.subfeatures, dim=-1)
+            self.__dict__["_subfeature_sims"] = (n @ n.transpose(-1, -2)).to(torch.float16)
+        return self.__dict__["_subfeature_sims"]
+
+    @property
+    def layer_norms(self):
+        if "_layer_norms" not in self.__dict__:
+            self.__dict__["_layer_norms"] = torch.tensor(
+                [l[1].weight.data.norm(dim=0).mean().item() for l in self.layers],
+                device=self.layers[0][1].weight.device)
+        return self.__dict__["_layer_norms"]

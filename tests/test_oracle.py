@@ -1,0 +1,107 @@
+"""CPU tests: both oracles against the golden vectors produced by the unmodified reference."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import rqae_oracle as orc
+from tests import parity, util
+
+
+@pytest.mark.parametrize("name", util.SMALL_CASES)
+def test_torch_oracle_bit_identical_to_reference(golden_small, name):
+    d = util.small_case(golden_small, name)
+    w = util.stacked(d)
+    x = torch.from_numpy(d["x"])
+    ml = float("inf") if d["max_layers"] is None else d["max_layers"]
+    q, idx = orc.forward(w, x, max_layers=ml)
+    assert np.array_equal(idx.numpy(), d["codes"].astype(np.int64))
+    assert np.array_equal(q.numpy(), d["q"])           # same ATen ops in the same order
+    w.codebook = torch.from_numpy(d["codebook_post"])   # decode() reads the table left by forward()
+    dec = orc.decode(w, torch.from_numpy(d["codes_full"].astype(np.int64)), d["dec_layers"])
+    assert np.array_equal(dec.numpy(), d["dec"])
+
+
+@pytest.mark.parametrize("name", util.SMALL_CASES)
+@pytest.mark.parametrize("order_nt", [0, 128])
+def test_c_oracle_matches_reference_modulo_near_ties(golden_small, name, order_nt):
+    d = util.small_case(golden_small, name)
+    cw = util.cweights(d)
+    if d["method"] not in ("fsq", "round_fsq"):
+        pytest.skip("learned codebooks are re-normalised per layer by the host wrapper, not by the C oracle")
+    q, codes = c_oracle.forward_f32(cw, d["x"], max_layers=d["max_layers"], order_nt=order_nt)
+    rep = parity.compare_codes(codes, d["codes"], d["margins_fp64"])
+    assert rep.failures == 0, str(rep)
+    ok = parity.exact_token_mask(codes, d["codes"])
+    qr = d["q"].reshape(-1, d["q"].shape[-1])[ok]
+    qt = q.reshape(-1, q.shape[-1])[ok]
+    scale = np.abs(qr).max()
+    assert np.abs(qt - qr).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("name", util.SMALL_CASES)
+def test_c_oracle_decode_bit_exact(golden_small, name):
+    d = util.small_case(golden_small, name)
+    cw = util.cweights(d)
+    cw.codebook = np.ascontiguousarray(d["codebook_post"][:1])  # decode always reads codebook[0] (model.py:234)
+    dec = c_oracle.decode_f32(cw, codes=d["codes_full"], layers=d["dec_layers"])
+    assert np.array_equal(dec, d["dec"])
+
+
+def test_c_oracle_fp64_margins_agree_with_golden(golden_small):
+    d = util.small_case(golden_small, "round_fsq_d768_trained")
+    cw = util.cweights(d)
+    _, codes, m = c_oracle.forward_f64(cw, d["x"], teacher=d["codes_full"])
+    big = d["margins_fp64"] > 1e-4
+    assert np.array_equal(codes[big], d["codes_full"].astype(np.int32)[big])
+    assert np.abs(m - d["margins_fp64"])[big].max() < 1e-5
+
+
+def test_nan_rule_zero_rows(golden_small):
+    """z == 0 makes x / x.norm() NaN; torch.argmax then returns index 0."""
+    d = util.small_case(golden_small, "round_fsq_d256_zero")
+    cw = util.cweights(d)
+    codes = c_oracle.forward_f32(cw, d["x"], order_nt=128, fold_bias=True, recon="x_minus_r")[1]
+    assert np.array_equal(codes.reshape(-1, codes.shape[-1])[[0, 5]], d["codes"].reshape(-1, codes.shape[-1])[[0, 5]])
+
+
+def test_tie_rule_lowest_index_among_duplicate_rows():
+    """round_fsq holds 80 bit-identical duplicate rows (e.g. 0/156); the first one must win."""
+    w = orc.random_init(dim=128, num_quantizers=2)
+    cb = w.codebook[0]
+    dup_hi = [k for k in range(cb.shape[0]) if any(torch.equal(cb[k], cb[j]) for j in range(k))]
+    assert len(dup_hi) == 80
+    x = torch.randn(64, 1, 128, generator=torch.Generator().manual_seed(3))
+    _, idx = orc.forward(w, x)
+    cw = c_oracle.CWeights.from_stacked(w)
+    codes = c_oracle.forward_f32(cw, x.numpy())[1]
+    assert not np.isin(idx.numpy(), dup_hi).any()
+    assert not np.isin(codes, dup_hi).any()
+
+
+def test_2b_fingerprints_and_first_tokens(golden_2b):
+    g = golden_2b
+    w = orc.random_init()  # torch.manual_seed(0); RQAE() parameter stream
+    h = hashlib.sha256()
+    for l in range(w.nq):
+        for t in (w.w_in[l], w.b_in[l], w.w_out[l], w.b_out[l]):
+            h.update(t.numpy().tobytes())
+    assert h.hexdigest()[:16] == str(g["fp_layers"])
+    assert hashlib.sha256(w.codebook[0].numpy().tobytes()).hexdigest()[:16] == str(g["fp_codebook0"])
+    x = util.x_2b()
+    assert hashlib.sha256(x.numpy().tobytes()).hexdigest()[:16] == str(g["fp_x"])
+    assert np.array_equal(x[0].numpy(), g["x128"])
+    # torch oracle on the first 4 tokens (full depth): same codes; q only to rounding, because MKL's
+    # K=2304 summation order depends on the batch size (the golden run used 4096 tokens)
+    q, idx = orc.forward(w, x[:1, :4])
+    assert np.array_equal(idx[0].numpy(), g["codes1024"][:4].astype(np.int64))
+    assert np.abs(q[0].numpy() - g["q128"][:4]).max() <= 2e-5 * np.abs(g["q128"][:4]).max()
+    # C oracle, SIMT summation order: near-tie protocol on 32 tokens
+    cw = c_oracle.CWeights.from_stacked(w)
+    _, codes = c_oracle.forward_f32(cw, g["x128"][:32], order_nt=128, fold_bias=True, recon="x_minus_r")
+    rep = parity.compare_codes(codes, g["codes1024"][:32], g["margins128_fp64"][:32])
+    assert rep.failures == 0, str(rep)
+    dec = c_oracle.decode_f32(cw, codes=g["codes1024"][:8])
+    assert np.array_equal(dec, g["dec128"][:8])
