@@ -10,8 +10,9 @@
 // (what torch's CPU F.linear computes for K=4, probed -- see DESIGN.md), two tokens per packed
 // FFMA2/FADD2 instruction, so the result is bit-identical to the reference up to the sign of zero.
 //
-// CTA = 288 threads: warps 0-3 / 4-7 are two compute groups of 128 threads (thread t owns
-// d = j*128 + t) with TGD tokens each, warp 8 lane 0 is the TMA producer.
+// CTA = 384 threads: warps 0-3 / 4-7 are two compute groups of 128 threads (thread t owns
+// d = j*128 + t) with TGD tokens each; the third warpgroup gives its registers to them (setmaxnreg)
+// and its first lane is the TMA producer.
 #pragma once
 #include "rq_common.cuh"
 #include "rq_layout.h"
@@ -32,7 +33,7 @@ struct DecParams {
   float* q_out;
 };
 
-constexpr int kDecThreads = 288;
+constexpr int kDecThreads = 384;
 constexpr int kDecLB = 16;  // layers of codewords staged per barrier
 
 template <int E, int EC, int CH, int NSLOT, int TGD>
@@ -66,8 +67,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) rq_decode_kernel(const DecPara
   }
   __syncthreads();
 
-  if (warp == 8) {
-    if (lane == 0) {
+  if (warp >= 8) {
+    reg_dec<40>();
+    if (warp == 8 && lane == 0) {
       const uint32_t ring = smem_u32(smem + C::SM_RING);
       const uint64_t pol = l2_policy_evict_last();
       uint32_t slot = 0, par = 1;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) rq_decode_kernel(const DecPara
     return;
   }
 
+  reg_inc<232>();
   const int g = warp >> 2;
   const int tg = threadIdx.x & 127;
   const uint32_t ring = smem_u32(smem + C::SM_RING);
@@ -207,11 +210,12 @@ inline int launch_decode_t(const DecParams& prm, int sms, cudaStream_t st) {
 inline int launch_decode(const DecParams& prm, int sms, cudaStream_t st) {
   // CH must match the packed layout (rq_pick_shape); E selects the instantiation.
   switch (prm.E) {
-    case 2: return launch_decode_t<2, 2, 1, 8, 16>(prm, sms, st);
-    case 6: return launch_decode_t<6, 3, 1, 6, 16>(prm, sms, st);
-    case 12: return launch_decode_t<12, 3, 2, 6, 16>(prm, sms, st);
-    case 18: return launch_decode_t<18, 3, 3, 8, 16>(prm, sms, st);
-    case 28: return launch_decode_t<28, 2, 7, 12, 8>(prm, sms, st);
+    // TGD tokens per group: the accumulator q2[TGD/2][E] must fit the 232-register budget (TGD * E <= 168)
+    case 2: return launch_decode_t<2, 2, 1, 8, 8>(prm, sms, st);
+    case 6: return launch_decode_t<6, 3, 1, 6, 8>(prm, sms, st);
+    case 12: return launch_decode_t<12, 3, 2, 6, 8>(prm, sms, st);
+    case 18: return launch_decode_t<18, 3, 3, 8, 8>(prm, sms, st);
+    case 28: return launch_decode_t<28, 2, 7, 12, 6>(prm, sms, st);
     default: return 2;
   }
 }

@@ -51,7 +51,7 @@ struct FwdParams {
 };
 
 constexpr int kComputeWarps = 8;
-constexpr int kQuantWarps = 3;
+constexpr int kQuantWarps = 4;     // two per compute group
 constexpr int kThreads = 384;
 constexpr int kCodeBuf = 16;  // layers buffered per token before a 128-byte code store
 
@@ -92,9 +92,11 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int E, int EC, int CH, int NSLOT, int TG, int REG_COMPUTE = 232, int REG_HELPER = 48>
+// Register budget: ptxas compiles the kernel for 384 threads/CTA at 168 registers, so the CTA owns a pool
+// of 384*168 = 64512 registers; setmaxnreg can only re-split THAT pool (an .inc beyond it spins forever).
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, int REG_COMPUTE = 232, int REG_HELPER = 40>
 __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams p) {
-  static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= 65536, "register file budget");
+  static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= kThreads * 168, "register pool budget");
   using C = FwdCfg<E, EC, CH, NSLOT, TG>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
   uint64_t* full = bars;                  // [NSLOT] producer -> compute
   uint64_t* empty = bars + NSLOT;         // [NSLOT] compute -> producer (8 warp arrivals)
   uint64_t* part_full = bars + 2 * NSLOT; // [2] compute group -> quantizer (4 warp arrivals)
-  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (3 warp arrivals)
+  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (2 warp arrivals)
 
   // work split: a unit is TG consecutive tokens; CTA b handles unit pairs b, b+grid, ...
   const long long n_units = (p.n_tokens + TG - 1) / TG;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kComputeWarps); }
-    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], kQuantWarps); }
+    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], 2); }
     mbar_fence_init();
   }
   // search table -> shared memory (shared-codebook mode with a table that fits)
@@ -250,122 +252,146 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     }
   } else {
     reg_dec<REG_HELPER>();
-    if (warp == kComputeWarps + kQuantWarps) {
-      // =============================== weight producer ===============================
-      if (lane == 0) {
-        const unsigned char* stages = p.packed + p.off_stage;
-        const uint32_t ring = smem_u32(smem + C::SM_RING);
-        const uint64_t pol = l2_policy_evict_last();
-        uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on parity 1
-        for (long long it = 0; it < my_iters; ++it) {
-          for (int l = 0; l <= p.nq_run; ++l) {
-            const unsigned char* src = stages + (size_t)l * (CH * (size_t)C::CHUNK_BYTES);
-            for (int c = 0; c < CH; c++) {
-              mbar_wait(&empty[slot], par);
-              mbar_arrive_expect_tx(&full[slot], C::CHUNK_BYTES);
-              tma_bulk_g2s_hint(ring + slot * C::CHUNK_BYTES, src + (size_t)c * C::CHUNK_BYTES, C::CHUNK_BYTES,
-                                &full[slot], pol);
-              if (++slot == NSLOT) { slot = 0; par ^= 1; }
-            }
-          }
-        }
+    // =============================== quantizer warps (+ weight producer) ===============================
+    // Warps 8,9 serve group A, warps 10,11 serve group B.  A warp handles 4 tokens at once, 8 lanes per
+    // token: each lane scans every 8th row of the search table with two independent running maxima, then
+    // the 8 lanes combine with 3 shuffle steps ((value desc, row asc) ordering == first maximum).
+    // Lane 0 of warp 11 doubles as the weight producer: whenever it is about to wait it first tops up the
+    // bulk-TMA ring (non-blocking mbarrier.test_wait on the slot's `empty` barrier).
+    const int hw = warp - kComputeWarps;       // 0..3
+    const int g = hw >> 1;
+    const int sub = lane & 7;                  // lane within the token's 8-lane team
+    const int tok = (hw & 1) * 4 + (lane >> 3);  // token within the group handled by this team
+    const bool tok_live = tok < TG;
+    const bool is_producer = (hw == 3 && lane == 0);
+    const uint32_t ring = smem_u32(smem + C::SM_RING);
+    const unsigned char* stages = p.packed + p.off_stage;
+    const uint64_t pol = l2_policy_evict_last();
+    // producer state: next chunk to fetch (it_f, l_f, c_f) -> ring slot slot_f; `empty` parity par_f
+    long long it_f = 0;
+    int l_f = 0, c_f = 0;
+    uint32_t slot_f = 0, par_f = 1;  // a fresh barrier passes a wait on parity 1
+    auto top_up = [&]() {
+      while (it_f < my_iters) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(&empty[slot_f])), "r"(par_f) : "memory");
+        if (!ok) break;
+        mbar_arrive_expect_tx(&full[slot_f], C::CHUNK_BYTES);
+        tma_bulk_g2s_hint(ring + slot_f * C::CHUNK_BYTES,
+                          stages + ((size_t)l_f * CH + c_f) * (size_t)C::CHUNK_BYTES, C::CHUNK_BYTES, &full[slot_f], pol);
+        if (++slot_f == NSLOT) { slot_f = 0; par_f ^= 1; }
+        if (++c_f == CH) { c_f = 0; if (++l_f > p.nq_run) { l_f = 0; ++it_f; } }
       }
-    } else {
-      // =============================== quantizer warps ===============================
-      const int hw = warp - kComputeWarps;
-      const float4* cb_s = cb_in_smem ? reinterpret_cast<const float4*>(smem + C::SM_CBT)
-                                      : reinterpret_cast<const float4*>(p.packed + p.off_cbt);
-      const unsigned short* map_s = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
-                                               : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
-      const uint32_t codes_s = smem_u32(smem + C::SM_CODES);
-      const uint32_t part0 = smem_u32(smem + C::SM_PART);
-      const uint32_t cpr0 = smem_u32(smem + C::SM_CPR);
-      const int n_rows = p.cb_shared ? kd_pad : p.K;
-      uint32_t pf_bits = 0;  // bit g = parity of part_full[g]
-      for (long long it = 0; it < my_iters; ++it) {
-        const long long pair_tok0 = 2 * ((long long)blockIdx.x + it * gridDim.x) * TG;  // first token of group 0
+    };
+
+    const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
+    const float4* cb_glob = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
+    const unsigned short* map_s = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
+                                             : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+    const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (g * 8 + tok) * kCodeBuf * 2;
+    const uint32_t pa = smem_u32(smem + C::SM_PART) + (g * 4 * 32 + tok * 4) * 4;
+    const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + g * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
+    const int n_rows = p.cb_shared ? kd_pad : p.K;
+    const unsigned team_lane0 = lane & ~7;
+    uint32_t pf_par = 0;
+
+    for (long long it = 0; it < my_iters; ++it) {
+      const long long token = (2 * ((long long)blockIdx.x + it * gridDim.x) + g) * TG + tok;
+      const bool tok_valid = tok_live && token < p.n_tokens;
 #pragma unroll 1
-        for (int l = 0; l < p.nq_run; ++l) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
-          const float4* cb_l = p.cb_shared ? cb_s : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
-#pragma unroll 1
-          for (int g = 0; g < 2; g++) {
-            mbar_wait(&part_full[g], (pf_bits >> g) & 1u);
-            pf_bits ^= 1u << g;
-#pragma unroll 1
-            for (int tok = hw; tok < TG; tok += kQuantWarps) {
-              // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
-              const uint32_t pa = part0 + (g * 4 * 32 + tok * 4) * 4;
-              const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
-              const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
-              const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
-              const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
-              const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
-              // x / x.norm()  (model.py:188): sqrt(((z0^2 + z1^2) + z2^2) + z3^2), IEEE divide
-              const float nrm = __fsqrt_rn(__fadd_rn(
-                  __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
-              const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
-              // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
-              float bv = -INFINITY;
-              int bk = 0x7fffffff;
+      for (int l = 0; l < p.nq_run; ++l) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
+        const float4* cb_l = p.cb_shared ? cb_glob : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
+        if (is_producer) top_up();
+        while (!mbar_try_wait(&part_full[g], pf_par)) {
+          if (is_producer) top_up();
+        }
+        pf_par ^= 1;
+        // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
+        const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
+        const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
+        const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
+        const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
+        const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
+        // x / x.norm()  (model.py:188): sqrt(((z0^2 + z1^2) + z2^2) + z3^2), IEEE divide
+        const float nrm = __fsqrt_rn(__fadd_rn(
+            __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
+        const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
+        // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
+        float va = -INFINITY, vb = -INFINITY;
+        int ka = 0x7fffffff, kb = 0x7fffffff;
+        if (cb_in_smem) {
 #pragma unroll 2
-              for (int k = lane; k < n_rows; k += 32) {
-                const float4 cw = cb_l[k];
-                const float v = __fmaf_rn(n3, cw.w, __fmaf_rn(n2, cw.z, __fmaf_rn(n1, cw.y, __fmul_rn(n0, cw.x))));
-                if (k == lane || v > bv) { bv = v; bk = k; }
-              }
-#pragma unroll
-              for (int s = 16; s >= 1; s >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, s);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, s);
-                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-              }
-              // a NaN row (z == 0, inf or NaN input) compares false everywhere: lane 0 still holds row 0,
-              // which is what torch.argmax returns for an all-NaN row
-              bk = __shfl_sync(0xffffffffu, bk, 0);
-              const int code = p.cb_shared ? (int)map_s[bk] : bk;
-              const long long token = pair_tok0 + g * TG + tok;
-              if (p.z_out != nullptr && lane == 0 && token < p.n_tokens)
-                reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
-              float4 cw;
-              if (p.teacher != nullptr) {
-                const int tc = (token < p.n_tokens) ? p.teacher[token * p.nq_run + l] : 0;
-                cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
-              } else {
-                cw = cb_l[bk];
-              }
-              // straight-through value c' = z + (c - z)  (model.py:218-220)
-              if (lane < 4) {
-                const float zc = lane == 0 ? z0 : lane == 1 ? z1 : lane == 2 ? z2 : z3;
-                const float cc = lane == 0 ? cw.x : lane == 1 ? cw.y : lane == 2 ? cw.z : cw.w;
-                sts32(cpr0 + g * 128 + (tok >> 1) * 32 + lane * 8 + (tok & 1) * 4, __fadd_rn(zc, __fsub_rn(cc, zc)));
-              }
-              if (lane == 0)
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + ((g * 8 + tok) * kCodeBuf + (l & (kCodeBuf - 1))) * 2),
-                             "h"((unsigned short)code)
-                             : "memory");
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&c_ready[g]);
-            // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
-            if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
-              const int l0 = l & ~(kCodeBuf - 1);
-              for (int tok = hw; tok < TG; tok += kQuantWarps) {
-                const long long token = pair_tok0 + g * TG + tok;
-                if (lane <= l - l0 && token < p.n_tokens) {
-                  unsigned short cval;
-                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cval) : "r"(codes_s + ((g * 8 + tok) * kCodeBuf + lane) * 2));
-                  const long long off = token * p.code_stride + l0 + lane;
-                  if (p.code_dtype == 2) reinterpret_cast<long long*>(p.codes)[off] = (long long)cval;
-                  else if (p.code_dtype == 1) reinterpret_cast<int*>(p.codes)[off] = (int)cval;
-                  else reinterpret_cast<short*>(p.codes)[off] = (short)cval;
-                }
-              }
-              __syncwarp();
-            }
+          for (int k = sub; k < n_rows; k += 16) {   // n_rows is a multiple of 32 in shared mode
+            const float4 ca = lds128(cb_smem + k * 16), cc = lds128(cb_smem + (k + 8) * 16);
+            const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
+            const float xb = __fmaf_rn(n3, cc.w, __fmaf_rn(n2, cc.z, __fmaf_rn(n1, cc.y, __fmul_rn(n0, cc.x))));
+            if (k == sub || xa > va) { va = xa; ka = k; }
+            if (k == sub || xb > vb) { vb = xb; kb = k + 8; }
+          }
+        } else {
+          for (int k = sub; k < n_rows; k += 8) {
+            const float4 ca = __ldg(cb_l + k);
+            const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
+            if (k == sub || xa > va) { va = xa; ka = k; }
           }
         }
+        if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
+#pragma unroll
+        for (int s = 4; s >= 1; s >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, va, s);
+          const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
+          if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
+        }
+        // a NaN row (z == 0, inf or NaN input) compares false everywhere: the team's lane 0 still holds
+        // row 0, which is what torch.argmax returns for an all-NaN row
+        ka = __shfl_sync(0xffffffffu, ka, team_lane0);
+        const int code = p.cb_shared ? (int)map_s[ka] : ka;
+        float4 cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
+        if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
+          if (p.z_out != nullptr && sub == 0 && tok_valid)
+            reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
+          if (p.teacher != nullptr) {
+            const int tc = tok_valid ? p.teacher[token * p.nq_run + l] : 0;
+            cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
+          }
+        }
+        // straight-through value c' = z + (c - z)  (model.py:218-220)
+        if (sub < 4 && tok_live) {
+          const float zc = sub == 0 ? z0 : sub == 1 ? z1 : sub == 2 ? z2 : z3;
+          const float cc = sub == 0 ? cw.x : sub == 1 ? cw.y : sub == 2 ? cw.z : cw.w;
+          sts32(cpr_t + sub * 8, __fadd_rn(zc, __fsub_rn(cc, zc)));
+        }
+        if (sub == 0 && tok_live)
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_ready[g]);
+        // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
+        if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
+          const int l0 = l & ~(kCodeBuf - 1);
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const int li = sub + 8 * r;
+            if (li <= l - l0 && tok_valid) {
+              unsigned short cval;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cval) : "r"(codes_s + li * 2));
+              const long long off = token * p.code_stride + l0 + li;
+              if (p.code_dtype == 2) reinterpret_cast<long long*>(p.codes)[off] = (long long)cval;
+              else if (p.code_dtype == 1) reinterpret_cast<int*>(p.codes)[off] = (int)cval;
+              else reinterpret_cast<short*>(p.codes)[off] = (short)cval;
+            }
+          }
+          __syncwarp();
+        }
       }
+    }
+    // drain: the last stages of the last unit are fetched while the quantizer has nothing left to wait for
+    if (is_producer) {
+      while (it_f < my_iters) top_up();
     }
   }
 }

@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(512, 1) fp32_probe_kernel(int iters, float* si
 // ---------------------------------------------------------------------------------------------
 // forward launch
 // ---------------------------------------------------------------------------------------------
-template <int E, int EC, int CH, int NSLOT, int TG>
-int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG>
+int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   using C = rq::FwdCfg<E, EC, CH, NSLOT, TG>;
-  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG>;
+  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG, DBG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL); });
@@ -167,6 +167,12 @@ int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   g_launches++;
   RQ_CUDA(cudaGetLastError());
   return RQAE_OK;
+}
+
+template <int E, int EC, int CH, int NSLOT, int TG>
+int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+  if (prm.teacher != nullptr || prm.z_out != nullptr) return launch_forward_t<E, EC, CH, NSLOT, TG, true>(prm, sms, st);
+  return launch_forward_t<E, EC, CH, NSLOT, TG, false>(prm, sms, st);
 }
 
 }  // namespace

@@ -1,0 +1,101 @@
+"""Host-side logic of rqae_b200.RQAE that needs no GPU: construction parity with the reference,
+state-dict contract, error behaviour, hook wiring, learned-codebook normalisation schedule."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from rqae_b200 import RQAE
+from tests import util
+
+
+def test_constructor_reproduces_reference_parameters(golden_2b):
+    torch.manual_seed(0)
+    m = RQAE()
+    h = hashlib.sha256()
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if k.startswith("layers."):
+            h.update(v.numpy().tobytes())
+    assert h.hexdigest()[:16] == str(golden_2b["fp_layers"])
+    assert hashlib.sha256(sd["codebook"][0].numpy().tobytes()).hexdigest()[:16] == str(golden_2b["fp_codebook0"])
+    assert len(sd) == 4098 and sum(p.numel() for p in m.parameters()) == 23_797_760 + 1024 * 625 * 4 - 1024 * 625 * 4
+    assert sd["layers.0.0.weight"].shape == (4, 2304) and sd["layers.0.1.weight"].shape == (2304, 4)
+    assert sd["codebook"].shape == (1024, 625, 4) and sd["codebook_counts"].shape == (1024, 625)
+    assert not m.codebook.requires_grad
+    assert (m.codebook[0] == m.codebook[-1]).all()
+
+
+def test_state_dict_round_trip_strict(golden_small):
+    d = util.small_case(golden_small, "round_fsq_d256")
+    m = util.module_from_case(d)
+    m2 = RQAE(dim=256, num_quantizers=8)
+    m2.load_state_dict(m.state_dict(), strict=True)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict({"bogus": torch.zeros(1)}, strict=True)
+
+
+def test_learned_codebook_shapes_and_normalisation():
+    torch.manual_seed(4)
+    m = RQAE(dim=256, num_quantizers=10, quantization_method="vq", codebook_size=64)
+    assert m.codebook.shape == (10, 64, 4) and m.codebook.requires_grad
+    assert torch.allclose(m.codebook.detach().norm(dim=-1), torch.ones(10, 64), atol=1e-6)
+
+
+def test_no_cpu_fallback():
+    m = RQAE(dim=256, num_quantizers=4).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 2, 256))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.decode(torch.zeros(1, 2, 4, dtype=torch.int64))
+
+
+def test_training_gumbel_path_not_supported():
+    m = RQAE(dim=256, num_quantizers=4).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 2, 256), temperature=0.5)
+
+
+def test_hook_argument_contract_and_wiring(monkeypatch):
+    m = RQAE(dim=64, num_quantizers=3).eval()
+    with pytest.raises(ValueError):
+        m.hook(denorm=lambda a, b: a)
+    with pytest.raises(ValueError):
+        m.hook(norm=lambda a: a)
+    with pytest.raises(AssertionError):
+        m.hook(llm=object())
+    calls = {}
+
+    def fake_forward(self, x, max_layers=float("inf"), temperature=0.0):
+        calls["x"] = x
+        return x * 0.5, torch.zeros(*x.shape[:-1], 3, dtype=torch.int64)
+
+    monkeypatch.setattr(RQAE, "forward", fake_forward)
+    stash = {}
+    hook = m.hook(norm=lambda h: h * 2, denorm=lambda q, h: q + 1, store=lambda k, v: stash.__setitem__(k, v))
+    hs = torch.arange(2 * 3 * 64, dtype=torch.float16).reshape(2, 3, 64) / 100
+    out = (hs.clone(),)
+    hook(None, None, out)
+    assert list(stash) == ["original", "normed", "quantized", "indices", "new"]
+    assert torch.equal(calls["x"], hs.float() * 2)
+    expect = hs.float() * 2 * 0.5 + 1
+    expect[:, 0] = hs.float()[:, 0]
+    assert torch.equal(out[0], expect.half())
+    out2 = (hs.clone(),)
+    m.hook(norm=lambda h: h, denorm=lambda q, h: q, replace=False, skip_bos=False)(None, None, out2)
+    assert torch.equal(out2[0], hs)
+
+
+def test_derived_tables_match_reference_formulas():
+    torch.manual_seed(1)
+    m = RQAE(dim=64, num_quantizers=3)
+    cs = m.codebook_sims
+    assert cs.shape == (625, 625) and cs.dtype == torch.float16
+    assert cs[312].abs().max() == 0               # the zero row normalises to zero (F.normalize eps)
+    assert m.layer_norms.shape == (3,)
+    assert m.subfeature_sims.shape == (3, 625, 625) and m.subfeature_sims.dtype == torch.float16
+    ln = torch.tensor([l[1].weight.data.norm(dim=0).mean().item() for l in m.layers])
+    assert torch.equal(m.layer_norms, ln)

@@ -1,0 +1,243 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI via
+rqae_b200.RQAE, against (a) the plain-C oracle evaluated in the kernel's documented summation order --
+bit-exact, codes AND reconstruction -- and (b) the golden vectors of the unmodified reference under the
+near-tie protocol of tests/parity.py."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from tests import parity, util
+
+pytestmark = pytest.mark.gpu
+
+KERNEL_ORDER = dict(order_nt=128, fold_bias=True, recon="x_minus_r")  # see rq_forward.cuh header
+
+
+def _cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def model_2b():
+    from rqae_b200 import RQAE
+    torch.manual_seed(0)
+    m = RQAE().eval()
+    w = util.stacked_from_module(m)
+    return m.to(_cuda()), c_oracle.CWeights.from_stacked(w)
+
+
+FSQ_CASES = [c for c in util.SMALL_CASES if not c.startswith("vq")]
+
+
+@pytest.mark.parametrize("name", FSQ_CASES)
+def test_small_forward_bit_exact_vs_c_oracle_and_reference(golden_small, name):
+    d = util.small_case(golden_small, name)
+    m = util.module_from_case(d, _cuda())
+    x = torch.from_numpy(d["x"]).to(_cuda())
+    kw = {} if d["max_layers"] is None else dict(max_layers=d["max_layers"])
+    q, idx = m(x, **kw)
+    assert idx.dtype == torch.int64 and idx.shape == d["codes"].shape and q.shape == d["q"].shape
+    qo, co = c_oracle.forward_f32(util.cweights(d), d["x"], max_layers=d["max_layers"], **KERNEL_ORDER)
+    assert np.array_equal(idx.cpu().numpy(), co.astype(np.int64))
+    assert np.array_equal(q.cpu().numpy(), qo)
+    rep = parity.compare_codes(idx.cpu().numpy(), d["codes"], d["margins_fp64"])
+    assert rep.failures == 0, str(rep)
+    ok = parity.exact_token_mask(idx.cpu().numpy(), d["codes"])
+    qr = d["q"].reshape(-1, d["q"].shape[-1])
+    qt = q.cpu().numpy().reshape(qr.shape)
+    assert np.abs(qt[ok] - qr[ok]).max() <= 2e-5 * np.abs(qr).max()   # stated fp tolerance
+
+
+def test_learned_codebook_matches_reference(golden_small):
+    d = util.small_case(golden_small, "vq_d256")
+    m = util.module_from_case(d, _cuda())
+    q, idx = m(torch.from_numpy(d["x"]).to(_cuda()))
+    rep = parity.compare_codes(idx.cpu().numpy(), d["codes"], d["margins_fp64"])
+    assert rep.failures == 0 and rep.exact >= rep.tokens - 1, str(rep)
+    # the reference leaves the parameter renormalised in place (model.py:126-131); the device's
+    # x / x.norm() differs from the CPU's in the last bit, hence a tolerance rather than equality
+    assert np.allclose(m.codebook.detach().cpu().numpy(), d["codebook_post"], rtol=0, atol=3e-7)
+    dec = m.decode(torch.from_numpy(d["codes_full"].astype(np.int64)).to(_cuda()))
+    assert np.abs(dec.cpu().numpy() - d["dec"]).max() <= 2e-5 * np.abs(d["dec"]).max()
+
+
+@pytest.mark.parametrize("name", FSQ_CASES)
+def test_small_decode_bit_exact_vs_reference(golden_small, name):
+    d = util.small_case(golden_small, name)
+    m = util.module_from_case(d, _cuda())
+    codes = torch.from_numpy(d["codes_full"].astype(np.int64)).to(_cuda())
+    dec = m.decode(codes, layers=d["dec_layers"])
+    assert np.array_equal(dec.cpu().numpy(), d["dec"])
+    cv = m.indices_to_codebook_values(codes)
+    dec2 = m.decode_from_codebook_values(cv, layers=d["dec_layers"])
+    assert np.array_equal(dec2.cpu().numpy(), d["dec"])
+    for dt in (torch.int16, torch.int32):
+        assert torch.equal(m.decode(codes.to(dt), layers=d["dec_layers"]), dec)
+    assert m.decode(codes, layers=[]) is None
+
+
+def test_2b_kat_128_tokens(model_2b, golden_2b):
+    m, cw = model_2b
+    g = golden_2b
+    x = torch.from_numpy(g["x128"]).to(_cuda())
+    q, idx = m(x.view(1, 128, 2304))
+    codes = idx[0].cpu().numpy()
+    # (a) bit-exact against the C oracle in the kernel's summation order
+    qo, co = c_oracle.forward_f32(cw, g["x128"], **KERNEL_ORDER)
+    assert np.array_equal(codes, co.astype(np.int64))
+    assert np.array_equal(q[0].cpu().numpy(), qo)
+    # (b) the reference's own codes: near-tie protocol with the committed fp64 margins
+    rep = parity.compare_codes(codes, g["codes1024"][:128], g["margins128_fp64"])
+    print("2B KAT, 128 tokens vs reference:", rep)
+    assert rep.failures == 0, str(rep)
+    assert rep.exact >= 120
+    ok = parity.exact_token_mask(codes, g["codes1024"][:128])
+    rel = np.abs(q[0].cpu().numpy()[ok] - g["q128"][ok]).max() / np.abs(g["q128"]).max()
+    print("   reconstruction max rel err on exact tokens:", rel)
+    assert rel <= 2e-5
+
+
+def test_2b_1024_tokens_vs_reference_codes(model_2b, golden_2b):
+    m, cw = model_2b
+    g = golden_2b
+    x = util.x_2b(1024)
+    assert hashlib.sha256(util.x_2b().numpy().tobytes()).hexdigest()[:16] == str(g["fp_x"])
+    codes = m.encode(x.to(_cuda()).view(8, 128, 2304), out_dtype=torch.int16).cpu().numpy().reshape(1024, 1024)
+    ref = g["codes1024"]
+    bad = np.flatnonzero((codes != ref).any(axis=1))
+    margins = np.full(ref.shape, np.inf, np.float32)
+    if len(bad):
+        _, _, mb = c_oracle.forward_f64(cw, x.numpy()[bad], teacher=ref[bad])
+        margins[bad] = mb
+    rep = parity.compare_codes(codes, ref, margins)
+    print("2B, 1024 tokens vs reference:", rep)
+    assert rep.failures == 0, str(rep)
+    assert rep.near_tie <= 32   # expected ~0.2-1 % of tokens at nq=1024
+
+
+def test_2b_decode_bit_exact(model_2b, golden_2b):
+    m, _ = model_2b
+    g = golden_2b
+    codes = torch.from_numpy(g["codes1024"][:128].astype(np.int64)).to(_cuda()).view(1, 128, 1024)
+    dec = m.decode(codes)
+    assert np.array_equal(dec[0].cpu().numpy(), g["dec128"])
+    dec3 = m.decode(codes, layers=list(range(0, 1024, 3)))
+    assert np.array_equal(dec3[0].cpu().numpy(), g["dec128_every3"])
+    # forward's reconstruction and decode(forward codes) agree to rounding (reference: 4.8e-7 rel)
+    q, idx = m(torch.from_numpy(g["x128"]).to(_cuda()).view(1, 128, 2304))
+    d2 = m.decode(idx)
+    assert (q - d2).abs().max().item() <= 2e-5 * q.abs().max().item()
+
+
+def test_position_tile_and_batch_invariance(model_2b):
+    """Codes of a token do not depend on where it sits in the batch, on the batch size, or on the
+    number of CTAs (the summation order is fixed by construction)."""
+    m, _ = model_2b
+    dev = _cuda()
+    base = torch.randn(37, 2304, generator=torch.Generator().manual_seed(7)).to(dev)
+    ref = m.encode(base.view(1, 37, 2304), max_layers=64)[0]
+    big = base.repeat(150, 1)[: 148 * 16 + 5]                 # more than one wave of unit pairs, ragged tail
+    out = m.encode(big.view(1, -1, 2304), max_layers=64)[0]
+    for i in range(0, big.shape[0], 37):
+        n = min(37, big.shape[0] - i)
+        assert torch.equal(out[i:i + n], ref[:n])
+    one = m.encode(base[5:6].view(1, 1, 2304), max_layers=64)[0]
+    assert torch.equal(one[0], ref[5])
+
+
+def test_max_layers_prefix_and_dtypes(model_2b):
+    m, _ = model_2b
+    x = torch.randn(2, 9, 2304, generator=torch.Generator().manual_seed(9)).to(_cuda())
+    q_full, idx_full = m(x, max_layers=48)
+    q16, idx16 = m(x, max_layers=16)
+    assert idx16.shape == (2, 9, 16) and torch.equal(idx16, idx_full[..., :16])
+    dec16 = m.decode(idx_full, layers=range(16))
+    assert (q16 - dec16).abs().max().item() <= 2e-5 * q16.abs().max().item()
+    for dt in (torch.int16, torch.int32, torch.int64):
+        assert torch.equal(m.encode(x, max_layers=48, out_dtype=dt).to(torch.int64), idx_full)
+    assert m.encode(x[:0], max_layers=8).shape == (0, 9, 8)
+
+
+def test_teacher_forced_mode_checks_every_layer(model_2b, golden_2b):
+    """Teacher forcing: the recurrence follows the reference's codes while the kernel reports its own
+    argmax per layer, so every (token, layer) is checked independently."""
+    m, cw = model_2b
+    g = golden_2b
+    x = torch.from_numpy(g["x128"][:64]).to(_cuda())
+    teacher = torch.from_numpy(g["codes1024"][:64].astype(np.int32)).to(_cuda())
+    _, codes, z = m._run_forward(x.view(1, 64, 2304), float("inf"), 0.0, False, torch.int32, teacher=teacher.view(1, 64, 1024), want_z=True)
+    codes = codes[0].cpu().numpy()
+    mism = codes != g["codes1024"][:64]
+    assert (g["margins128_fp64"][:64][mism] < parity.EPS).all()
+    assert mism.mean() < 1e-4
+    assert torch.isfinite(z).all()
+
+
+def test_nan_and_inf_rows(model_2b):
+    m, _ = model_2b
+    x = torch.randn(1, 8, 2304, generator=torch.Generator().manual_seed(11)).to(_cuda())
+    x[0, 3, 17] = float("inf")
+    x[0, 5, 100] = float("nan")
+    _, idx = m(x, max_layers=8)
+    clean = m.encode(torch.randn(1, 8, 2304, generator=torch.Generator().manual_seed(11)).to(_cuda()), max_layers=8)
+    assert (idx[0, 3] == 0).all() and (idx[0, 5] == 0).all()     # NaN row -> first NaN index = 0
+    keep = [0, 1, 2, 4, 6, 7]
+    assert torch.equal(idx[0, keep], clean[0, keep])              # neighbours in the same unit unaffected
+
+
+def test_hook_with_stub_llm(model_2b):
+    m, _ = model_2b
+
+    class Stub:
+        w = torch.linspace(-0.1, 0.1, 2304, device="cuda")
+
+        def norm(self, hs):
+            return hs * torch.rsqrt(hs.pow(2).mean(-1, keepdim=True) + 1e-6) * (1.0 + self.w)
+
+        def denorm(self, hs, orig):
+            return hs / (1.0 + self.w) / torch.rsqrt(orig.float().pow(2).mean(-1, keepdim=True) + 1e-6)
+
+    stash = {}
+    hook = m.hook(llm=Stub(), store=lambda k, v: stash.__setitem__(k, v))
+    hs = (torch.randn(2, 6, 2304, generator=torch.Generator().manual_seed(13)) * 3).to(_cuda()).half()
+    out = (hs.clone(),)
+    old = m.num_quantizers
+    hook(None, None, out)
+    assert set(stash) == {"original", "normed", "quantized", "indices", "new"}
+    assert stash["indices"].shape == (2, 6, old) and stash["indices"].dtype == torch.int64
+    assert torch.equal(out[0][:, 0], hs[:, 0])                    # BOS passthrough
+    assert torch.equal(out[0], stash["new"].half())
+    q, idx = m(stash["normed"])
+    assert torch.equal(idx, stash["indices"]) and torch.equal(q, stash["quantized"])
+
+
+def test_forward_host_matches_device_path(model_2b):
+    m, _ = model_2b
+    x = torch.randn(3000, 2304, generator=torch.Generator().manual_seed(17))
+    q_d, idx_d = m(x.to(_cuda()).view(1, -1, 2304), max_layers=32)
+    q_h, idx_h = m.forward_host(x.pin_memory(), max_layers=32, chunk_tokens=1024)
+    assert torch.equal(idx_h, idx_d[0].cpu()) and torch.equal(q_h, q_d[0].cpu())
+
+
+def test_gemma9b_width_bit_exact_vs_c_oracle():
+    from rqae_b200 import RQAE
+    torch.manual_seed(5)
+    m = RQAE(dim=3584, num_quantizers=24).eval()
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    m = m.to(_cuda())
+    x = torch.randn(1, 29, 3584, generator=torch.Generator().manual_seed(6))
+    q, idx = m(x.to(_cuda()))
+    qo, co = c_oracle.forward_f32(cw, x.numpy(), **KERNEL_ORDER)
+    assert np.array_equal(idx.cpu().numpy(), co.astype(np.int64)) and np.array_equal(q.cpu().numpy(), qo)
+    dec = m.decode(idx)
+    assert np.array_equal(dec.cpu().numpy(), c_oracle.decode_f32(cw, codes=co))
+
+
+def test_cpu_tensors_are_rejected(model_2b):
+    m, _ = model_2b
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 2304))

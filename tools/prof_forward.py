@@ -1,0 +1,28 @@
+"""Small driver for ncu captures: one forward (and optionally decode) launch of the 2B-shape model."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from rqae_b200 import RQAE
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--tokens", type=int, default=148 * 16 * 2)
+ap.add_argument("--dim", type=int, default=2304)
+ap.add_argument("--nq", type=int, default=1024)
+ap.add_argument("--decode", action="store_true")
+ap.add_argument("--reps", type=int, default=1)
+a = ap.parse_args()
+torch.manual_seed(0)
+m = RQAE(dim=a.dim, num_quantizers=a.nq).eval().cuda()
+x = torch.randn(1, a.tokens, a.dim, device="cuda")
+for _ in range(a.reps):
+    q, idx = m(x)
+    if a.decode:
+        d = m.decode(idx)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); q, idx = m(x); e1.record(); torch.cuda.synchronize()
+print("forward ms", e0.elapsed_time(e1), "tokens", a.tokens, "tok/s", a.tokens / e0.elapsed_time(e1) * 1e3)
+if a.decode:
+    e0.record(); d = m.decode(idx); e1.record(); torch.cuda.synchronize()
+    print("decode ms", e0.elapsed_time(e1), "tok/s", a.tokens / e0.elapsed_time(e1) * 1e3)
