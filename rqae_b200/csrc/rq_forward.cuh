@@ -34,7 +34,7 @@ namespace rq {
 
 struct FwdParams {
   const unsigned char* packed;  // packed buffer (rq_layout.h)
-  unsigned long long off_bin, off_cbt, off_map, off_stage;
+  unsigned long long off_bin, off_cbt, off_map, off_ort, off_ortmap, off_stage;
   const float* codebook;        // original codebook, device: [nq][K][4] or [1][K][4]
   int cb_shared;                // 1: one table for all layers (fsq / round_fsq)
   int K;
@@ -50,6 +50,10 @@ struct FwdParams {
   float* z_out;                 // nullable debug: [n_tokens][nq_run][4] in-projection values
 };
 
+#ifndef RQ_REGC
+#define RQ_REGC 224
+#define RQ_REGH 56
+#endif
 constexpr int kComputeWarps = 8;
 constexpr int kQuantWarps = 4;     // two per compute group
 constexpr int kThreads = 384;
@@ -66,9 +70,9 @@ struct FwdCfg {
   static_assert(E % CH == 0 && JC % EC == 0 && TG % 2 == 0 && TG <= 8, "bad shape");
   // shared memory carve-up (bytes)
   static constexpr int SM_RING = 0;
-  static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[1024]
-  static constexpr int SM_MAP = SM_CBT + RQ_MAX_SMEM_CODEBOOK * 16;         // uint16[1024]
-  static constexpr int SM_PART = SM_MAP + RQ_MAX_SMEM_CODEBOOK * 2;         // float[2][4][32]
+  static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[RQ_SMEM_ROWS]: orthant lists or full table
+  static constexpr int SM_MAP = SM_CBT + RQ_SMEM_ROWS * 16;                 // uint16[RQ_SMEM_ROWS]
+  static constexpr int SM_PART = SM_MAP + RQ_SMEM_ROWS * 2;                 // float[2][4][32]
   static constexpr int SM_CPR = SM_PART + 2 * 4 * 32 * 4;                   // u64[2][NP][4]
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
   static constexpr int SM_BAR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // mbarriers
@@ -94,7 +98,7 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
 
 // Register budget: ptxas compiles the kernel for 384 threads/CTA at 168 registers, so the CTA owns a pool
 // of 384*168 = 64512 registers; setmaxnreg can only re-split THAT pool (an .inc beyond it spins forever).
-template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, int REG_COMPUTE = 232, int REG_HELPER = 40>
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, int REG_COMPUTE = RQ_REGC, int REG_HELPER = RQ_REGH>
 __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams p) {
   static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= kThreads * 168, "register pool budget");
   using C = FwdCfg<E, EC, CH, NSLOT, TG>;
@@ -117,16 +121,21 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], 2); }
     mbar_fence_init();
   }
-  // search table -> shared memory (shared-codebook mode with a table that fits)
+  // search tables -> shared memory (shared-codebook mode): the 16 sign-orthant lists when the table is
+  // sign-symmetric (the full table then stays in global memory / L2 for the rare full scan), else the whole
+  // de-duplicated table if it fits
   const RqHeader* hdr = reinterpret_cast<const RqHeader*>(p.packed);
   const int kd_pad = p.cb_shared ? hdr->kd_pad : 0;
-  const bool cb_in_smem = p.cb_shared && kd_pad <= RQ_MAX_SMEM_CODEBOOK;
-  if (cb_in_smem) {
-    const float4* src = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
-    const unsigned short* msrc = reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+  const int ort_rows = p.cb_shared ? hdr->ort_rows : 0;
+  const float ort_thr = hdr->ort_thr;
+  const bool cb_in_smem = p.cb_shared && ort_rows == 0 && kd_pad <= RQ_SMEM_ROWS;
+  if (ort_rows > 0 || cb_in_smem) {
+    const float4* src = reinterpret_cast<const float4*>(p.packed + (ort_rows > 0 ? p.off_ort : p.off_cbt));
+    const unsigned short* msrc = reinterpret_cast<const unsigned short*>(p.packed + (ort_rows > 0 ? p.off_ortmap : p.off_map));
     float4* dst = reinterpret_cast<float4*>(smem + C::SM_CBT);
     unsigned short* mdst = reinterpret_cast<unsigned short*>(smem + C::SM_MAP);
-    for (int i = threadIdx.x; i < kd_pad; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
+    const int nrow = ort_rows > 0 ? RQ_SMEM_ROWS : kd_pad;
+    for (int i = threadIdx.x; i < nrow; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
   }
   __syncthreads();
 
@@ -290,8 +299,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
 
     const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
     const float4* cb_glob = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
-    const unsigned short* map_s = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
-                                             : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+    const unsigned short* map_s = reinterpret_cast<const unsigned short*>(smem + C::SM_MAP);   // orthant lists / full table in smem
+    const unsigned short* map_full = cb_in_smem ? map_s : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
     const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (g * 8 + tok) * kCodeBuf * 2;
     const uint32_t pa = smem_u32(smem + C::SM_PART) + (g * 4 * 32 + tok * 4) * 4;
     const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + g * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
@@ -322,36 +331,70 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
         const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
         // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
-        float va = -INFINITY, vb = -INFINITY;
-        int ka = 0x7fffffff, kb = 0x7fffffff;
-        if (cb_in_smem) {
+        int code = 0;
+        float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool fast = false;
+        if (ort_rows > 0) {
+          // ---- sign-orthant search (rq_layout.h / pack_codebook_kernel): list picked by the signs of n ----
+          fast = (fabsf(n0) >= ort_thr) && (fabsf(n1) >= ort_thr) && (fabsf(n2) >= ort_thr) && (fabsf(n3) >= ort_thr);
+          const int sidx = (n0 < 0.f ? 1 : 0) | (n1 < 0.f ? 2 : 0) | (n2 < 0.f ? 4 : 0) | (n3 < 0.f ? 8 : 0);
+          const uint32_t lb = cb_smem + sidx * (RQ_ORT_MAX * 16);
+          float va = -INFINITY, vb = -INFINITY;
+          int ka = 0x7fffffff, kb = 0x7fffffff;
 #pragma unroll 2
-          for (int k = sub; k < n_rows; k += 16) {   // n_rows is a multiple of 32 in shared mode
-            const float4 ca = lds128(cb_smem + k * 16), cc = lds128(cb_smem + (k + 8) * 16);
+          for (int k = sub; k < ort_rows; k += 16) {
+            const float4 ca = lds128(lb + k * 16), cc = lds128(lb + (k + 8) * 16);
             const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
             const float xb = __fmaf_rn(n3, cc.w, __fmaf_rn(n2, cc.z, __fmaf_rn(n1, cc.y, __fmul_rn(n0, cc.x))));
             if (k == sub || xa > va) { va = xa; ka = k; }
             if (k == sub || xb > vb) { vb = xb; kb = k + 8; }
           }
-        } else {
-          for (int k = sub; k < n_rows; k += 8) {
-            const float4 ca = __ldg(cb_l + k);
-            const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
-            if (k == sub || xa > va) { va = xa; ka = k; }
+          if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
+#pragma unroll
+          for (int s = 4; s >= 1; s >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, va, s);
+            const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
+            if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
+          }
+          ka = __shfl_sync(0xffffffffu, ka, team_lane0);
+          code = (int)map_s[sidx * RQ_ORT_MAX + ka];
+          cw = lds128(lb + ka * 16);
+        }
+        if (ort_rows == 0 || __any_sync(0xffffffffu, !fast)) {
+          // ---- full scan: generic tables, and tokens with a tiny / zero / NaN coordinate ----
+          float va = -INFINITY, vb = -INFINITY;
+          int ka = 0x7fffffff, kb = 0x7fffffff;
+          if (cb_in_smem) {
+#pragma unroll 2
+            for (int k = sub; k < n_rows; k += 16) {   // n_rows is a multiple of 32 in shared mode
+              const float4 ca = lds128(cb_smem + k * 16), cc = lds128(cb_smem + (k + 8) * 16);
+              const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
+              const float xb = __fmaf_rn(n3, cc.w, __fmaf_rn(n2, cc.z, __fmaf_rn(n1, cc.y, __fmul_rn(n0, cc.x))));
+              if (k == sub || xa > va) { va = xa; ka = k; }
+              if (k == sub || xb > vb) { vb = xb; kb = k + 8; }
+            }
+          } else {
+            for (int k = sub; k < n_rows; k += 8) {
+              const float4 ca = __ldg(cb_l + k);
+              const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
+              if (k == sub || xa > va) { va = xa; ka = k; }
+            }
+          }
+          if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
+#pragma unroll
+          for (int s = 4; s >= 1; s >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, va, s);
+            const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
+            if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
+          }
+          // a NaN row (z == 0, inf or NaN input) compares false everywhere: the team's lane 0 still holds
+          // row 0, which is what torch.argmax returns for an all-NaN row
+          ka = __shfl_sync(0xffffffffu, ka, team_lane0);
+          if (!fast) {
+            code = p.cb_shared ? (int)map_full[ka] : ka;
+            cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
           }
         }
-        if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
-#pragma unroll
-        for (int s = 4; s >= 1; s >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, va, s);
-          const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
-          if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
-        }
-        // a NaN row (z == 0, inf or NaN input) compares false everywhere: the team's lane 0 still holds
-        // row 0, which is what torch.argmax returns for an all-NaN row
-        ka = __shfl_sync(0xffffffffu, ka, team_lane0);
-        const int code = p.cb_shared ? (int)map_s[ka] : ka;
-        float4 cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
         if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
           if (p.z_out != nullptr && sub == 0 && tok_valid)
             reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);

@@ -16,7 +16,8 @@
 #define RQ_GROUP_THREADS 128
 #define RQ_BYTES_PER_ELEM 36 /* float4 + float4 + float */
 #define RQ_HDR_BYTES 256
-#define RQ_MAX_SMEM_CODEBOOK 1024 /* rows of the search table kept in shared memory */
+#define RQ_ORT_MAX 96   /* rows per sign-orthant list (padded, multiple of 16) */
+#define RQ_SMEM_ROWS (16 * RQ_ORT_MAX) /* search-table rows kept in shared memory (16 orthant lists, or one full table) */
 
 struct RqShape {
   int E;     /* elements per thread: D_pad = 128 * E */
@@ -48,6 +49,8 @@ struct RqLayout {
   size_t off_bin;    /* float4[nq+1]          in-projection biases                    */
   size_t off_cbt;    /* float4[KT]            de-duplicated search table (shared mode) */
   size_t off_map;    /* uint16[KT]            search row -> lowest original index      */
+  size_t off_ort;    /* float4[16][RQ_ORT_MAX] per-sign-orthant search lists (shared mode)     */
+  size_t off_ortmap; /* uint16[16][RQ_ORT_MAX] list row -> lowest original index               */
   size_t off_stage;  /* (nq+1) stages                                                  */
   size_t stage_bytes;
   size_t chunk_bytes;
@@ -62,7 +65,9 @@ static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLa
   L->off_bin = RQ_HDR_BYTES;
   L->off_cbt = rq_align_up(L->off_bin + (size_t)(nq + 1) * 16, 256);
   L->off_map = rq_align_up(L->off_cbt + (size_t)L->KT * 16, 256);
-  L->off_stage = rq_align_up(L->off_map + (size_t)L->KT * 2, 1024);
+  L->off_ort = rq_align_up(L->off_map + (size_t)L->KT * 2, 256);
+  L->off_ortmap = L->off_ort + (size_t)16 * RQ_ORT_MAX * 16;
+  L->off_stage = rq_align_up(L->off_ortmap + (size_t)16 * RQ_ORT_MAX * 2, 1024);
   L->stage_bytes = (size_t)s->E * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
   L->chunk_bytes = L->stage_bytes / s->CH;
   L->total = L->off_stage + (size_t)(nq + 1) * L->stage_bytes;
@@ -72,5 +77,7 @@ static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLa
 struct RqHeader {
   int kd_pad;    /* rows in the search table (multiple of 32), written by the pack kernel */
   int kd;        /* distinct rows */
-  int reserved[62];
+  int ort_rows;  /* rows per orthant list (multiple of 16); 0 = table is not sign-symmetric, lists unused */
+  float ort_thr; /* a token takes the orthant search only if every |n_i| >= ort_thr */
+  int reserved[60];
 };

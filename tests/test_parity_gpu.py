@@ -189,6 +189,31 @@ def test_nan_and_inf_rows(model_2b):
     assert torch.equal(idx[0, keep], clean[0, keep])              # neighbours in the same unit unaffected
 
 
+def test_zero_and_tiny_coordinates_fall_back_to_full_scan():
+    """The sign-orthant search is only valid when no coordinate of the normalised in-projection is tiny;
+    rows that differ in the sign of a coordinate multiplied by (almost) zero tie exactly and the LOWEST index
+    must win (torch.argmax).  Layer 0 has z1 == 0 exactly, layer 1 a denormal-scale z2, layer 2 two zeros."""
+    from rqae_b200 import RQAE
+    torch.manual_seed(21)
+    m = RQAE(dim=256, num_quantizers=6).eval()
+    with torch.no_grad():
+        m.layers[0][0].weight[1].zero_(); m.layers[0][0].bias[1] = 0.0
+        m.layers[1][0].weight[2].mul_(1e-12); m.layers[1][0].bias[2] = 0.0
+        m.layers[2][0].weight[0].zero_(); m.layers[2][0].bias[0] = 0.0
+        m.layers[2][0].weight[3].zero_(); m.layers[2][0].bias[3] = 0.0
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    m = m.to(_cuda())
+    x = torch.randn(5, 23, 256, generator=torch.Generator().manual_seed(22))
+    q, idx = m(x.to(_cuda()))
+    qo, co = c_oracle.forward_f32(cw, x.numpy(), **KERNEL_ORDER)
+    assert np.array_equal(idx.cpu().numpy(), co.astype(np.int64))
+    assert np.array_equal(q.cpu().numpy(), qo)
+    # the tie really is resolved towards the negative twin (lower index) at layer 0: coordinate 1 of the
+    # chosen codeword is never positive
+    cb = m.codebook[0].cpu().numpy()
+    assert (cb[idx[..., 0].cpu().numpy()][..., 1] <= 0).all()
+
+
 def test_hook_with_stub_llm(model_2b):
     m, _ = model_2b
 
