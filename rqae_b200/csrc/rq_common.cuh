@@ -53,6 +53,19 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// four 128-bit loads at addr, addr+STRIDE, ... issued back to back (one asm block: the loads cannot be
+// interleaved with their consumers, so their latencies overlap)
+template <int STRIDE>
+__device__ __forceinline__ void lds128x4(uint32_t addr, float4& a, float4& b, float4& c, float4& d) {
+  asm volatile(
+      "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n\t"
+      "ld.shared.v4.f32 {%4, %5, %6, %7}, [%16+%17];\n\t"
+      "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+%18];\n\t"
+      "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+%19];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w), "=f"(c.x), "=f"(c.y),
+        "=f"(c.z), "=f"(c.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w)
+      : "r"(addr), "n"(STRIDE), "n"(2 * STRIDE), "n"(3 * STRIDE));
+}
 __device__ __forceinline__ void lds128_u64(uint32_t addr, u64& a, u64& b) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }

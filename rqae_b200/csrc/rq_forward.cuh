@@ -34,7 +34,7 @@ namespace rq {
 
 struct FwdParams {
   const unsigned char* packed;  // packed buffer (rq_layout.h)
-  unsigned long long off_bin, off_cbt, off_map, off_ort, off_ortmap, off_stage;
+  unsigned long long off_bin, off_cbt, off_map, off_tp, off_map3, off_stage;
   const float* codebook;        // original codebook, device: [nq][K][4] or [1][K][4]
   int cb_shared;                // 1: one table for all layers (fsq / round_fsq)
   int K;
@@ -55,7 +55,7 @@ struct FwdParams {
 #define RQ_REGH 56
 #endif
 constexpr int kComputeWarps = 8;
-constexpr int kQuantWarps = 4;     // two per compute group
+constexpr int kQuantWarps = 2;     // one per compute group (warps 8, 9); warp 10 = producer, warp 11 idle
 constexpr int kThreads = 384;
 constexpr int kCodeBuf = 16;  // layers buffered per token before a 128-byte code store
 
@@ -70,9 +70,11 @@ struct FwdCfg {
   static_assert(E % CH == 0 && JC % EC == 0 && TG % 2 == 0 && TG <= 8, "bad shape");
   // shared memory carve-up (bytes)
   static constexpr int SM_RING = 0;
-  static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[RQ_SMEM_ROWS]: orthant lists or full table
+  static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[RQ_SMEM_ROWS] de-duplicated table
   static constexpr int SM_MAP = SM_CBT + RQ_SMEM_ROWS * 16;                 // uint16[RQ_SMEM_ROWS]
-  static constexpr int SM_PART = SM_MAP + RQ_SMEM_ROWS * 2;                 // float[2][4][32]
+  static constexpr int SM_TP = SM_MAP + RQ_SMEM_ROWS * 2;                   // float4[24][RQ_CAN_MAX] canonical rows per order
+  static constexpr int SM_MAP3 = SM_TP + RQ_NPERM * RQ_CAN_MAX * 16;        // uint16[16][24][RQ_CAN_MAX]
+  static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[2][4][32]
   static constexpr int SM_CPR = SM_PART + 2 * 4 * 32 * 4;                   // u64[2][NP][4]
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
   static constexpr int SM_BAR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // mbarriers
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
   uint64_t* full = bars;                  // [NSLOT] producer -> compute
   uint64_t* empty = bars + NSLOT;         // [NSLOT] compute -> producer (8 warp arrivals)
   uint64_t* part_full = bars + 2 * NSLOT; // [2] compute group -> quantizer (4 warp arrivals)
-  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (2 warp arrivals)
+  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (1 warp arrival)
 
   // work split: a unit is TG consecutive tokens; CTA b handles unit pairs b, b+grid, ...
   const long long n_units = (p.n_tokens + TG - 1) / TG;
@@ -118,24 +120,29 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kComputeWarps); }
-    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], 2); }
+    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], 1); }
     mbar_fence_init();
   }
-  // search tables -> shared memory (shared-codebook mode): the 16 sign-orthant lists when the table is
-  // sign-symmetric (the full table then stays in global memory / L2 for the rare full scan), else the whole
-  // de-duplicated table if it fits
+  // search tables -> shared memory (shared-codebook mode): the de-duplicated table if it fits, and the
+  // canonical-row tables when the codebook is sign/permutation symmetric (rqae_capi.cu, build_search_tables)
   const RqHeader* hdr = reinterpret_cast<const RqHeader*>(p.packed);
   const int kd_pad = p.cb_shared ? hdr->kd_pad : 0;
-  const int ort_rows = p.cb_shared ? hdr->ort_rows : 0;
-  const float ort_thr = hdr->ort_thr;
-  const bool cb_in_smem = p.cb_shared && ort_rows == 0 && kd_pad <= RQ_SMEM_ROWS;
-  if (ort_rows > 0 || cb_in_smem) {
-    const float4* src = reinterpret_cast<const float4*>(p.packed + (ort_rows > 0 ? p.off_ort : p.off_cbt));
-    const unsigned short* msrc = reinterpret_cast<const unsigned short*>(p.packed + (ort_rows > 0 ? p.off_ortmap : p.off_map));
+  const int can_rows = p.cb_shared ? hdr->can_rows : 0;
+  const bool cb_in_smem = p.cb_shared && kd_pad <= RQ_SMEM_ROWS;
+  if (cb_in_smem) {
+    const float4* src = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
+    const unsigned short* msrc = reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
     float4* dst = reinterpret_cast<float4*>(smem + C::SM_CBT);
     unsigned short* mdst = reinterpret_cast<unsigned short*>(smem + C::SM_MAP);
-    const int nrow = ort_rows > 0 ? RQ_SMEM_ROWS : kd_pad;
-    for (int i = threadIdx.x; i < nrow; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
+    for (int i = threadIdx.x; i < kd_pad; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
+  }
+  if (can_rows > 0) {
+    const float4* src = reinterpret_cast<const float4*>(p.packed + p.off_tp);
+    const uint32_t* msrc = reinterpret_cast<const uint32_t*>(p.packed + p.off_map3);
+    float4* dst = reinterpret_cast<float4*>(smem + C::SM_TP);
+    uint32_t* mdst = reinterpret_cast<uint32_t*>(smem + C::SM_MAP3);
+    for (int i = threadIdx.x; i < RQ_NPERM * RQ_CAN_MAX; i += kThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX / 2; i += kThreads) mdst[i] = msrc[i];
   }
   __syncthreads();
 
@@ -261,180 +268,183 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     }
   } else {
     reg_dec<REG_HELPER>();
-    // =============================== quantizer warps (+ weight producer) ===============================
-    // Warps 8,9 serve group A, warps 10,11 serve group B.  A warp handles 4 tokens at once, 8 lanes per
-    // token: each lane scans every 8th row of the search table with two independent running maxima, then
-    // the 8 lanes combine with 3 shuffle steps ((value desc, row asc) ordering == first maximum).
-    // Lane 0 of warp 11 doubles as the weight producer: whenever it is about to wait it first tops up the
-    // bulk-TMA ring (non-blocking mbarrier.test_wait on the slot's `empty` barrier).
     const int hw = warp - kComputeWarps;       // 0..3
-    const int g = hw >> 1;
-    const int sub = lane & 7;                  // lane within the token's 8-lane team
-    const int tok = (hw & 1) * 4 + (lane >> 3);  // token within the group handled by this team
-    const bool tok_live = tok < TG;
-    const bool is_producer = (hw == 3 && lane == 0);
-    const uint32_t ring = smem_u32(smem + C::SM_RING);
-    const unsigned char* stages = p.packed + p.off_stage;
-    const uint64_t pol = l2_policy_evict_last();
-    // producer state: next chunk to fetch (it_f, l_f, c_f) -> ring slot slot_f; `empty` parity par_f
-    long long it_f = 0;
-    int l_f = 0, c_f = 0;
-    uint32_t slot_f = 0, par_f = 1;  // a fresh barrier passes a wait on parity 1
-    auto top_up = [&]() {
-      while (it_f < my_iters) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(&empty[slot_f])), "r"(par_f) : "memory");
-        if (!ok) break;
-        mbar_arrive_expect_tx(&full[slot_f], C::CHUNK_BYTES);
-        tma_bulk_g2s_hint(ring + slot_f * C::CHUNK_BYTES,
-                          stages + ((size_t)l_f * CH + c_f) * (size_t)C::CHUNK_BYTES, C::CHUNK_BYTES, &full[slot_f], pol);
-        if (++slot_f == NSLOT) { slot_f = 0; par_f ^= 1; }
-        if (++c_f == CH) { c_f = 0; if (++l_f > p.nq_run) { l_f = 0; ++it_f; } }
-      }
-    };
-
-    const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
-    const float4* cb_glob = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
-    const unsigned short* map_s = reinterpret_cast<const unsigned short*>(smem + C::SM_MAP);   // orthant lists / full table in smem
-    const unsigned short* map_full = cb_in_smem ? map_s : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
-    const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (g * 8 + tok) * kCodeBuf * 2;
-    const uint32_t pa = smem_u32(smem + C::SM_PART) + (g * 4 * 32 + tok * 4) * 4;
-    const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + g * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
-    const int n_rows = p.cb_shared ? kd_pad : p.K;
-    const unsigned team_lane0 = lane & ~7;
-    uint32_t pf_par = 0;
-
-    for (long long it = 0; it < my_iters; ++it) {
-      const long long token = (2 * ((long long)blockIdx.x + it * gridDim.x) + g) * TG + tok;
-      const bool tok_valid = tok_live && token < p.n_tokens;
+    if (hw == 2) {
+      // =============================== weight producer (warp 10, one lane) ===============================
+      // Streams stage chunks L2 -> shared memory with bulk TMA through the NSLOT-deep ring; blocks on the
+      // slot's `empty` barrier (hardware-suspended try_wait, no polling).
+      if (lane == 0) {
+        const uint32_t ring = smem_u32(smem + C::SM_RING);
+        const unsigned char* stages = p.packed + p.off_stage;
+        const uint64_t pol = l2_policy_evict_last();
+        uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on parity 1
+        for (long long it = 0; it < my_iters; ++it) {
+          for (int l = 0; l <= p.nq_run; ++l) {
 #pragma unroll 1
-      for (int l = 0; l < p.nq_run; ++l) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
-        const float4* cb_l = p.cb_shared ? cb_glob : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
-        if (is_producer) top_up();
-        while (!mbar_try_wait(&part_full[g], pf_par)) {
-          if (is_producer) top_up();
-        }
-        pf_par ^= 1;
-        // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
-        const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
-        const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
-        const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
-        const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
-        const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
-        // x / x.norm()  (model.py:188): sqrt(((z0^2 + z1^2) + z2^2) + z3^2), IEEE divide
-        const float nrm = __fsqrt_rn(__fadd_rn(
-            __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
-        const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
-        // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
-        int code = 0;
-        float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool fast = false;
-        if (ort_rows > 0) {
-          // ---- sign-orthant search (rq_layout.h / pack_codebook_kernel): list picked by the signs of n ----
-          fast = (fabsf(n0) >= ort_thr) && (fabsf(n1) >= ort_thr) && (fabsf(n2) >= ort_thr) && (fabsf(n3) >= ort_thr);
-          const int sidx = (n0 < 0.f ? 1 : 0) | (n1 < 0.f ? 2 : 0) | (n2 < 0.f ? 4 : 0) | (n3 < 0.f ? 8 : 0);
-          const uint32_t lb = cb_smem + sidx * (RQ_ORT_MAX * 16);
-          float va = -INFINITY, vb = -INFINITY;
-          int ka = 0x7fffffff, kb = 0x7fffffff;
-#pragma unroll 2
-          for (int k = sub; k < ort_rows; k += 16) {
-            const float4 ca = lds128(lb + k * 16), cc = lds128(lb + (k + 8) * 16);
-            const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
-            const float xb = __fmaf_rn(n3, cc.w, __fmaf_rn(n2, cc.z, __fmaf_rn(n1, cc.y, __fmul_rn(n0, cc.x))));
-            if (k == sub || xa > va) { va = xa; ka = k; }
-            if (k == sub || xb > vb) { vb = xb; kb = k + 8; }
-          }
-          if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
-#pragma unroll
-          for (int s = 4; s >= 1; s >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, va, s);
-            const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
-            if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
-          }
-          ka = __shfl_sync(0xffffffffu, ka, team_lane0);
-          code = (int)map_s[sidx * RQ_ORT_MAX + ka];
-          cw = lds128(lb + ka * 16);
-        }
-        if (ort_rows == 0 || __any_sync(0xffffffffu, !fast)) {
-          // ---- full scan: generic tables, and tokens with a tiny / zero / NaN coordinate ----
-          float va = -INFINITY, vb = -INFINITY;
-          int ka = 0x7fffffff, kb = 0x7fffffff;
-          if (cb_in_smem) {
-#pragma unroll 2
-            for (int k = sub; k < n_rows; k += 16) {   // n_rows is a multiple of 32 in shared mode
-              const float4 ca = lds128(cb_smem + k * 16), cc = lds128(cb_smem + (k + 8) * 16);
-              const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
-              const float xb = __fmaf_rn(n3, cc.w, __fmaf_rn(n2, cc.z, __fmaf_rn(n1, cc.y, __fmul_rn(n0, cc.x))));
-              if (k == sub || xa > va) { va = xa; ka = k; }
-              if (k == sub || xb > vb) { vb = xb; kb = k + 8; }
-            }
-          } else {
-            for (int k = sub; k < n_rows; k += 8) {
-              const float4 ca = __ldg(cb_l + k);
-              const float xa = __fmaf_rn(n3, ca.w, __fmaf_rn(n2, ca.z, __fmaf_rn(n1, ca.y, __fmul_rn(n0, ca.x))));
-              if (k == sub || xa > va) { va = xa; ka = k; }
+            for (int c = 0; c < CH; ++c) {
+              mbar_wait(&empty[slot], par);
+              mbar_arrive_expect_tx(&full[slot], C::CHUNK_BYTES);
+              tma_bulk_g2s_hint(ring + slot * C::CHUNK_BYTES, stages + ((size_t)l * CH + c) * (size_t)C::CHUNK_BYTES,
+                                C::CHUNK_BYTES, &full[slot], pol);
+              if (++slot == NSLOT) { slot = 0; par ^= 1; }
             }
           }
-          if (vb > va || (vb == va && kb < ka)) { va = vb; ka = kb; }
-#pragma unroll
-          for (int s = 4; s >= 1; s >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, va, s);
-            const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
-            if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
-          }
-          // a NaN row (z == 0, inf or NaN input) compares false everywhere: the team's lane 0 still holds
-          // row 0, which is what torch.argmax returns for an all-NaN row
-          ka = __shfl_sync(0xffffffffu, ka, team_lane0);
-          if (!fast) {
-            code = p.cb_shared ? (int)map_full[ka] : ka;
-            cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
-          }
-        }
-        if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
-          if (p.z_out != nullptr && sub == 0 && tok_valid)
-            reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
-          if (p.teacher != nullptr) {
-            const int tc = tok_valid ? p.teacher[token * p.nq_run + l] : 0;
-            cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
-          }
-        }
-        // straight-through value c' = z + (c - z)  (model.py:218-220)
-        if (sub < 4 && tok_live) {
-          const float zc = sub == 0 ? z0 : sub == 1 ? z1 : sub == 2 ? z2 : z3;
-          const float cc = sub == 0 ? cw.x : sub == 1 ? cw.y : sub == 2 ? cw.z : cw.w;
-          sts32(cpr_t + sub * 8, __fadd_rn(zc, __fsub_rn(cc, zc)));
-        }
-        if (sub == 0 && tok_live)
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c_ready[g]);
-        // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
-        if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
-          const int l0 = l & ~(kCodeBuf - 1);
-#pragma unroll
-          for (int r = 0; r < 2; r++) {
-            const int li = sub + 8 * r;
-            if (li <= l - l0 && tok_valid) {
-              unsigned short cval;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cval) : "r"(codes_s + li * 2));
-              const long long off = token * p.code_stride + l0 + li;
-              if (p.code_dtype == 2) reinterpret_cast<long long*>(p.codes)[off] = (long long)cval;
-              else if (p.code_dtype == 1) reinterpret_cast<int*>(p.codes)[off] = (int)cval;
-              else reinterpret_cast<short*>(p.codes)[off] = (short)cval;
-            }
-          }
-          __syncwarp();
         }
       }
-    }
-    // drain: the last stages of the last unit are fetched while the quantizer has nothing left to wait for
-    if (is_producer) {
-      while (it_f < my_iters) top_up();
+    } else if (hw < 2) {
+      // =============================== quantizer warps ===============================
+      // Warp 8 serves group A, warp 9 group B: 8 tokens per warp, a team of 4 lanes per token.
+      //
+      // Common case (symmetric codebook; no division, no square root on the path to the code): the argmax of
+      // cos(n, c_k), n = z/|z|, is the argmax of s_k = z . c_k, and by symmetry it is attained by a canonical
+      // row (c0 >= c1 >= c2 >= c3 >= 0) laid out in the magnitude order of z and signed like z.  Each lane
+      // scores 4 of the <= 16 canonical rows on |z| and keeps its two largest; the team combines them with
+      // redux.sync.  If the best score leads the runner-up by more than thr_gap*|z|, no |z_i| is below
+      // thr_tiny*|z| and no two |z_i| are closer than thr_sep*|z| -- margins that the rounding of the
+      // reference's normalise-then-dot sequence cannot overturn ("Search") -- the leader IS the
+      // reference's first maximum.  Otherwise the whole warp runs the reference's exact sequence (IEEE sqrt /
+      // divide, fp32 fma chain, first maximum over the whole table).
+      const int g = hw;
+      const int sub = lane & 3;                  // lane within the token's team
+      const int tok = lane >> 2;                 // token within the group
+      const bool tok_live = tok < TG;
+      const unsigned team_mask = 0xFu << (lane & ~3);
+      const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
+      const uint32_t tp_smem = smem_u32(smem + C::SM_TP);
+      const float4* cb_glob = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
+      const unsigned short* map3_s = reinterpret_cast<const unsigned short*>(smem + C::SM_MAP3);
+      const unsigned short* map_full = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
+                                                  : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
+      const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (g * 8 + tok) * kCodeBuf * 2;
+      const uint32_t pa = smem_u32(smem + C::SM_PART) + (g * 4 * 32 + tok * 4) * 4;
+      const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + g * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
+      const int n_rows = p.cb_shared ? kd_pad : p.K;
+      const float thr_tiny = hdr->thr_tiny, thr_gap = hdr->thr_gap, thr_sep = hdr->thr_sep;
+      uint32_t pf_par = 0;
+
+      for (long long it = 0; it < my_iters; ++it) {
+        const long long token = (2 * ((long long)blockIdx.x + it * gridDim.x) + g) * TG + tok;
+        const bool tok_valid = tok_live && token < p.n_tokens;
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin));
+#pragma unroll 1
+        for (int l = 0; l < p.nq_run; ++l) {
+          const float4* cb_l = p.cb_shared ? cb_glob : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
+          mbar_wait(&part_full[g], pf_par);
+          pf_par ^= 1;
+          // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
+          const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
+          const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
+          const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
+          const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
+          const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
+          b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l + 1);   // next layer's bias (nq+1 entries)
+          int code = 0;
+          float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
+          bool fast = false;
+          if (can_rows > 0) {
+            const float a0 = fabsf(z0), a1 = fabsf(z1), a2 = fabsf(z2), a3 = fabsf(z3);
+            // magnitude order as a Lehmer code (must match lehmer_order() in rqae_capi.cu)
+            const int ord = 6 * ((a1 > a0) + (a2 > a0) + (a3 > a0)) + 2 * ((a2 > a1) + (a3 > a1)) + (a3 > a2);
+            const int sidx = (z0 < 0.f ? 1 : 0) | (z1 < 0.f ? 2 : 0) | (z2 < 0.f ? 4 : 0) | (z3 < 0.f ? 8 : 0);
+            const uint32_t tb = tp_smem + ord * (RQ_CAN_MAX * 16);
+            float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
+            lds128x4<64>(tb + sub * 16, c0, c1, c2, c3);
+            const float sa = __fmaf_rn(a3, c0.w, __fmaf_rn(a2, c0.z, __fmaf_rn(a1, c0.y, __fmul_rn(a0, c0.x))));
+            const float sb = __fmaf_rn(a3, c1.w, __fmaf_rn(a2, c1.z, __fmaf_rn(a1, c1.y, __fmul_rn(a0, c1.x))));
+            const float sc = __fmaf_rn(a3, c2.w, __fmaf_rn(a2, c2.z, __fmaf_rn(a1, c2.y, __fmul_rn(a0, c2.x))));
+            const float sd = __fmaf_rn(a3, c3.w, __fmaf_rn(a2, c3.z, __fmaf_rn(a1, c3.y, __fmul_rn(a0, c3.x))));
+            // largest two of the lane's four scores and the row of the largest (all scores are >= +0)
+            const float h1 = fmaxf(sa, sb), l1 = fminf(sa, sb), h2 = fmaxf(sc, sd), l2 = fminf(sc, sd);
+            const int p1 = sb > sa ? 4 : 0, p2 = sd > sc ? 12 : 8;
+            const float m1 = fmaxf(h1, h2);
+            const float m2 = fmaxf(fminf(h1, h2), fmaxf(l1, l2));
+            const int k1 = (h2 > h1 ? p2 : p1) + sub;
+            const unsigned best = __reduce_max_sync(team_mask, __float_as_uint(m1));
+            const bool mine = __float_as_uint(m1) == best;
+            const unsigned owners = __ballot_sync(0xffffffffu, mine) & team_mask;
+            // runner-up over the team: the owner contributes its second score, the others their first
+            const unsigned second = __reduce_max_sync(team_mask, __float_as_uint(mine ? m2 : m1));
+            const int kw = __shfl_sync(0xffffffffu, k1, __ffs(owners) - 1);   // winning canonical row
+            const float4 cm = lds128(tb + kw * 16);
+            code = (int)map3_s[(sidx * RQ_NPERM + ord) * RQ_CAN_MAX + kw];
+            cw = make_float4(copysignf(cm.x, z0), copysignf(cm.y, z1), copysignf(cm.z, z2), copysignf(cm.w, z3));
+            // validity of the shortcut (NaN / inf / zero input fail these comparisons)
+            const float zz = __fmaf_rn(a3, a3, __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0))));
+            float nz;
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(nz) : "f"(zz));
+            const float zmin = fminf(fminf(a0, a1), fminf(a2, a3));
+            const float sep = fminf(fminf(fminf(fabsf(a0 - a1), fabsf(a0 - a2)), fminf(fabsf(a0 - a3), fabsf(a1 - a2))),
+                                    fminf(fabsf(a1 - a3), fabsf(a2 - a3)));
+            const float lead = __fsub_rn(__uint_as_float(best), __uint_as_float(second));
+            fast = (owners & (owners - 1)) == 0 && lead > thr_gap * nz && zmin >= thr_tiny * nz && sep >= thr_sep * nz &&
+                   zz >= 1.0e-30f && zz <= 1.0e30f;
+          }
+          if (can_rows == 0 || __any_sync(0xffffffffu, !fast)) {
+            // ---- the reference's own sequence, whole warp (teams with `fast` keep their result) ----
+            // x / x.norm()  (model.py:188): sqrt(((z0^2 + z1^2) + z2^2) + z3^2), IEEE divide
+            const float nrm = __fsqrt_rn(__fadd_rn(
+                __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
+            const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
+            // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
+            float va = -INFINITY;
+            int ka = 0x7fffffff;
+#pragma unroll 2
+            for (int k = sub; k < n_rows; k += 4) {
+              const float4 c = cb_in_smem ? lds128(cb_smem + k * 16) : __ldg(cb_l + k);
+              const float x = __fmaf_rn(n3, c.w, __fmaf_rn(n2, c.z, __fmaf_rn(n1, c.y, __fmul_rn(n0, c.x))));
+              if (k == sub || x > va) { va = x; ka = k; }
+            }
+#pragma unroll
+            for (int s = 2; s >= 1; s >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, va, s);
+              const int ok = __shfl_xor_sync(0xffffffffu, ka, s);
+              if (ov > va || (ov == va && ok < ka)) { va = ov; ka = ok; }
+            }
+            // a NaN row (z == 0, inf or NaN input) compares false everywhere: the team's lane 0 still holds
+            // row 0, which is what torch.argmax returns for an all-NaN row
+            ka = __shfl_sync(0xffffffffu, ka, lane & ~3);
+            if (!fast) {
+              code = p.cb_shared ? (int)map_full[ka] : ka;
+              cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
+            }
+          }
+          if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
+            if (p.z_out != nullptr && sub == 0 && tok_valid)
+              reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
+            if (p.teacher != nullptr) {
+              const int tc = tok_valid ? p.teacher[token * p.nq_run + l] : 0;
+              cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
+            }
+          }
+          // straight-through value c' = z + (c - z)  (model.py:218-220)
+          if (tok_live) {
+            const float zc = sub == 0 ? z0 : sub == 1 ? z1 : sub == 2 ? z2 : z3;
+            const float cc = sub == 0 ? cw.x : sub == 1 ? cw.y : sub == 2 ? cw.z : cw.w;
+            sts32(cpr_t + sub * 8, __fadd_rn(zc, __fsub_rn(cc, zc)));
+          }
+          if (sub == 0 && tok_live)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_ready[g]);
+          // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
+          if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
+            const int l0 = l & ~(kCodeBuf - 1);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              const int li = sub * 4 + r;
+              if (li <= l - l0 && tok_valid) {
+                unsigned short cval;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cval) : "r"(codes_s + li * 2));
+                const long long off = token * p.code_stride + l0 + li;
+                if (p.code_dtype == 2) reinterpret_cast<long long*>(p.codes)[off] = (long long)cval;
+                else if (p.code_dtype == 1) reinterpret_cast<int*>(p.codes)[off] = (int)cval;
+                else reinterpret_cast<short*>(p.codes)[off] = (short)cval;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
     }
   }
 }

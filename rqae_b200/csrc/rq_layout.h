@@ -16,8 +16,10 @@
 #define RQ_GROUP_THREADS 128
 #define RQ_BYTES_PER_ELEM 36 /* float4 + float4 + float */
 #define RQ_HDR_BYTES 256
-#define RQ_ORT_MAX 96   /* rows per sign-orthant list (padded, multiple of 16) */
-#define RQ_SMEM_ROWS (16 * RQ_ORT_MAX) /* search-table rows kept in shared memory (16 orthant lists, or one full table) */
+#define RQ_SMEM_ROWS 1024 /* rows of the de-duplicated search table kept in shared memory */
+#define RQ_CAN_MAX 16     /* canonical rows (c0 >= c1 >= c2 >= c3 >= 0) of a sign/permutation-symmetric table */
+#define RQ_NPERM 24
+#define RQ_NSIGN 16
 
 struct RqShape {
   int E;     /* elements per thread: D_pad = 128 * E */
@@ -34,7 +36,7 @@ static inline int rq_pick_shape(int D, struct RqShape* s) {
       {6, 3, 1, 4, 8},    /* D <=  768 */
       {12, 3, 2, 6, 8},   /* D <= 1536 */
       {18, 3, 3, 7, 8},   /* D <= 2304  (Gemma-2-2B) */
-      {28, 2, 7, 11, 6},  /* D <= 3584  (Gemma-2-9B) */
+      {28, 2, 7, 10, 6},  /* D <= 3584  (Gemma-2-9B) */
   };
   for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
     if (D <= table[i].E * RQ_GROUP_THREADS) {
@@ -49,8 +51,8 @@ struct RqLayout {
   size_t off_bin;    /* float4[nq+1]          in-projection biases                    */
   size_t off_cbt;    /* float4[KT]            de-duplicated search table (shared mode) */
   size_t off_map;    /* uint16[KT]            search row -> lowest original index      */
-  size_t off_ort;    /* float4[16][RQ_ORT_MAX] per-sign-orthant search lists (shared mode)     */
-  size_t off_ortmap; /* uint16[16][RQ_ORT_MAX] list row -> lowest original index               */
+  size_t off_tp;     /* float4[24][RQ_CAN_MAX] canonical rows, coordinates arranged per magnitude order */
+  size_t off_map3;   /* uint16[16][24][RQ_CAN_MAX] (signs, order, canonical row) -> lowest original index */
   size_t off_stage;  /* (nq+1) stages                                                  */
   size_t stage_bytes;
   size_t chunk_bytes;
@@ -65,9 +67,9 @@ static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLa
   L->off_bin = RQ_HDR_BYTES;
   L->off_cbt = rq_align_up(L->off_bin + (size_t)(nq + 1) * 16, 256);
   L->off_map = rq_align_up(L->off_cbt + (size_t)L->KT * 16, 256);
-  L->off_ort = rq_align_up(L->off_map + (size_t)L->KT * 2, 256);
-  L->off_ortmap = L->off_ort + (size_t)16 * RQ_ORT_MAX * 16;
-  L->off_stage = rq_align_up(L->off_ortmap + (size_t)16 * RQ_ORT_MAX * 2, 1024);
+  L->off_tp = rq_align_up(L->off_map + (size_t)L->KT * 2, 256);
+  L->off_map3 = L->off_tp + (size_t)RQ_NPERM * RQ_CAN_MAX * 16;
+  L->off_stage = rq_align_up(L->off_map3 + (size_t)RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2, 1024);
   L->stage_bytes = (size_t)s->E * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
   L->chunk_bytes = L->stage_bytes / s->CH;
   L->total = L->off_stage + (size_t)(nq + 1) * L->stage_bytes;
@@ -75,9 +77,11 @@ static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLa
 
 /* Device-resident header at offset 0 of the packed buffer. */
 struct RqHeader {
-  int kd_pad;    /* rows in the search table (multiple of 32), written by the pack kernel */
+  int kd_pad;    /* rows in the search table (multiple of 32) */
   int kd;        /* distinct rows */
-  int ort_rows;  /* rows per orthant list (multiple of 16); 0 = table is not sign-symmetric, lists unused */
-  float ort_thr; /* a token takes the orthant search only if every |n_i| >= ort_thr */
-  int reserved[60];
+  int can_rows;   /* canonical rows, padded to a multiple of 4; 0 = table not symmetric, canonical search unused */
+  float thr_tiny; /* canonical search needs every |z_i| >= thr_tiny * |z|                     */
+  float thr_gap;  /*   ... the best score z.c leading the runner-up by more than thr_gap * |z| */
+  float thr_sep;  /*   ... and any two |z_i| differing by at least thr_sep * |z|              */
+  int reserved[58];
 };

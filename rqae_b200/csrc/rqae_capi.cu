@@ -4,7 +4,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <array>
+#include <map>
 #include <mutex>
+#include <vector>
+#include <math.h>
 
 #include "../../include/rqae_b200.h"
 #include "rq_decode.cuh"
@@ -77,103 +82,125 @@ __global__ void pack_stages_kernel(const float* __restrict__ w_in, const float* 
   reinterpret_cast<float*>(chunk + (size_t)JC * RQ_GROUP_THREADS * 32)[e] = bo;
 }
 
-// Search tables for the shared-codebook mode.
+// Search tables for the shared-codebook mode, built on the host (the table is a few KB; this runs once per
+// weight load).
 //  (1) De-duplicated table: rows that are value-identical to an earlier row are dropped (torch.argmax
-//      returns the first maximum, so a later duplicate can never be selected); the original index of
-//      every surviving row is kept; padded to a multiple of 32 with copies of row 0 (a copy ties with
-//      row 0 and loses on the position).
-//  (2) Sign-orthant lists, built when the table is closed under flipping the sign of any coordinate
-//      (true for the fsq / round_fsq grids): list s (bit i of s = "n_i is negative") holds, in ascending
-//      original index, the distinct rows whose every coordinate is zero or has the sign s prescribes.
-//      For a query n with no tiny coordinate the fp32 score fma(n3,c3,fma(n2,c2,fma(n1,c1,n0*c0))) of a
-//      row is strictly smaller than the score of its sign-aligned twin (each rounding is monotone and the
-//      exact gap 2*|n_i c_i| exceeds the accumulated rounding error), so the first maximum
-//      over the whole table is the first maximum over list s: 66 rows instead of 545 for round_fsq 5^4.
-//      ort_thr is the "no tiny coordinate" bound; tokens below it take the full scan.
-// Single block; runs once per weight load.
-__global__ void pack_codebook_kernel(const float* __restrict__ cb, int K, int KT, unsigned char* __restrict__ packed,
-                                     size_t off_cbt, size_t off_map, size_t off_ort, size_t off_ortmap) {
-  extern __shared__ unsigned char keep[];
-  __shared__ int s_nonsym;
-  __shared__ unsigned s_cmin_bits, s_n2max_bits;
-  const float4* rows = reinterpret_cast<const float4*>(cb);
-  if (threadIdx.x == 0) { s_nonsym = (K > 4096) ? 1 : 0; s_cmin_bits = 0x7f800000u; s_n2max_bits = 0u; }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float4 a = rows[k];
-    bool dup = false;
-    for (int j = 0; j < k && !dup; j++) {
-      const float4 b = rows[j];
-      dup = (a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w);
-    }
-    keep[k] = dup ? 0 : 1;
-    const float v[4] = {a.x, a.y, a.z, a.w};
+//      returns the first maximum, so a later duplicate can never be selected); the original index of every
+//      surviving row is kept; padded to a multiple of 32 with copies of row 0 (a copy ties with row 0 and
+//      loses on the position).
+//  (2) Canonical-row tables, built when the table is closed under flipping the sign of any coordinate and
+//      under exchanging any two coordinates (true for the fsq / round_fsq grids).  Then for a query z
+//          max_k z.c_k  is attained by a row whose signs follow z and whose magnitudes are ordered like |z|
+//      (rearrangement inequality), i.e. by a *canonical* row c0 >= c1 >= c2 >= c3 >= 0 re-arranged to the
+//      magnitude order of z: 10 candidates instead of 625 for round_fsq 5^4.  tp[order][r] holds canonical
+//      row r with its coordinates placed per `order` (the Lehmer code of the magnitude ranks, see
+//      rq_forward.cuh); map3[signs][order][r] is the lowest original index of the resulting signed row.
+//      The thresholds bound when this shortcut provably returns the reference's first maximum (DESIGN.md,
+//      "Search"); any token outside them takes the exhaustive scan in the reference's own arithmetic.
+struct SearchTables {
+  RqHeader hdr;
+  std::vector<float> cbt;
+  std::vector<unsigned short> map;
+  std::vector<float> tp;
+  std::vector<unsigned short> map3;
+};
+
+typedef std::array<uint32_t, 4> RowKey;
+static RowKey row_key(const float* v) {
+  RowKey k;
+  for (int i = 0; i < 4; i++) {
+    float f = v[i] == 0.f ? 0.f : v[i];   // -0 -> +0
+    memcpy(&k[i], &f, 4);
+  }
+  return k;
+}
+
+static int lehmer_order(const float* a) {   // a = magnitudes; must match the kernel's formula
+  const int c01 = a[1] > a[0], c02 = a[2] > a[0], c03 = a[3] > a[0], c12 = a[2] > a[1], c13 = a[3] > a[1], c23 = a[3] > a[2];
+  return 6 * (c01 + c02 + c03) + 2 * (c12 + c13) + c23;
+}
+
+static void build_search_tables(const float* cb, int K, int KT, SearchTables* T) {
+  memset(&T->hdr, 0, sizeof(T->hdr));
+  T->cbt.assign((size_t)KT * 4, 0.f);
+  T->map.assign((size_t)KT, 0);
+  T->tp.assign((size_t)RQ_NPERM * RQ_CAN_MAX * 4, 0.f);
+  T->map3.assign((size_t)RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX, 0);
+  std::map<RowKey, int> first;   // value -> lowest original index
+  std::vector<int> keep;
+  bool finite = true;
+  float cmin = INFINITY, n2max = 0.f;
+  for (int k = 0; k < K; k++) {
+    const float* r = cb + (size_t)k * 4;
     float n2 = 0.f;
-    bool finite = true;
     for (int i = 0; i < 4; i++) {
-      const float m = fabsf(v[i]);
+      const float m = fabsf(r[i]);
       if (!(m <= 3.0e38f)) finite = false;
-      if (m > 0.f) atomicMin(&s_cmin_bits, __float_as_uint(m));   // positive floats order like their bit patterns
+      if (m > 0.f && m < cmin) cmin = m;
       n2 += m * m;
     }
-    if (finite) atomicMax(&s_n2max_bits, __float_as_uint(n2));
-    if (!finite) s_nonsym = 1;
-    if (!dup && K <= 4096) {
-      for (int i = 0; i < 4 && !s_nonsym; i++) {
-        if (v[i] == 0.f) continue;
-        float f[4] = {v[0], v[1], v[2], v[3]};
-        f[i] = -f[i];
-        bool found = false;
-        for (int j = 0; j < K && !found; j++) {
-          const float4 b = rows[j];
-          found = (f[0] == b.x && f[1] == b.y && f[2] == b.z && f[3] == b.w);
-        }
-        if (!found) s_nonsym = 1;
-      }
+    if (n2 > n2max) n2max = n2;
+    if (first.emplace(row_key(r), k).second) keep.push_back(k);
+  }
+  int n = 0;
+  for (int k : keep) { memcpy(&T->cbt[(size_t)n * 4], cb + (size_t)k * 4, 16); T->map[n] = (unsigned short)k; n++; }
+  const int kd = n, kd_pad = (kd + 31) / 32 * 32;
+  for (; n < kd_pad && n < KT; n++) { memcpy(&T->cbt[(size_t)n * 4], &T->cbt[0], 16); T->map[n] = T->map[0]; }
+  T->hdr.kd = kd;
+  T->hdr.kd_pad = kd_pad;
+  if (!finite || !(cmin < INFINITY) || K > 16384) return;
+  // closure under the generators of the hyperoctahedral group: 4 sign flips, 3 adjacent transpositions
+  for (int k : keep) {
+    const float* r = cb + (size_t)k * 4;
+    for (int i = 0; i < 4; i++) {
+      float f[4] = {r[0], r[1], r[2], r[3]};
+      f[i] = -f[i];
+      if (!first.count(row_key(f))) return;
+    }
+    for (int i = 0; i < 3; i++) {
+      float f[4] = {r[0], r[1], r[2], r[3]};
+      const float t = f[i]; f[i] = f[i + 1]; f[i + 1] = t;
+      if (!first.count(row_key(f))) return;
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float4* out = reinterpret_cast<float4*>(packed + off_cbt);
-    unsigned short* map = reinterpret_cast<unsigned short*>(packed + off_map);
-    int n = 0;
-    for (int k = 0; k < K; k++)
-      if (keep[k]) { out[n] = rows[k]; map[n] = (unsigned short)k; n++; }
-    const int kd = n;
-    const int kd_pad = (kd + 31) / 32 * 32;
-    for (; n < kd_pad && n < KT; n++) { out[n] = out[0]; map[n] = map[0]; }
-    RqHeader* h = reinterpret_cast<RqHeader*>(packed);
-    h->kd = kd;
-    h->kd_pad = kd_pad;
-    // ---- orthant lists ----
-    float4* ort = reinterpret_cast<float4*>(packed + off_ort);
-    unsigned short* omap = reinterpret_cast<unsigned short*>(packed + off_ortmap);
-    int ort_rows = 0;
-    bool ok = (s_nonsym == 0) && s_cmin_bits != 0x7f800000u;
-    for (int s = 0; s < 16 && ok; s++) {
-      int m = 0;
-      for (int r = 0; r < kd; r++) {
-        const float4 c = out[r];
-        const float v[4] = {c.x, c.y, c.z, c.w};
-        bool aligned = true;
-        for (int i = 0; i < 4; i++)
-          if (v[i] != 0.f && ((v[i] < 0.f) != (((s >> i) & 1) != 0))) aligned = false;
-        if (!aligned) continue;
-        if (m >= RQ_ORT_MAX) { ok = false; break; }
-        ort[s * RQ_ORT_MAX + m] = c;
-        omap[s * RQ_ORT_MAX + m] = map[r];
-        m++;
-      }
-      if (!ok || m == 0) { ok = false; break; }
-      const int mp = (m + 15) / 16 * 16;
-      if (mp > ort_rows) ort_rows = mp;
-      for (; m < RQ_ORT_MAX; m++) { ort[s * RQ_ORT_MAX + m] = ort[s * RQ_ORT_MAX]; omap[s * RQ_ORT_MAX + m] = omap[s * RQ_ORT_MAX]; }
+  // canonical rows (ascending original index), zero row excluded
+  std::vector<int> can;
+  float dmin = INFINITY;
+  for (int k : keep) {
+    const float* r = cb + (size_t)k * 4;
+    if (r[0] >= r[1] && r[1] >= r[2] && r[2] >= r[3] && r[3] >= 0.f && r[0] > 0.f) {
+      can.push_back(k);
+      const float seq[5] = {r[0], r[1], r[2], r[3], 0.f};
+      for (int i = 0; i < 4; i++)
+        if (seq[i] != seq[i + 1] && seq[i] - seq[i + 1] < dmin) dmin = seq[i] - seq[i + 1];
     }
-    h->ort_rows = ok ? ort_rows : 0;
-    // every |n_i| >= thr  =>  2*|n_i|*cmin >= 8 * 2^-24 * 4 roundings * max row norm  (4x safety)
-    const float cmin = __uint_as_float(s_cmin_bits), nmax = sqrtf(__uint_as_float(s_n2max_bits));
-    h->ort_thr = ok ? (1.0e-6f * fmaxf(nmax, 1.0f) / cmin) : 0.f;
   }
+  if (can.empty() || (int)can.size() > RQ_CAN_MAX || !(dmin < INFINITY)) return;
+  int rank[4] = {0, 1, 2, 3};
+  do {   // rank[i] = position of coordinate i in the descending magnitude order
+    float a[4];
+    for (int i = 0; i < 4; i++) a[i] = (float)(4 - rank[i]);
+    const int ord = lehmer_order(a);
+    for (size_t r = 0; r < can.size(); r++) {
+      const float* m = cb + (size_t)can[r] * 4;
+      float* dst = &T->tp[((size_t)ord * RQ_CAN_MAX + r) * 4];
+      for (int i = 0; i < 4; i++) dst[i] = m[rank[i]];
+      for (int sg = 0; sg < RQ_NSIGN; sg++) {
+        float f[4];
+        for (int i = 0; i < 4; i++) f[i] = ((sg >> i) & 1) ? -dst[i] : dst[i];
+        auto itf = first.find(row_key(f));
+        if (itf == first.end()) return;   // cannot happen for a closed table
+        T->map3[((size_t)sg * RQ_NPERM + ord) * RQ_CAN_MAX + r] = (unsigned short)itf->second;
+      }
+    }
+  } while (std::next_permutation(rank, rank + 4));
+  const float nmax = fmaxf(sqrtf(n2max), 1.0f);
+  // error budget, in units of |z|: the reference's sqrt + divide + 4-term fma chain moves a
+  // score by <= 4.8e-7*nmax, our un-normalised fp32 score by <= 2.4e-7*nmax
+  T->hdr.can_rows = ((int)can.size() + 3) / 4 * 4;
+  T->hdr.thr_tiny = 1.0e-6f * nmax / cmin;   // sign-flipped twin loses by >= 2*tiny*cmin      (2x margin)
+  T->hdr.thr_gap = 3.0e-6f * nmax;           // runner-up cannot overtake                        (2x margin)
+  T->hdr.thr_sep = 2.5e-6f * nmax / dmin;    // coordinate-swapped twin loses by >= sep*dmin     (2.6x margin)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,9 +320,19 @@ int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, 
   g_launches++;
   RQ_CUDA(cudaGetLastError());
   if (codebook_shared) {
-    pack_codebook_kernel<<<1, 1024, (size_t)K, st>>>(codebook, K, L.KT, pk, L.off_cbt, L.off_map, L.off_ort, L.off_ortmap);
-    g_launches++;
-    RQ_CUDA(cudaGetLastError());
+    // the table is tiny: fetch it, build the search tables on the host, upload (this entry point therefore
+    // synchronises `stream`; it runs once per weight load, never on the hot path)
+    std::vector<float> cb_host((size_t)K * 4);
+    RQ_CUDA(cudaMemcpyAsync(cb_host.data(), codebook, (size_t)K * 16, cudaMemcpyDeviceToHost, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+    SearchTables T;
+    build_search_tables(cb_host.data(), K, L.KT, &T);
+    RQ_CUDA(cudaMemcpyAsync(pk, &T.hdr, sizeof(T.hdr), cudaMemcpyHostToDevice, st));
+    RQ_CUDA(cudaMemcpyAsync(pk + L.off_cbt, T.cbt.data(), T.cbt.size() * 4, cudaMemcpyHostToDevice, st));
+    RQ_CUDA(cudaMemcpyAsync(pk + L.off_map, T.map.data(), T.map.size() * 2, cudaMemcpyHostToDevice, st));
+    RQ_CUDA(cudaMemcpyAsync(pk + L.off_tp, T.tp.data(), T.tp.size() * 4, cudaMemcpyHostToDevice, st));
+    RQ_CUDA(cudaMemcpyAsync(pk + L.off_map3, T.map3.data(), T.map3.size() * 2, cudaMemcpyHostToDevice, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
   }
   return RQAE_OK;
 }
@@ -317,7 +354,7 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
   rq::FwdParams prm;
   prm.packed = (const unsigned char*)packed;
   prm.off_bin = L.off_bin; prm.off_cbt = L.off_cbt; prm.off_map = L.off_map; prm.off_stage = L.off_stage;
-  prm.off_ort = L.off_ort; prm.off_ortmap = L.off_ortmap;
+  prm.off_tp = L.off_tp; prm.off_map3 = L.off_map3;
   prm.codebook = codebook; prm.cb_shared = codebook_shared ? 1 : 0; prm.K = K; prm.nq_run = nq_run; prm.D = dim;
   prm.x = x; prm.n_tokens = n_tokens; prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride;
   prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
@@ -327,7 +364,7 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
     case 6: return launch_forward<6, 3, 1, 4, 8>(prm, sms, st);
     case 12: return launch_forward<12, 3, 2, 6, 8>(prm, sms, st);
     case 18: return launch_forward<18, 3, 3, 7, 8>(prm, sms, st);
-    case 28: return launch_forward<28, 2, 7, 11, 6>(prm, sms, st);
+    case 28: return launch_forward<28, 2, 7, 10, 6>(prm, sms, st);
     default: return RQAE_EUNSUPPORTED;
   }
 }

@@ -214,6 +214,66 @@ def test_zero_and_tiny_coordinates_fall_back_to_full_scan():
     assert (cb[idx[..., 0].cpu().numpy()][..., 1] <= 0).all()
 
 
+def _designed_z_model(method="round_fsq", cbs=5):
+    """Layer 0 copies x[..., :4] into z exactly (unit in-projection rows, zero bias), so a test can place z on
+    the decision boundaries of the codebook search."""
+    from rqae_b200 import RQAE
+    torch.manual_seed(31)
+    m = RQAE(dim=256, num_quantizers=3, quantization_method=method, codebook_size=cbs).eval()
+    with torch.no_grad():
+        m.layers[0][0].weight.zero_()
+        m.layers[0][0].bias.zero_()
+        for k in range(4):
+            m.layers[0][0].weight[k, k] = 1.0
+    return m
+
+
+@pytest.mark.parametrize("method,cbs", [("round_fsq", 5), ("fsq", 5), ("round_fsq", 3), ("round_fsq", 4)])
+def test_search_shortcut_on_decision_boundaries(method, cbs):
+    """Adversarial inputs for the canonical-row search: exact and near ties between codewords (bisectors of
+    row pairs), equal and nearly equal coordinate magnitudes, tiny and zero coordinates, huge and tiny scales.
+    Codes and reconstruction must equal the exhaustive fp32 argmax of the C oracle bit for bit."""
+    m = _designed_z_model(method, cbs)
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    cb = m.codebook[0].double()
+    K = cb.shape[0]
+    g = torch.Generator().manual_seed(32)
+    zs = []
+    ia, ib = torch.randint(0, K, (6000,), generator=g), torch.randint(0, K, (6000,), generator=g)
+    bis = cb[ia] + cb[ib]                                   # bisectors: exact ties in exact arithmetic
+    zs.append(bis)
+    zs.append(bis * (1 + 3e-7 * torch.randn(6000, 4, generator=g, dtype=torch.float64)))   # near ties
+    base = torch.randn(4000, 4, generator=g, dtype=torch.float64)
+    eq = base.clone(); eq[:, 1] = eq[:, 0] * torch.where(torch.rand(4000, generator=g) < 0.5, 1.0, -1.0)
+    zs.append(eq)                                           # |z0| == |z1|
+    zs.append(eq * (1 + 2e-7 * torch.randn(4000, 4, generator=g, dtype=torch.float64)))
+    tiny = base.clone(); tiny[:, 2] *= 1e-7; tiny[:2000, 3] = 0.0
+    zs.append(tiny)                                         # tiny / zero coordinates
+    zs.append(cb[torch.randint(0, K, (2000,), generator=g)] * 3.0)          # exactly on codewords
+    zs.append(torch.randn(4000, 4, generator=g, dtype=torch.float64))       # generic
+    z = torch.cat(zs).float()
+    z = z * torch.logspace(-6, 6, z.shape[0]).view(-1, 1)[torch.randperm(z.shape[0], generator=g)]
+    x = torch.randn(z.shape[0], 256, generator=g)
+    x[:, :4] = z
+    m = m.to(_cuda())
+    q, idx = m(x.to(_cuda()).view(1, -1, 256))
+    qo, co = c_oracle.forward_f32(cw, x.numpy(), **KERNEL_ORDER)
+    assert np.array_equal(idx[0].cpu().numpy(), co.astype(np.int64))
+    assert np.array_equal(q[0].cpu().numpy(), qo)
+
+
+def test_search_shortcut_random_stress():
+    """1.3 M (token, layer) decisions of a small random model against the exhaustive C oracle."""
+    from rqae_b200 import RQAE
+    torch.manual_seed(41)
+    m = RQAE(dim=256, num_quantizers=64).eval()
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    x = torch.randn(20000, 256, generator=torch.Generator().manual_seed(42))
+    codes = m.to(_cuda()).encode(x.to(_cuda()).view(1, -1, 256), out_dtype=torch.int32)[0].cpu().numpy()
+    _, co = c_oracle.forward_f32(cw, x.numpy(), want_q=False, **KERNEL_ORDER)
+    assert np.array_equal(codes, co)
+
+
 def test_hook_with_stub_llm(model_2b):
     m, _ = model_2b
 
