@@ -6,24 +6,29 @@
 // 1024 layers -- by ONE persistent kernel in which the residual never leaves registers.
 //
 // CTA = 384 threads, one CTA per SM (the register file is the capacity that matters):
-//   warps 0-3   compute group A : TG tokens, residual r[TG][D] in registers (D split over 128 threads)
-//   warps 4-7   compute group B : TG other tokens; runs half a layer out of phase with A so that
-//                                 one group's argmax latency is hidden behind the other's FMA work
-//   warps 8-10  quantizer       : cross-warp sum of the in-projection partials, cos-sim argmax over
-//                                 the de-duplicated codebook (lowest original index wins ties, NaN
-//                                 -> index 0 as torch.argmax), straight-through value, code output
-//   warp  11    producer        : one lane streaming weight chunks L2 -> shared memory with bulk TMA
-//                                 (cp.async.bulk + mbarrier complete_tx) through an NSLOT-deep ring
-// Registers are re-split with setmaxnreg: compute warpgroups grow, the helper warpgroup shrinks.
+//   warps 0-7   compute   : 256 threads; thread t owns elements d = j*256 + t (j < E) of the D axis for ALL
+//                           2*TG tokens of the CTA's current unit, residual r[2*TG][E] in registers.
+//                           The tokens form two *phases* A and B of TG tokens each.  Every warp runs
+//                               pass(A, l)  pass(B, l)  pass(A, l+1)  pass(B, l+1) ...
+//                           so the layer-l argmax of phase A is computed (by a quantizer warp) while the
+//                           same compute warps are busy with pass(B, l): the serial dependency of the
+//                           residual recurrence is hidden by construction, not by timing luck.
+//   warp  8, 9  quantizer : warp 8 serves phase A, warp 9 phase B: cross-warp sum of the in-projection
+//                           partials, cos-sim argmax (lowest original index wins ties, NaN -> index 0 as
+//                           torch.argmax), straight-through value, code output
+//   warp  10    producer  : one lane streaming weight chunks L2 -> shared memory with bulk TMA
+//                           (cp.async.bulk + mbarrier complete_tx) through an NSLOT-deep ring; a chunk is
+//                           read by pass(A, l) and again by pass(B, l), then released
+// Registers are re-split with setmaxnreg: the compute warpgroups grow, the helper warpgroup shrinks.
 //
-// One *pass* of a compute group over stage s (see rq_layout.h) does, per owned element d and per
-// token pair, with packed FFMA2 (two tokens per instruction, each half IEEE fp32 round-to-nearest):
+// One *pass* over stage s (see rq_layout.h) does, per owned element d and per token pair, with packed
+// FFMA2 (two tokens per instruction, each half IEEE fp32 round-to-nearest):
 //     o   = fma(w_out[d][3], c'3, fma(w_out[d][2], c'2, fma(w_out[d][1], c'1, fma(w_out[d][0], c'0, b_out[d]))))
 //     r_d = r_d - o                                  (model.py:221-223)
 //     acc[k] = fma(w_in[k][d], r_d, acc[k]), k<4     (model.py:211, partial over the thread's elements)
-// then reduces acc over the warp with a shuffle butterfly and hands 4 per-warp partials per (token, k)
-// to the quantizer warps through shared memory.  Summation order is fixed (thread-sequential over j,
-// lane tree with strides 16,8,4,2,1, warps 0..3 sequentially, then + b_in), so results do not depend on
+// then reduces acc over the warp with a shuffle butterfly and hands 8 per-warp partials per (token, k)
+// to the quantizer warp through shared memory.  Summation order is fixed (thread-sequential over j,
+// lane tree with strides 16,8,4,2,1, warps 0..7 sequentially, then + b_in), so results do not depend on
 // the tile a token lands in, on the grid size or on timing.  The reconstruction is emitted as
 // q = x - r_final (one extra read of x) instead of a second register-resident accumulator.
 #pragma once
@@ -51,31 +56,30 @@ struct FwdParams {
 };
 
 #ifndef RQ_REGC
-#define RQ_REGC 224
-#define RQ_REGH 56
+#define RQ_REGC 232
+#define RQ_REGH 40
 #endif
 constexpr int kComputeWarps = 8;
-constexpr int kQuantWarps = 2;     // one per compute group (warps 8, 9); warp 10 = producer, warp 11 idle
 constexpr int kThreads = 384;
 constexpr int kCodeBuf = 16;  // layers buffered per token before a 128-byte code store
 
 template <int E, int EC, int CH, int NSLOT, int TG>
 struct FwdCfg {
-  static constexpr int NP = TG / 2;              // token pairs per group
+  static constexpr int NP = TG / 2;              // token pairs per phase
   static constexpr int JC = E / CH;              // elements per thread per chunk
   static constexpr int NB = JC / EC;             // register blocks per chunk
   static constexpr int CHUNK_BYTES = JC * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
   static constexpr int OFF_WIN = JC * RQ_GROUP_THREADS * 16;
   static constexpr int OFF_BO = JC * RQ_GROUP_THREADS * 32;
-  static_assert(E % CH == 0 && JC % EC == 0 && TG % 2 == 0 && TG <= 8, "bad shape");
+  static_assert(E % CH == 0 && JC % EC == 0 && TG % 2 == 0 && TG <= 8 && CH < NSLOT, "bad shape");
   // shared memory carve-up (bytes)
   static constexpr int SM_RING = 0;
   static constexpr int SM_CBT = NSLOT * CHUNK_BYTES;                        // float4[RQ_SMEM_ROWS] de-duplicated table
   static constexpr int SM_MAP = SM_CBT + RQ_SMEM_ROWS * 16;                 // uint16[RQ_SMEM_ROWS]
   static constexpr int SM_TP = SM_MAP + RQ_SMEM_ROWS * 2;                   // float4[24][RQ_CAN_MAX] canonical rows per order
   static constexpr int SM_MAP3 = SM_TP + RQ_NPERM * RQ_CAN_MAX * 16;        // uint16[16][24][RQ_CAN_MAX]
-  static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[2][4][32]
-  static constexpr int SM_CPR = SM_PART + 2 * 4 * 32 * 4;                   // u64[2][NP][4]
+  static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[2][8][32]
+  static constexpr int SM_CPR = SM_PART + 2 * kComputeWarps * 32 * 4;       // u64[2][4][4] (pairs padded to 4)
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
   static constexpr int SM_BAR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // mbarriers
   static constexpr int N_BAR = 2 * NSLOT + 4;
@@ -98,6 +102,72 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// One pass of phase PH over the CH chunks of one stage (ring slots slot0, slot0+1, ...): out-projection of the
+// previous layer's codeword, residual update, in-projection partials of this layer.
+template <int PH, int E, int EC, int CH, int NSLOT, int TG>
+__device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4], const uint32_t ring,
+                                         const uint32_t cpr_ph, uint64_t* full, uint64_t* empty, const uint32_t slot0,
+                                         const uint32_t par0, const int ct, const int lane) {
+  using C = FwdCfg<E, EC, CH, NSLOT, TG>;
+  const u64 neg1 = pack2(-1.0f, -1.0f);
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    uint32_t s = slot0 + c, par = par0;
+    if (s >= (uint32_t)NSLOT) { s -= NSLOT; par ^= 1; }
+    if (PH == 0) mbar_wait(&full[s], par);   // phase B re-reads a chunk this warp has already seen arrive
+    const uint32_t sb = ring + s * C::CHUNK_BYTES + ct * 16;
+#pragma unroll
+    for (int nb = 0; nb < C::NB; nb++) {
+      {
+        float4 wo[EC];
+        float bo[EC];
+#pragma unroll
+        for (int e = 0; e < EC; e++) {
+          const int jj = nb * EC + e;
+          wo[e] = lds128(sb + jj * (RQ_GROUP_THREADS * 16));
+          bo[e] = lds32(sb + C::OFF_BO - ct * 12 + jj * (RQ_GROUP_THREADS * 4));
+        }
+#pragma unroll
+        for (int pi = 0; pi < C::NP; pi++) {
+          u64 c0, c1, c2, c3;
+          lds128_u64(cpr_ph + pi * 32, c0, c1);
+          lds128_u64(cpr_ph + pi * 32 + 16, c2, c3);
+#pragma unroll
+          for (int e = 0; e < EC; e++) {
+            const int j = c * C::JC + nb * EC + e;
+            u64 o = fma2(pack2(wo[e].x, wo[e].x), c0, pack2(bo[e], bo[e]));
+            o = fma2(pack2(wo[e].y, wo[e].y), c1, o);
+            o = fma2(pack2(wo[e].z, wo[e].z), c2, o);
+            o = fma2(pack2(wo[e].w, wo[e].w), c3, o);
+            r2[PH * C::NP + pi][j] = fma2(o, neg1, r2[PH * C::NP + pi][j]);
+          }
+        }
+      }
+      {
+        float4 wi[EC];
+#pragma unroll
+        for (int e = 0; e < EC; e++) wi[e] = lds128(sb + C::OFF_WIN + (nb * EC + e) * (RQ_GROUP_THREADS * 16));
+#pragma unroll
+        for (int pi = 0; pi < C::NP; pi++) {
+#pragma unroll
+          for (int e = 0; e < EC; e++) {
+            const int j = c * C::JC + nb * EC + e;
+            const u64 r = r2[PH * C::NP + pi][j];
+            acc[pi][0] = fma2(pack2(wi[e].x, wi[e].x), r, acc[pi][0]);
+            acc[pi][1] = fma2(pack2(wi[e].y, wi[e].y), r, acc[pi][1]);
+            acc[pi][2] = fma2(pack2(wi[e].z, wi[e].z), r, acc[pi][2]);
+            acc[pi][3] = fma2(pack2(wi[e].w, wi[e].w), r, acc[pi][3]);
+          }
+        }
+      }
+    }
+    if (PH == 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
 // Register budget: ptxas compiles the kernel for 384 threads/CTA at 168 registers, so the CTA owns a pool
 // of 384*168 = 64512 registers; setmaxnreg can only re-split THAT pool (an .inc beyond it spins forever).
 template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, int REG_COMPUTE = RQ_REGC, int REG_HELPER = RQ_REGH>
@@ -109,18 +179,18 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
   const int lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);
   uint64_t* full = bars;                  // [NSLOT] producer -> compute
-  uint64_t* empty = bars + NSLOT;         // [NSLOT] compute -> producer (8 warp arrivals)
-  uint64_t* part_full = bars + 2 * NSLOT; // [2] compute group -> quantizer (4 warp arrivals)
-  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute group (1 warp arrival)
+  uint64_t* empty = bars + NSLOT;         // [NSLOT] compute -> producer (8 warp arrivals, after phase B)
+  uint64_t* part_full = bars + 2 * NSLOT; // [2] compute -> quantizer of the phase (8 warp arrivals)
+  uint64_t* c_ready = part_full + 2;      // [2] quantizer -> compute (1 warp arrival)
 
-  // work split: a unit is TG consecutive tokens; CTA b handles unit pairs b, b+grid, ...
-  const long long n_units = (p.n_tokens + TG - 1) / TG;
-  const long long n_pairs = (n_units + 1) / 2;
-  const long long my_iters = (n_pairs > (long long)blockIdx.x) ? (n_pairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  // work split: a unit is 2*TG consecutive tokens (phase A = first TG, phase B = next TG); CTA b handles
+  // units b, b+grid, ...
+  const long long n_units = (p.n_tokens + 2 * TG - 1) / (2 * TG);
+  const long long my_iters = (n_units > (long long)blockIdx.x) ? (n_units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kComputeWarps); }
-    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], 4); mbar_init(&c_ready[g], 1); }
+    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], kComputeWarps); mbar_init(&c_ready[g], 1); }
     mbar_fence_init();
   }
   // search tables -> shared memory (shared-codebook mode): the de-duplicated table if it fits, and the
@@ -147,115 +217,81 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
   __syncthreads();
 
   if (warp < kComputeWarps) {
-    // =============================== compute groups ===============================
+    // =============================== compute warps ===============================
     reg_inc<REG_COMPUTE>();
-    const int g = warp >> 2;
-    const int wg = warp & 3;                 // warp within group
-    const int tg = threadIdx.x & 127;        // thread within group
+    const int ct = threadIdx.x;              // 0..255
     const uint32_t ring = smem_u32(smem + C::SM_RING);
-    const uint32_t cpr = smem_u32(smem + C::SM_CPR) + g * (4 * 4 * 8);
-    const uint32_t part = smem_u32(smem + C::SM_PART) + (g * 4 + wg) * 32 * 4 + lane * 4;
-    const u64 neg1 = pack2(-1.0f, -1.0f);
+    const uint32_t cpr = smem_u32(smem + C::SM_CPR);
+    const uint32_t part = smem_u32(smem + C::SM_PART) + warp * 32 * 4 + lane * 4;   // + phase * 1024
     uint32_t slot = 0, full_par = 0, cr_par = 0;
 
     for (long long it = 0; it < my_iters; ++it) {
-      const long long unit = 2 * ((long long)blockIdx.x + it * gridDim.x) + g;
-      const long long tok0 = unit * TG;
+      const long long tok0 = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG);
       // ---- load the unit's activations into registers (zeros outside [0,n_tokens) x [0,D)) ----
-      u64 r2[C::NP][E];
+      u64 r2[TG][E];   // [phase * NP + pair][element]
 #pragma unroll
-      for (int pi = 0; pi < C::NP; pi++) {
+      for (int pi = 0; pi < TG; pi++) {
         const long long ta = tok0 + 2 * pi, tb = ta + 1;
         const float* xa = p.x + ta * (long long)p.D;
         const float* xb = p.x + tb * (long long)p.D;
 #pragma unroll
         for (int j = 0; j < E; j++) {
-          const int d = j * RQ_GROUP_THREADS + tg;
+          const int d = j * RQ_GROUP_THREADS + ct;
           const float a = (ta < p.n_tokens && d < p.D) ? __ldcs(xa + d) : 0.0f;
           const float b = (tb < p.n_tokens && d < p.D) ? __ldcs(xb + d) : 0.0f;
           r2[pi][j] = pack2(a, b);
         }
       }
 
-      // Pass 0 has no code to project out yet: stage 0 carries W_out = b_out = 0 and the group zeroes
-      // its c' slots, so o = fma(0, 0, 0) = 0 and r is unchanged.  The quantizer warps cannot touch the
-      // slots again before this group's pass-0 partials arrive, hence a group-local barrier suffices.
-      if (tg < 32) sts32(cpr + tg * 4, 0.0f);
-      named_bar_sync(1 + g, RQ_GROUP_THREADS);
+      // Pass 0 has no code to project out yet: stage 0 carries W_out = b_out = 0 and the c' slots are zeroed,
+      // so o = fma(0, 0, 0) = 0 and r is unchanged.  First barrier: every warp has finished reading the
+      // previous unit's last c'; second: the zeros are visible.  (The quantizer warps cannot touch the slots
+      // before this unit's pass-0 partials arrive.)
+      named_bar_sync(1, RQ_GROUP_THREADS);
+      if (ct < 64) sts32(cpr + ct * 4, 0.0f);
+      named_bar_sync(1, RQ_GROUP_THREADS);
 
       for (int l = 0; l <= p.nq_run; ++l) {
-        u64 acc[C::NP][4];
 #pragma unroll
-        for (int pi = 0; pi < C::NP; pi++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) acc[pi][k] = 0ull;
-        if (l > 0) { mbar_wait(&c_ready[g], cr_par); cr_par ^= 1; }
-
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-          mbar_wait(&full[slot], full_par);
-          const uint32_t sb = ring + slot * C::CHUNK_BYTES + tg * 16;
-#pragma unroll
-          for (int nb = 0; nb < C::NB; nb++) {
-            float4 wo[EC], wi[EC];
-            float bo[EC];
-#pragma unroll
-            for (int e = 0; e < EC; e++) {
-              const int jj = nb * EC + e;
-              wo[e] = lds128(sb + jj * (RQ_GROUP_THREADS * 16));
-              wi[e] = lds128(sb + C::OFF_WIN + jj * (RQ_GROUP_THREADS * 16));
-              bo[e] = lds32(sb + C::OFF_BO - tg * 12 + jj * (RQ_GROUP_THREADS * 4));
-            }
-#pragma unroll
-            for (int pi = 0; pi < C::NP; pi++) {
-              u64 c0, c1, c2, c3;
-              lds128_u64(cpr + pi * 32, c0, c1);
-              lds128_u64(cpr + pi * 32 + 16, c2, c3);
-#pragma unroll
-              for (int e = 0; e < EC; e++) {
-                const int j = c * C::JC + nb * EC + e;
-                u64 o = fma2(pack2(wo[e].x, wo[e].x), c0, pack2(bo[e], bo[e]));
-                o = fma2(pack2(wo[e].y, wo[e].y), c1, o);
-                o = fma2(pack2(wo[e].z, wo[e].z), c2, o);
-                o = fma2(pack2(wo[e].w, wo[e].w), c3, o);
-                const u64 r = fma2(o, neg1, r2[pi][j]);
-                r2[pi][j] = r;
-                acc[pi][0] = fma2(pack2(wi[e].x, wi[e].x), r, acc[pi][0]);
-                acc[pi][1] = fma2(pack2(wi[e].y, wi[e].y), r, acc[pi][1]);
-                acc[pi][2] = fma2(pack2(wi[e].z, wi[e].z), r, acc[pi][2]);
-                acc[pi][3] = fma2(pack2(wi[e].w, wi[e].w), r, acc[pi][3]);
-              }
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[slot]);
-          if (++slot == NSLOT) { slot = 0; full_par ^= 1; }
-        }
-
-        if (l < p.nq_run) {
-          // logical value index = token * 4 + k, token = 2*pair + half
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = 0.0f;
+        for (int ph = 0; ph < 2; ph++) {
+          u64 acc[C::NP][4];
 #pragma unroll
           for (int pi = 0; pi < C::NP; pi++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) unpack2(acc[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
-          const float s = butterfly32(v, lane);
-          sts32(part, s);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&part_full[g]);
+            for (int k = 0; k < 4; k++) acc[pi][k] = 0ull;
+          if (l > 0) mbar_wait(&c_ready[ph], cr_par);
+          if (ph == 0)
+            fwd_pass<0, E, EC, CH, NSLOT, TG>(r2, acc, ring, cpr, full, empty, slot, full_par, ct, lane);
+          else
+            fwd_pass<1, E, EC, CH, NSLOT, TG>(r2, acc, ring, cpr + 128, full, empty, slot, full_par, ct, lane);
+          if (l < p.nq_run) {
+            // logical value index = token * 4 + k, token = 2*pair + half
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+#pragma unroll
+            for (int pi = 0; pi < C::NP; pi++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) unpack2(acc[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
+            const float s = butterfly32(v, lane);
+            sts32(part + ph * (kComputeWarps * 32 * 4), s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_full[ph]);
+          }
         }
+        if (l > 0) cr_par ^= 1;
+        slot += CH;
+        if (slot >= (uint32_t)NSLOT) { slot -= NSLOT; full_par ^= 1; }
       }
 
       // ---- reconstruction q = x - r_final ----
       if (p.q_out != nullptr) {
 #pragma unroll
-        for (int pi = 0; pi < C::NP; pi++) {
+        for (int pi = 0; pi < TG; pi++) {
           const long long ta = tok0 + 2 * pi, tb = ta + 1;
 #pragma unroll
           for (int j = 0; j < E; j++) {
-            const int d = j * RQ_GROUP_THREADS + tg;
+            const int d = j * RQ_GROUP_THREADS + ct;
             float ra, rb;
             unpack2(r2[pi][j], ra, rb);
             if (d < p.D) {
@@ -293,51 +329,45 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       }
     } else if (hw < 2) {
       // =============================== quantizer warps ===============================
-      // Warp 8 serves group A, warp 9 group B: 8 tokens per warp, a team of 4 lanes per token.
+      // Warp 8 serves phase A, warp 9 phase B: TG <= 8 tokens per warp, a team of 4 lanes per token.
       //
       // Common case (symmetric codebook; no division, no square root on the path to the code): the argmax of
       // cos(n, c_k), n = z/|z|, is the argmax of s_k = z . c_k, and by symmetry it is attained by a canonical
       // row (c0 >= c1 >= c2 >= c3 >= 0) laid out in the magnitude order of z and signed like z.  Each lane
-      // scores 4 of the <= 16 canonical rows on |z| and keeps its two largest; the team combines them with
-      // redux.sync.  If the best score leads the runner-up by more than thr_gap*|z|, no |z_i| is below
+      // scores 4 of the <= 16 canonical rows on |z| and keeps its two largest; the team combines them with two
+      // xor-shuffle steps.  If the best score leads the runner-up by more than thr_gap*|z|, no |z_i| is below
       // thr_tiny*|z| and no two |z_i| are closer than thr_sep*|z| -- margins that the rounding of the
       // reference's normalise-then-dot sequence cannot overturn ("Search") -- the leader IS the
       // reference's first maximum.  Otherwise the whole warp runs the reference's exact sequence (IEEE sqrt /
       // divide, fp32 fma chain, first maximum over the whole table).
-      const int g = hw;
+      const int ph = hw;
       const int sub = lane & 3;                  // lane within the token's team
-      const int tok = lane >> 2;                 // token within the group
+      const int tok = lane >> 2;                 // token within the phase
       const bool tok_live = tok < TG;
-      const unsigned team_mask = 0xFu << (lane & ~3);
       const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
       const uint32_t tp_smem = smem_u32(smem + C::SM_TP);
-      const float4* cb_glob = reinterpret_cast<const float4*>(p.packed + p.off_cbt);
-      const unsigned short* map3_s = reinterpret_cast<const unsigned short*>(smem + C::SM_MAP3);
-      const unsigned short* map_full = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
-                                                  : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
-      const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (g * 8 + tok) * kCodeBuf * 2;
-      const uint32_t pa = smem_u32(smem + C::SM_PART) + (g * 4 * 32 + tok * 4) * 4;
-      const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + g * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
-      const int n_rows = p.cb_shared ? kd_pad : p.K;
-      const float thr_tiny = hdr->thr_tiny, thr_gap = hdr->thr_gap, thr_sep = hdr->thr_sep;
+      const uint32_t map3_smem = smem_u32(smem + C::SM_MAP3);
+      const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (ph * 8 + tok) * kCodeBuf * 2;
+      const uint32_t pa = smem_u32(smem + C::SM_PART) + (ph * kComputeWarps * 32 + tok * 4) * 4;
+      const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + ph * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
       uint32_t pf_par = 0;
 
       for (long long it = 0; it < my_iters; ++it) {
-        const long long token = (2 * ((long long)blockIdx.x + it * gridDim.x) + g) * TG + tok;
-        const bool tok_valid = tok_live && token < p.n_tokens;
-        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin));
 #pragma unroll 1
         for (int l = 0; l < p.nq_run; ++l) {
-          const float4* cb_l = p.cb_shared ? cb_glob : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
-          mbar_wait(&part_full[g], pf_par);
+          // this layer's in-projection bias: requested before the wait so that its L2 latency is hidden
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
+          mbar_wait(&part_full[ph], pf_par);
           pf_par ^= 1;
-          // z = (((P0 + P1) + P2) + P3) + b_in   (model.py:211)
-          const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
-          const float z0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), s3.x), b4.x);
-          const float z1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.y, s1.y), s2.y), s3.y), b4.y);
-          const float z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.z, s1.z), s2.z), s3.z), b4.z);
-          const float z3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.w, s1.w), s2.w), s3.w), b4.w);
-          b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l + 1);   // next layer's bias (nq+1 entries)
+          // z = (((((((P0 + P1) + P2) + P3) + P4) + P5) + P6) + P7) + b_in   (model.py:211)
+          float z0, z1, z2, z3;
+          {
+            const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
+            const float4 s4 = lds128(pa + 512), s5 = lds128(pa + 640), s6 = lds128(pa + 768), s7 = lds128(pa + 896);
+#define RQ_SUM8(f) __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.f, s1.f), s2.f), s3.f), s4.f), s5.f), s6.f), s7.f), b4.f)
+            z0 = RQ_SUM8(x); z1 = RQ_SUM8(y); z2 = RQ_SUM8(z); z3 = RQ_SUM8(w);
+#undef RQ_SUM8
+          }
           int code = 0;
           float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
           bool fast = false;
@@ -347,26 +377,39 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             const int ord = 6 * ((a1 > a0) + (a2 > a0) + (a3 > a0)) + 2 * ((a2 > a1) + (a3 > a1)) + (a3 > a2);
             const int sidx = (z0 < 0.f ? 1 : 0) | (z1 < 0.f ? 2 : 0) | (z2 < 0.f ? 4 : 0) | (z3 < 0.f ? 8 : 0);
             const uint32_t tb = tp_smem + ord * (RQ_CAN_MAX * 16);
-            float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
-            lds128x4<64>(tb + sub * 16, c0, c1, c2, c3);
-            const float sa = __fmaf_rn(a3, c0.w, __fmaf_rn(a2, c0.z, __fmaf_rn(a1, c0.y, __fmul_rn(a0, c0.x))));
-            const float sb = __fmaf_rn(a3, c1.w, __fmaf_rn(a2, c1.z, __fmaf_rn(a1, c1.y, __fmul_rn(a0, c1.x))));
-            const float sc = __fmaf_rn(a3, c2.w, __fmaf_rn(a2, c2.z, __fmaf_rn(a1, c2.y, __fmul_rn(a0, c2.x))));
-            const float sd = __fmaf_rn(a3, c3.w, __fmaf_rn(a2, c3.z, __fmaf_rn(a1, c3.y, __fmul_rn(a0, c3.x))));
-            // largest two of the lane's four scores and the row of the largest (all scores are >= +0)
-            const float h1 = fmaxf(sa, sb), l1 = fminf(sa, sb), h2 = fmaxf(sc, sd), l2 = fminf(sc, sd);
-            const int p1 = sb > sa ? 4 : 0, p2 = sd > sc ? 12 : 8;
-            const float m1 = fmaxf(h1, h2);
-            const float m2 = fmaxf(fminf(h1, h2), fmaxf(l1, l2));
-            const int k1 = (h2 > h1 ? p2 : p1) + sub;
-            const unsigned best = __reduce_max_sync(team_mask, __float_as_uint(m1));
-            const bool mine = __float_as_uint(m1) == best;
-            const unsigned owners = __ballot_sync(0xffffffffu, mine) & team_mask;
-            // runner-up over the team: the owner contributes its second score, the others their first
-            const unsigned second = __reduce_max_sync(team_mask, __float_as_uint(mine ? m2 : m1));
-            const int kw = __shfl_sync(0xffffffffu, k1, __ffs(owners) - 1);   // winning canonical row
+            float m1, m2;
+            int kw;
+            {
+              float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
+              lds128x4<64>(tb + sub * 16, c0, c1, c2, c3);
+              const float sa = __fmaf_rn(a3, c0.w, __fmaf_rn(a2, c0.z, __fmaf_rn(a1, c0.y, __fmul_rn(a0, c0.x))));
+              const float sb = __fmaf_rn(a3, c1.w, __fmaf_rn(a2, c1.z, __fmaf_rn(a1, c1.y, __fmul_rn(a0, c1.x))));
+              const float sc = __fmaf_rn(a3, c2.w, __fmaf_rn(a2, c2.z, __fmaf_rn(a1, c2.y, __fmul_rn(a0, c2.x))));
+              const float sd = __fmaf_rn(a3, c3.w, __fmaf_rn(a2, c3.z, __fmaf_rn(a1, c3.y, __fmul_rn(a0, c3.x))));
+              // largest two of the lane's four scores and the row of the largest (all scores are >= +0)
+              const float h1 = fmaxf(sa, sb), l1 = fminf(sa, sb), h2 = fmaxf(sc, sd), l2 = fminf(sc, sd);
+              const int p1 = sb > sa ? 4 : 0, p2 = sd > sc ? 12 : 8;
+              m1 = fmaxf(h1, h2);
+              m2 = fmaxf(fminf(h1, h2), fmaxf(l1, l2));
+              kw = (h2 > h1 ? p2 : p1) + sub;
+            }
+            // team combine (lanes 4*tok .. 4*tok+3): best, runner-up and row of the best.  An exact tie for the
+            // lead makes runner-up == best, the lead 0, and the token takes the exhaustive path below.
+#pragma unroll
+            for (int s = 1; s <= 2; s <<= 1) {
+              const float om1 = __shfl_xor_sync(0xffffffffu, m1, s);
+              const float om2 = __shfl_xor_sync(0xffffffffu, m2, s);
+              const int ok = __shfl_xor_sync(0xffffffffu, kw, s);
+              m2 = fmaxf(fminf(m1, om1), fmaxf(m2, om2));
+              kw = (om1 > m1 || (om1 == m1 && ok < kw)) ? ok : kw;
+              m1 = fmaxf(m1, om1);
+            }
             const float4 cm = lds128(tb + kw * 16);
-            code = (int)map3_s[(sidx * RQ_NPERM + ord) * RQ_CAN_MAX + kw];
+            {
+              unsigned short cs;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cs) : "r"(map3_smem + ((sidx * RQ_NPERM + ord) * RQ_CAN_MAX + kw) * 2));
+              code = (int)cs;
+            }
             cw = make_float4(copysignf(cm.x, z0), copysignf(cm.y, z1), copysignf(cm.z, z2), copysignf(cm.w, z3));
             // validity of the shortcut (NaN / inf / zero input fail these comparisons)
             const float zz = __fmaf_rn(a3, a3, __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0))));
@@ -375,8 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             const float zmin = fminf(fminf(a0, a1), fminf(a2, a3));
             const float sep = fminf(fminf(fminf(fabsf(a0 - a1), fabsf(a0 - a2)), fminf(fabsf(a0 - a3), fabsf(a1 - a2))),
                                     fminf(fabsf(a1 - a3), fabsf(a2 - a3)));
-            const float lead = __fsub_rn(__uint_as_float(best), __uint_as_float(second));
-            fast = (owners & (owners - 1)) == 0 && lead > thr_gap * nz && zmin >= thr_tiny * nz && sep >= thr_sep * nz &&
+            const float lead = __fsub_rn(m1, m2);
+            fast = lead > hdr->thr_gap * nz && zmin >= hdr->thr_tiny * nz && sep >= hdr->thr_sep * nz &&
                    zz >= 1.0e-30f && zz <= 1.0e30f;
           }
           if (can_rows == 0 || __any_sync(0xffffffffu, !fast)) {
@@ -386,6 +429,9 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
                 __fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)), __fmul_rn(z3, z3)));
             const float n0 = __fdiv_rn(z0, nrm), n1 = __fdiv_rn(z1, nrm), n2 = __fdiv_rn(z2, nrm), n3 = __fdiv_rn(z3, nrm);
             // cos = fma(n3,c3, fma(n2,c2, fma(n1,c1, n0*c0)))  (model.py:190); first maximum (model.py:182)
+            const int n_rows = p.cb_shared ? kd_pad : p.K;
+            const float4* cb_l = p.cb_shared ? reinterpret_cast<const float4*>(p.packed + p.off_cbt)
+                                             : reinterpret_cast<const float4*>(p.codebook) + (size_t)l * p.K;
             float va = -INFINITY;
             int ka = 0x7fffffff;
 #pragma unroll 2
@@ -404,10 +450,14 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             // row 0, which is what torch.argmax returns for an all-NaN row
             ka = __shfl_sync(0xffffffffu, ka, lane & ~3);
             if (!fast) {
+              const unsigned short* map_full = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
+                                                          : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
               code = p.cb_shared ? (int)map_full[ka] : ka;
               cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
             }
           }
+          const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+          const bool tok_valid = tok_live && token < p.n_tokens;
           if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
             if (p.z_out != nullptr && sub == 0 && tok_valid)
               reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
@@ -425,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           if (sub == 0 && tok_live)
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&c_ready[g]);
+          if (lane == 0) mbar_arrive(&c_ready[ph]);
           // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
           if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
             const int l0 = l & ~(kCodeBuf - 1);

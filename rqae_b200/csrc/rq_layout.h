@@ -5,38 +5,38 @@
 //     W_out[s-1] rows + b_out[s-1]   (out-projection of the code chosen at layer s-1)
 //     W_in[s] columns                (in-projection of layer s)
 // with zeros for W_out[-1], b_out[-1] and W_in[nq].  A stage is cut into CH chunks, one
-// bulk-TMA copy each.  A compute group has 128 threads; thread t owns elements
-// d = j*128 + t (j < E) of the D axis, so inside a chunk (JC = E/CH values of j):
-//     [ float4 w_out4 [JC][128] | float4 w_in4 [JC][128] | float b_out [JC][128] ]
+// bulk-TMA copy each.  A CTA has 256 compute threads; thread t owns elements
+// d = j*256 + t (j < E) of the D axis, so inside a chunk (JC = E/CH values of j):
+//     [ float4 w_out4 [JC][256] | float4 w_in4 [JC][256] | float b_out [JC][256] ]
 // and a warp's 128-bit shared loads are 512 contiguous bytes (conflict free).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
 
-#define RQ_GROUP_THREADS 128
+#define RQ_GROUP_THREADS 256 /* compute threads per CTA */
 #define RQ_BYTES_PER_ELEM 36 /* float4 + float4 + float */
 #define RQ_HDR_BYTES 256
-#define RQ_SMEM_ROWS 1024 /* rows of the de-duplicated search table kept in shared memory */
+#define RQ_SMEM_ROWS 640 /* rows of the de-duplicated search table kept in shared memory */
 #define RQ_CAN_MAX 16     /* canonical rows (c0 >= c1 >= c2 >= c3 >= 0) of a sign/permutation-symmetric table */
 #define RQ_NPERM 24
 #define RQ_NSIGN 16
 
 struct RqShape {
-  int E;     /* elements per thread: D_pad = 128 * E */
+  int E;     /* elements per thread: D_pad = 256 * E */
   int EC;    /* register block (elements per inner block) */
   int CH;    /* chunks per stage */
   int NSLOT; /* ring slots */
-  int TG;    /* tokens per group */
+  int TG;    /* tokens per phase (a CTA iteration handles 2 phases = 2*TG tokens) */
 };
 
 /* Supported instantiations, smallest first. Returns 0 on success. */
 static inline int rq_pick_shape(int D, struct RqShape* s) {
   static const struct RqShape table[] = {
-      {2, 2, 1, 4, 8},    /* D <=  256 */
-      {6, 3, 1, 4, 8},    /* D <=  768 */
-      {12, 3, 2, 6, 8},   /* D <= 1536 */
-      {18, 3, 3, 7, 8},   /* D <= 2304  (Gemma-2-2B) */
-      {28, 2, 7, 10, 6},  /* D <= 3584  (Gemma-2-9B) */
+      {1, 1, 1, 4, 8},    /* D <=  256 */
+      {3, 3, 1, 4, 8},    /* D <=  768 */
+      {6, 3, 2, 6, 8},    /* D <= 1536 */
+      {9, 3, 3, 7, 8},    /* D <= 2304  (Gemma-2-2B) */
+      {14, 2, 7, 10, 6},  /* D <= 3584  (Gemma-2-9B) */
   };
   for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
     if (D <= table[i].E * RQ_GROUP_THREADS) {

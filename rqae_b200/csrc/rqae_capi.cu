@@ -253,9 +253,8 @@ int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL); });
   RQ_CUDA(attr_err);
-  const long long n_units = (prm.n_tokens + TG - 1) / TG;
-  const long long n_pairs = (n_units + 1) / 2;
-  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  const long long n_units = (prm.n_tokens + 2 * TG - 1) / (2 * TG);
+  const int grid = (int)(n_units < sms ? n_units : sms);
   kern<<<grid, rq::kThreads, C::SM_TOTAL, st>>>(prm);
   g_launches++;
   RQ_CUDA(cudaGetLastError());
@@ -360,11 +359,11 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
   prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
   cudaStream_t st = (cudaStream_t)stream;
   switch (s.E) {
-    case 2: return launch_forward<2, 2, 1, 4, 8>(prm, sms, st);
-    case 6: return launch_forward<6, 3, 1, 4, 8>(prm, sms, st);
-    case 12: return launch_forward<12, 3, 2, 6, 8>(prm, sms, st);
-    case 18: return launch_forward<18, 3, 3, 7, 8>(prm, sms, st);
-    case 28: return launch_forward<28, 2, 7, 10, 6>(prm, sms, st);
+    case 1: return launch_forward<1, 1, 1, 4, 8>(prm, sms, st);
+    case 3: return launch_forward<3, 3, 1, 4, 8>(prm, sms, st);
+    case 6: return launch_forward<6, 3, 2, 6, 8>(prm, sms, st);
+    case 9: return launch_forward<9, 3, 3, 7, 8>(prm, sms, st);
+    case 14: return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
     default: return RQAE_EUNSUPPORTED;
   }
 }

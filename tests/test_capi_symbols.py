@@ -28,10 +28,10 @@ def test_host_only_entry_points():
     lib = _lib.load()
     assert b"sm_100a" in lib.rqae_version()
     assert lib.rqae_strerror(0) == b"ok" and lib.rqae_strerror(2).startswith(b"unsupported")
-    # packed size model: header + biases + search table + (nq+1) stages of E*128*36 bytes
+    # packed size model: header + biases + search table + (nq+1) stages of E*256*36 bytes
     n = lib.rqae_packed_bytes(1024, 2304, 4, 625)
-    assert n >= 1025 * 18 * 128 * 36 and n < 1025 * 18 * 128 * 36 + (1 << 16)
-    assert lib.rqae_packed_bytes(2048, 3584, 4, 625) >= 2049 * 28 * 128 * 36
+    assert n >= 1025 * 9 * 256 * 36 and n < 1025 * 9 * 256 * 36 + (1 << 16)
+    assert lib.rqae_packed_bytes(2048, 3584, 4, 625) >= 2049 * 14 * 256 * 36
     assert lib.rqae_packed_bytes(8, 2304, 8, 625) == 0      # codebook_dim != 4
     assert lib.rqae_packed_bytes(8, 5000, 4, 625) == 0      # dim beyond the compiled shapes
     # argument validation happens before any CUDA call

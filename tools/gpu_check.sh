@@ -8,6 +8,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
 
+echo "=== smoke ==="
+timeout 180 python __graft_entry__.py --smoke 2>&1 | tail -5 || { echo "SMOKE FAILED/HUNG"; exit 1; }
 echo "=== pytest -m gpu ==="
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/pytest_gpu_$TAG.log
 
