@@ -17,8 +17,9 @@
  * defined by the reference, so the fp32 entry point takes the order as a
  * parameter: order_nt = 0 sums sequentially over d; order_nt = NT > 0 uses NT interleaved
  * partial sums (lane t takes d = t, t+NT, ...), combines each aligned group of 32 lanes
- * with a stride-16,8,4,2,1 pairwise tree, then adds the groups sequentially -- the shape a
- * 32-wide SIMT machine produces.  Where the reference's fp32 arithmetic IS defined (the
+ * with a pairwise tree (tree = 0: lanes paired by strides 16,8,4,2,1; tree = 1: strides
+ * 1,2,16,8,4), then adds the groups sequentially -- the shape a 32-wide SIMT machine
+ * produces.  Where the reference's fp32 arithmetic IS defined (the
  * K=4 contractions and the norm; probed against torch 2.11 CPU) this file
  * uses exactly that arithmetic:
  *   cos  = fmaf(z3,c3, fmaf(z2,c2, fmaf(z1,c1, z0*c0)))        (matmul, model.py:190)
@@ -57,8 +58,9 @@ int rqo_num_threads(void) {
 /* ---- fp32 pieces -------------------------------------------------------------------- */
 
 /* z[k] = sum_d w_in[k][d] * r[d] in the requested order (bias added by the caller). */
-static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int cd, int nt,
+static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int cd, int nt, int tree,
                        float *scratch /*[nt]*/, float *z) {
+  static const int strides[2][5] = {{16, 8, 4, 2, 1}, {1, 2, 16, 8, 4}};
   for (int k = 0; k < cd; k++) {
     const float *w = w_in + (size_t)k * D;
     if (nt <= 0) {
@@ -76,8 +78,13 @@ static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int
     for (int g = 0; g < nt; g += 32) {
       float v[32];
       for (int i = 0; i < 32; i++) v[i] = (g + i < nt) ? scratch[g + i] : 0.0f;
-      for (int s = 16; s >= 1; s >>= 1)
-        for (int i = 0; i < s; i++) v[i] = v[i] + v[i + s];
+      int done = 0; /* lane bits already folded: only lanes with those bits clear stay live */
+      for (int si = 0; si < 5; si++) {
+        const int s = strides[tree][si];
+        for (int i = 0; i < 32; i++)
+          if ((i & done) == 0 && (i & s) == 0) v[i] = v[i] + v[i | s];
+        done |= s;
+      }
       total = (g == 0) ? v[0] : total + v[0];
     }
     z[k] = total;
@@ -99,9 +106,10 @@ static int argmax_cos_f32(const float *zn, const float *cb /*[K][cd]*/, int K, i
 
 int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
                     const float *codebook, int cb_shared, int nq_run, int D, int cd, int K,
-                    const float *x, long n_tokens, int order_nt, int fold_bias, int recon_mode,
+                    const float *x, long n_tokens, int order_nt, int tree, int fold_bias, int recon_mode,
                     const int32_t *teacher, int32_t *codes, float *q_out) {
   if (D <= 0 || cd <= 0 || cd > 16 || K <= 0 || nq_run < 0 || n_tokens < 0 || order_nt < 0) return RQO_EINVAL;
+  if (tree < 0 || tree > 1) return RQO_EINVAL;
   int err = 0;
 #pragma omp parallel
   {
@@ -118,7 +126,7 @@ int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, co
         memcpy(r, xt, sizeof(float) * (size_t)D);
         for (int l = 0; l < nq_run; l++) {
           float z[16], zn[16], c2[16];
-          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, scr, z);
+          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, tree, scr, z);
           const float *bi = b_in + (size_t)l * cd;
           for (int k = 0; k < cd; k++) z[k] = z[k] + bi[k];
           float ss = z[0] * z[0];

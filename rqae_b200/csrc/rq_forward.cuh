@@ -28,7 +28,7 @@
 //     acc[k] = fma(w_in[k][d], r_d, acc[k]), k<4     (model.py:211, partial over the thread's elements)
 // then reduces acc over the warp with a shuffle butterfly and hands 8 per-warp partials per (token, k)
 // to the quantizer warp through shared memory.  Summation order is fixed (thread-sequential over j,
-// lane tree with strides 16,8,4,2,1, warps 0..7 sequentially, then + b_in), so results do not depend on
+// lane tree with strides 1,2,16,8,4, warps 0..7 sequentially, then + b_in), so results do not depend on
 // the tile a token lands in, on the grid size or on timing.  The reconstruction is emitted as
 // q = x - r_final (one extra read of x) instead of a second register-resident accumulator.
 #pragma once
@@ -81,44 +81,66 @@ struct FwdCfg {
   static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[2][8][32]
   static constexpr int SM_CPR = SM_PART + 2 * kComputeWarps * 32 * 4;       // u64[2][4][4] (pairs padded to 4)
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
-  static constexpr int SM_BAR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // mbarriers
+  static constexpr int SM_THR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // float[4] search thresholds
+  static constexpr int SM_BAR = SM_THR + 16;                                // mbarriers
   static constexpr int N_BAR = 2 * NSLOT + 4;
   static constexpr int SM_TOTAL = SM_BAR + N_BAR * 8;
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-// lane L ends with the sum over the 32 lanes of logical value L (see file header for the order)
+// Warp reduction of 32 values per lane: lane L ends with the sum over the 32 lanes of *logical* value L
+// (token = L >> 2, k = L & 3).  Register v[4*t + c] of lane L holds the partial of token t and logical
+// k = c ^ (L & 3): the in-projection weights are stored with their four k components XOR-permuted by the
+// owning thread's low lane bits (pack_stages_kernel), so in the two widest exchange steps (lane bits 0 and 1
+// against the k bits) every lane keeps the registers whose index bit is 0 and sends those whose bit is 1 --
+// no per-lane selects.  The token bits follow with lane bits 4, 3, 2.  Summation tree per logical value:
+// lanes paired by strides 1, 2, 16, 8, 4 (oracle: tree order 1).
 __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
+  for (int i = 0; i < 32; i += 2) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i + 1], 1));
 #pragma unroll
-    for (int i = 0; i < s; i++) {
-      const float keep = up ? v[i + s] : v[i];
-      const float send = up ? v[i] : v[i + s];
-      v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+  for (int i = 0; i < 32; i += 4) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i + 2], 2));
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {      // token stride s <-> lane stride 4*s
+    const bool up = (lane & (4 * s)) != 0;
+#pragma unroll
+    for (int t = 0; t < s; t++) {
+      const float keep = up ? v[4 * (t + s)] : v[4 * t];
+      const float send = up ? v[4 * t] : v[4 * (t + s)];
+      v[4 * t] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4 * s));
     }
   }
   return v[0];
 }
 
-// One pass of phase PH over the CH chunks of one stage (ring slots slot0, slot0+1, ...): out-projection of the
-// previous layer's codeword, residual update, in-projection partials of this layer.
+// One pass of phase PH over the CH chunks of one stage (ring slots slot0, slot0+1, ...), as two sweeps over
+// the thread's E elements:
+//   sweep 1  out-projection of the previous layer's codeword + residual update.  The phase's c' values (NP
+//            pairs x 4 packed values) stay in registers for the whole sweep -- the in-projection accumulators
+//            are not live yet, so there is room -- and are read from shared memory once per pass.
+//   sweep 2  in-projection partials of this layer from the updated residual.
+// Phase B releases a ring slot after its sweep-2 reads of it.
 template <int PH, int E, int EC, int CH, int NSLOT, int TG>
 __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4], const uint32_t ring,
                                          const uint32_t cpr_ph, uint64_t* full, uint64_t* empty, const uint32_t slot0,
                                          const uint32_t par0, const int ct, const int lane) {
   using C = FwdCfg<E, EC, CH, NSLOT, TG>;
   const u64 neg1 = pack2(-1.0f, -1.0f);
+  {
+    u64 cp[C::NP][4];
 #pragma unroll
-  for (int c = 0; c < CH; c++) {
-    uint32_t s = slot0 + c, par = par0;
-    if (s >= (uint32_t)NSLOT) { s -= NSLOT; par ^= 1; }
-    if (PH == 0) mbar_wait(&full[s], par);   // phase B re-reads a chunk this warp has already seen arrive
-    const uint32_t sb = ring + s * C::CHUNK_BYTES + ct * 16;
+    for (int pi = 0; pi < C::NP; pi++) {
+      lds128_u64(cpr_ph + pi * 32, cp[pi][0], cp[pi][1]);
+      lds128_u64(cpr_ph + pi * 32 + 16, cp[pi][2], cp[pi][3]);
+    }
 #pragma unroll
-    for (int nb = 0; nb < C::NB; nb++) {
-      {
+    for (int c = 0; c < CH; c++) {
+      uint32_t s = slot0 + c, par = par0;
+      if (s >= (uint32_t)NSLOT) { s -= NSLOT; par ^= 1; }
+      if (PH == 0) mbar_wait(&full[s], par);   // phase B re-reads a chunk this warp has already seen arrive
+      const uint32_t sb = ring + s * C::CHUNK_BYTES + ct * 16;
+#pragma unroll
+      for (int nb = 0; nb < C::NB; nb++) {
         float4 wo[EC];
         float bo[EC];
 #pragma unroll
@@ -129,35 +151,43 @@ __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4]
         }
 #pragma unroll
         for (int pi = 0; pi < C::NP; pi++) {
-          u64 c0, c1, c2, c3;
-          lds128_u64(cpr_ph + pi * 32, c0, c1);
-          lds128_u64(cpr_ph + pi * 32 + 16, c2, c3);
 #pragma unroll
           for (int e = 0; e < EC; e++) {
             const int j = c * C::JC + nb * EC + e;
-            u64 o = fma2(pack2(wo[e].x, wo[e].x), c0, pack2(bo[e], bo[e]));
-            o = fma2(pack2(wo[e].y, wo[e].y), c1, o);
-            o = fma2(pack2(wo[e].z, wo[e].z), c2, o);
-            o = fma2(pack2(wo[e].w, wo[e].w), c3, o);
+            u64 o = fma2(pack2(wo[e].x, wo[e].x), cp[pi][0], pack2(bo[e], bo[e]));
+            o = fma2(pack2(wo[e].y, wo[e].y), cp[pi][1], o);
+            o = fma2(pack2(wo[e].z, wo[e].z), cp[pi][2], o);
+            o = fma2(pack2(wo[e].w, wo[e].w), cp[pi][3], o);
             r2[PH * C::NP + pi][j] = fma2(o, neg1, r2[PH * C::NP + pi][j]);
           }
         }
       }
-      {
-        float4 wi[EC];
+    }
+  }
 #pragma unroll
-        for (int e = 0; e < EC; e++) wi[e] = lds128(sb + C::OFF_WIN + (nb * EC + e) * (RQ_GROUP_THREADS * 16));
+  for (int pi = 0; pi < C::NP; pi++)
 #pragma unroll
-        for (int pi = 0; pi < C::NP; pi++) {
+    for (int k = 0; k < 4; k++) acc[pi][k] = 0ull;
 #pragma unroll
-          for (int e = 0; e < EC; e++) {
-            const int j = c * C::JC + nb * EC + e;
-            const u64 r = r2[PH * C::NP + pi][j];
-            acc[pi][0] = fma2(pack2(wi[e].x, wi[e].x), r, acc[pi][0]);
-            acc[pi][1] = fma2(pack2(wi[e].y, wi[e].y), r, acc[pi][1]);
-            acc[pi][2] = fma2(pack2(wi[e].z, wi[e].z), r, acc[pi][2]);
-            acc[pi][3] = fma2(pack2(wi[e].w, wi[e].w), r, acc[pi][3]);
-          }
+  for (int c = 0; c < CH; c++) {
+    uint32_t s = slot0 + c;
+    if (s >= (uint32_t)NSLOT) s -= NSLOT;
+    const uint32_t sb = ring + s * C::CHUNK_BYTES + ct * 16;
+#pragma unroll
+    for (int nb = 0; nb < C::NB; nb++) {
+      float4 wi[EC];
+#pragma unroll
+      for (int e = 0; e < EC; e++) wi[e] = lds128(sb + C::OFF_WIN + (nb * EC + e) * (RQ_GROUP_THREADS * 16));
+#pragma unroll
+      for (int pi = 0; pi < C::NP; pi++) {
+#pragma unroll
+        for (int e = 0; e < EC; e++) {
+          const int j = c * C::JC + nb * EC + e;
+          const u64 r = r2[PH * C::NP + pi][j];
+          acc[pi][0] = fma2(pack2(wi[e].x, wi[e].x), r, acc[pi][0]);
+          acc[pi][1] = fma2(pack2(wi[e].y, wi[e].y), r, acc[pi][1]);
+          acc[pi][2] = fma2(pack2(wi[e].z, wi[e].z), r, acc[pi][2]);
+          acc[pi][3] = fma2(pack2(wi[e].w, wi[e].w), r, acc[pi][3]);
         }
       }
     }
@@ -206,6 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     unsigned short* mdst = reinterpret_cast<unsigned short*>(smem + C::SM_MAP);
     for (int i = threadIdx.x; i < kd_pad; i += kThreads) { dst[i] = src[i]; mdst[i] = msrc[i]; }
   }
+  if (threadIdx.x == 32)
+    *reinterpret_cast<float4*>(smem + C::SM_THR) = make_float4(hdr->thr_tiny, hdr->thr_gap, hdr->thr_sep, 0.f);
   if (can_rows > 0) {
     const float4* src = reinterpret_cast<const float4*>(p.packed + p.off_tp);
     const uint32_t* msrc = reinterpret_cast<const uint32_t*>(p.packed + p.off_map3);
@@ -255,10 +287,6 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
 #pragma unroll
         for (int ph = 0; ph < 2; ph++) {
           u64 acc[C::NP][4];
-#pragma unroll
-          for (int pi = 0; pi < C::NP; pi++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) acc[pi][k] = 0ull;
           if (l > 0) mbar_wait(&c_ready[ph], cr_par);
           if (ph == 0)
             fwd_pass<0, E, EC, CH, NSLOT, TG>(r2, acc, ring, cpr, full, empty, slot, full_par, ct, lane);
@@ -414,13 +442,13 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             // validity of the shortcut (NaN / inf / zero input fail these comparisons)
             const float zz = __fmaf_rn(a3, a3, __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0))));
             float nz;
-            asm("sqrt.approx.f32 %0, %1;" : "=f"(nz) : "f"(zz));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nz) : "f"(zz));
             const float zmin = fminf(fminf(a0, a1), fminf(a2, a3));
             const float sep = fminf(fminf(fminf(fabsf(a0 - a1), fabsf(a0 - a2)), fminf(fabsf(a0 - a3), fabsf(a1 - a2))),
                                     fminf(fabsf(a1 - a3), fabsf(a2 - a3)));
             const float lead = __fsub_rn(m1, m2);
-            fast = lead > hdr->thr_gap * nz && zmin >= hdr->thr_tiny * nz && sep >= hdr->thr_sep * nz &&
-                   zz >= 1.0e-30f && zz <= 1.0e30f;
+            const float4 thr = lds128(smem_u32(smem + C::SM_THR));   // (tiny, gap, sep, -)
+            fast = lead > thr.y * nz && zmin >= thr.x * nz && sep >= thr.z * nz && zz >= 1.0e-30f && zz <= 1.0e30f;
           }
           if (can_rows == 0 || __any_sync(0xffffffffu, !fast)) {
             // ---- the reference's own sequence, whole warp (teams with `fast` keep their result) ----
@@ -456,9 +484,9 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
               cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
             }
           }
-          const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
-          const bool tok_valid = tok_live && token < p.n_tokens;
           if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
+            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+            const bool tok_valid = tok_live && token < p.n_tokens;
             if (p.z_out != nullptr && sub == 0 && tok_valid)
               reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
             if (p.teacher != nullptr) {
@@ -479,6 +507,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
           if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
             const int l0 = l & ~(kCodeBuf - 1);
+            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+            const bool tok_valid = tok_live && token < p.n_tokens;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
               const int li = sub * 4 + r;

@@ -73,7 +73,9 @@ __global__ void pack_stages_kernel(const float* __restrict__ w_in, const float* 
     }
     if (s < nq) {
       const float* w = w_in + (size_t)s * 4 * D + d;
-      wi = make_float4(w[0], w[(size_t)D], w[2 * (size_t)D], w[3 * (size_t)D]);
+      // component c holds k = c ^ (t & 3): see butterfly32 in rq_forward.cuh
+      const int x = t & 3;
+      wi = make_float4(w[(size_t)(0 ^ x) * D], w[(size_t)(1 ^ x) * D], w[(size_t)(2 ^ x) * D], w[(size_t)(3 ^ x) * D]);
     }
   }
   const size_t e = (size_t)jj * RQ_GROUP_THREADS + t;

@@ -63,7 +63,7 @@ def test_nan_rule_zero_rows(golden_small):
     """z == 0 makes x / x.norm() NaN; torch.argmax then returns index 0."""
     d = util.small_case(golden_small, "round_fsq_d256_zero")
     cw = util.cweights(d)
-    codes = c_oracle.forward_f32(cw, d["x"], order_nt=256, fold_bias=True, recon="x_minus_r")[1]
+    codes = c_oracle.forward_f32(cw, d["x"], **c_oracle.KERNEL_ORDER)[1]
     assert np.array_equal(codes.reshape(-1, codes.shape[-1])[[0, 5]], d["codes"].reshape(-1, codes.shape[-1])[[0, 5]])
 
 
@@ -100,7 +100,7 @@ def test_2b_fingerprints_and_first_tokens(golden_2b):
     assert np.abs(q[0].numpy() - g["q128"][:4]).max() <= 2e-5 * np.abs(g["q128"][:4]).max()
     # C oracle, SIMT summation order: near-tie protocol on 32 tokens
     cw = c_oracle.CWeights.from_stacked(w)
-    _, codes = c_oracle.forward_f32(cw, g["x128"][:32], order_nt=256, fold_bias=True, recon="x_minus_r")
+    _, codes = c_oracle.forward_f32(cw, g["x128"][:32], **c_oracle.KERNEL_ORDER)
     rep = parity.compare_codes(codes, g["codes1024"][:32], g["margins128_fp64"][:32])
     assert rep.failures == 0, str(rep)
     dec = c_oracle.decode_f32(cw, codes=g["codes1024"][:8])

@@ -13,7 +13,7 @@ from tests import parity, util
 
 pytestmark = pytest.mark.gpu
 
-KERNEL_ORDER = dict(order_nt=256, fold_bias=True, recon="x_minus_r")  # see rq_forward.cuh header
+KERNEL_ORDER = c_oracle.KERNEL_ORDER  # see rq_forward.cuh header
 
 
 def _cuda():
