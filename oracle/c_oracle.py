@@ -12,10 +12,10 @@ from . import build as _build
 _lib = None
 
 # The fp32 summation order of the sm_100a forward kernel (rqae_b200/csrc/rq_forward.cuh): 256 interleaved
-# per-thread partial sums, warp tree with lane strides 1,2,16,8,4, warps added sequentially, bias folded into
-# the out-projection fma chain, reconstruction emitted as x - r_final.  With these switches the C oracle is
+# per-thread partial sums, warp tree with lane strides 1,2,16,8,4, the 8 warp sums combined as a pairwise tree,
+# bias folded into the out-projection fma chain, reconstruction emitted as x - r_final.  With these switches the C oracle is
 # bit-identical to the kernel (codes AND reconstruction), which is what the GPU tests assert.
-KERNEL_ORDER = dict(order_nt=256, tree=1, fold_bias=True, recon="x_minus_r")
+KERNEL_ORDER = dict(order_nt=256, tree=1, gtree=1, fold_bias=True, recon="x_minus_r")
 
 
 def lib():
@@ -63,7 +63,7 @@ def num_threads() -> int:
 
 
 def forward_f32(w: CWeights, x, max_layers: Optional[int] = None, order_nt: int = 0, fold_bias: bool = False,
-                recon: str = "accumulate", teacher=None, want_q: bool = True, tree: int = 0):
+                recon: str = "accumulate", teacher=None, want_q: bool = True, tree: int = 0, gtree: int = 0):
     x = _f32(x)
     lead = x.shape[:-1]
     x2 = x.reshape(-1, w.D)
@@ -75,7 +75,7 @@ def forward_f32(w: CWeights, x, max_layers: Optional[int] = None, order_nt: int 
     rc = lib().rqo_forward_f32(_p(w.w_in), _p(w.b_in), _p(w.w_out), _p(w.b_out), _p(w.codebook),
                                ctypes.c_int(int(w.shared)), ctypes.c_int(nq_run), ctypes.c_int(w.D),
                                ctypes.c_int(w.cd), ctypes.c_int(w.K), _p(x2), ctypes.c_long(n),
-                               ctypes.c_int(order_nt), ctypes.c_int(int(tree)), ctypes.c_int(int(fold_bias)),
+                               ctypes.c_int(order_nt), ctypes.c_int(int(tree)), ctypes.c_int(int(gtree)), ctypes.c_int(int(fold_bias)),
                                ctypes.c_int({"accumulate": 0, "x_minus_r": 1}[recon]), _p(t), _p(codes), _p(q))
     if rc:
         raise RuntimeError(f"rqo_forward_f32 failed: {rc}")

@@ -18,8 +18,8 @@
  * parameter: order_nt = 0 sums sequentially over d; order_nt = NT > 0 uses NT interleaved
  * partial sums (lane t takes d = t, t+NT, ...), combines each aligned group of 32 lanes
  * with a pairwise tree (tree = 0: lanes paired by strides 16,8,4,2,1; tree = 1: strides
- * 1,2,16,8,4), then adds the groups sequentially -- the shape a 32-wide SIMT machine
- * produces.  Where the reference's fp32 arithmetic IS defined (the
+ * 1,2,16,8,4), then adds the groups sequentially (gtree = 0) or as a pairwise tree
+ * ((g0+g1)+(g2+g3))+... (gtree = 1) -- the shapes a 32-wide SIMT machine produces.  Where the reference's fp32 arithmetic IS defined (the
  * K=4 contractions and the norm; probed against torch 2.11 CPU) this file
  * uses exactly that arithmetic:
  *   cos  = fmaf(z3,c3, fmaf(z2,c2, fmaf(z1,c1, z0*c0)))        (matmul, model.py:190)
@@ -58,7 +58,7 @@ int rqo_num_threads(void) {
 /* ---- fp32 pieces -------------------------------------------------------------------- */
 
 /* z[k] = sum_d w_in[k][d] * r[d] in the requested order (bias added by the caller). */
-static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int cd, int nt, int tree,
+static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int cd, int nt, int tree, int gtree,
                        float *scratch /*[nt]*/, float *z) {
   static const int strides[2][5] = {{16, 8, 4, 2, 1}, {1, 2, 16, 8, 4}};
   for (int k = 0; k < cd; k++) {
@@ -75,6 +75,8 @@ static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int
       for (int t = 0; t < nt; t++) scratch[t] = fmaf(w[d0 + t], r[d0 + t], scratch[t]);
     for (int t = 0; d0 + t < D; t++) scratch[t] = fmaf(w[d0 + t], r[d0 + t], scratch[t]);
     float total = 0.0f;
+    float gsum[64];
+    int ng = 0;
     for (int g = 0; g < nt; g += 32) {
       float v[32];
       for (int i = 0; i < 32; i++) v[i] = (g + i < nt) ? scratch[g + i] : 0.0f;
@@ -86,6 +88,12 @@ static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int
         done |= s;
       }
       total = (g == 0) ? v[0] : total + v[0];
+      if (ng < 64) gsum[ng++] = v[0];
+    }
+    if (gtree) {
+      for (int step = 1; step < ng; step *= 2)
+        for (int i = 0; i + step < ng; i += 2 * step) gsum[i] = gsum[i] + gsum[i + step];
+      total = gsum[0];
     }
     z[k] = total;
   }
@@ -106,10 +114,10 @@ static int argmax_cos_f32(const float *zn, const float *cb /*[K][cd]*/, int K, i
 
 int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
                     const float *codebook, int cb_shared, int nq_run, int D, int cd, int K,
-                    const float *x, long n_tokens, int order_nt, int tree, int fold_bias, int recon_mode,
+                    const float *x, long n_tokens, int order_nt, int tree, int gtree, int fold_bias, int recon_mode,
                     const int32_t *teacher, int32_t *codes, float *q_out) {
   if (D <= 0 || cd <= 0 || cd > 16 || K <= 0 || nq_run < 0 || n_tokens < 0 || order_nt < 0) return RQO_EINVAL;
-  if (tree < 0 || tree > 1) return RQO_EINVAL;
+  if (tree < 0 || tree > 1 || (gtree && order_nt > 64 * 32)) return RQO_EINVAL;
   int err = 0;
 #pragma omp parallel
   {
@@ -126,7 +134,7 @@ int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, co
         memcpy(r, xt, sizeof(float) * (size_t)D);
         for (int l = 0; l < nq_run; l++) {
           float z[16], zn[16], c2[16];
-          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, tree, scr, z);
+          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, tree, gtree, scr, z);
           const float *bi = b_in + (size_t)l * cd;
           for (int k = 0; k < cd; k++) z[k] = z[k] + bi[k];
           float ss = z[0] * z[0];

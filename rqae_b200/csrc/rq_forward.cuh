@@ -28,7 +28,7 @@
 //     acc[k] = fma(w_in[k][d], r_d, acc[k]), k<4     (model.py:211, partial over the thread's elements)
 // then reduces acc over the warp with a shuffle butterfly and hands 8 per-warp partials per (token, k)
 // to the quantizer warp through shared memory.  Summation order is fixed (thread-sequential over j,
-// lane tree with strides 1,2,16,8,4, warps 0..7 sequentially, then + b_in), so results do not depend on
+// lane tree with strides 1,2,16,8,4, the 8 warps as a pairwise tree, then + b_in), so results do not depend on
 // the tile a token lands in, on the grid size or on timing.  The reconstruction is emitted as
 // q = x - r_final (one extra read of x) instead of a second register-resident accumulator.
 #pragma once
@@ -357,70 +357,75 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       }
     } else if (hw < 2) {
       // =============================== quantizer warps ===============================
-      // Warp 8 serves phase A, warp 9 phase B: TG <= 8 tokens per warp, a team of 4 lanes per token.
+      // Warp 8 serves phase A, warp 9 phase B: TG <= 8 tokens per warp, a team of 4 lanes per token; lane
+      // `sub` of a team owns coordinate k = sub of z and of c'.
       //
-      // Common case (symmetric codebook; no division, no square root on the path to the code): the argmax of
-      // cos(n, c_k), n = z/|z|, is the argmax of s_k = z . c_k, and by symmetry it is attained by a canonical
-      // row (c0 >= c1 >= c2 >= c3 >= 0) laid out in the magnitude order of z and signed like z.  Each lane
-      // scores 4 of the <= 16 canonical rows on |z| and keeps its two largest; the team combines them with two
-      // xor-shuffle steps.  If the best score leads the runner-up by more than thr_gap*|z|, no |z_i| is below
-      // thr_tiny*|z| and no two |z_i| are closer than thr_sep*|z| -- margins that the rounding of the
-      // reference's normalise-then-dot sequence cannot overturn ("Search") -- the leader IS the
-      // reference's first maximum.  Otherwise the whole warp runs the reference's exact sequence (IEEE sqrt /
-      // divide, fp32 fma chain, first maximum over the whole table).
+      // Common case (sign/permutation-symmetric codebook; no division or square root on the way to the code):
+      // the argmax of cos(n, c_k), n = z/|z|, is the argmax of s_k = z . c_k, and by symmetry it is attained by
+      // a canonical row (c0 >= c1 >= c2 >= c3 >= 0) matched to the magnitudes of z in descending order and
+      // signed like z.  The team sorts |z| (min/max network), each lane scores 4 of the <= 16 canonical rows
+      // and keeps its two largest, and two xor-shuffle steps combine them.  If the best score leads the
+      // runner-up by more than thr_gap*|z|, no |z_i| is below thr_tiny*|z| and no two |z_i| are closer than
+      // thr_sep*|z| -- margins that the rounding of the reference's normalise-then-dot sequence cannot
+      // overturn ("Search"; |z| is bounded by 2*max|z_i| here) -- the leader IS the reference's
+      // first maximum.  Otherwise the whole warp runs the reference's exact sequence (IEEE sqrt / divide,
+      // fp32 fma chain, first maximum over the whole table).
+      //
+      // The hand-over to the compute warps (c' in shared memory, c_ready) happens as early as possible; the
+      // code index itself is looked up after it.
       const int ph = hw;
-      const int sub = lane & 3;                  // lane within the token's team
+      const int sub = lane & 3;                  // lane within the token's team = owned coordinate
       const int tok = lane >> 2;                 // token within the phase
       const bool tok_live = tok < TG;
       const uint32_t cb_smem = smem_u32(smem + C::SM_CBT);
-      const uint32_t tp_smem = smem_u32(smem + C::SM_TP);
+      const uint32_t can_smem = smem_u32(smem + C::SM_TP);    // order 0 = canonical rows as stored
       const uint32_t map3_smem = smem_u32(smem + C::SM_MAP3);
       const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (ph * 8 + tok) * kCodeBuf * 2;
-      const uint32_t pa = smem_u32(smem + C::SM_PART) + (ph * kComputeWarps * 32 + tok * 4) * 4;
-      const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + ph * 128 + (tok >> 1) * 32 + (tok & 1) * 4;
+      const uint32_t pa = smem_u32(smem + C::SM_PART) + (ph * kComputeWarps * 32 + lane) * 4;
+      const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + ph * 128 + (tok >> 1) * 32 + (tok & 1) * 4 + sub * 8;
       uint32_t pf_par = 0;
 
       for (long long it = 0; it < my_iters; ++it) {
 #pragma unroll 1
         for (int l = 0; l < p.nq_run; ++l) {
-          // this layer's in-projection bias: requested before the wait so that its L2 latency is hidden
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.packed + p.off_bin) + l);
+          // requested before the wait so that the latencies are hidden: this layer's in-projection bias
+          // (coordinate `sub`) and the lane's four canonical rows
+          const float bsub = __ldg(reinterpret_cast<const float*>(p.packed + p.off_bin) + l * 4 + sub);
+          float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
+          lds128x4<64>(can_smem + sub * 16, c0, c1, c2, c3);
           mbar_wait(&part_full[ph], pf_par);
           pf_par ^= 1;
-          // z = (((((((P0 + P1) + P2) + P3) + P4) + P5) + P6) + P7) + b_in   (model.py:211)
-          float z0, z1, z2, z3;
+          // z_sub = ((P0 + P1) + (P2 + P3)) + ((P4 + P5) + (P6 + P7)) + b_in   (model.py:211)
+          float zm;
           {
-            const float4 s0 = lds128(pa), s1 = lds128(pa + 128), s2 = lds128(pa + 256), s3 = lds128(pa + 384);
-            const float4 s4 = lds128(pa + 512), s5 = lds128(pa + 640), s6 = lds128(pa + 768), s7 = lds128(pa + 896);
-#define RQ_SUM8(f) __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0.f, s1.f), s2.f), s3.f), s4.f), s5.f), s6.f), s7.f), b4.f)
-            z0 = RQ_SUM8(x); z1 = RQ_SUM8(y); z2 = RQ_SUM8(z); z3 = RQ_SUM8(w);
-#undef RQ_SUM8
+            const float p0 = lds32(pa), p1 = lds32(pa + 128), p2 = lds32(pa + 256), p3 = lds32(pa + 384);
+            const float p4 = lds32(pa + 512), p5 = lds32(pa + 640), p6 = lds32(pa + 768), p7 = lds32(pa + 896);
+            zm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)),
+                                     __fadd_rn(__fadd_rn(p4, p5), __fadd_rn(p6, p7))), bsub);
           }
-          int code = 0;
-          float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int base = lane & ~3;
+          const float z0 = __shfl_sync(0xffffffffu, zm, base), z1 = __shfl_sync(0xffffffffu, zm, base + 1);
+          const float z2 = __shfl_sync(0xffffffffu, zm, base + 2), z3 = __shfl_sync(0xffffffffu, zm, base + 3);
+          const float a0 = fabsf(z0), a1 = fabsf(z1), a2 = fabsf(z2), a3 = fabsf(z3);
+          int code = -1;       // -1: fast path, looked up after the hand-over
+          float cwm = 0.f;     // coordinate `sub` of the chosen codeword
           bool fast = false;
+          int kw = 0;
           if (can_rows > 0) {
-            const float a0 = fabsf(z0), a1 = fabsf(z1), a2 = fabsf(z2), a3 = fabsf(z3);
-            // magnitude order as a Lehmer code (must match lehmer_order() in rqae_capi.cu)
-            const int ord = 6 * ((a1 > a0) + (a2 > a0) + (a3 > a0)) + 2 * ((a2 > a1) + (a3 > a1)) + (a3 > a2);
-            const int sidx = (z0 < 0.f ? 1 : 0) | (z1 < 0.f ? 2 : 0) | (z2 < 0.f ? 4 : 0) | (z3 < 0.f ? 8 : 0);
-            const uint32_t tb = tp_smem + ord * (RQ_CAN_MAX * 16);
-            float m1, m2;
-            int kw;
-            {
-              float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
-              lds128x4<64>(tb + sub * 16, c0, c1, c2, c3);
-              const float sa = __fmaf_rn(a3, c0.w, __fmaf_rn(a2, c0.z, __fmaf_rn(a1, c0.y, __fmul_rn(a0, c0.x))));
-              const float sb = __fmaf_rn(a3, c1.w, __fmaf_rn(a2, c1.z, __fmaf_rn(a1, c1.y, __fmul_rn(a0, c1.x))));
-              const float sc = __fmaf_rn(a3, c2.w, __fmaf_rn(a2, c2.z, __fmaf_rn(a1, c2.y, __fmul_rn(a0, c2.x))));
-              const float sd = __fmaf_rn(a3, c3.w, __fmaf_rn(a2, c3.z, __fmaf_rn(a1, c3.y, __fmul_rn(a0, c3.x))));
-              // largest two of the lane's four scores and the row of the largest (all scores are >= +0)
-              const float h1 = fmaxf(sa, sb), l1 = fminf(sa, sb), h2 = fmaxf(sc, sd), l2 = fminf(sc, sd);
-              const int p1 = sb > sa ? 4 : 0, p2 = sd > sc ? 12 : 8;
-              m1 = fmaxf(h1, h2);
-              m2 = fmaxf(fminf(h1, h2), fmaxf(l1, l2));
-              kw = (h2 > h1 ? p2 : p1) + sub;
-            }
+            // |z| in descending order: 5-comparator network (min/max run on the ALU pipe)
+            const float h01 = fmaxf(a0, a1), l01 = fminf(a0, a1), h23 = fmaxf(a2, a3), l23 = fminf(a2, a3);
+            const float s1 = fmaxf(h01, h23), mx = fminf(h01, h23), my = fmaxf(l01, l23), s4 = fminf(l01, l23);
+            const float s2 = fmaxf(mx, my), s3 = fminf(mx, my);
+            const float sa = __fmaf_rn(s4, c0.w, __fmaf_rn(s3, c0.z, __fmaf_rn(s2, c0.y, __fmul_rn(s1, c0.x))));
+            const float sb = __fmaf_rn(s4, c1.w, __fmaf_rn(s3, c1.z, __fmaf_rn(s2, c1.y, __fmul_rn(s1, c1.x))));
+            const float sc = __fmaf_rn(s4, c2.w, __fmaf_rn(s3, c2.z, __fmaf_rn(s2, c2.y, __fmul_rn(s1, c2.x))));
+            const float sd = __fmaf_rn(s4, c3.w, __fmaf_rn(s3, c3.z, __fmaf_rn(s2, c3.y, __fmul_rn(s1, c3.x))));
+            // largest two of the lane's four scores and the row of the largest (all scores are >= +0)
+            const float h1 = fmaxf(sa, sb), l1 = fminf(sa, sb), h2 = fmaxf(sc, sd), l2 = fminf(sc, sd);
+            const int p1 = sb > sa ? 4 : 0, p2 = sd > sc ? 12 : 8;
+            float m1 = fmaxf(h1, h2);
+            float m2 = fmaxf(fminf(h1, h2), fmaxf(l1, l2));
+            kw = (h2 > h1 ? p2 : p1) + sub;
             // team combine (lanes 4*tok .. 4*tok+3): best, runner-up and row of the best.  An exact tie for the
             // lead makes runner-up == best, the lead 0, and the token takes the exhaustive path below.
 #pragma unroll
@@ -432,23 +437,16 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
               kw = (om1 > m1 || (om1 == m1 && ok < kw)) ? ok : kw;
               m1 = fmaxf(m1, om1);
             }
-            const float4 cm = lds128(tb + kw * 16);
-            {
-              unsigned short cs;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cs) : "r"(map3_smem + ((sidx * RQ_NPERM + ord) * RQ_CAN_MAX + kw) * 2));
-              code = (int)cs;
-            }
-            cw = make_float4(copysignf(cm.x, z0), copysignf(cm.y, z1), copysignf(cm.z, z2), copysignf(cm.w, z3));
-            // validity of the shortcut (NaN / inf / zero input fail these comparisons)
-            const float zz = __fmaf_rn(a3, a3, __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0))));
-            float nz;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nz) : "f"(zz));
-            const float zmin = fminf(fminf(a0, a1), fminf(a2, a3));
-            const float sep = fminf(fminf(fminf(fabsf(a0 - a1), fabsf(a0 - a2)), fminf(fabsf(a0 - a3), fabsf(a1 - a2))),
-                                    fminf(fabsf(a1 - a3), fabsf(a2 - a3)));
-            const float lead = __fsub_rn(m1, m2);
+            // coordinate `sub` of the winner: the canonical value at the rank of |z_sub|, signed like z_sub
+            const float am = fabsf(zm);
+            const int rank = (a0 > am) + (a1 > am) + (a2 > am) + (a3 > am);
+            cwm = copysignf(lds32(can_smem + kw * 16 + rank * 4), zm);
+            // validity of the shortcut (NaN / inf / zero input fail these comparisons); |z| <= 2 * s1
             const float4 thr = lds128(smem_u32(smem + C::SM_THR));   // (tiny, gap, sep, -)
-            fast = lead > thr.y * nz && zmin >= thr.x * nz && sep >= thr.z * nz && zz >= 1.0e-30f && zz <= 1.0e30f;
+            const float nz = s1 + s1;
+            const float sep = fminf(fminf(s1 - s2, s2 - s3), s3 - s4);
+            const float lead = __fsub_rn(m1, m2);
+            fast = lead > thr.y * nz && s4 >= thr.x * nz && sep >= thr.z * nz && s1 >= 1.0e-15f && s1 <= 1.0e15f;
           }
           if (can_rows == 0 || __any_sync(0xffffffffu, !fast)) {
             // ---- the reference's own sequence, whole warp (teams with `fast` keep their result) ----
@@ -481,31 +479,40 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
               const unsigned short* map_full = cb_in_smem ? reinterpret_cast<const unsigned short*>(smem + C::SM_MAP)
                                                           : reinterpret_cast<const unsigned short*>(p.packed + p.off_map);
               code = p.cb_shared ? (int)map_full[ka] : ka;
-              cw = cb_in_smem ? lds128(cb_smem + ka * 16) : __ldg(cb_l + ka);
+              cwm = cb_in_smem ? lds32(cb_smem + ka * 16 + sub * 4) : __ldg(reinterpret_cast<const float*>(cb_l + ka) + sub);
             }
           }
-          if (DBG) {  // parity-test instantiation only: export z, let given codes drive the recurrence
-            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
-            const bool tok_valid = tok_live && token < p.n_tokens;
-            if (p.z_out != nullptr && sub == 0 && tok_valid)
-              reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
+          if (DBG) {  // parity-test instantiation only: let given codes drive the recurrence
             if (p.teacher != nullptr) {
-              const int tc = tok_valid ? p.teacher[token * p.nq_run + l] : 0;
-              cw = reinterpret_cast<const float4*>(p.codebook)[(p.cb_shared ? 0 : (size_t)l * p.K) + tc];
+              const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+              const int tc = (tok_live && token < p.n_tokens) ? p.teacher[token * p.nq_run + l] : 0;
+              cwm = p.codebook[((p.cb_shared ? 0 : (size_t)l * p.K) + tc) * 4 + sub];
             }
           }
           // straight-through value c' = z + (c - z)  (model.py:218-220)
-          if (tok_live) {
-            const float zc = sub == 0 ? z0 : sub == 1 ? z1 : sub == 2 ? z2 : z3;
-            const float cc = sub == 0 ? cw.x : sub == 1 ? cw.y : sub == 2 ? cw.z : cw.w;
-            sts32(cpr_t + sub * 8, __fadd_rn(zc, __fsub_rn(cc, zc)));
+          if (tok_live) sts32(cpr_t, __fadd_rn(zm, __fsub_rn(cwm, zm)));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_ready[ph]);
+
+          // ---- after the hand-over: the code index of the fast path ----
+          if (code < 0) {
+            // magnitude order as a Lehmer code (must match lehmer_order() in rqae_capi.cu) and sign pattern
+            const int ord = 6 * ((a1 > a0) + (a2 > a0) + (a3 > a0)) + 2 * ((a2 > a1) + (a3 > a1)) + (a3 > a2);
+            const int sidx = (z0 < 0.f ? 1 : 0) | (z1 < 0.f ? 2 : 0) | (z2 < 0.f ? 4 : 0) | (z3 < 0.f ? 8 : 0);
+            unsigned short cs;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cs) : "r"(map3_smem + ((sidx * RQ_NPERM + ord) * RQ_CAN_MAX + kw) * 2));
+            code = (int)cs;
+          }
+          if (DBG) {
+            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+            if (p.z_out != nullptr && sub == 0 && tok_live && token < p.n_tokens)
+              reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
           }
           if (sub == 0 && tok_live)
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&c_ready[ph]);
           // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
           if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
+            __syncwarp();
             const int l0 = l & ~(kCodeBuf - 1);
             const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
             const bool tok_valid = tok_live && token < p.n_tokens;
