@@ -278,12 +278,15 @@ def run_b200(args, rank, local_rank, world):
         for c0 in range(0, Te, 1 << 16):
             c1 = min(Te, c0 + (1 << 16))
             xh[c0:c1].copy_(x[c0 % T:c0 % T + (c1 - c0)] if c0 % T + (c1 - c0) <= T else torch.randn(c1 - c0, D))
+        # result buffers are allocated (page-locked) once, as a caller that loops over shards would
+        qh = torch.empty(Te, D, dtype=torch.float32, pin_memory=True)
+        ch = torch.empty(Te, NQ, dtype=torch.int64, pin_memory=True)
         steps_e = args.e2e_steps or min(args.steps, 3)
-        model.forward_host(xh[: 1 << 14])  # warm-up of the host path
+        model.forward_host(xh[: 1 << 15], out=(qh[: 1 << 15], ch[: 1 << 15]))  # warm-up of the host path
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps_e):
-            qh, ch = model.forward_host(xh, chunk_tokens=1 << 16)
+            model.forward_host(xh, out=(qh, ch))
         t_e = time.perf_counter() - t0    # forward_host returns after the last D2H copy completed
         barrier()
         if world > 1:
@@ -292,9 +295,30 @@ def run_b200(args, rank, local_rank, world):
             t_e = float(t.item())
         e2e = {"value": world * Te * steps_e / t_e, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4,
                "d2h_bytes_per_step": Te * (NQ * 8 + D * 4), "tokens_per_step_per_gpu": Te, "steps": steps_e,
-               "timing": "host wall clock around RQAE.forward_host (pinned buffers; returns after the last D2H), max over ranks",
+               "timing": "host wall clock around RQAE.forward_host (pinned host buffers in and out; H2D, kernel and "
+                         "D2H of 33152-token chunks pipelined inside the C library; returns after the last D2H), "
+                         "max over ranks",
                "checksum_codes": int(ch[: 1 << 12].sum().item())}
         del xh, qh, ch
+
+    # ---- side measurements (outside the timed region): encode-only and decode-only throughput ----
+    extra = None
+    if rank == 0:
+        Ts = min(T, 1 << 18)
+        xs = xv[:, :Ts]
+        def timed(fn, reps=2):
+            fn(); torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record(); torch.cuda.synchronize(dev)
+            return out, Ts * reps / (a.elapsed_time(b) * 1e-3)
+        codes_s, enc_rate = timed(lambda: model.encode(xs, out_dtype=torch.int16))
+        _, dec_rate = timed(lambda: model.decode(codes_s))
+        extra = {"encode_only_int16_tokens_per_s": enc_rate, "decode_only_tokens_per_s": dec_rate, "tokens": Ts,
+                 "decode_frac_of_fp32_peak": None}
+        del codes_s
 
     if rank != 0:
         if world > 1:
@@ -306,11 +330,22 @@ def run_b200(args, rank, local_rank, world):
     fp32_peak = max(fp32.values())
     ach_tflops = FLOP_PER_TOKEN_FWD * T / (ms_step * 1e-3) / 1e12
     ach_gbs = HBM_BYTES_PER_TOKEN_FWD * T / (ms_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "forward_traffic.json")))
+        if int(tj.get("tokens_per_launch", 0)) == T:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
+    if extra is not None:
+        extra["decode_frac_of_fp32_peak"] = extra["decode_only_tokens_per_s"] * NQ * (6 * D) * 2 / 1e12 / fp32_peak
     roofline = {
-        "kernel": "rq_forward_kernel<18,3,3,7,8> (one launch per step)",
+        "kernel": "rq_forward_kernel<9,3,3,7,8> (one launch per step)",
         "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak,
         "peak_source": "measured live: rqae_fp32_peak_probe, best of FFMA2 %.1f / FFMA %.1f TFLOP/s" % (fp32["ffma2"], fp32["ffma"]),
-        "flop_per_token": FLOP_PER_TOKEN_FWD, "traffic": None,
+        "flop_per_token": FLOP_PER_TOKEN_FWD, "traffic": traffic,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this size (ncu, "
+                        "profiles/forward_traffic.json); algorithmic bytes per launch = %d" % (HBM_BYTES_PER_TOKEN_FWD * T),
         "why_not_hbm_or_tensor": "bit-exact fp32 parity confines the layer recurrence to the FP32 FMA pipe "
                                  "(arithmetic intensity 1787 FLOP/B; TF32/bf16 splits flip codes, see DESIGN.md)",
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
@@ -332,6 +367,7 @@ def run_b200(args, rank, local_rank, world):
                    "l2": "per-step inputs+outputs (%.1f GB) exceed the 126 MB L2; the 85 MB of weights are L2-resident by design"
                          % (HBM_BYTES_PER_TOKEN_FWD * T / 1e9)},
         "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "checksum_codes": checksum,
+        "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)

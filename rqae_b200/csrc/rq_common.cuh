@@ -132,6 +132,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// `fraction` of the addressed lines (chosen by an address hash) are kept with evict_last priority, the rest are
+// streamed with evict_first: pins a hot subset of a working set that does not fit the L2 as a whole.
+__device__ __forceinline__ uint64_t l2_policy_hot_fraction(float fraction) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+  return p;
+}
 
 // ---- register re-allocation between warp roles (warpgroup-aligned) -----------------------
 template <int N>

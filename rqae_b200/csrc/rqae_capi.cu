@@ -2,10 +2,12 @@
 // launch.  Host logic only; the kernels live in rq_forward.cuh / rq_decode.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -16,7 +18,16 @@
 #include "rq_forward.cuh"
 #include "rq_layout.h"
 
+#ifndef RQ_L2_HOT_DEFAULT
+#define RQ_L2_HOT_DEFAULT 1.0f
+#endif
+
 namespace {
+
+// Lock-step counters of the forward kernel (rq_forward.cuh, "grid lock-step"): one slot per launch in flight.
+constexpr int kSyncSlots = 64;
+__device__ unsigned int g_sync_ctr[kSyncSlots * 32];   // 128 bytes apart
+std::atomic<unsigned int> g_launch_seq{0};
 
 thread_local cudaError_t g_last_cuda = cudaSuccess;
 thread_local int64_t g_launches = 0;
@@ -257,9 +268,23 @@ int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   RQ_CUDA(attr_err);
   const long long n_units = (prm.n_tokens + 2 * TG - 1) / (2 * TG);
   const int grid = (int)(n_units < sms ? n_units : sms);
-  kern<<<grid, rq::kThreads, C::SM_TOTAL, st>>>(prm);
+  rq::FwdParams p2 = prm;
+  p2.sync_ctr = nullptr;
+  static const bool lockstep = [] { const char* e = getenv("RQAE_LOCKSTEP"); return e ? atoi(e) != 0 : true; }();
+  if (lockstep && n_units > grid) {
+    // more than one unit per CTA: keep the CTAs' weight streams in step (one counter per launch in flight).
+    // The kernel spins on the counter, so all CTAs must be co-resident: cooperative launch guarantees it.
+    unsigned int* base = nullptr;
+    RQ_CUDA(cudaGetSymbolAddress((void**)&base, g_sync_ctr));
+    p2.sync_ctr = base + (g_launch_seq.fetch_add(1) % kSyncSlots) * 32;
+    RQ_CUDA(cudaMemsetAsync(p2.sync_ctr, 0, sizeof(unsigned int), st));
+    void* args[] = {(void*)&p2};
+    RQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(rq::kThreads), args, C::SM_TOTAL, st));
+  } else {
+    kern<<<grid, rq::kThreads, C::SM_TOTAL, st>>>(p2);
+    RQ_CUDA(cudaGetLastError());
+  }
   g_launches++;
-  RQ_CUDA(cudaGetLastError());
   return RQAE_OK;
 }
 
@@ -359,6 +384,14 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
   prm.codebook = codebook; prm.cb_shared = codebook_shared ? 1 : 0; prm.K = K; prm.nq_run = nq_run; prm.D = dim;
   prm.x = x; prm.n_tokens = n_tokens; prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride;
   prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
+  {
+    static const float l2_hot = [] {   // tuning knob ("L2 residency of the weight stream")
+      const char* e = getenv("RQAE_L2_HOT");
+      const float v = e ? (float)atof(e) : RQ_L2_HOT_DEFAULT;
+      return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    }();
+    prm.l2_hot = l2_hot;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (s.E) {
     case 1: return launch_forward<1, 1, 1, 4, 8>(prm, sms, st);
@@ -442,8 +475,9 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
     const int b = (int)(c & 1);
     const int64_t t0 = c * chunk_tokens;
     const int64_t nt = (n_tokens - t0 < chunk_tokens) ? (n_tokens - t0) : chunk_tokens;
-    // buffer b is free once the D2H copies of chunk c-2 are done
-    if (c >= 2) cudaStreamWaitEvent(s_in, ev_out[b], 0);
+    // the input buffer b is free once the kernel of chunk c-2 has run; the output buffers once the D2H copies
+    // of chunk c-2 are done (waited for by the compute stream below)
+    if (c >= 2) cudaStreamWaitEvent(s_in, ev_cmp[b], 0);
     cudaError_t e = cudaMemcpyAsync(dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, s_in);
     if (e != cudaSuccess) { fail(e); break; }
     cudaEventRecord(ev_in[b], s_in);

@@ -329,13 +329,21 @@ class RQAE(nn.Module):
         return self._run_decode(indices, None, layers)
 
     def forward_host(self, x_host: torch.Tensor, max_layers=float("inf"), want_q: bool = True,
-                     out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 65536, device=None):
+                     out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 33152, device=None,
+                     out: Optional[tuple] = None):
         """End-to-end variant for host-resident activations: ``x_host`` is a CPU tensor (pinned for full
         copy speed); codes and reconstruction come back in (pinned) CPU tensors.  H2D copy, kernel and D2H
-        copies of consecutive chunks overlap inside ``rqae_forward_host_f32``."""
+        copies of consecutive chunks overlap inside ``rqae_forward_host_f32``.  ``out=(q, codes)`` reuses
+        caller-owned (pinned) result tensors -- page-locking fresh result buffers costs more than the whole
+        computation, so a caller that loops should allocate them once.  The default chunk is 14 full waves of
+        the forward kernel (148 SMs x 16 tokens)."""
         if x_host.is_cuda or x_host.dtype != torch.float32:
             raise RuntimeError("forward_host expects a float32 CPU tensor")
+        if x_host.shape[-1] != self.dim:
+            raise RuntimeError(f"last dimension must be {self.dim}, got {tuple(x_host.shape)}")
         nq_run = int(min(max_layers, self.num_quantizers))
+        if nq_run <= 0:
+            raise RuntimeError("max_layers must be >= 1")
         _, packed, shared, cb_arg = self._ensure_packed()
         if not shared and self.quantization_method not in _FSQ:
             cb_arg = self._learned_tables(nq_run)
@@ -344,15 +352,27 @@ class RQAE(nn.Module):
         lead = xc.shape[:-1]
         n = xc.numel() // self.dim
         pin = torch.cuda.is_available()
-        codes = torch.empty(*lead, nq_run, dtype=out_dtype, pin_memory=pin)
-        q = torch.empty(*lead, self.dim, dtype=torch.float32, pin_memory=pin) if want_q else None
+        if out is not None:
+            q, codes = out
+            if codes is None or codes.is_cuda or codes.dtype != out_dtype or tuple(codes.shape) != (*lead, nq_run) \
+                    or not codes.is_contiguous():
+                raise RuntimeError("out[1] must be a contiguous CPU tensor of shape (*lead, nq') and dtype out_dtype")
+            if want_q and (q is None or q.is_cuda or q.dtype != torch.float32 or tuple(q.shape) != (*lead, self.dim)
+                           or not q.is_contiguous()):
+                raise RuntimeError("out[0] must be a contiguous float32 CPU tensor shaped like x_host")
+            if not want_q:
+                q = None
+        else:
+            codes = torch.empty(*lead, nq_run, dtype=out_dtype, pin_memory=pin)
+            q = torch.empty(*lead, self.dim, dtype=torch.float32, pin_memory=pin) if want_q else None
         torch.cuda.current_stream(dev).synchronize()  # packed weights are produced on the current stream
-        with torch.cuda.device(dev):
-            rc = _lib.load().rqae_forward_host_f32(
-                packed.data_ptr(), cb_arg.data_ptr(), int(shared), self.num_quantizers, nq_run, self.dim,
-                self.codebook_dim, self.codebook.shape[1], xc.data_ptr(), n, codes.data_ptr(),
-                _lib.CODE_DTYPE[str(out_dtype).split(".")[-1]], 0 if q is None else q.data_ptr(), int(chunk_tokens))
-        _lib.check(rc, "rqae_forward_host_f32")
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = _lib.load().rqae_forward_host_f32(
+                    packed.data_ptr(), cb_arg.data_ptr(), int(shared), self.num_quantizers, nq_run, self.dim,
+                    self.codebook_dim, self.codebook.shape[1], xc.data_ptr(), n, codes.data_ptr(),
+                    _lib.CODE_DTYPE[str(out_dtype).split(".")[-1]], 0 if q is None else q.data_ptr(), int(chunk_tokens))
+            _lib.check(rc, "rqae_forward_host_f32")
         return q, codes
 
     # ------------------------------------------------------------------ hook (model.py:254-291)

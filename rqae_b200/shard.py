@@ -1,0 +1,82 @@
+"""Token sharding of the RQ hot path across the GPUs of one box (one process per GPU).
+
+The reference has no multi-GPU code: it fans shards of 1024 sequences out to separate containers and
+meets again on a network volume (scripts/1_create_activations.py:283-305).  Tokens are independent in
+``RQAE.forward`` (rqae/model.py:199-224 has no cross-token op), so the B200 build shards the flattened
+token axis into contiguous ranges, replicates the 85 MB of weights on every GPU, and needs NO collective on
+the data path.  The only exchange is the optional gather of the code tensors when a caller wants them in
+one place; it runs over ``torch.distributed`` (NCCL on the GPUs, gloo in the CPU tests).
+
+Because the kernel's arithmetic does not depend on where in a tile, chunk or grid a token lands
+(rq_forward.cuh: fixed summation order), the concatenation of the per-rank results is bit-identical to
+the single-GPU result (tests/test_shard_gloo.py checks the plumbing on CPU with the oracle standing in
+for the kernel; tests/test_parity_gpu.py checks the position invariance of the kernel itself).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def token_range(n_tokens: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced range [start, stop) of the flattened token axis owned by ``rank``."""
+    if world <= 0 or not (0 <= rank < world) or n_tokens < 0:
+        raise ValueError(f"bad shard request: n_tokens={n_tokens} rank={rank} world={world}")
+    return (n_tokens * rank) // world, (n_tokens * (rank + 1)) // world
+
+
+def shard_tokens(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """The rows of ``x`` (any leading shape, last dim = model dim) that ``rank`` processes, as a (n, D) view."""
+    flat = x.reshape(-1, x.shape[-1])
+    a, b = token_range(flat.shape[0], rank, world)
+    return flat[a:b]
+
+
+def gather_codes(codes_local: torch.Tensor, n_tokens: int, group: Optional[dist.ProcessGroup] = None,
+                 dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Assemble the (n_tokens, nq) code tensor from the per-rank shards produced with ``token_range``.
+
+    ``codes_local`` is this rank's (n_local, nq) tensor (int16/int32/int64, on the device the process group
+    communicates on).  With ``dst=None`` every rank receives the full tensor (all_gather); otherwise only
+    rank ``dst`` does and the others get None.  Shards may differ by one row; they are padded to the largest
+    for the collective and trimmed afterwards."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    a, b = token_range(n_tokens, rank, world)
+    if codes_local.dim() != 2 or codes_local.shape[0] != b - a:
+        raise ValueError(f"rank {rank} must pass its ({b - a}, nq) shard, got {tuple(codes_local.shape)}")
+    nq = codes_local.shape[1]
+    sizes = [token_range(n_tokens, r, world)[1] - token_range(n_tokens, r, world)[0] for r in range(world)]
+    m = max(sizes) if sizes else 0
+    send = codes_local
+    if codes_local.shape[0] != m:
+        send = torch.zeros(m, nq, dtype=codes_local.dtype, device=codes_local.device)
+        send[: codes_local.shape[0]] = codes_local
+    # codes travel as raw bytes: int16 is not a collective dtype of every backend (gloo rejects it)
+    send = send.contiguous().view(torch.uint8)
+    if dst is None:
+        bufs = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(bufs, send, group=group)
+    else:
+        bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+        dist.gather(send, bufs, dst=dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([buf.view(codes_local.dtype)[:n] for buf, n in zip(bufs, sizes)], dim=0)
+
+
+def encode_sharded(model, x: torch.Tensor, max_layers=float("inf"), out_dtype: torch.dtype = torch.int16,
+                   gather: bool = False, group: Optional[dist.ProcessGroup] = None):
+    """Encode this rank's contiguous share of ``x`` (identical on every rank, or at least identically shaped)
+    on the current CUDA device; optionally all_gather the codes.  Returns (codes, (start, stop))."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    flat = x.reshape(-1, x.shape[-1])
+    a, b = token_range(flat.shape[0], rank, world)
+    codes = model.encode(flat[a:b].unsqueeze(0), max_layers=max_layers, out_dtype=out_dtype)[0]
+    if gather and world > 1:
+        codes = gather_codes(codes, flat.shape[0], group=group)
+        return codes, (0, flat.shape[0])
+    return codes, (a, b)

@@ -326,3 +326,29 @@ def test_cpu_tensors_are_rejected(model_2b):
     m, _ = model_2b
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 2304))
+
+
+def test_many_units_per_cta_lockstep_path_bit_exact():
+    """More units than SMs: every CTA loops over several units and the grid lock-step (cooperative launch,
+    rq_forward.cuh) is active; a ragged last unit leaves some CTAs with one unit fewer."""
+    from rqae_b200 import RQAE
+    torch.manual_seed(11)
+    m = RQAE(dim=256, num_quantizers=6).eval()
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    m = m.to(_cuda())
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = sms * 16 * 3 + 16 * 7 + 5
+    x = torch.randn(1, n, 256, generator=torch.Generator().manual_seed(12))
+    q, idx = m(x.to(_cuda()))
+    qo, co = c_oracle.forward_f32(cw, x.numpy(), **KERNEL_ORDER)
+    assert np.array_equal(idx.cpu().numpy(), co.astype(np.int64)) and np.array_equal(q.cpu().numpy(), qo)
+    # two launches in flight on different streams use different lock-step counters
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    xd = x.to(_cuda())
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        i1 = m.encode(xd, out_dtype=torch.int32)
+    with torch.cuda.stream(s2):
+        i2 = m.encode(xd, out_dtype=torch.int32)
+    torch.cuda.synchronize()
+    assert np.array_equal(i1.cpu().numpy(), co) and np.array_equal(i2.cpu().numpy(), co)

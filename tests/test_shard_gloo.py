@@ -1,0 +1,77 @@
+"""N>1 plumbing on CPU: two gloo ranks shard a token batch with rqae_b200.shard, each runs the ORACLE on its
+shard (standing in for the kernel -- there is no CPU compute path in the product), the codes are gathered
+and must equal the single-process result bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from rqae_b200 import shard  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_tokens, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import c_oracle
+        from oracle import rqae_oracle as orc
+        w = orc.random_init(dim=256, num_quantizers=12, seed=3)
+        cw = c_oracle.CWeights.from_stacked(w)
+        x = torch.randn(n_tokens, 256, generator=torch.Generator().manual_seed(5))
+        mine = shard.shard_tokens(x, rank, world)
+        a, b = shard.token_range(n_tokens, rank, world)
+        assert mine.shape[0] == b - a
+        _, codes = c_oracle.forward_f32(cw, mine.numpy(), want_q=False, **c_oracle.KERNEL_ORDER)
+        local = torch.from_numpy(codes.astype(np.int16))
+        full = shard.gather_codes(local, n_tokens)                 # all ranks
+        only0 = shard.gather_codes(local, n_tokens, dst=0)         # rank 0 only
+        assert (only0 is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(full, only0)
+        np.save(os.path.join(out_dir, f"codes_{rank}.npy"), full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_tokens", [37, 64])
+def test_two_rank_shard_and_gather_equals_single_process(tmp_path, n_tokens):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_tokens, str(tmp_path)), nprocs=world, join=True)
+    from oracle import c_oracle
+    from oracle import rqae_oracle as orc
+    w = orc.random_init(dim=256, num_quantizers=12, seed=3)
+    cw = c_oracle.CWeights.from_stacked(w)
+    x = torch.randn(n_tokens, 256, generator=torch.Generator().manual_seed(5))
+    _, ref = c_oracle.forward_f32(cw, x.numpy(), want_q=False, **c_oracle.KERNEL_ORDER)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"codes_{r}.npy"))
+        assert got.shape == ref.shape and np.array_equal(got, ref.astype(np.int16))
+
+
+def test_token_range_partitions_exactly():
+    for n in [0, 1, 7, 16, 1000, 1 << 20]:
+        for world in [1, 2, 3, 4, 8]:
+            spans = [shard.token_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.token_range(10, 2, 2)

@@ -30,6 +30,10 @@ echo "=== ncu full capture of the forward kernel ==="
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_forward -s 1 -c 1 -f \
   -o $OUT/prof_fwd_$TAG python tools/prof_forward.py --tokens 9472 --reps 1 > $OUT/ncu_fwd_$TAG.log 2>&1
 tail -3 $OUT/ncu_fwd_$TAG.log
+echo "=== DRAM traffic of one bench-sized forward launch (1Mi tokens) ==="
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:rq_forward -s 1 -c 1 --csv \
+  --log-file $OUT/traffic_$TAG.csv python tools/prof_forward.py --tokens 1048576 --reps 1 > $OUT/traffic_$TAG.log 2>&1
+python tools/traffic_json.py $OUT/traffic_$TAG.csv 1048576 > $OUT/forward_traffic_$TAG.json; cat $OUT/forward_traffic_$TAG.json
 echo "=== ncu full capture of the decode kernel ==="
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_decode -s 1 -c 1 -f \
   -o $OUT/prof_dec_$TAG python tools/prof_forward.py --tokens 9472 --reps 1 --decode > $OUT/ncu_dec_$TAG.log 2>&1
