@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librqae_b200.so")
+# RQAE_B200_LIB points the binding at another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.so")
 
 # every symbol include/rqae_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [

@@ -236,7 +236,7 @@ inline int launch_decode(const DecParams& prm, int sms, cudaStream_t st) {
     case 1: return launch_decode_t<1, 1, 1, 8, 16>(prm, sms, st);
     case 3: return launch_decode_t<3, 3, 1, 6, 16>(prm, sms, st);
     case 6: return launch_decode_t<6, 3, 2, 6, 16>(prm, sms, st);
-    case 9: return launch_decode_t<9, 3, 3, 8, 16>(prm, sms, st);
+    case 9: return launch_decode_t<9, 3, RQ_E9_CH, RQ_E9_DEC_NSLOT, 16>(prm, sms, st);
     case 14: return launch_decode_t<14, 2, 7, 12, 12>(prm, sms, st);
     default: return 2;
   }

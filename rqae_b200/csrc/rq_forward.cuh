@@ -58,8 +58,8 @@ struct FwdParams {
 };
 
 #ifndef RQ_REGC
-#define RQ_REGC 232
-#define RQ_REGH 40
+#define RQ_REGC 224
+#define RQ_REGH 56
 #endif
 constexpr int kComputeWarps = 8;
 constexpr int kThreads = 384;

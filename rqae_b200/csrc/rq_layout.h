@@ -21,6 +21,13 @@
 #define RQ_NPERM 24
 #define RQ_NSIGN 16
 
+/* ring geometry of the Gemma-2-2B shape: chunks per stage and ring slots (tuning knobs) */
+#ifndef RQ_E9_CH
+#define RQ_E9_CH 1
+#define RQ_E9_NSLOT 2
+#endif
+#define RQ_E9_DEC_NSLOT (RQ_E9_CH == 1 ? 4 : 8)
+
 struct RqShape {
   int E;     /* elements per thread: D_pad = 256 * E */
   int EC;    /* register block (elements per inner block) */
@@ -35,7 +42,7 @@ static inline int rq_pick_shape(int D, struct RqShape* s) {
       {1, 1, 1, 4, 8},    /* D <=  256 */
       {3, 3, 1, 4, 8},    /* D <=  768 */
       {6, 3, 2, 6, 8},    /* D <= 1536 */
-      {9, 3, 3, 7, 8},    /* D <= 2304  (Gemma-2-2B) */
+      {9, 3, RQ_E9_CH, RQ_E9_NSLOT, 8}, /* D <= 2304  (Gemma-2-2B) */
       {14, 2, 7, 10, 6},  /* D <= 3584  (Gemma-2-9B) */
   };
   for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {

@@ -397,7 +397,7 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
     case 1: return launch_forward<1, 1, 1, 4, 8>(prm, sms, st);
     case 3: return launch_forward<3, 3, 1, 4, 8>(prm, sms, st);
     case 6: return launch_forward<6, 3, 2, 6, 8>(prm, sms, st);
-    case 9: return launch_forward<9, 3, 3, 7, 8>(prm, sms, st);
+    case 9: return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 8>(prm, sms, st);
     case 14: return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
     default: return RQAE_EUNSUPPORTED;
   }

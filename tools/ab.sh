@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B timing of library builds on ONE box: usage  gpurun -- 'bash tools/ab.sh build/a.so build/b.so ...'
+# (build variants with: nvcc $FLAGS -DXXX -o build/x.so rqae_b200/csrc/rqae_capi.cu)
+TOK=${TOKENS:-524288}
+for rep in 1 2 3; do
+  for so in "$@"; do
+    r=$(RQAE_B200_LIB=$PWD/$so timeout 300 python tools/prof_forward.py --tokens $TOK --reps 2 2>&1 | grep "forward ms" | awk '{print $NF}')
+    echo "rep$rep $so $r"
+  done
+done
