@@ -97,23 +97,22 @@ struct FwdCfg {
 // against the k bits) every lane keeps the registers whose index bit is 0 and sends those whose bit is 1 --
 // no per-lane selects.  The token bits follow with lane bits 4, 3, 2.  Summation tree per logical value:
 // lanes paired by strides 1, 2, 16, 8, 4 (oracle: tree order 1).
-__device__ __forceinline__ void bf_k0(float (&v)[32]) {   // lane bit 0 <-> k bit 0: 16 exchanges
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i + 1], 1));
-}
-__device__ __forceinline__ void bf_k1(float (&v)[32]) {   // lane bit 1 <-> k bit 1: 8 exchanges
 #pragma unroll
   for (int i = 0; i < 32; i += 4) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i + 2], 2));
-}
-template <int S>
-__device__ __forceinline__ void bf_tok(float (&v)[32], int lane) {   // token stride S <-> lane stride 4*S
-  const bool up = (lane & (4 * S)) != 0;
 #pragma unroll
-  for (int t = 0; t < S; t++) {
-    const float keep = up ? v[4 * (t + S)] : v[4 * t];
-    const float send = up ? v[4 * t] : v[4 * (t + S)];
-    v[4 * t] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4 * S));
+  for (int s = 4; s >= 1; s >>= 1) {      // token stride s <-> lane stride 4*s
+    const bool up = (lane & (4 * s)) != 0;
+#pragma unroll
+    for (int t = 0; t < s; t++) {
+      const float keep = up ? v[4 * (t + s)] : v[4 * t];
+      const float send = up ? v[4 * t] : v[4 * (t + s)];
+      v[4 * t] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4 * s));
+    }
   }
+  return v[0];
 }
 
 // One pass of phase PH over the CH chunks of one stage (ring slots slot0, slot0+1, ...), as two sweeps over
@@ -124,15 +123,18 @@ __device__ __forceinline__ void bf_tok(float (&v)[32], int lane) {   // token st
 //   sweep 2  in-projection partials of this layer from the updated residual.
 // Phase B releases a ring slot after its sweep-2 reads of it.
 template <int PH, int E, int EC, int CH, int NSLOT, int TG>
-__device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc_prev)[TG / 2][4], u64 (&acc)[TG / 2][4],
-                                         const uint32_t ring, const uint32_t cpr_ph, uint64_t* full, uint64_t* empty,
-                                         const uint32_t slot0, const uint32_t par0, const int ct, const int lane,
-                                         const uint32_t part_prev, uint64_t* bar_prev, const bool arrive_prev) {
+__device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4], const uint32_t ring,
+                                         const uint32_t cpr_ph, uint64_t* full, uint64_t* empty, const uint32_t slot0,
+                                         const uint32_t par0, const int ct, const int lane) {
   using C = FwdCfg<E, EC, CH, NSLOT, TG>;
   const u64 neg1 = pack2(-1.0f, -1.0f);
   {
     u64 cp[C::NP][4];
-    float v[32];   // the other phase's partials of the pass that has just ended (see below)
+#pragma unroll
+    for (int pi = 0; pi < C::NP; pi++) {
+      lds128_u64(cpr_ph + pi * 32, cp[pi][0], cp[pi][1]);
+      lds128_u64(cpr_ph + pi * 32 + 16, cp[pi][2], cp[pi][3]);
+    }
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       uint32_t s = slot0 + c, par = par0;
@@ -149,25 +151,8 @@ __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc_prev)[TG / 
           wo[e] = lds128(sb + jj * (RQ_GROUP_THREADS * 16));
           bo[e] = lds32(sb + C::OFF_BO - ct * 12 + jj * (RQ_GROUP_THREADS * 4));
         }
-        if (c == 0 && nb == 0) {
-          // Warp reduction of the OTHER phase's in-projection partials from the pass that has just ended.
-          // Its five exchange steps are spread over this block's token pairs so that the shuffle latency
-          // overlaps FMA work of the same warp; this phase's c' values are fetched pair by pair as the
-          // reduction frees registers.  logical value index = token * 4 + k, token = 2*pair + half
-#pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = 0.0f;
-#pragma unroll
-          for (int pi = 0; pi < C::NP; pi++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) unpack2(acc_prev[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
-          bf_k0(v);
-        }
 #pragma unroll
         for (int pi = 0; pi < C::NP; pi++) {
-          if (c == 0 && nb == 0) {
-            lds128_u64(cpr_ph + pi * 32, cp[pi][0], cp[pi][1]);
-            lds128_u64(cpr_ph + pi * 32 + 16, cp[pi][2], cp[pi][3]);
-          }
 #pragma unroll
           for (int e = 0; e < EC; e++) {
             const int j = c * C::JC + nb * EC + e;
@@ -177,21 +162,6 @@ __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc_prev)[TG / 
             o = fma2(pack2(wo[e].w, wo[e].w), cp[pi][3], o);
             r2[PH * C::NP + pi][j] = fma2(o, neg1, r2[PH * C::NP + pi][j]);
           }
-          if (c == 0 && nb == 0) {
-            if (C::NP >= 4) {
-              if (pi == 0) bf_k1(v);
-              if (pi == 1) bf_tok<4>(v, lane);
-              if (pi == 2) { bf_tok<2>(v, lane); bf_tok<1>(v, lane); }
-            } else {
-              if (pi == 0) { bf_k1(v); bf_tok<4>(v, lane); }
-              if (pi == C::NP - 2 || C::NP == 1) { bf_tok<2>(v, lane); bf_tok<1>(v, lane); }
-            }
-            if (pi == C::NP - 1) sts32(part_prev, v[0]);
-          }
-        }
-        if (c == 0 && nb == 0) {
-          __syncwarp();
-          if (arrive_prev && lane == 0) mbar_arrive(bar_prev);
         }
       }
     }
@@ -315,22 +285,30 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       if (ct < 64) sts32(cpr + ct * 4, 0.0f);
       named_bar_sync(1, RQ_GROUP_THREADS);
 
-      // Software pipeline over passes: the warp reduction of pass n's partials (and the hand-over to the
-      // quantizer warp) happens inside pass n+1, which belongs to the other phase.
-      u64 accA[C::NP][4], accB[C::NP][4];
-#pragma unroll
-      for (int pi = 0; pi < C::NP; pi++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) accB[pi][k] = 0ull;
       for (int l = 0; l <= p.nq_run; ++l) {
-        // pass(A, l); reduces and publishes the partials of pass(B, l-1)
-        if (l > 0) mbar_wait(&c_ready[0], cr_par);
-        fwd_pass<0, E, EC, CH, NSLOT, TG>(r2, accB, accA, ring, cpr, full, empty, slot, full_par, ct, lane,
-                                          part + kComputeWarps * 32 * 4, &part_full[1], l > 0);
-        // pass(B, l); reduces and publishes the partials of pass(A, l)
-        if (l > 0) mbar_wait(&c_ready[1], cr_par);
-        fwd_pass<1, E, EC, CH, NSLOT, TG>(r2, accA, accB, ring, cpr + 128, full, empty, slot, full_par, ct, lane,
-                                          part, &part_full[0], l < p.nq_run);
+#pragma unroll
+        for (int ph = 0; ph < 2; ph++) {
+          u64 acc[C::NP][4];
+          if (l > 0) mbar_wait(&c_ready[ph], cr_par);
+          if (ph == 0)
+            fwd_pass<0, E, EC, CH, NSLOT, TG>(r2, acc, ring, cpr, full, empty, slot, full_par, ct, lane);
+          else
+            fwd_pass<1, E, EC, CH, NSLOT, TG>(r2, acc, ring, cpr + 128, full, empty, slot, full_par, ct, lane);
+          if (l < p.nq_run) {
+            // logical value index = token * 4 + k, token = 2*pair + half
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 0.0f;
+#pragma unroll
+            for (int pi = 0; pi < C::NP; pi++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) unpack2(acc[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
+            const float s = butterfly32(v, lane);
+            sts32(part + ph * (kComputeWarps * 32 * 4), s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_full[ph]);
+          }
+        }
         if (l > 0) cr_par ^= 1;
         slot += CH;
         if (slot >= (uint32_t)NSLOT) { slot -= NSLOT; full_par ^= 1; }
