@@ -102,8 +102,14 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
                           int64_t chunk_tokens);
 
 /* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
- * sustained packed-FFMA2 / scalar-FFMA rate of the FP32 pipe, in FLOP per call; time it with
- * CUDA events on `stream`. */
+ * sustained rate of the FP32 pipe, in FLOP per call; time it with CUDA events on `stream`.
+ *   packed_f32x2 = 1  dense FFMA2 (the peak the roofline fraction is quoted against)
+ *                = 0  scalar FFMA
+ *                = 2  the operand pattern of the forward kernel's in-projection sweep
+ *                     (scalar weight x token pair + pair accumulator), registers only
+ *                = 3  the pattern of its out-projection sweep (fma chain over k, residual update)
+ * Modes 2/3 read `sink[64..191]` as data (fill >= 192 floats) and show what the register file lets
+ * the FMA pipe deliver for the kernel's instruction mix. */
 int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, float* sink, void* stream);
 
 /* Number of kernels this library has launched on this thread since the last reset

@@ -255,6 +255,65 @@ __global__ void __launch_bounds__(512, 1) fp32_probe_kernel(int iters, float* si
   }
 }
 
+// Probe modes 2 / 3: the operand patterns of the forward kernel's two sweeps with everything in registers
+// (no shared-memory traffic, no barriers), 2 warps per scheduler as in the kernel: what the FMA pipe delivers
+// for (scalar weight) x (token pair) + (pair) chains -- the register-operand ceiling of the kernel's inner loops.
+__device__ __forceinline__ rq::u64 fma2v(rq::u64 a, rq::u64 b, rq::u64 c) {   // volatile: not hoisted out of the probe loop
+  rq::u64 d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) fma_pattern_probe_kernel(int iters, float* sink, const float* src) {
+  using namespace rq;
+  u64 r[4][3], acc[4][4], cp[4][4];
+  float w[12], b[3];
+  int n = threadIdx.x;   // every register gets its own source element so that nothing is merged
+#pragma unroll
+  for (int i = 0; i < 12; i++) w[i] = src[n++ & 127];
+#pragma unroll
+  for (int i = 0; i < 3; i++) b[i] = src[n++ & 127];
+#pragma unroll
+  for (int pi = 0; pi < 4; pi++) {
+#pragma unroll
+    for (int e = 0; e < 3; e++) { r[pi][e] = pack2(src[n & 127], src[(n + 1) & 127]); n += 2; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { acc[pi][k] = pack2(src[n & 127], src[(n + 1) & 127]); n += 2; cp[pi][k] = pack2(src[n & 127], src[(n + 1) & 127]); n += 2; }
+  }
+  const u64 neg1 = pack2(-1.0f, -1.0f);
+  for (int it = 0; it < iters; it++) {
+    if (MODE == 2) {   // sweep 2: acc[pi][k] += w[e][k] * r[pi][e]
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+#pragma unroll
+        for (int pi = 0; pi < 4; pi++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) acc[pi][k] = fma2(pack2(w[e * 4 + k], w[e * 4 + k]), r[pi][e], acc[pi][k]);
+    } else {           // sweep 1: o = fma chain over k; r -= o
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+#pragma unroll
+        for (int pi = 0; pi < 4; pi++) {
+          // first multiplicand is loop-carried (another residual pair) so that ptxas cannot hoist the chain
+          u64 o = fma2v(pack2(w[e * 4], w[e * 4]), r[pi][(e + 1) % 3], pack2(b[e], b[e]));
+          o = fma2v(pack2(w[e * 4 + 1], w[e * 4 + 1]), cp[pi][1], o);
+          o = fma2v(pack2(w[e * 4 + 2], w[e * 4 + 2]), cp[pi][2], o);
+          o = fma2v(pack2(w[e * 4 + 3], w[e * 4 + 3]), cp[pi][3], o);
+          r[pi][e] = fma2v(o, neg1, r[pi][e]);
+        }
+    }
+  }
+  float a = 0.f;
+#pragma unroll
+  for (int pi = 0; pi < 4; pi++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) { float lo, hi; unpack2(acc[pi][k], lo, hi); a += lo + hi; }
+#pragma unroll
+    for (int e = 0; e < 3; e++) { float lo, hi; unpack2(r[pi][e], lo, hi); a += lo + hi; }
+  }
+  if (a == 12345.678f) sink[0] = a;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward launch
 // ---------------------------------------------------------------------------------------------
@@ -434,6 +493,14 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc) return rc;
+  if (packed_f32x2 >= 2) {   // operand-pattern probes (see fma_pattern_probe_kernel); sink doubles as the data source
+    if (packed_f32x2 == 2) fma_pattern_probe_kernel<2><<<sms, 256, 0, (cudaStream_t)stream>>>(iters, sink, sink + 64);
+    else fma_pattern_probe_kernel<3><<<sms, 256, 0, (cudaStream_t)stream>>>(iters, sink, sink + 64);
+    g_launches++;
+    RQ_CUDA(cudaGetLastError());
+    if (flops_per_launch) *flops_per_launch = (double)sms * 256 * (double)iters * (packed_f32x2 == 2 ? 48.0 : 60.0) * 4.0;
+    return RQAE_OK;
+  }
   const int grid = sms * 2, block = 512;
   if (packed_f32x2) fp32_probe_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
   else fp32_probe_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
