@@ -86,8 +86,9 @@ class CpuArm:
         return time.perf_counter() - t0
 
     def calibrate(self, target_s: float) -> int:
-        t = self.run(32)
-        rate = 32 / t
+        self.run(32)            # first call pays thread-pool and allocator warm-up
+        t = self.run(96)
+        rate = 96 / t
         n = int(max(32, min(4096, rate * target_s)))
         return (n + 31) // 32 * 32
 
@@ -297,8 +298,10 @@ def run_b200(args, rank, local_rank, world):
         e2e = {"value": world * Te * steps_e / t_e, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4,
                "d2h_bytes_per_step": Te * (NQ * 8 + D * 4), "tokens_per_step_per_gpu": Te, "steps": steps_e,
                "timing": "host wall clock around RQAE.forward_host (pinned host buffers in and out; H2D, kernel and "
-                         "D2H of 33152-token chunks pipelined inside the C library; returns after the last D2H), "
+                         "D2H of 33152-token chunks pipelined inside the C library; codes cross PCIe as int16 and "
+                         "are widened to the int64 result by host threads; returns after the last D2H), "
                          "max over ranks",
+               "pcie_bytes_per_step": {"h2d": Te * D * 4, "d2h": Te * (NQ * 2 + D * 4)},
                "checksum_codes": int(ch[: 1 << 12].sum().item())}
         del xh, qh, ch
 

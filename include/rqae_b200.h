@@ -95,11 +95,15 @@ int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_c
 /* Host-buffer front end of rqae_forward_f32 (the end-to-end path bench.py times as `e2e`):
  * x_host / codes_host / q_host are HOST pointers (pinned for full speed).  The call stages
  * chunks of `chunk_tokens` tokens through internal device buffers on three internal streams
- * (H2D, compute, D2H double-buffered) and returns after the last D2H copy has completed. */
+ * (H2D, compute, D2H double-buffered) and returns after the last D2H copy has completed.
+ * int32 / int64 codes cross PCIe as int16 and are widened into `codes_host` by host threads while
+ * the next chunk is in flight.  The staging buffers, streams and events are cached per calling
+ * thread between calls; rqae_forward_host_release() frees them. */
 int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq,
                           int nq_run, int dim, int codebook_dim, int K, const float* x_host,
                           int64_t n_tokens, void* codes_host, int code_dtype, float* q_host,
                           int64_t chunk_tokens);
+int rqae_forward_host_release(void);
 
 /* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
  * sustained rate of the FP32 pipe, in FLOP per call; time it with CUDA events on `stream`.

@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.
 # every symbol include/rqae_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
-    "rqae_forward_f32", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_fp32_peak_probe", "rqae_launch_count",
+    "rqae_forward_f32", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_release", "rqae_fp32_peak_probe",
+    "rqae_launch_count",
 ]
 
 CODE_DTYPE = {"int16": 0, "int32": 1, "int64": 2}
@@ -52,6 +53,8 @@ def load() -> ctypes.CDLL:
     lib.rqae_decode_f32.argtypes = [vp, vp, i, i, i, i, i, vp, i, i64, vp, vp, i64, vp, vp]
     lib.rqae_forward_host_f32.restype = i
     lib.rqae_forward_host_f32.argtypes = [vp, vp, i, i, i, i, i, i, vp, i64, vp, i, vp, i64]
+    lib.rqae_forward_host_release.restype = i
+    lib.rqae_forward_host_release.argtypes = []
     lib.rqae_fp32_peak_probe.restype = i
     lib.rqae_fp32_peak_probe.argtypes = [i, i, c.POINTER(c.c_double), vp, vp]
     lib.rqae_launch_count.restype = i64

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <math.h>
 
@@ -510,65 +511,143 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
   return RQAE_OK;
 }
 
+// Cached resources of the host pipeline (per calling thread): device staging buffers, a pinned staging
+// area for narrow codes, streams and events.  Re-created when a call needs more room or another device.
+struct HostPipe {
+  int dev = -1;
+  size_t x_bytes = 0, q_bytes = 0, c_bytes = 0, h_bytes = 0;
+  float* dx[2] = {nullptr, nullptr};
+  float* dq[2] = {nullptr, nullptr};
+  void* dc[2] = {nullptr, nullptr};
+  void* hc[2] = {nullptr, nullptr};   // pinned
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  void release() {
+    for (int b = 0; b < 2; b++) {
+      if (dx[b]) cudaFree(dx[b]);
+      if (dq[b]) cudaFree(dq[b]);
+      if (dc[b]) cudaFree(dc[b]);
+      if (hc[b]) cudaFreeHost(hc[b]);
+      if (ev_in[b]) cudaEventDestroy(ev_in[b]);
+      if (ev_cmp[b]) cudaEventDestroy(ev_cmp[b]);
+      if (ev_out[b]) cudaEventDestroy(ev_out[b]);
+      dx[b] = dq[b] = nullptr; dc[b] = hc[b] = nullptr; ev_in[b] = ev_cmp[b] = ev_out[b] = nullptr;
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_cmp) cudaStreamDestroy(s_cmp);
+    if (s_out) cudaStreamDestroy(s_out);
+    s_in = s_cmp = s_out = nullptr;
+    x_bytes = q_bytes = c_bytes = h_bytes = 0;
+    dev = -1;
+  }
+};
+static thread_local HostPipe g_pipe;
+
+// int16 -> int32 / int64 on `threads` host threads (codes cross PCIe as int16 and are widened here)
+static void widen_codes(const int16_t* src, void* dst, size_t n, int code_dtype, int threads) {
+  auto work = [=](size_t lo, size_t hi) {
+    if (code_dtype == 2) { int64_t* d = (int64_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
+    else { int32_t* d = (int32_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
+  };
+  if (threads <= 1 || n < (1u << 16)) { work(0, n); return; }
+  std::vector<std::thread> pool;
+  const size_t per = (n + threads - 1) / threads;
+  for (int t = 1; t < threads; t++) {
+    const size_t lo = per * t, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  work(0, per < n ? per : n);
+  for (auto& th : pool) th.join();
+}
+
+int rqae_forward_host_release(void) {
+  g_pipe.release();
+  return RQAE_OK;
+}
+
 int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
                           int codebook_dim, int K, const float* x_host, int64_t n_tokens, void* codes_host,
                           int code_dtype, float* q_host, int64_t chunk_tokens) {
   if (!packed || !codebook || !x_host || n_tokens < 0 || chunk_tokens <= 0 || code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
   if (nq_run <= 0 || nq_run > nq) return RQAE_EINVAL;
   if (n_tokens == 0) return RQAE_OK;
-  const size_t csz = code_dtype == 2 ? 8 : (code_dtype == 1 ? 4 : 2);
   if (chunk_tokens > n_tokens) chunk_tokens = n_tokens;
-  cudaStream_t s_in, s_cmp, s_out;
-  RQ_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  RQ_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
-  RQ_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  float* dx[2] = {nullptr, nullptr};
-  float* dq[2] = {nullptr, nullptr};
-  void* dc[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+  // Codes are < K <= 32767 in every supported model, so they cross PCIe as int16 (a quarter of the int64 bytes)
+  // and host threads widen them into the caller's tensor while the next chunk is in flight.
+  const bool narrow = codes_host != nullptr && code_dtype != RQAE_CODE_I16 && K <= 32767;
+  const int dev_dtype = narrow ? RQAE_CODE_I16 : code_dtype;
+  const size_t dsz = dev_dtype == 2 ? 8 : (dev_dtype == 1 ? 4 : 2);     // code size on the device / on the wire
+  const size_t usz = code_dtype == 2 ? 8 : (code_dtype == 1 ? 4 : 2);   // code size in the caller's tensor
   int rc = RQAE_OK;
   auto fail = [&](cudaError_t e) { g_last_cuda = e; rc = RQAE_ECUDA; };
-  for (int b = 0; b < 2 && rc == 0; b++) {
-    cudaError_t e;
-    if ((e = cudaMalloc(&dx[b], (size_t)chunk_tokens * dim * 4)) != cudaSuccess) fail(e);
-    if (rc == 0 && q_host && (e = cudaMalloc(&dq[b], (size_t)chunk_tokens * dim * 4)) != cudaSuccess) fail(e);
-    if (rc == 0 && codes_host && (e = cudaMalloc(&dc[b], (size_t)chunk_tokens * nq_run * csz)) != cudaSuccess) fail(e);
-    cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_cmp[b], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming);
+
+  HostPipe& P = g_pipe;
+  int dev = 0;
+  RQ_CUDA(cudaGetDevice(&dev));
+  const size_t need_x = (size_t)chunk_tokens * dim * 4, need_q = q_host ? need_x : 0;
+  const size_t need_c = codes_host ? (size_t)chunk_tokens * nq_run * dsz : 0, need_h = narrow ? need_c : 0;
+  if (P.dev != dev || P.x_bytes < need_x || P.q_bytes < need_q || P.c_bytes < need_c || P.h_bytes < need_h) {
+    P.release();
+    P.dev = dev;
+    RQ_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+    RQ_CUDA(cudaStreamCreateWithFlags(&P.s_cmp, cudaStreamNonBlocking));
+    RQ_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      RQ_CUDA(cudaMalloc(&P.dx[b], need_x));
+      if (need_q) RQ_CUDA(cudaMalloc(&P.dq[b], need_q));
+      if (need_c) RQ_CUDA(cudaMalloc(&P.dc[b], need_c));
+      if (need_h) RQ_CUDA(cudaHostAlloc(&P.hc[b], need_h, cudaHostAllocDefault));
+      RQ_CUDA(cudaEventCreateWithFlags(&P.ev_in[b], cudaEventDisableTiming));
+      RQ_CUDA(cudaEventCreateWithFlags(&P.ev_cmp[b], cudaEventDisableTiming));
+      RQ_CUDA(cudaEventCreateWithFlags(&P.ev_out[b], cudaEventDisableTiming));
+    }
+    P.x_bytes = need_x; P.q_bytes = need_q; P.c_bytes = need_c; P.h_bytes = need_h;
   }
-  int64_t n_chunks = (n_tokens + chunk_tokens - 1) / chunk_tokens;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int wthreads = (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+
+  const int64_t n_chunks = (n_tokens + chunk_tokens - 1) / chunk_tokens;
+  auto chunk_len = [&](int64_t c) { const int64_t t0 = c * chunk_tokens; return (n_tokens - t0 < chunk_tokens) ? (n_tokens - t0) : chunk_tokens; };
+  auto finish_chunk = [&](int64_t c) {   // host side of chunk c: wait for its D2H copies, widen the codes
+    const int b = (int)(c & 1);
+    cudaError_t e = cudaEventSynchronize(P.ev_out[b]);
+    if (e != cudaSuccess) { fail(e); return; }
+    widen_codes((const int16_t*)P.hc[b], (char*)codes_host + (size_t)c * chunk_tokens * nq_run * usz,
+                (size_t)chunk_len(c) * nq_run, code_dtype, wthreads);
+  };
   for (int64_t c = 0; c < n_chunks && rc == 0; c++) {
     const int b = (int)(c & 1);
     const int64_t t0 = c * chunk_tokens;
-    const int64_t nt = (n_tokens - t0 < chunk_tokens) ? (n_tokens - t0) : chunk_tokens;
+    const int64_t nt = chunk_len(c);
     // the input buffer b is free once the kernel of chunk c-2 has run; the output buffers once the D2H copies
     // of chunk c-2 are done (waited for by the compute stream below)
-    if (c >= 2) cudaStreamWaitEvent(s_in, ev_cmp[b], 0);
-    cudaError_t e = cudaMemcpyAsync(dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, s_in);
+    if (c >= 2) cudaStreamWaitEvent(P.s_in, P.ev_cmp[b], 0);
+    cudaError_t e = cudaMemcpyAsync(P.dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, P.s_in);
     if (e != cudaSuccess) { fail(e); break; }
-    cudaEventRecord(ev_in[b], s_in);
-    cudaStreamWaitEvent(s_cmp, ev_in[b], 0);
-    if (c >= 2) cudaStreamWaitEvent(s_cmp, ev_out[b], 0);
-    rc = rqae_forward_f32(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, dx[b], nt, dc[b],
-                          code_dtype, nq_run, dq[b], nullptr, nullptr, (void*)s_cmp);
+    cudaEventRecord(P.ev_in[b], P.s_in);
+    cudaStreamWaitEvent(P.s_cmp, P.ev_in[b], 0);
+    if (c >= 2) cudaStreamWaitEvent(P.s_cmp, P.ev_out[b], 0);
+    rc = rqae_forward_f32(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, P.dx[b], nt,
+                          codes_host ? P.dc[b] : nullptr, dev_dtype, nq_run, q_host ? P.dq[b] : nullptr, nullptr, nullptr,
+                          (void*)P.s_cmp);
     if (rc) break;
-    cudaEventRecord(ev_cmp[b], s_cmp);
-    cudaStreamWaitEvent(s_out, ev_cmp[b], 0);
-    if (codes_host)
-      cudaMemcpyAsync((char*)codes_host + (size_t)t0 * nq_run * csz, dc[b], (size_t)nt * nq_run * csz, cudaMemcpyDeviceToHost, s_out);
-    if (q_host) cudaMemcpyAsync(q_host + (size_t)t0 * dim, dq[b], (size_t)nt * dim * 4, cudaMemcpyDeviceToHost, s_out);
-    cudaEventRecord(ev_out[b], s_out);
+    cudaEventRecord(P.ev_cmp[b], P.s_cmp);
+    cudaStreamWaitEvent(P.s_out, P.ev_cmp[b], 0);
+    if (codes_host) {
+      void* dst = narrow ? P.hc[b] : (void*)((char*)codes_host + (size_t)t0 * nq_run * usz);
+      cudaMemcpyAsync(dst, P.dc[b], (size_t)nt * nq_run * dsz, cudaMemcpyDeviceToHost, P.s_out);
+    }
+    if (q_host) cudaMemcpyAsync(q_host + (size_t)t0 * dim, P.dq[b], (size_t)nt * dim * 4, cudaMemcpyDeviceToHost, P.s_out);
+    cudaEventRecord(P.ev_out[b], P.s_out);
+    // chunk c is queued; while the GPU works on it, finish chunk c-1 on the host.  (Its staging buffer is
+    // reused by chunk c+1, which is enqueued only after this returns.)
+    if (narrow && c >= 1) finish_chunk(c - 1);
   }
-  cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+  if (rc == 0 && narrow) finish_chunk(n_chunks - 1);
+  cudaError_t e1 = cudaStreamSynchronize(P.s_in), e2 = cudaStreamSynchronize(P.s_cmp), e3 = cudaStreamSynchronize(P.s_out);
   if (rc == 0 && e1 != cudaSuccess) fail(e1);
   if (rc == 0 && e2 != cudaSuccess) fail(e2);
   if (rc == 0 && e3 != cudaSuccess) fail(e3);
-  for (int b = 0; b < 2; b++) {
-    cudaFree(dx[b]); cudaFree(dq[b]); cudaFree(dc[b]);
-    cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_cmp[b]); cudaEventDestroy(ev_out[b]);
-  }
-  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
   return rc;
 }
 

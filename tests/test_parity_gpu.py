@@ -306,6 +306,17 @@ def test_forward_host_matches_device_path(model_2b):
     q_d, idx_d = m(x.to(_cuda()).view(1, -1, 2304), max_layers=32)
     q_h, idx_h = m.forward_host(x.pin_memory(), max_layers=32, chunk_tokens=1024)
     assert torch.equal(idx_h, idx_d[0].cpu()) and torch.equal(q_h, q_d[0].cpu())
+    # int32 / int16 codes, caller-owned result tensors reused across calls, codes-only mode, ragged last chunk
+    for dt in (torch.int32, torch.int16):
+        qo = torch.empty(3000, 2304).pin_memory()
+        co = torch.empty(3000, 32, dtype=dt).pin_memory()
+        for chunk in (700, 4096):
+            co.zero_()
+            q2, c2 = m.forward_host(x.pin_memory(), max_layers=32, chunk_tokens=chunk, out_dtype=dt, out=(qo, co))
+            assert c2 is co and q2 is qo
+            assert torch.equal(co.to(torch.int64), idx_d[0].cpu()) and torch.equal(qo, q_d[0].cpu())
+    _, c3 = m.forward_host(x.pin_memory(), max_layers=32, want_q=False, chunk_tokens=999)
+    assert torch.equal(c3, idx_d[0].cpu())
 
 
 def test_gemma9b_width_bit_exact_vs_c_oracle():
