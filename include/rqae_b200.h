@@ -105,6 +105,29 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
                           int64_t chunk_tokens);
 int rqae_forward_host_release(void);
 
+/* RQAEFeature.intensity (rqae/feature.py:102-129) for `n_features` features at once -- the inner
+ * computation of the mining loop scripts/3_make_rqae_features.py:98-114.  For feature f (center codes
+ * centers[f][l]), token t and every cut c (cuts_host: strictly ascending layer indices, the
+ * reference's `layers` list):
+ *     out[f][c][t] = fp16( fp16( sum_{l<=cut} w_l * sims[center_f[l]][code_t[l]] ) / fp16( sum_{l<=cut} w_l ) )
+ * with sims = codebook_sims (rqae/model.py:133-143) and w = the fp16 layer weights (feature.py:97-99).
+ * Computed as one tcgen05 GEMM over the rank-4 factors of sims; the sum is accumulated in
+ * fp32 from fp16 factors, so values agree with the reference within the tolerance DESIGN.md states,
+ * not bitwise.  The roundings after the sum are the reference's.
+ *   cb_norm            [K][4] fp32 = F.normalize(codebook[0], dim=-1)            (K + 1 <= 2048)
+ *   codes              [n_tokens][code_stride] of code_dtype (codes outside [0,K) contribute 0)
+ *   centers            int32 [n_features][center_stride]
+ *   layer_weights_f16  fp16 [>= max cut + 1]
+ *   out                fp16 [n_features][n_cuts][out_stride]; out_stride >= n_tokens rounded up to a
+ *                      multiple of 256 (whole token tiles are written), 16-byte aligned rows
+ *   workspace          device scratch of rqae_intensity_workspace_bytes(...) bytes, 1024-byte aligned
+ * Four launches on `stream` (schedule, code transpose, feature operand, GEMM); no synchronisation. */
+size_t rqae_intensity_workspace_bytes(const int32_t* cuts_host, int n_cuts, int n_features, int64_t n_tokens);
+int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_dtype, int64_t code_stride,
+                       int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
+                       const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                       int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
  * sustained rate of the FP32 pipe, in FLOP per call; time it with CUDA events on `stream`.
  *   packed_f32x2 = 1  dense FFMA2 (the peak the roofline fraction is quoted against)

@@ -1,0 +1,422 @@
+// Feature intensities for many features at once, as a tcgen05 GEMM over code tensors (sm_100a).
+//
+// Replaces RQAEFeature.intensity (rqae/feature.py:102-129, reference harish-kamath/rqae) as it is used by the
+// mining loop of scripts/3_make_rqae_features.py:98-114: for feature f with center codes center_f[l] and
+// token t with codes code_t[l],
+//     intensity[t, f, cut] = fp16( fp16( sum_{l <= cut} w_l * sims[center_f[l], code_t[l]] ) / fp16( sum_{l <= cut} w_l ) )
+// where sims = (n n^T).half(), n = F.normalize(codebook[0]) (rqae/model.py:140-142) and w_l = the fp16 layer
+// weight (feature.py:97-99).  Because sims is the Gram matrix of the 4-wide rows n_c, the numerator is a dense
+// contraction over k = (l, j), j < 4:
+//     S[f, t] = sum_k U[f, k] * V[t, k],   U[f, 4l+j] = fp16(w_l * n[center_f[l]][j]),   V[t, 4l+j] = fp16(n[code_t[l]][j])
+// which is what this kernel computes on the 5th-generation tensor cores (kind::f16, fp32 accumulators in
+// TMEM), evaluated as a running prefix at every cut.  The reference rounds every term to fp16 and sums in
+// fp32; here the fp16-rounded factors are multiplied exactly and summed in fp32 by the tensor core, so the
+// numerators differ by rounding noise (tests state the tolerance); the roundings AFTER the sum -- prefix to
+// fp16, fp32 divide by the fp16 weight prefix, quotient to fp16 -- are the reference's own.
+//
+// One CTA (448 threads, 1 per SM, persistent) computes units of 256 tokens x 256 features (two feature tiles
+// of 128 = two 128x256 fp32 accumulators = all 512 TMEM columns):
+//   warp 0      U producer : one lane, bulk-TMA copies of pre-swizzled 128x64 fp16 tiles (16 KB) from L2
+//   warp 1      MMA issuer : one lane, tcgen05.mma M=128 (features) x N=256 (tokens) x K=16, 4 per tile and
+//                            K-block; owns the TMEM allocation
+//   warps 2-5   V builders : the token operand never exists in memory: each thread turns the codes of two tokens
+//                            (layer-major int16, coalesced) into 128-byte K-major rows through a 4 x fp16
+//                            lookup table in shared memory, written in the 128-byte swizzle the MMA expects
+//   warps 6-13  epilogue   : at every cut the MMA issuer pauses, the 8 warps read the running prefix from
+//                            TMEM (tcgen05.ld 32x32b.x32), release the accumulators, apply the reference's
+//                            fp16 roundings and store fp16 rows of out[f][cut][t]
+// The K axis is cut into K-blocks of 16 layers (64 k = one 128-byte swizzle row); a segment between two cuts
+// that is not a multiple of 16 layers is padded with zero slots (schedule built by int_prep_kernel).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "rq_common.cuh"
+
+namespace rq {
+
+constexpr int IT_TOK = 256;                     // tokens per unit = MMA N
+constexpr int IT_FT = 128;                      // features per tile = MMA M
+constexpr int IT_LPB = 16;                      // layers per K-block (64 k values, 128 bytes of fp16)
+constexpr int IT_STAGES = 3;
+constexpr int IT_V_BYTES = IT_TOK * 128;        // 32 KB
+constexpr int IT_U_TILE = IT_FT * 128;          // 16 KB
+constexpr int IT_STAGE_BYTES = IT_V_BYTES + 2 * IT_U_TILE;   // 64 KB
+constexpr int IT_MAX_CUTS = 64;
+constexpr int IT_MAX_KB = 256;
+constexpr int IT_LUT_ROWS = 2048;               // codebook rows + the zero row must fit
+constexpr int IT_THREADS = 448;
+constexpr int IT_EPI_WARPS = 8;
+constexpr int IT_BUILDERS = 128;
+
+struct IntKBlock {   // one K-block of the schedule: layers l0 .. l0+n-1 (n <= 16), the rest of the 16 slots zero
+  int l0, n, cut, pad;   // cut >= 0: this block ends the segment of that cut (the epilogue emits it)
+};
+
+struct IntParams {
+  const short* codes_t;          // [L][T_pad] layer-major codes, out-of-range and padding = K (the zero row)
+  long long T_pad;               // multiple of IT_TOK
+  const unsigned char* u_tiles;  // [F_tiles][NKB][16 KB]
+  const IntKBlock* sched;        // [NKB]
+  const float* wcum;             // [n_cuts] float(fp16(sum_{l<=cut} w_l)), then [n_cuts] its fp32 reciprocal
+  const uint2* lut;              // [K+1] fp16x4 normalised codebook rows, row K = 0
+  int K, NKB, n_cuts, F, F_tiles;
+  __half* out;                   // [F][n_cuts][out_stride]
+  long long out_stride;
+  long long n_tok_tiles;
+};
+
+struct IntSmem {
+  static constexpr int STAGES = 0;
+  static constexpr int LUT = IT_STAGES * IT_STAGE_BYTES;
+  static constexpr int SCHED = LUT + IT_LUT_ROWS * 8;
+  static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
+  static constexpr int BARS = WCUM + 2 * IT_MAX_CUTS * 4;
+  static constexpr int TMEM_PTR = BARS + (2 * IT_STAGES + 2) * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+static_assert(IntSmem::TOTAL <= 227 * 1024, "shared memory budget");
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {   // arrives on `bar` when all MMAs issued so far have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major operand tile in the canonical 128-byte-swizzle layout: rows of 128 bytes, 8-row groups 1024 bytes
+// apart (SBO), 16-byte chunk index XORed with (row & 7); descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// The reference's post-sum arithmetic for one value: prefix -> fp16, fp32 divide by the fp16 weight prefix,
+// quotient -> fp16 (feature.py:123-127 on CPU tensors).  The divide is a reciprocal multiply plus one
+// Newton correction (correctly rounded for these operand ranges).
+__device__ __forceinline__ uint32_t finish2(float a, float b, float wc, float inv) {
+  const float2 p = __half22float2(__floats2half2_rn(a, b));
+  float q0 = p.x * inv, q1 = p.y * inv;
+  q0 = __fmaf_rn(__fmaf_rn(-q0, wc, p.x), inv, q0);
+  q1 = __fmaf_rn(__fmaf_rn(-q1, wc, p.y), inv, q1);
+  const __half2 h = __floats2half2_rn(q0, q1);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + IntSmem::BARS);
+  uint64_t* full = bars;                        // [S] U bytes landed + 128 builder arrivals
+  uint64_t* empty = bars + IT_STAGES;           // [S] MMAs reading the stage have completed (tcgen05.commit)
+  uint64_t* acc_full = bars + 2 * IT_STAGES;    // segment complete (tcgen05.commit)
+  uint64_t* acc_free = acc_full + 1;            // 8 epilogue warps have read the accumulators
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + IntSmem::TMEM_PTR);
+  const IntKBlock* sched = reinterpret_cast<const IntKBlock*>(smem + IntSmem::SCHED);
+  const float* wcum_s = reinterpret_cast<const float*>(smem + IntSmem::WCUM);
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i <= p.K; i += IT_THREADS) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
+  for (int i = threadIdx.x; i < p.NKB * 4; i += IT_THREADS)
+    reinterpret_cast<int*>(smem + IntSmem::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
+  for (int i = threadIdx.x; i < 2 * p.n_cuts; i += IT_THREADS)
+    reinterpret_cast<float*>(smem + IntSmem::WCUM)[i] = p.wcum[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < IT_STAGES; s++) { mbar_init(&full[s], 1 + IT_BUILDERS); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, IT_EPI_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_pairs = (p.F_tiles + 1) / 2;
+  const long long n_units = p.n_tok_tiles * n_pairs;
+  const uint32_t stage0 = smem_u32(smem + IntSmem::STAGES);
+  if (stage0 & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
+
+  if (warp == 0) {
+    // ======================= U producer =======================
+    if (lane == 0) {
+      uint32_t s = 0, par = 1;   // a fresh barrier passes a wait on parity 1
+      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int pr = (int)(u % n_pairs);
+        const int nft = min(2, p.F_tiles - 2 * pr);
+        for (int kb = 0; kb < p.NKB; kb++) {
+          mbar_wait(&empty[s], par);
+          mbar_arrive_expect_tx(&full[s], nft * IT_U_TILE);
+          for (int ft = 0; ft < nft; ft++)
+            tma_bulk_g2s(stage0 + s * IT_STAGE_BYTES + IT_V_BYTES + ft * IT_U_TILE,
+                         p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE, &full[s]);
+          if (++s == IT_STAGES) { s = 0; par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(IT_FT, IT_TOK);
+      uint32_t s = 0, par = 0, free_par = 0;
+      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int pr = (int)(u % n_pairs);
+        const int nft = min(2, p.F_tiles - 2 * pr);
+        for (int kb = 0; kb < p.NKB; kb++) {
+          mbar_wait(&full[s], par);
+          tc_fence_after();
+          const uint32_t vb = stage0 + s * IT_STAGE_BYTES;
+          for (int ft = 0; ft < nft; ft++) {
+            const uint64_t ad = umma_desc_sw128(vb + IT_V_BYTES + ft * IT_U_TILE);
+            const uint64_t bd = umma_desc_sw128(vb);
+#pragma unroll
+            for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
+              umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[s]);
+          if (sched[kb].cut >= 0) {   // pause: the epilogue reads the running prefix
+            tc_commit(acc_full);
+            mbar_wait(acc_free, free_par);
+            free_par ^= 1;
+            tc_fence_after();
+          }
+          if (++s == IT_STAGES) { s = 0; par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ======================= V builders =======================
+    const int b = threadIdx.x - 64;   // rows b and b + 128 of the token tile
+    const uint32_t lut = smem_u32(smem + IntSmem::LUT);
+    const uint32_t row_off0 = b * 128, row_off1 = (b + 128) * 128;
+    const uint32_t sw = (uint32_t)(b & 7);   // (b + 128) & 7 is the same
+    uint32_t s = 0, par = 1;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const long long tok0 = (u / n_pairs) * IT_TOK;
+      for (int kb = 0; kb < p.NKB; kb++) {
+        const int l0 = sched[kb].l0, n = sched[kb].n;
+        unsigned short c0[IT_LPB], c1[IT_LPB];
+        const short* src = p.codes_t + (size_t)l0 * p.T_pad + tok0 + b;
+#pragma unroll
+        for (int i = 0; i < IT_LPB; i++) {
+          c0[i] = (unsigned short)p.K;
+          c1[i] = (unsigned short)p.K;
+          if (i < n) {
+            c0[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad);
+            c1[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad + 128);
+          }
+        }
+        mbar_wait(&empty[s], par);
+        const uint32_t vb = stage0 + s * IT_STAGE_BYTES;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(lut + c0[2 * c] * 8u));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(lut + c0[2 * c + 1] * 8u));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)c ^ sw) << 4)), "r"(a0),
+                       "r"(a1), "r"(a2), "r"(a3)
+                       : "memory");
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(lut + c1[2 * c] * 8u));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(lut + c1[2 * c + 1] * 8u));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)c ^ sw) << 4)), "r"(a0),
+                       "r"(a1), "r"(a2), "r"(a3)
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        mbar_arrive(&full[s]);
+        if (++s == IT_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue =======================
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int acc = (warp - 6) >> 2;   // accumulator (feature tile of the pair)
+    uint32_t full_par = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int pr = (int)(u % n_pairs);
+      const long long tok0 = (u / n_pairs) * IT_TOK;
+      const int nft = min(2, p.F_tiles - 2 * pr);
+      const int f = (2 * pr + acc) * IT_FT + q * 32 + lane;
+      const bool live = acc < nft;
+      for (int kb = 0; kb < p.NKB; kb++) {
+        const int cut = sched[kb].cut;
+        if (cut < 0) continue;
+        mbar_wait(acc_full, full_par);
+        full_par ^= 1;
+        tc_fence_after();
+        if (!live) {
+          if (lane == 0) mbar_arrive(acc_free);
+          continue;
+        }
+        const float wc = wcum_s[cut], inv = wcum_s[p.n_cuts + cut];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * IT_TOK;
+        __half* orow = p.out + ((size_t)f * p.n_cuts + cut) * (size_t)p.out_stride + tok0;
+#pragma unroll 1
+        for (int ch = 0; ch < IT_TOK / 32; ch++) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == IT_TOK / 32 - 1) {   // everything is in registers: let the MMA issuer go on
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+          }
+          if (f < p.F) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              uint4 o;
+              o.x = finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), wc, inv);
+              o.y = finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), wc, inv);
+              o.z = finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), wc, inv);
+              o.w = finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), wc, inv);
+              __stcs(reinterpret_cast<uint4*>(orow + ch * 32 + g * 8), o);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// preparation kernels (once per call; tiny next to the GEMM)
+// ---------------------------------------------------------------------------------------------------
+struct IntPrepParams {
+  int cuts[IT_MAX_CUTS];
+  int n_cuts, K;
+  const float* cb_norm;            // [K][4] F.normalize(codebook[0])
+  const __half* w;                 // [L] fp16 layer weights
+  IntKBlock* sched;
+  float* wcum;                     // [2 * n_cuts]
+  uint2* lut;                      // [K + 1]
+};
+
+// block 0 thread 0: schedule + weight prefixes (sequential fp32 sum, every prefix rounded to fp16, as
+// torch's CPU cumsum on a Half tensor does); all threads: the fp16 lookup table.
+__global__ void int_prep_kernel(const IntPrepParams p) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int c = gid; c <= p.K; c += gridDim.x * blockDim.x) {
+    uint2 r = make_uint2(0u, 0u);
+    if (c < p.K) {
+      const float4 v = reinterpret_cast<const float4*>(p.cb_norm)[c];
+      const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      r = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+    p.lut[c] = r;
+  }
+  if (gid != 0) return;
+  int kb = 0, prev = -1;
+  float run = 0.f;
+  int l = 0;
+  for (int c = 0; c < p.n_cuts; c++) {
+    const int cut = p.cuts[c];
+    for (int l0 = prev + 1; l0 <= cut; l0 += IT_LPB) {
+      const int n = min(IT_LPB, cut - l0 + 1);
+      IntKBlock b;
+      b.l0 = l0; b.n = n; b.cut = (l0 + n - 1 == cut) ? c : -1; b.pad = 0;
+      p.sched[kb++] = b;
+    }
+    for (; l <= cut; l++) run = __fadd_rn(run, __half2float(p.w[l]));
+    const float wc = __half2float(__float2half_rn(run));
+    p.wcum[c] = wc;
+    p.wcum[p.n_cuts + c] = __fdiv_rn(1.0f, wc);
+    prev = cut;
+  }
+}
+
+// codes [T][stride] (int16 / int32 / int64) -> layer-major int16 [L][T_pad]; out-of-range codes and the
+// padding tokens map to K (the zero row of the lookup table)
+template <typename CT>
+__global__ void int_transpose_kernel(const CT* __restrict__ codes, long long stride, long long T, int L, int K,
+                                     short* __restrict__ out, long long T_pad) {
+  __shared__ short tile[64][65];
+  const long long t0 = (long long)blockIdx.x * 64;
+  const int l0 = blockIdx.y * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {   // token i, layer threadIdx.x (+32)
+    for (int j = threadIdx.x; j < 64; j += 32) {
+      short v = (short)K;
+      const long long t = t0 + i;
+      const int l = l0 + j;
+      if (t < T && l < L) {
+        const long long c = (long long)codes[t * stride + l];
+        if (c >= 0 && c < K) v = (short)c;
+      }
+      tile[i][j] = v;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 64; j += blockDim.y) {   // layer j, token threadIdx.x (+32)
+    const int l = l0 + j;
+    if (l >= L) continue;
+    for (int i = threadIdx.x; i < 64; i += 32) {
+      const long long t = t0 + i;
+      if (t < T_pad) out[(size_t)l * T_pad + t] = tile[i][j];
+    }
+  }
+}
+
+// U tiles: [F_tiles][NKB] tiles of 128 features x 64 k fp16 in the swizzled K-major layout;
+// U[f][4 s + j] = fp16(float(w_l) * n[center_f[l]][j]) for slot s < n of the K-block (l = l0 + s), else 0
+__global__ void int_pack_u_kernel(const int* __restrict__ centers, long long center_stride, int F, int F_tiles, int NKB,
+                                  const IntKBlock* __restrict__ sched, const float* __restrict__ cb_norm, int K,
+                                  const __half* __restrict__ w, unsigned char* __restrict__ u_tiles) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)F_tiles * NKB * IT_FT * IT_LPB;
+  if (gid >= total) return;
+  const int s = (int)(gid % IT_LPB);
+  const int r = (int)((gid / IT_LPB) % IT_FT);
+  const int kb = (int)((gid / (IT_LPB * IT_FT)) % NKB);
+  const int ft = (int)(gid / ((long long)IT_LPB * IT_FT * NKB));
+  const IntKBlock b = sched[kb];
+  const int f = ft * IT_FT + r;
+  uint2 val = make_uint2(0u, 0u);
+  if (f < F && s < b.n) {
+    const int l = b.l0 + s;
+    const int c = centers[(size_t)f * center_stride + l];
+    if (c >= 0 && c < K) {
+      const float wl = __half2float(w[l]);
+      const float4 v = reinterpret_cast<const float4*>(cb_norm)[c];
+      const __half2 a = __floats2half2_rn(wl * v.x, wl * v.y), bb = __floats2half2_rn(wl * v.z, wl * v.w);
+      val = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&bb));
+    }
+  }
+  unsigned char* tile = u_tiles + ((size_t)ft * NKB + kb) * (size_t)IT_U_TILE;
+  const int chunk = s >> 1;
+  *reinterpret_cast<uint2*>(tile + r * 128 + (((chunk ^ (r & 7)) << 4) | ((s & 1) << 3))) = val;
+}
+
+}  // namespace rq

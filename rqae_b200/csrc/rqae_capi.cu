@@ -17,6 +17,7 @@
 #include "../../include/rqae_b200.h"
 #include "rq_decode.cuh"
 #include "rq_forward.cuh"
+#include "rq_intensity.cuh"
 #include "rq_layout.h"
 
 #ifndef RQ_L2_HOT_DEFAULT
@@ -649,6 +650,109 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
   if (rc == 0 && e2 != cudaSuccess) fail(e2);
   if (rc == 0 && e3 != cudaSuccess) fail(e3);
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature intensities (rq_intensity.cuh)
+// ---------------------------------------------------------------------------------------------
+struct IntLayout {
+  int L, NKB, F_tiles;
+  long long T_pad;
+  size_t off_sched, off_wcum, off_lut, off_u, off_codes, total;
+};
+
+static int int_layout(const int32_t* cuts, int n_cuts, int F, int64_t n_tokens, int nq, IntLayout* o) {
+  if (!cuts || n_cuts <= 0 || n_cuts > rq::IT_MAX_CUTS || F <= 0 || n_tokens < 0) return RQAE_EINVAL;
+  int prev = -1, nkb = 0;
+  for (int c = 0; c < n_cuts; c++) {
+    if (cuts[c] <= prev || (nq > 0 && cuts[c] >= nq)) return RQAE_EINVAL;   // strictly ascending layer indices
+    nkb += (cuts[c] - prev + rq::IT_LPB - 1) / rq::IT_LPB;
+    prev = cuts[c];
+  }
+  if (nkb > rq::IT_MAX_KB) return RQAE_EUNSUPPORTED;
+  o->L = prev + 1;
+  o->NKB = nkb;
+  o->F_tiles = (F + rq::IT_FT - 1) / rq::IT_FT;
+  o->T_pad = (n_tokens + rq::IT_TOK - 1) / rq::IT_TOK * rq::IT_TOK;
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  size_t off = 0;
+  o->off_sched = off; off = up(off + (size_t)rq::IT_MAX_KB * sizeof(rq::IntKBlock));
+  o->off_wcum = off;  off = up(off + 2 * (size_t)rq::IT_MAX_CUTS * 4);
+  o->off_lut = off;   off = up(off + (size_t)rq::IT_LUT_ROWS * 8);
+  o->off_u = off;     off = up(off + (size_t)o->F_tiles * nkb * rq::IT_U_TILE);
+  o->off_codes = off; off = up(off + (size_t)o->L * (size_t)o->T_pad * 2);
+  o->total = off;
+  return RQAE_OK;
+}
+
+size_t rqae_intensity_workspace_bytes(const int32_t* cuts_host, int n_cuts, int n_features, int64_t n_tokens) {
+  IntLayout L;
+  if (int_layout(cuts_host, n_cuts, n_features, n_tokens, 0, &L)) return 0;
+  return L.total;
+}
+
+int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_dtype, int64_t code_stride,
+                       int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
+                       const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                       int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!cb_norm || !codes || !centers || !layer_weights_f16 || !out || !workspace || K <= 0) return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
+  if (K + 1 > rq::IT_LUT_ROWS) return RQAE_EUNSUPPORTED;
+  IntLayout L;
+  int rc = int_layout(cuts_host, n_cuts, n_features, n_tokens, 0, &L);
+  if (rc) return rc;
+  if (code_stride < L.L || center_stride < L.L) return RQAE_EINVAL;
+  if (out_stride < L.T_pad || (out_stride & 7) || ((uintptr_t)out & 15)) return RQAE_EINVAL;   // 16-byte row stores of 256 tokens
+  if (((uintptr_t)workspace & 1023) || workspace_bytes < L.total) return RQAE_ESIZE;
+  if (n_tokens == 0) return RQAE_OK;
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  // 1. schedule, weight prefixes, fp16 lookup table
+  rq::IntPrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int c = 0; c < n_cuts; c++) pp.cuts[c] = cuts_host[c];
+  pp.n_cuts = n_cuts; pp.K = K; pp.cb_norm = cb_norm; pp.w = (const __half*)layer_weights_f16;
+  pp.sched = (rq::IntKBlock*)(ws + L.off_sched); pp.wcum = (float*)(ws + L.off_wcum); pp.lut = (uint2*)(ws + L.off_lut);
+  rq::int_prep_kernel<<<4, 256, 0, st>>>(pp);
+  RQ_CUDA(cudaGetLastError());
+  // 2. codes -> layer-major int16
+  {
+    dim3 grid((unsigned)(L.T_pad / 64), (unsigned)((L.L + 63) / 64)), block(32, 8);
+    short* ct = (short*)(ws + L.off_codes);
+    if (code_dtype == 2) rq::int_transpose_kernel<long long><<<grid, block, 0, st>>>((const long long*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
+    else if (code_dtype == 1) rq::int_transpose_kernel<int><<<grid, block, 0, st>>>((const int*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
+    else rq::int_transpose_kernel<short><<<grid, block, 0, st>>>((const short*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
+    RQ_CUDA(cudaGetLastError());
+  }
+  // 3. feature operand tiles
+  {
+    const long long total = (long long)L.F_tiles * L.NKB * rq::IT_FT * rq::IT_LPB;
+    rq::int_pack_u_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        centers, center_stride, n_features, L.F_tiles, L.NKB, (const rq::IntKBlock*)(ws + L.off_sched), cb_norm, K,
+        (const __half*)layer_weights_f16, ws + L.off_u);
+    RQ_CUDA(cudaGetLastError());
+  }
+  // 4. the GEMM
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(rq::rq_intensity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rq::IntSmem::TOTAL);
+  });
+  RQ_CUDA(attr_err);
+  rq::IntParams ip;
+  ip.codes_t = (const short*)(ws + L.off_codes); ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
+  ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
+  ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
+  ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
+  const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
+  const int grid = (int)(units < sms ? units : sms);
+  rq::rq_intensity_kernel<<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
+  RQ_CUDA(cudaGetLastError());
+  g_launches += 4;
+  return RQAE_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,189 @@
+"""``Feature`` / ``RQAEFeature`` -- host-side mirror of ``rqae/feature.py`` (harish-kamath/rqae) whose
+``intensity`` runs on the B200 tensor cores (``rqae_intensity_f16`` in ``librqae_b200.so``).
+
+Kept as in the reference: constructor arguments and attributes (feature.py:42-84), ``to_feature``
+(:86-93), ``load_model`` (:95-100: fp16 layer weights = mean column norm of every out-projection),
+``from_quantizer`` (:131-137), ``save`` / ``load`` (:139-153, plain ``np.savez``), and the signature
+and result of ``intensity(token_indices, layers=None) -> (..., len(layers))`` fp16 (:102-129).
+
+New: ``intensity_many`` evaluates MANY features over a code tensor in one launch sequence -- the inner
+loop of ``scripts/3_make_rqae_features.py:98-114`` (one ``intensity`` call per feature and 1024-sequence
+batch there) -- and returns the feature-major layout the mining step consumes.
+
+There is no CPU path: code tensors must live on the GPU next to the model.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+TOKEN_TILE = 256   # the kernel writes whole tiles of 256 tokens
+
+
+class Feature:
+    """feature.py:9-40."""
+
+    def __init__(self, id: str = "", explanation: str = "", scores: dict = {}, model: str = "", activations: list = []):
+        self.id = str(id)
+        self.explanation = str(explanation)
+        self.scores = scores
+        self.model = str(model)
+        self.activations = activations  # list of {"text": [str], "activations": [float]}
+
+    def save(self, file_path: str):
+        np.savez(file_path, **self.__dict__)
+
+    @classmethod
+    def load(cls, file_path: str):
+        params = dict(np.load(file_path, allow_pickle=True))
+        for k, v in params.items():
+            try:
+                params[k] = v.item()
+            except Exception:
+                pass
+        return cls(**params)
+
+
+def layer_weights_f16(rqae) -> torch.Tensor:
+    """feature.py:97-99, expression for expression (load-time host logic)."""
+    return torch.tensor([l[1].weight.data.norm(dim=0).mean().item() for l in rqae.layers]).to(torch.float16)
+
+
+def _cuts(layers: Sequence[int]):
+    cuts = sorted(set(int(l) for l in layers))
+    pos = {l: i for i, l in enumerate(cuts)}
+    return cuts, [pos[int(l)] for l in layers]
+
+
+def intensity_many(rqae, token_indices: torch.Tensor, centers: torch.Tensor, layers: Sequence[int],
+                   layer_weights: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Intensities of F features over T tokens at the given layer cuts.
+
+    token_indices (..., nq) integer codes on the GPU (int16 / int32 / int64); centers (F, nq) integer;
+    returns fp16 (F, len(layers), T) with T = prod(...), feature-major: ``result[f, j]`` is the contiguous
+    vector the reference calls ``all_intensities[:, j]`` for feature f (scripts/3:115-119).  ``out`` may be
+    a caller-owned fp16 buffer (F, n_cuts_sorted, >= T rounded up to 256) to reuse between calls."""
+    if rqae.quantization_method != "round_fsq":
+        raise ValueError("Codebook sims only supported for round_fsq for now")   # model.py:139
+    if not token_indices.is_cuda:
+        raise RuntimeError("rqae_b200 intensity needs the code tensor on the GPU; there is no CPU fallback")
+    dev = token_indices.device
+    lib = _lib.load()
+    codes = token_indices
+    if codes.dtype not in (torch.int16, torch.int32, torch.int64):
+        codes = codes.to(torch.int64)
+    nq_codes = codes.shape[-1]
+    codes = codes.reshape(-1, nq_codes)
+    if codes.stride(-1) != 1 or (codes.shape[0] > 1 and codes.stride(0) < nq_codes):
+        codes = codes.contiguous()
+    T = codes.shape[0]
+    cuts, order = _cuts(layers)
+    if cuts[0] < 0 or cuts[-1] >= min(nq_codes, centers.shape[-1]):
+        raise IndexError(f"layer cut {cuts[-1]} outside the code tensors")
+    centers = centers.to(device=dev, dtype=torch.int32).reshape(-1, centers.shape[-1]).contiguous()
+    Fn = centers.shape[0]
+    w = layer_weights if layer_weights is not None else layer_weights_f16(rqae)
+    w = w.to(device=dev, dtype=torch.float16).contiguous()
+    if w.numel() <= cuts[-1]:
+        raise IndexError("layer_weights shorter than the deepest cut")
+    cb_norm = F.normalize(rqae.codebook.data.detach()[0].to(device=dev, dtype=torch.float32), dim=-1).contiguous()
+    K = cb_norm.shape[0]
+    cuts_arr = np.asarray(cuts, dtype=np.int32)
+    T_pad = (T + TOKEN_TILE - 1) // TOKEN_TILE * TOKEN_TILE
+    if out is None:
+        out = torch.empty(Fn, len(cuts), T_pad, dtype=torch.float16, device=dev)
+    elif out.dtype != torch.float16 or out.device != dev or out.dim() != 3 or out.shape[0] != Fn \
+            or out.shape[1] != len(cuts) or out.shape[2] < T_pad or not out.is_contiguous():
+        raise RuntimeError("out must be a contiguous fp16 CUDA tensor (F, unique cuts, >= T rounded up to 256)")
+    if T > 0:
+        nbytes = lib.rqae_intensity_workspace_bytes(cuts_arr.ctypes.data, len(cuts), Fn, T)
+        if nbytes == 0:
+            raise NotImplementedError("unsupported intensity shape (at most 64 distinct cuts / 256 K-blocks)")
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        with torch.cuda.device(dev):
+            rc = lib.rqae_intensity_f16(
+                cb_norm.data_ptr(), K, codes.data_ptr(), _lib.CODE_DTYPE[str(codes.dtype).split(".")[-1]],
+                codes.stride(0) if T > 1 else nq_codes, T, centers.data_ptr(), centers.shape[1], Fn, w.data_ptr(),
+                cuts_arr.ctypes.data, len(cuts), out.data_ptr(), out.shape[2], ws_ptr, nbytes,
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "rqae_intensity_f16")
+        for t in (ws, cb_norm, w, centers, codes):
+            t.record_stream(torch.cuda.current_stream(dev))
+    res = out[:, :, :T]
+    if order != list(range(len(cuts))):
+        res = res[:, order]
+    return res
+
+
+class RQAEFeature:
+    """feature.py:42-153."""
+
+    def __init__(self, id: str = "", explanations: List[str] = None, scores: List[dict] = None, activations: list = None,
+                 model: str = "", num_quantizers: int = 1024, dim: int = 4, layers: List[int] = None,
+                 layer_weights: List[float] = None, center: Optional[np.ndarray] = None, **kwargs):
+        self.num_quantizers = num_quantizers
+        self.dim = dim
+        self.model = model
+        self.id = id
+        if layers is None:
+            layers = [num_quantizers - 1]
+        if layer_weights is None:
+            layer_weights = np.ones(num_quantizers)
+        if center is None:
+            center = np.zeros((num_quantizers,))
+        self.layers = layers
+        self.layer_weights = torch.tensor(layer_weights)
+        self.center = torch.tensor(center).int()
+        if explanations is None:
+            explanations = ["" for _ in layers]
+        if scores is None:
+            scores = [{} for _ in layers]
+        if activations is None:
+            activations = {k: [] for k in layers}
+        self.explanations = explanations
+        self.scores = scores
+        self.activations = activations
+        self.rqae = None
+
+    def to_feature(self, layer: int = 0):
+        return Feature(id=self.id, model=self.model, explanation=self.explanations[layer], scores=self.scores[layer],
+                       activations=self.activations[self.layers[layer]])
+
+    def load_model(self, rqae):
+        self.rqae = rqae
+        self.layer_weights = layer_weights_f16(rqae)
+        return self
+
+    def intensity(self, token_indices: torch.Tensor, layers=None):
+        """feature.py:102-129: (..., num_quantizers) codes -> (..., len(layers)) fp16 intensities."""
+        if layers is None:
+            layers = self.layers
+        if self.rqae is None:
+            raise ValueError("Model not loaded. Needed for intensity calculation.")
+        res = intensity_many(self.rqae, token_indices, self.center.reshape(1, -1), layers, layer_weights=self.layer_weights)
+        return res[0].transpose(0, 1).reshape(*token_indices.shape[:-1], len(layers))
+
+    @classmethod
+    def from_quantizer(cls, quantizer, **kwargs):
+        return cls(num_quantizers=quantizer.num_quantizers, dim=quantizer.codebook_dim, **kwargs).load_model(quantizer)
+
+    def save(self, file_path: str):
+        np.savez(file_path, **{k: v for k, v in self.__dict__.items() if k != "rqae"})
+
+    @classmethod
+    def load(cls, file_path: str):
+        params = dict(np.load(file_path, allow_pickle=True))
+        for k, v in params.items():
+            try:
+                if k == "explanations":
+                    params[k] = [str(e) for e in v]
+                params[k] = v.item()
+            except Exception:
+                pass
+        return cls(**params)

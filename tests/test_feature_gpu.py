@@ -1,0 +1,116 @@
+"""GPU parity tests of the feature-intensity path (tcgen05 GEMM, through the C ABI via
+rqae_b200.feature) against outputs of the unmodified reference (tests/golden/kat_feature.npz) and the
+oracle.  Tolerance: the kernel sums exact products of fp16-rounded factors in fp32 where the reference
+sums fp16-rounded products; both sit within 1e-3 of the exact value (tests/test_feature_oracle.py), and
+the roundings after the sum are shared, so |kernel - reference| <= ATOL below."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import feature_oracle as fo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ATOL = 1.5e-3   # absolute, intensities are in [-1, 1]
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(ROOT, "tests", "golden", "kat_feature.npz"))
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+class _Stub:
+    """What intensity_many needs from the model: the codebook and the method name."""
+    quantization_method = "round_fsq"
+
+    def __init__(self, cb0, dev):
+        self.codebook = torch.nn.Parameter(cb0[None].to(dev), requires_grad=False)
+
+
+def _run(kat, name, lk="layers", dtype=torch.int16):
+    from rqae_b200.feature import intensity_many
+    dev = _dev()
+    cb0 = torch.from_numpy(kat[f"{name}/cb0"])
+    lw = torch.from_numpy(kat[f"{name}/lw"])
+    codes = torch.from_numpy(kat[f"{name}/codes"].astype(np.int64))
+    centers = torch.from_numpy(kat[f"{name}/centers"])
+    layers = [int(l) for l in kat[f"{name}/{lk}"]]
+    out = intensity_many(_Stub(cb0, dev), codes.to(dev).to(dtype), centers, layers, layer_weights=lw)
+    torch.cuda.synchronize()
+    return out.cpu(), codes, centers, layers, cb0, lw
+
+
+@pytest.mark.parametrize("name,lk,ok", [("small", "layers", "out"), ("small", "layers_unsorted", "out_unsorted"),
+                                        ("2b", "layers", "out")])
+def test_intensity_matches_reference_golden(kat, name, lk, ok):
+    out, codes, centers, layers, _, _ = _run(kat, name, lk)
+    ref = torch.from_numpy(kat[f"{name}/{ok}"])                     # (F, ..., C)
+    F = centers.shape[0]
+    ref = ref.reshape(F, -1, len(layers)).transpose(1, 2)           # (F, C, T)
+    assert out.shape == ref.shape and out.dtype == torch.float16
+    err = (out.float() - ref.float()).abs()
+    assert float(err.max()) <= ATOL, f"max |kernel - reference| = {float(err.max())}"
+    # the rest are one or two fp16 roundings apart: at least a third of the values are bit-identical
+    assert float((out == ref).float().mean()) > 0.3
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64])
+def test_code_dtypes_agree(kat, dtype):
+    a = _run(kat, "small", dtype=torch.int16)[0]
+    b = _run(kat, "small", dtype=dtype)[0]
+    assert torch.equal(a, b)
+
+
+def test_many_features_many_tokens_against_exact_value():
+    """F = 300 features (3 feature tiles: a full pair and a half pair), 1000 tokens (4 token tiles, ragged),
+    nq = 160 with cuts that are not multiples of 16: every value within ATOL of the float64 evaluation of the
+    reference formula, and a token whose codes equal the center gives 1."""
+    from rqae_b200 import RQAE
+    from rqae_b200.feature import intensity_many
+    dev = _dev()
+    torch.manual_seed(0)
+    m = RQAE(dim=64, num_quantizers=160).eval()
+    g = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, 625, (1000, 160), generator=g)
+    centers = torch.randint(0, 625, (300, 160), generator=g)
+    centers[7] = codes[123]
+    centers[7][centers[7] == 312] = 0   # the zero codeword has similarity 0 with itself
+    codes[123] = centers[7]
+    layers = [0, 1, 5, 16, 17, 40, 99, 159]
+    lw = fo.layer_weights(torch.stack([l[1].weight.data for l in m.layers]))
+    out = intensity_many(m.to(dev), codes.to(dev), centers, layers, layer_weights=lw).cpu()
+    assert out.shape == (300, len(layers), 1000)
+    sims = fo.codebook_sims(m.codebook.data[0].cpu())
+    for f in (0, 7, 127, 128, 255, 256, 299):
+        exact = fo.intensity_f64(sims, centers[f], codes, lw, layers).T      # (C, T)
+        ref = fo.intensity(sims, centers[f], codes, lw, layers).T
+        assert float((out[f].double() - exact).abs().max()) <= ATOL
+        assert float((out[f].float() - ref.float()).abs().max()) <= ATOL
+    assert float((out[7, :, 123].float() - 1.0).abs().max()) <= ATOL
+
+
+def test_rqae_feature_api_shapes(kat):
+    """RQAEFeature.intensity keeps the reference's (..., nq) -> (..., len(layers)) contract."""
+    from rqae_b200 import RQAE, RQAEFeature
+    dev = _dev()
+    torch.manual_seed(0)
+    m = RQAE(dim=64, num_quantizers=64).eval().to(dev)
+    codes = torch.from_numpy(kat["small/codes"].astype(np.int64)).to(dev)      # (5, 7, 64)
+    centers = torch.from_numpy(kat["small/centers"])
+    layers = [int(l) for l in kat["small/layers"]]
+    f = RQAEFeature.from_quantizer(m, center=centers[0].numpy(), layers=layers)
+    assert torch.equal(f.layer_weights, torch.from_numpy(kat["small/lw"]))
+    out = f.intensity(codes)
+    assert out.shape == (5, 7, len(layers)) and out.dtype == torch.float16
+    ref = torch.from_numpy(kat["small/out"])[0]
+    assert float((out.cpu().float() - ref.float()).abs().max()) <= ATOL
+    sub = f.intensity(codes[0, :3], layers=[6, 2])
+    assert sub.shape == (3, 2)
+    assert torch.equal(sub.cpu(), out[0, :3][:, [2, 0]].cpu())
