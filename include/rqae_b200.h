@@ -114,7 +114,7 @@ int rqae_forward_host_release(void);
  * Computed as one tcgen05 GEMM over the rank-4 factors of sims; the sum is accumulated in
  * fp32 from fp16 factors, so values agree with the reference within the tolerance DESIGN.md states,
  * not bitwise.  The roundings after the sum are the reference's.
- *   cb_norm            [K][4] fp32 = F.normalize(codebook[0], dim=-1)            (K + 1 <= 2048)
+ *   cb_norm            [K][4] fp32 = F.normalize(codebook[0], dim=-1)            (K + 1 <= 1024)
  *   codes              [n_tokens][code_stride] of code_dtype (codes outside [0,K) contribute 0)
  *   centers            int32 [n_features][center_stride]
  *   layer_weights_f16  fp16 [>= max cut + 1]
@@ -127,6 +127,19 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
                        int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
                        const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
                        int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The selection step of the mining loop, scripts/3_make_rqae_features.py:116-128: for every row
+ * (one feature at one cut) of `vals`, the positions of the top_k largest values, of the 2*(top_k/2)
+ * values around the median rank and of the top_k smallest, i.e. argsort(descending)[:k],
+ * [n/2 - k/2 : n/2 + k/2] and [-k:], by an exact radix select instead of a full sort.  Total order:
+ * value descending, index ascending (the reference's argsort leaves ties unspecified).
+ *   vals     fp16 [rows][row_stride], 16-byte aligned rows (row_stride % 8 == 0), readable up to n
+ *            rounded up to 8 -- the layout rqae_intensity_f16 writes
+ *   idx_out  int32 [rows][3][top_k] (top, middle, bottom), -1 in unused middle slots
+ *   val_out  nullable fp16 [rows][3][top_k], the selected values
+ * top_k <= 256, top_k <= n < 2^31. */
+int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t row_stride, int64_t n, int top_k,
+                                      int32_t* idx_out, void* val_out, void* stream);
 
 /* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
  * sustained rate of the FP32 pipe, in FLOP per call; time it with CUDA events on `stream`.

@@ -37,13 +37,16 @@ namespace rq {
 constexpr int IT_TOK = 256;                     // tokens per unit = MMA N
 constexpr int IT_FT = 128;                      // features per tile = MMA M
 constexpr int IT_LPB = 16;                      // layers per K-block (64 k values, 128 bytes of fp16)
-constexpr int IT_STAGES = 3;
+constexpr int IT_VSTAGES = 2;                   // token operand: built locally, latency = the builders' own work
+constexpr int IT_USTAGES = 4;                   // feature operand: bulk copies from L2, deeper ring hides their latency
 constexpr int IT_V_BYTES = IT_TOK * 128;        // 32 KB
 constexpr int IT_U_TILE = IT_FT * 128;          // 16 KB
-constexpr int IT_STAGE_BYTES = IT_V_BYTES + 2 * IT_U_TILE;   // 64 KB
+constexpr int IT_U_BYTES = 2 * IT_U_TILE;       // both feature tiles of the pair
 constexpr int IT_MAX_CUTS = 64;
-constexpr int IT_MAX_KB = 256;
-constexpr int IT_LUT_ROWS = 2048;               // codebook rows + the zero row must fit
+constexpr int IT_MAX_KB = 192;
+constexpr int IT_LUT_ROWS = 1024;               // codebook rows + the zero row must fit
+constexpr int IT_STG_PITCH = 80;                // bytes per staged row: 32 tokens fp16 + 16 (conflict-free 128-bit access)
+constexpr int IT_STG_WARP = 32 * IT_STG_PITCH;  // per epilogue warp
 constexpr int IT_THREADS = 448;
 constexpr int IT_EPI_WARPS = 8;
 constexpr int IT_BUILDERS = 128;
@@ -66,12 +69,14 @@ struct IntParams {
 };
 
 struct IntSmem {
-  static constexpr int STAGES = 0;
-  static constexpr int LUT = IT_STAGES * IT_STAGE_BYTES;
+  static constexpr int VRING = 0;
+  static constexpr int URING = IT_VSTAGES * IT_V_BYTES;
+  static constexpr int LUT = URING + IT_USTAGES * IT_U_BYTES;
   static constexpr int SCHED = LUT + IT_LUT_ROWS * 8;
   static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
-  static constexpr int BARS = WCUM + 2 * IT_MAX_CUTS * 4;
-  static constexpr int TMEM_PTR = BARS + (2 * IT_STAGES + 2) * 8;
+  static constexpr int STG = WCUM + 2 * IT_MAX_CUTS * 4;
+  static constexpr int BARS = STG + IT_EPI_WARPS * IT_STG_WARP;
+  static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 2) * 8;
   static constexpr int TOTAL = TMEM_PTR + 16;
 };
 static_assert(IntSmem::TOTAL <= 227 * 1024, "shared memory budget");
@@ -111,25 +116,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// The reference's post-sum arithmetic for one value: prefix -> fp16, fp32 divide by the fp16 weight prefix,
-// quotient -> fp16 (feature.py:123-127 on CPU tensors).  The divide is a reciprocal multiply plus one
-// Newton correction (correctly rounded for these operand ranges).
-__device__ __forceinline__ uint32_t finish2(float a, float b, float wc, float inv) {
+// The reference's post-sum arithmetic for a pair of values: prefix -> fp16, fp32 divide by the fp16 weight
+// prefix, quotient -> fp16 (feature.py:123-127 on CPU tensors).  The divide is a multiply by the fp32
+// reciprocal: it can differ from the correctly rounded quotient by one fp32 ulp, which changes the fp16
+// result for ~2e-4 of the values by one fp16 ulp -- far inside the tolerance of the sum itself.
+__device__ __forceinline__ uint32_t finish2(float a, float b, float inv) {
   const float2 p = __half22float2(__floats2half2_rn(a, b));
-  float q0 = p.x * inv, q1 = p.y * inv;
-  q0 = __fmaf_rn(__fmaf_rn(-q0, wc, p.x), inv, q0);
-  q1 = __fmaf_rn(__fmaf_rn(-q1, wc, p.y), inv, q1);
-  const __half2 h = __floats2half2_rn(q0, q1);
+  const __half2 h = __floats2half2_rn(p.x * inv, p.y * inv);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// latency-critical waits (MMA issuer, producers): poll without the suspend hint
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + IntSmem::BARS);
-  uint64_t* full = bars;                        // [S] U bytes landed + 128 builder arrivals
-  uint64_t* empty = bars + IT_STAGES;           // [S] MMAs reading the stage have completed (tcgen05.commit)
-  uint64_t* acc_full = bars + 2 * IT_STAGES;    // segment complete (tcgen05.commit)
+  uint64_t* v_full = bars;                      // [VS] 128 builder arrivals
+  uint64_t* v_empty = v_full + IT_VSTAGES;      // [VS] MMAs reading the stage have completed (tcgen05.commit)
+  uint64_t* u_full = v_empty + IT_VSTAGES;      // [US] bulk copies landed
+  uint64_t* u_empty = u_full + IT_USTAGES;      // [US] tcgen05.commit
+  uint64_t* acc_full = u_empty + IT_USTAGES;    // segment complete (tcgen05.commit)
   uint64_t* acc_free = acc_full + 1;            // 8 epilogue warps have read the accumulators
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + IntSmem::TMEM_PTR);
   const IntKBlock* sched = reinterpret_cast<const IntKBlock*>(smem + IntSmem::SCHED);
@@ -142,7 +161,8 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   for (int i = threadIdx.x; i < 2 * p.n_cuts; i += IT_THREADS)
     reinterpret_cast<float*>(smem + IntSmem::WCUM)[i] = p.wcum[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < IT_STAGES; s++) { mbar_init(&full[s], 1 + IT_BUILDERS); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < IT_VSTAGES; s++) { mbar_init(&v_full[s], IT_BUILDERS); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < IT_USTAGES; s++) { mbar_init(&u_full[s], 1); mbar_init(&u_empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_free, IT_EPI_WARPS);
     mbar_fence_init();
@@ -158,8 +178,8 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 
   const int n_pairs = (p.F_tiles + 1) / 2;
   const long long n_units = p.n_tok_tiles * n_pairs;
-  const uint32_t stage0 = smem_u32(smem + IntSmem::STAGES);
-  if (stage0 & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
+  const uint32_t vring = smem_u32(smem + IntSmem::VRING), uring = smem_u32(smem + IntSmem::URING);
+  if (vring & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
 
   if (warp == 0) {
     // ======================= U producer =======================
@@ -169,12 +189,12 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
-          mbar_wait(&empty[s], par);
-          mbar_arrive_expect_tx(&full[s], nft * IT_U_TILE);
+          mbar_wait_spin(&u_empty[s], par);
+          mbar_arrive_expect_tx(&u_full[s], nft * IT_U_TILE);
           for (int ft = 0; ft < nft; ft++)
-            tma_bulk_g2s(stage0 + s * IT_STAGE_BYTES + IT_V_BYTES + ft * IT_U_TILE,
-                         p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE, &full[s]);
-          if (++s == IT_STAGES) { s = 0; par ^= 1; }
+            tma_bulk_g2s(uring + s * IT_U_BYTES + ft * IT_U_TILE,
+                         p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE, &u_full[s]);
+          if (++s == IT_USTAGES) { s = 0; par ^= 1; }
         }
       }
     }
@@ -183,29 +203,31 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(IT_FT, IT_TOK);
-      uint32_t s = 0, par = 0, free_par = 0;
+      uint32_t vs = 0, vpar = 0, us = 0, upar = 0, free_par = 0;
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
-          mbar_wait(&full[s], par);
+          mbar_wait_spin(&u_full[us], upar);
+          mbar_wait_spin(&v_full[vs], vpar);
           tc_fence_after();
-          const uint32_t vb = stage0 + s * IT_STAGE_BYTES;
           for (int ft = 0; ft < nft; ft++) {
-            const uint64_t ad = umma_desc_sw128(vb + IT_V_BYTES + ft * IT_U_TILE);
-            const uint64_t bd = umma_desc_sw128(vb);
+            const uint64_t ad = umma_desc_sw128(uring + us * IT_U_BYTES + ft * IT_U_TILE);
+            const uint64_t bd = umma_desc_sw128(vring + vs * IT_V_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
               umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty[s]);
+          tc_commit(&v_empty[vs]);
+          tc_commit(&u_empty[us]);
           if (sched[kb].cut >= 0) {   // pause: the epilogue reads the running prefix
             tc_commit(acc_full);
-            mbar_wait(acc_free, free_par);
+            mbar_wait_spin(acc_free, free_par);
             free_par ^= 1;
             tc_fence_after();
           }
-          if (++s == IT_STAGES) { s = 0; par ^= 1; }
+          if (++vs == IT_VSTAGES) { vs = 0; vpar ^= 1; }
+          if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
         }
       }
     }
@@ -217,52 +239,62 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     const uint32_t row_off0 = b * 128, row_off1 = (b + 128) * 128;
     const uint32_t sw = (uint32_t)(b & 7);   // (b + 128) & 7 is the same
     uint32_t s = 0, par = 1;
-    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+    // codes of the next K-block are requested before the current one is written (the layer-major code rows
+    // come from L2 / HBM: one K-block of latency is hidden behind the previous block's table look-ups)
+    unsigned short c0[IT_LPB], c1[IT_LPB];
+    auto fetch = [&](long long u, int kb) {
       const long long tok0 = (u / n_pairs) * IT_TOK;
-      for (int kb = 0; kb < p.NKB; kb++) {
-        const int l0 = sched[kb].l0, n = sched[kb].n;
-        unsigned short c0[IT_LPB], c1[IT_LPB];
-        const short* src = p.codes_t + (size_t)l0 * p.T_pad + tok0 + b;
+      const int l0 = sched[kb].l0, n = sched[kb].n;
+      const short* src = p.codes_t + (size_t)l0 * p.T_pad + tok0 + b;
 #pragma unroll
-        for (int i = 0; i < IT_LPB; i++) {
-          c0[i] = (unsigned short)p.K;
-          c1[i] = (unsigned short)p.K;
-          if (i < n) {
-            c0[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad);
-            c1[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad + 128);
-          }
+      for (int i = 0; i < IT_LPB; i++) {
+        c0[i] = (unsigned short)p.K;
+        c1[i] = (unsigned short)p.K;
+        if (i < n) {
+          c0[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad);
+          c1[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad + 128);
         }
-        mbar_wait(&empty[s], par);
-        const uint32_t vb = stage0 + s * IT_STAGE_BYTES;
+      }
+    };
+    if ((long long)blockIdx.x < n_units) fetch(blockIdx.x, 0);
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int kb = 0; kb < p.NKB; kb++) {
+        uint32_t a0[IT_LPB], a1[IT_LPB];   // table byte offsets of the current block
+#pragma unroll
+        for (int i = 0; i < IT_LPB; i++) { a0[i] = c0[i] * 8u; a1[i] = c1[i] * 8u; }
+        if (kb + 1 < p.NKB) fetch(u, kb + 1);
+        else if (u + gridDim.x < n_units) fetch(u + gridDim.x, 0);
+        mbar_wait_spin(&v_empty[s], par);
+        const uint32_t vb = vring + s * IT_V_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(lut + c0[2 * c] * 8u));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(lut + c0[2 * c + 1] * 8u));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)c ^ sw) << 4)), "r"(a0),
-                       "r"(a1), "r"(a2), "r"(a3)
+          uint32_t x0, x1, x2, x3;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a0[2 * c]));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a0[2 * c + 1]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)c ^ sw) << 4)), "r"(x0),
+                       "r"(x1), "r"(x2), "r"(x3)
                        : "memory");
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(lut + c1[2 * c] * 8u));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(lut + c1[2 * c + 1] * 8u));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)c ^ sw) << 4)), "r"(a0),
-                       "r"(a1), "r"(a2), "r"(a3)
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a1[2 * c]));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a1[2 * c + 1]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)c ^ sw) << 4)), "r"(x0),
+                       "r"(x1), "r"(x2), "r"(x3)
                        : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        mbar_arrive(&full[s]);
-        if (++s == IT_STAGES) { s = 0; par ^= 1; }
+        mbar_arrive(&v_full[s]);
+        if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
       }
     }
   } else {
     // ======================= epilogue =======================
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int acc = (warp - 6) >> 2;   // accumulator (feature tile of the pair)
+    const uint32_t stg = smem_u32(smem + IntSmem::STG) + (warp - 6) * IT_STG_WARP;
     uint32_t full_par = 0;
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int pr = (int)(u % n_pairs);
       const long long tok0 = (u / n_pairs) * IT_TOK;
       const int nft = min(2, p.F_tiles - 2 * pr);
-      const int f = (2 * pr + acc) * IT_FT + q * 32 + lane;
       const bool live = acc < nft;
       for (int kb = 0; kb < p.NKB; kb++) {
         const int cut = sched[kb].cut;
@@ -274,9 +306,13 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           if (lane == 0) mbar_arrive(acc_free);
           continue;
         }
-        const float wc = wcum_s[cut], inv = wcum_s[p.n_cuts + cut];
+        const float inv = wcum_s[p.n_cuts + cut];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * IT_TOK;
-        __half* orow = p.out + ((size_t)f * p.n_cuts + cut) * (size_t)p.out_stride + tok0;
+        // After the reference's roundings the warp's 32 features x 32 tokens go through a private staging
+        // tile so that a store instruction writes 8 rows x 64 contiguous bytes instead of 32 rows x 16.
+        const int frow0 = (2 * pr + acc) * IT_FT + q * 32;
+        const size_t row_stride = (size_t)p.n_cuts * (size_t)p.out_stride;
+        __half* obase = p.out + ((size_t)frow0 * p.n_cuts + cut) * (size_t)p.out_stride + tok0 + (lane & 3) * 8;
 #pragma unroll 1
         for (int ch = 0; ch < IT_TOK / 32; ch++) {
           uint32_t v[32];
@@ -287,17 +323,27 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
           }
-          if (f < p.F) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              uint4 o;
-              o.x = finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), wc, inv);
-              o.y = finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), wc, inv);
-              o.z = finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), wc, inv);
-              o.w = finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), wc, inv);
-              __stcs(reinterpret_cast<uint4*>(orow + ch * 32 + g * 8), o);
-            }
+          for (int g = 0; g < 4; g++) {
+            const uint32_t o0 = finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), inv);
+            const uint32_t o1 = finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), inv);
+            const uint32_t o2 = finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), inv);
+            const uint32_t o3 = finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * IT_STG_PITCH + g * 16), "r"(o0), "r"(o1),
+                         "r"(o2), "r"(o3)
+                         : "memory");
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int r = i * 8 + (lane >> 2);
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg + r * IT_STG_PITCH + (lane & 3) * 16));
+            if (frow0 + r < p.F) __stcs(reinterpret_cast<uint4*>(obase + (size_t)r * row_stride + ch * 32), o);
+          }
+          __syncwarp();
         }
       }
     }

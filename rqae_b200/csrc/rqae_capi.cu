@@ -18,6 +18,7 @@
 #include "rq_decode.cuh"
 #include "rq_forward.cuh"
 #include "rq_intensity.cuh"
+#include "rq_mine.cuh"
 #include "rq_layout.h"
 
 #ifndef RQ_L2_HOT_DEFAULT
@@ -752,6 +753,25 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   rq::rq_intensity_kernel<<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
   RQ_CUDA(cudaGetLastError());
   g_launches += 4;
+  return RQAE_OK;
+}
+
+int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t row_stride, int64_t n, int top_k,
+                                      int32_t* idx_out, void* val_out, void* stream) {
+  if (!vals || !idx_out || rows < 0 || top_k < 1 || n < top_k || n >= (int64_t)1 << 31) return RQAE_EINVAL;
+  if (top_k > rq::MN_KMAX) return RQAE_EUNSUPPORTED;
+  if ((row_stride & 7) || row_stride < (n + 7) / 8 * 8 || ((uintptr_t)vals & 15)) return RQAE_EINVAL;   // 16-byte row loads
+  if (rows == 0) return RQAE_OK;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  rq::MineParams mp;
+  mp.vals = (const __half*)vals; mp.rows = rows; mp.row_stride = row_stride; mp.n = n; mp.k = top_k;
+  mp.idx_out = idx_out; mp.val_out = (__half*)val_out;
+  const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
+  rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
   return RQAE_OK;
 }
 

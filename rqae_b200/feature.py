@@ -121,6 +121,50 @@ def intensity_many(rqae, token_indices: torch.Tensor, centers: torch.Tensor, lay
     return res
 
 
+def select_top_middle_bottom(intensities: torch.Tensor, top_k: int = 100, n: Optional[int] = None):
+    """The selection of scripts/3_make_rqae_features.py:116-128 for every row of ``intensities`` (fp16, CUDA,
+    (..., T) as returned by ``intensity_many``): positions of the ``top_k`` largest, the values around the
+    median rank and the ``top_k`` smallest, without sorting the rows.  Returns (indices int32 (..., 3, top_k),
+    values fp16 (..., 3, top_k)); order inside a window: value descending, then index ascending."""
+    if not intensities.is_cuda or intensities.dtype != torch.float16:
+        raise RuntimeError("select_top_middle_bottom needs an fp16 CUDA tensor; there is no CPU fallback")
+    T = intensities.shape[-1] if n is None else int(n)
+    v = intensities
+    ok = v.dim() >= 1 and v.stride(-1) == 1 and v.data_ptr() % 16 == 0
+    lead = v.shape[:-1]
+    if ok and v.dim() > 1:
+        rs = v.stride(-2)
+        flat_ok = rs % 8 == 0 and rs >= (T + 7) // 8 * 8
+        # all leading dims must collapse onto a single row stride
+        exp = rs
+        for d in range(v.dim() - 2, -1, -1):
+            if v.shape[d] != 1 and v.stride(d) != exp:
+                flat_ok = False
+            exp *= v.shape[d]
+        ok = flat_ok
+    elif ok:
+        rs = (T + 7) // 8 * 8
+        ok = v.shape[0] >= rs or T % 8 == 0
+    if not ok:   # repack into rows padded to a multiple of 8
+        rs = (T + 7) // 8 * 8
+        buf = torch.zeros(*lead, rs, dtype=torch.float16, device=v.device)
+        buf[..., :T] = v[..., :T]
+        v = buf
+    rows = 1
+    for d in lead:
+        rows *= int(d)
+    dev = v.device
+    idx = torch.empty(*lead, 3, top_k, dtype=torch.int32, device=dev)
+    val = torch.empty(*lead, 3, top_k, dtype=torch.float16, device=dev)
+    if rows > 0:
+        with torch.cuda.device(dev):
+            rc = _lib.load().rqae_select_top_middle_bottom_f16(v.data_ptr(), rows, rs, T, int(top_k), idx.data_ptr(),
+                                                                val.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "rqae_select_top_middle_bottom_f16")
+        v.record_stream(torch.cuda.current_stream(dev))
+    return idx, val
+
+
 class RQAEFeature:
     """feature.py:42-153."""
 

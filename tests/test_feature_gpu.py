@@ -114,3 +114,64 @@ def test_rqae_feature_api_shapes(kat):
     sub = f.intensity(codes[0, :3], layers=[6, 2])
     assert sub.shape == (3, 2)
     assert torch.equal(sub.cpu(), out[0, :3][:, [2, 0]].cpu())
+
+
+# ---------------------------------------------------------------------------------------------------
+# selection (scripts/3_make_rqae_features.py:116-128)
+# ---------------------------------------------------------------------------------------------------
+def _stable_windows(v: torch.Tensor, k: int):
+    """argsort(descending) of the reference with the one tie order that is deterministic: index ascending."""
+    order = torch.sort(v.float(), descending=True, stable=True).indices
+    n = len(order)
+    return order[:k], order[n // 2 - k // 2: n // 2 + k // 2], order[n - k:]
+
+
+@pytest.mark.parametrize("T,k,quant", [(5000, 100, None), (5000, 100, 0.05), (4097, 7, 0.25), (300003, 100, 0.01),
+                                       (100, 100, None), (257, 1, 0.5), (65536, 256, 0.002)])
+def test_select_top_middle_bottom_matches_stable_argsort(T, k, quant):
+    from rqae_b200.feature import select_top_middle_bottom
+    dev = _dev()
+    g = torch.Generator().manual_seed(T + k)
+    v = torch.randn(3, 2, T, generator=g) * 0.3
+    if quant:
+        v = (v / quant).round() * quant          # many exact ties, also across the window boundaries
+    v = v.half()
+    v[v == 0] = 0.0                              # no -0: float compare cannot tell it from +0, the radix key can
+    idx, val = select_top_middle_bottom(v.to(dev), k)
+    torch.cuda.synchronize()
+    idx, val = idx.cpu().long(), val.cpu()
+    assert idx.shape == (3, 2, 3, k)
+    for a in range(3):
+        for b in range(2):
+            top, mid, bot = _stable_windows(v[a, b], k)
+            assert torch.equal(idx[a, b, 0], top)
+            assert torch.equal(idx[a, b, 1, :len(mid)], mid) and torch.all(idx[a, b, 1, len(mid):] == -1)
+            assert torch.equal(idx[a, b, 2], bot)
+            assert torch.equal(val[a, b, 0], v[a, b][top]) and torch.equal(val[a, b, 2], v[a, b][bot])
+            # the reference's own (unstable) argsort selects the same VALUES
+            t2, m2, b2 = fo.select_top_middle_bottom(v[a, b], k)
+            assert torch.equal(v[a, b][t2].float(), val[a, b, 0].float())
+            assert torch.equal(v[a, b][b2].float(), val[a, b, 2].float())
+            assert torch.equal(v[a, b][m2].float(), val[a, b, 1, :len(m2)].float())
+
+
+def test_mining_pipeline_intensity_then_selection(kat):
+    """intensity_many -> select_top_middle_bottom on the kernel's own output layout (rows of T_pad)."""
+    from rqae_b200.feature import intensity_many, select_top_middle_bottom
+    dev = _dev()
+    cb0 = torch.from_numpy(kat["2b/cb0"])
+    lw = torch.from_numpy(kat["2b/lw"])
+    codes = torch.from_numpy(kat["2b/codes"].astype(np.int64))
+    centers = torch.from_numpy(kat["2b/centers"])
+    layers = [int(l) for l in kat["2b/layers"]]
+    out = intensity_many(_Stub(cb0, dev), codes.to(dev), centers, layers, layer_weights=lw)   # (8, 14, 512) view of T_pad rows
+    idx, val = select_top_middle_bottom(out, 50)
+    torch.cuda.synchronize()
+    o = out.cpu()
+    o[o == 0] = 0.0
+    for f in (0, 7):
+        for c in (0, 13):
+            top, mid, bot = _stable_windows(o[f, c], 50)
+            assert torch.equal(o[f, c][idx[f, c, 0].cpu().long()].float(), o[f, c][top].float())
+            assert torch.equal(o[f, c][idx[f, c, 1].cpu().long()].float(), o[f, c][mid].float())
+            assert torch.equal(o[f, c][idx[f, c, 2].cpu().long()].float(), o[f, c][bot].float())

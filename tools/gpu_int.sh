@@ -7,8 +7,6 @@ mkdir -p $OUT
 echo "=== int_debug ==="
 timeout 300 python tools/int_debug.py 2>&1 | tail -60 | tee $OUT/int_debug_$TAG.log
 echo "=== pytest feature ==="
-timeout 600 python -m pytest tests/test_feature_gpu.py -x -q 2>&1 | tail -25 | tee $OUT/pytest_feature_$TAG.log
-if [ -f tools/bench_intensity.py ]; then
-  echo "=== bench intensity ==="
-  timeout 300 python tools/bench_intensity.py 2>&1 | tail -20 | tee $OUT/bench_intensity_$TAG.log
-fi
+timeout 600 python -m pytest tests/test_feature_gpu.py -q 2>&1 | tail -40 | tee $OUT/pytest_feature_$TAG.log
+echo "=== bench intensity ==="
+timeout 300 python tools/bench_intensity.py 2>&1 | tail -20 | tee $OUT/bench_intensity_$TAG.log
