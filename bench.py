@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (mining stage, 9B encode)")
     return ap.parse_args()
 
 
@@ -210,6 +211,83 @@ def fp32_peak_tflops(torch, lib, dev):
     return best
 
 
+SCRIPT3_CUTS = [2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1023]   # scripts/3_make_rqae_features.py:178
+
+
+def _event_ms(torch, dev, fn, reps=2):
+    fn(); torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record(); torch.cuda.synchronize(dev)
+    return out, a.elapsed_time(b) / reps
+
+
+def mining_extras(torch, model, codes, dev):
+    """BASELINE configs[4] pattern on this GPU's own codes: intensities of F = 1024 feature centers (codes of 1024
+    tokens) at the 14 cuts of scripts/3 over the token shard (tcgen05 GEMM), then the top / middle / bottom-100
+    selection per (feature, cut).  Side measurement, CUDA events, outside the timed region."""
+    from rqae_b200.feature import intensity_many, select_top_middle_bottom, layer_weights_f16
+    T = codes.shape[0]
+    Fn = 1024
+    centers = codes[torch.randperm(T, device=dev)[:Fn]].to(torch.int32)
+    lw = layer_weights_f16(model).to(dev)
+    buf = torch.empty(Fn, len(SCRIPT3_CUTS), (T + 255) // 256 * 256, dtype=torch.float16, device=dev)
+    out, ms_int = _event_ms(torch, dev, lambda: intensity_many(model, codes, centers, SCRIPT3_CUTS, layer_weights=lw, out=buf))
+    (idx, val), ms_sel = _event_ms(torch, dev, lambda: select_top_middle_bottom(out, 100))
+    peaks = measured_peaks()
+    tensor_peak = peaks["bf16_tflops"] if peaks else 1590.0
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    flop = 2.0 * T * Fn * 4 * (SCRIPT3_CUTS[-1] + 1)
+    out_bytes = Fn * len(SCRIPT3_CUTS) * T * 2
+    res = {
+        "tokens": T, "features": Fn, "cuts": len(SCRIPT3_CUTS),
+        "intensity_ms": ms_int, "intensity_tokens_per_s": T / ms_int * 1e3,
+        "intensity_tflops": flop / ms_int / 1e9, "intensity_frac_of_tensor_peak": flop / ms_int / 1e9 / tensor_peak,
+        "intensity_out_gbs": out_bytes / ms_int / 1e6, "intensity_frac_of_hbm_peak": out_bytes / ms_int / 1e6 / hbm_peak,
+        "tensor_peak_source": "MEASURED_PEAKS.json (burst)" if peaks else "fallback 1.59 PFLOP/s (B200_PROFILING.md)",
+        "select_ms": ms_sel, "select_rows_per_s": Fn * len(SCRIPT3_CUTS) / ms_sel * 1e3,
+        "select_gbs": out_bytes / ms_sel / 1e6,
+        "checksum_top_idx": int(idx[:, :, 0].sum().item()),
+    }
+    # the reference's CPU path for the same step (one feature at a time, rqae/feature.py:102-129), bounded sample
+    try:
+        from oracle import feature_oracle as fo
+        import time as _t
+        n = min(T, 16384)
+        cc = codes[:n].cpu().long()
+        sims = fo.codebook_sims(model.codebook.data[0].cpu())
+        c0 = centers[0].cpu()
+        lwc = lw.cpu()
+        fo.intensity(sims, c0, cc[:256], lwc, SCRIPT3_CUTS)
+        t0 = _t.perf_counter()
+        v = fo.intensity(sims, c0, cc, lwc, SCRIPT3_CUTS)
+        t1 = _t.perf_counter()
+        for j in range(len(SCRIPT3_CUTS)):
+            fo.select_top_middle_bottom(v[:, j], 100)
+        t2 = _t.perf_counter()
+        res["cpu_port"] = {"feature_tokens_per_s_intensity": n / (t1 - t0), "feature_tokens_per_s_select": n / (t2 - t1),
+                           "gpu_feature_tokens_per_s_intensity": T * Fn / ms_int * 1e3,
+                           "sample": f"1 feature x {n} tokens x {len(SCRIPT3_CUTS)} cuts, torch CPU (oracle port of feature.py)"}
+    except Exception as e:
+        res["cpu_port"] = {"error": repr(e)}
+    return res
+
+
+def encode_9b_extra(torch, dev, tokens=1 << 16):
+    """BASELINE configs[3]: Gemma-2-9B width (d=3584), deeper stack (nq=2048), encode-only code extraction."""
+    from rqae_b200 import RQAE
+    torch.manual_seed(0)
+    m = RQAE(dim=3584, num_quantizers=2048).eval().to(dev)
+    m.freeze_packed()
+    x = torch.randn(1, tokens, 3584, device=dev, generator=torch.Generator(device=dev).manual_seed(99))
+    _, ms = _event_ms(torch, dev, lambda: m.encode(x, out_dtype=torch.int16))
+    flop_tok = 2048 * (2 * 2 * 4 * 3584 + 5000 + 3584)
+    return {"tokens": tokens, "dim": 3584, "num_quantizers": 2048, "tokens_per_s": tokens / ms * 1e3,
+            "tflops_fp32": flop_tok * tokens / ms / 1e9, "flop_per_token": flop_tok}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -334,7 +412,17 @@ def run_b200(args, rank, local_rank, world):
         _, dec_rate = timed(lambda: model.decode(codes_s))
         extra = {"encode_only_int16_tokens_per_s": enc_rate, "decode_only_tokens_per_s": dec_rate, "tokens": Ts,
                  "decode_frac_of_fp32_peak": None}
+        if not args.no_extras:
+            try:
+                extra["mining"] = mining_extras(torch, model, codes_s[0, : 1 << 17], dev)
+            except Exception as e:   # side measurement only: never lose the bench line over it
+                extra["mining"] = {"error": repr(e)}
         del codes_s
+        if not args.no_extras:
+            try:
+                extra["config4_9b_encode_only"] = encode_9b_extra(torch, dev)
+            except Exception as e:
+                extra["config4_9b_encode_only"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -355,8 +443,11 @@ def run_b200(args, rank, local_rank, world):
         pass
     if extra is not None:
         extra["decode_frac_of_fp32_peak"] = extra["decode_only_tokens_per_s"] * NQ * (6 * D) * 2 / 1e12 / fp32_peak
+        c4 = extra.get("config4_9b_encode_only")
+        if isinstance(c4, dict) and "tflops_fp32" in c4:
+            c4["frac_of_fp32_peak"] = c4["tflops_fp32"] / fp32_peak
     roofline = {
-        "kernel": "rq_forward_kernel<9,3,3,7,8> (one launch per step)",
+        "kernel": "rq::rq_forward_kernel (E=9 instantiation for d=2304; one cooperative launch per step)",
         "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak,
         "peak_source": "measured live: rqae_fp32_peak_probe, best of FFMA2 %.1f / FFMA %.1f TFLOP/s" % (fp32["ffma2"], fp32["ffma"]),
         "operand_pattern_ceiling": {"inproj_sweep": fp32["pattern_inproj"], "outproj_sweep": fp32["pattern_outproj"],

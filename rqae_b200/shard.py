@@ -80,3 +80,54 @@ def encode_sharded(model, x: torch.Tensor, max_layers=float("inf"), out_dtype: t
         codes = gather_codes(codes, flat.shape[0], group=group)
         return codes, (0, flat.shape[0])
     return codes, (a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# feature mining across GPUs (BASELINE configs[4]: encode + per-feature intensities on 8 GPUs)
+# ---------------------------------------------------------------------------------------------------
+def exchange_to_feature_shards(intens_local: torch.Tensor, n_tokens: int,
+                               group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, Tuple[int, int]]:
+    """Token-sharded intensities -> feature-sharded intensities, the one exchange step of the mining path.
+
+    Every rank holds ``intens_local`` (F, C, T_r) fp16 for its contiguous token range (``token_range``) and
+    ALL F features -- what ``rqae_b200.feature.intensity_many`` returns for the rank's codes.  The selection
+    of scripts/3_make_rqae_features.py:116-128 ranks each (feature, cut) row over the WHOLE dataset, and the
+    median window does not compose from per-shard results, so rows are made whole instead: rank d receives
+    features ``token_range(F, d, world)`` from everybody (one all_to_all, NVLink/NVSwitch under NCCL) and
+    concatenates the pieces in rank order = global token order.  Returns ((F_d, C, n_tokens) with rows padded
+    to a multiple of 8 tokens, (f_start, f_stop))."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    F, C, T_r = intens_local.shape
+    a, b = token_range(n_tokens, rank, world)
+    if T_r != b - a:
+        raise ValueError(f"rank {rank} must pass its {b - a} tokens, got {T_r}")
+    fa, fb = token_range(F, rank, world)
+    send = [intens_local[token_range(F, d, world)[0]:token_range(F, d, world)[1]].contiguous().view(torch.uint8).reshape(-1)
+            for d in range(world)]
+    sizes = [token_range(n_tokens, s, world)[1] - token_range(n_tokens, s, world)[0] for s in range(world)]
+    esz = intens_local.element_size()
+    out_splits = [(fb - fa) * C * sizes[s] * esz for s in range(world)]
+    recv_flat = torch.empty(sum(out_splits), dtype=torch.uint8, device=intens_local.device)
+    dist.all_to_all_single(recv_flat, torch.cat(send), output_split_sizes=out_splits,
+                           input_split_sizes=[t.numel() for t in send], group=group)
+    recv = list(torch.split(recv_flat, out_splits))
+    stride = (n_tokens + 7) // 8 * 8
+    full = torch.zeros(fb - fa, C, stride, dtype=intens_local.dtype, device=intens_local.device)
+    t0 = 0
+    for s in range(world):
+        full[:, :, t0:t0 + sizes[s]] = recv[s].view(intens_local.dtype).reshape(fb - fa, C, sizes[s])
+        t0 += sizes[s]
+    return full[:, :, :n_tokens], (fa, fb)
+
+
+def mine_sharded(intens_local: torch.Tensor, n_tokens: int, top_k: int = 100, select_fn=None,
+                 group: Optional[dist.ProcessGroup] = None):
+    """Top / middle / bottom-k over the whole dataset for this rank's share of the features.
+    ``select_fn(rows (F_d, C, n_tokens) fp16, top_k) -> (idx, val)`` defaults to the CUDA radix select;
+    returned indices are global token positions.  Returns (idx, val, (f_start, f_stop))."""
+    if select_fn is None:
+        from .feature import select_top_middle_bottom as select_fn
+    rows, frange = exchange_to_feature_shards(intens_local, n_tokens, group=group)
+    idx, val = select_fn(rows, top_k)
+    return idx, val, frange

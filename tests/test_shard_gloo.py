@@ -75,3 +75,49 @@ def test_token_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard.token_range(10, 2, 2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# mining exchange: token-sharded intensities -> feature-sharded rows -> selection over the whole dataset
+# ---------------------------------------------------------------------------------------------------
+def _oracle_select(rows, k):
+    """Stand-in for the CUDA radix select on CPU ranks: stable argsort windows (value desc, index asc)."""
+    F, C, n = rows.shape
+    idx = torch.full((F, C, 3, k), -1, dtype=torch.int32)
+    for f in range(F):
+        for c in range(C):
+            order = torch.sort(rows[f, c].float(), descending=True, stable=True).indices
+            idx[f, c, 0] = order[:k]
+            mid = order[n // 2 - k // 2: n // 2 + k // 2]
+            idx[f, c, 1, :len(mid)] = mid
+            idx[f, c, 2] = order[n - k:]
+    return idx, None
+
+
+def _mine_worker(rank, world, port, n_tokens, n_feat, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = (torch.randn(n_feat, 3, n_tokens, generator=torch.Generator().manual_seed(9)) * 0.2).half()
+        a, b = shard.token_range(n_tokens, rank, world)
+        idx, _, (fa, fb) = shard.mine_sharded(full[:, :, a:b].contiguous(), n_tokens, top_k=5, select_fn=_oracle_select)
+        np.save(os.path.join(out_dir, f"mine_{rank}.npy"), idx.numpy())
+        np.save(os.path.join(out_dir, f"range_{rank}.npy"), np.array([fa, fb]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_mining_exchange_equals_single_process(tmp_path):
+    world, n_tokens, n_feat = 2, 101, 7
+    port = _free_port()
+    mp.spawn(_mine_worker, args=(world, port, n_tokens, n_feat, str(tmp_path)), nprocs=world, join=True)
+    full = (torch.randn(n_feat, 3, n_tokens, generator=torch.Generator().manual_seed(9)) * 0.2).half()
+    ref, _ = _oracle_select(full, 5)
+    got = torch.empty_like(ref)
+    seen = 0
+    for r in range(world):
+        fa, fb = np.load(os.path.join(str(tmp_path), f"range_{r}.npy"))
+        got[fa:fb] = torch.from_numpy(np.load(os.path.join(str(tmp_path), f"mine_{r}.npy")))
+        seen += fb - fa
+    assert seen == n_feat and torch.equal(got, ref)
