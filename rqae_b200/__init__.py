@@ -7,6 +7,7 @@ compute is hand-written CUDA behind the C ABI of ``librqae_b200.so``
 from .model import RQAE  # noqa: F401
 from .feature import Feature, RQAEFeature, intensity_many  # noqa: F401
 from . import shard  # noqa: F401
+from . import store  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["RQAE", "Feature", "RQAEFeature", "intensity_many"]
