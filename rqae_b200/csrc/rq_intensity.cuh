@@ -66,6 +66,7 @@ struct IntParams {
   __half* out;                   // [F][n_cuts][out_stride]
   long long out_stride;
   long long n_tok_tiles;
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA
 };
 
 struct IntSmem {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           mbar_wait_spin(&u_full[us], upar);
           mbar_wait_spin(&v_full[vs], vpar);
           tc_fence_after();
-          for (int ft = 0; ft < nft; ft++) {
+          for (int ft = 0; ft < ((p.dbg & 8) ? 0 : nft); ft++) {
             const uint64_t ad = umma_desc_sw128(uring + us * IT_U_BYTES + ft * IT_U_TILE);
             const uint64_t bd = umma_desc_sw128(vring + vs * IT_V_BYTES);
 #pragma unroll
@@ -222,9 +223,11 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           tc_commit(&u_empty[us]);
           if (sched[kb].cut >= 0) {   // pause: the epilogue reads the running prefix
             tc_commit(acc_full);
-            mbar_wait_spin(acc_free, free_par);
-            free_par ^= 1;
-            tc_fence_after();
+            if (!(p.dbg & 4)) {
+              mbar_wait_spin(acc_free, free_par);
+              free_par ^= 1;
+              tc_fence_after();
+            }
           }
           if (++vs == IT_VSTAGES) { vs = 0; vpar ^= 1; }
           if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         else if (u + gridDim.x < n_units) fetch(u + gridDim.x, 0);
         mbar_wait_spin(&v_empty[s], par);
         const uint32_t vb = vring + s * IT_V_BYTES;
+        if (!(p.dbg & 2))
 #pragma unroll
         for (int c = 0; c < 8; c++) {
           uint32_t x0, x1, x2, x3;
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                          : "r"(stg + r * IT_STG_PITCH + (lane & 3) * 16));
-            if (frow0 + r < p.F) __stcs(reinterpret_cast<uint4*>(obase + (size_t)r * row_stride + ch * 32), o);
+            if (frow0 + r < p.F && !(p.dbg & 1)) __stcs(reinterpret_cast<uint4*>(obase + (size_t)r * row_stride + ch * 32), o);
           }
           __syncwarp();
         }

@@ -747,6 +747,7 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   ip.codes_t = (const short*)(ws + L.off_codes); ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
   ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
+  { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
   ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
   const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
