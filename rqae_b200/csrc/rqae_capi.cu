@@ -366,7 +366,7 @@ const char* rqae_strerror(int code) {
   switch (code) {
     case RQAE_OK: return "ok";
     case RQAE_EINVAL: return "invalid argument";
-    case RQAE_EUNSUPPORTED: return "unsupported shape (codebook_dim must be 4, dim <= 3584, K <= 65535)";
+    case RQAE_EUNSUPPORTED: return "unsupported shape (codebook_dim must be 4, dim <= 3584, K <= 65535; intensity: K < 1024, <= 64 cuts; selection: top_k <= 256)";
     case RQAE_ECUDA: return "CUDA runtime error";
     case RQAE_ENODEVICE: return "current device is not an sm_100 (B200) GPU";
     case RQAE_ESIZE: return "buffer too small";

@@ -37,3 +37,26 @@ def test_host_only_entry_points():
     # argument validation happens before any CUDA call
     assert lib.rqae_forward_f32(None, None, 1, 8, 8, 256, 4, 625, None, 4, None, 2, 8, None, None, None, None) == 1
     assert lib.rqae_decode_f32(None, None, 8, 8, 256, 4, 625, None, 2, 8, None, None, 4, None, None) == 1
+
+
+def test_mining_entry_points_validate_before_touching_the_gpu():
+    import ctypes
+    import numpy as np
+    lib = _lib.load()
+    cuts = np.array([2, 4, 1023], dtype=np.int32)
+    n = lib.rqae_intensity_workspace_bytes(cuts.ctypes.data, 3, 1024, 1 << 20)
+    # schedule + tables + 8 feature tiles x (1+1+64) K-blocks x 16 KB + layer-major int16 codes
+    assert n >= 8 * 66 * 16384 + 1024 * (1 << 20) * 2 and n < 8 * 66 * 16384 + 1024 * (1 << 20) * 2 + (1 << 16)
+    bad = np.array([4, 2], dtype=np.int32)                       # not ascending
+    assert lib.rqae_intensity_workspace_bytes(bad.ctypes.data, 2, 8, 100) == 0
+    assert lib.rqae_intensity_workspace_bytes(cuts.ctypes.data, 0, 8, 100) == 0
+    one = ctypes.c_void_p(4096)
+    assert lib.rqae_intensity_f16(None, 625, one, 0, 1024, 8, one, 1024, 1, one, cuts.ctypes.data, 3, one, 256, one, n, None) == 1
+    assert lib.rqae_intensity_f16(one, 5000, one, 0, 1024, 8, one, 1024, 1, one, cuts.ctypes.data, 3, one, 256, one, n, None) == 2
+    assert lib.rqae_intensity_f16(one, 625, one, 0, 16, 8, one, 1024, 1, one, cuts.ctypes.data, 3, one, 256, one, n, None) == 1   # stride < layers
+    assert lib.rqae_intensity_f16(one, 625, one, 0, 1024, 8, one, 1024, 1, one, cuts.ctypes.data, 3, one, 100, one, n, None) == 1  # out rows too short
+    assert lib.rqae_intensity_f16(one, 625, one, 0, 1024, 8, one, 1024, 1, one, cuts.ctypes.data, 3, one, 256, one, 16, None) == 5  # workspace too small
+    assert lib.rqae_select_top_middle_bottom_f16(one, 4, 256, 200, 300, one, None, None) == 1      # k > n
+    assert lib.rqae_select_top_middle_bottom_f16(one, 4, 512, 400, 300, one, None, None) == 2      # k > 256
+    assert lib.rqae_select_top_middle_bottom_f16(one, 4, 250, 250, 10, one, None, None) == 1       # rows not 16-byte aligned
+    assert lib.rqae_select_top_middle_bottom_f16(one, 0, 256, 250, 10, one, None, None) == 0       # nothing to do
