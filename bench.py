@@ -412,13 +412,13 @@ def run_b200(args, rank, local_rank, world):
         _, dec_rate = timed(lambda: model.decode(codes_s))
         extra = {"encode_only_int16_tokens_per_s": enc_rate, "decode_only_tokens_per_s": dec_rate, "tokens": Ts,
                  "decode_frac_of_fp32_peak": None}
-        if not args.no_extras:
+        if not args.no_extras and world == 1:
             try:
                 extra["mining"] = mining_extras(torch, model, codes_s[0, : 1 << 17], dev)
             except Exception as e:   # side measurement only: never lose the bench line over it
                 extra["mining"] = {"error": repr(e)}
         del codes_s
-        if not args.no_extras:
+        if not args.no_extras and world == 1:
             try:
                 extra["config4_9b_encode_only"] = encode_9b_extra(torch, dev)
             except Exception as e:

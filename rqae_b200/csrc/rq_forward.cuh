@@ -57,6 +57,9 @@ struct FwdParams {
   unsigned int* sync_ctr;       // nullable: grid lock-step counter of this launch (zeroed before the launch)
 };
 
+#ifndef RQ_SKEW_CLK
+#define RQ_SKEW_CLK 350
+#endif
 #ifndef RQ_REGC
 #define RQ_REGC 224
 #define RQ_REGH 56
@@ -284,6 +287,17 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       named_bar_sync(1, RQ_GROUP_THREADS);
       if (ct < 64) sts32(cpr + ct * 4, 0.0f);
       named_bar_sync(1, RQ_GROUP_THREADS);
+#if RQ_SKEW_CLK > 0
+      // The two compute warps of a scheduler (w and w+4) leave this barrier together and would reach the
+      // shuffle-bound reduction at the end of every pass together, leaving the FMA pipe idle twice per
+      // pass pair.  Starting warps 4-7 a fraction of a pass late puts one warp's reduction under the other
+      // warp's FMA stream; nothing re-aligns them until the next unit (the hand-overs have a pass of slack).
+      if (warp >= 4) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < RQ_SKEW_CLK) {
+        }
+      }
+#endif
 
       for (int l = 0; l <= p.nq_run; ++l) {
 #pragma unroll

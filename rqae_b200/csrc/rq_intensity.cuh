@@ -56,7 +56,9 @@ struct IntKBlock {   // one K-block of the schedule: layers l0 .. l0+n-1 (n <= 1
 };
 
 struct IntParams {
-  const short* codes_t;          // [L][T_pad] layer-major codes, out-of-range and padding = K (the zero row)
+  const uint32_t* codes_p;       // [T_pad/256][L][128] tile-major codes: word b of (tile, layer) = code(token b) | code(token b+128) << 16;
+                                 // out-of-range and padding codes = K (the zero row)
+  int L;                         // layers present in codes_p
   long long T_pad;               // multiple of IT_TOK
   const unsigned char* u_tiles;  // [F_tiles][NKB][16 KB]
   const IntKBlock* sched;        // [NKB]
@@ -66,7 +68,7 @@ struct IntParams {
   __half* out;                   // [F][n_cuts][out_stride]
   long long out_stride;
   long long n_tok_tiles;
-  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work
 };
 
 struct IntSmem {
@@ -242,52 +244,68 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     const uint32_t row_off0 = b * 128, row_off1 = (b + 128) * 128;
     const uint32_t sw = (uint32_t)(b & 7);   // (b + 128) & 7 is the same
     uint32_t s = 0, par = 1;
-    // codes of the next K-block are requested before the current one is written (the layer-major code rows
-    // come from L2 / HBM: one K-block of latency is hidden behind the previous block's table look-ups)
-    unsigned short c0[IT_LPB], c1[IT_LPB];
-    auto fetch = [&](long long u, int kb) {
-      const long long tok0 = (u / n_pairs) * IT_TOK;
-      const int l0 = sched[kb].l0, n = sched[kb].n;
-      const short* src = p.codes_t + (size_t)l0 * p.T_pad + tok0 + b;
+    // The codes of a K-block are 16 coalesced 128-byte warp loads (one word = the thread's two tokens).  They are
+    // requested TWO K-blocks ahead into registers, and the K-block IT_PF steps ahead is pulled into L2 with one
+    // bulk prefetch: the code rows stream from HBM and their latency must stay off the V hand-over path.
+    struct Pos { long long u; int kb; };
+    auto next = [&](Pos& q) { if (++q.kb == p.NKB) { q.kb = 0; q.u += gridDim.x; } };
+    auto fetch = [&](uint32_t (&c)[IT_LPB], const Pos& q) {
+      const uint32_t padw = (uint32_t)p.K | ((uint32_t)p.K << 16);
+      if (q.u < n_units) {
+        const int l0 = sched[q.kb].l0, n = sched[q.kb].n;
+        const uint32_t* src = p.codes_p + ((size_t)(q.u / n_pairs) * p.L + l0) * 128 + b;
 #pragma unroll
-      for (int i = 0; i < IT_LPB; i++) {
-        c0[i] = (unsigned short)p.K;
-        c1[i] = (unsigned short)p.K;
-        if (i < n) {
-          c0[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad);
-          c1[i] = (unsigned short)__ldg(src + (size_t)i * p.T_pad + 128);
-        }
+        for (int i = 0; i < IT_LPB; i++) c[i] = (i < n) ? __ldg(src + i * 128) : padw;
       }
     };
-    if ((long long)blockIdx.x < n_units) fetch(blockIdx.x, 0);
-    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-      for (int kb = 0; kb < p.NKB; kb++) {
-        uint32_t a0[IT_LPB], a1[IT_LPB];   // table byte offsets of the current block
-#pragma unroll
-        for (int i = 0; i < IT_LPB; i++) { a0[i] = c0[i] * 8u; a1[i] = c1[i] * 8u; }
-        if (kb + 1 < p.NKB) fetch(u, kb + 1);
-        else if (u + gridDim.x < n_units) fetch(u + gridDim.x, 0);
-        mbar_wait_spin(&v_empty[s], par);
-        const uint32_t vb = vring + s * IT_V_BYTES;
-        if (!(p.dbg & 2))
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a0[2 * c]));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a0[2 * c + 1]));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)c ^ sw) << 4)), "r"(x0),
-                       "r"(x1), "r"(x2), "r"(x3)
-                       : "memory");
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a1[2 * c]));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a1[2 * c + 1]));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)c ^ sw) << 4)), "r"(x0),
-                       "r"(x1), "r"(x2), "r"(x3)
-                       : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        mbar_arrive(&v_full[s]);
-        if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
+    auto l2_prefetch = [&](const Pos& q) {
+      if (b == 0 && q.u < n_units) {
+        const int l0 = sched[q.kb].l0, n = sched[q.kb].n;
+        const uint32_t* src = p.codes_p + ((size_t)(q.u / n_pairs) * p.L + l0) * 128;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 512) : "memory");
       }
+    };
+    auto step = [&](uint32_t (&c)[IT_LPB], Pos& fut, Pos& pf) {
+      uint32_t a0[IT_LPB], a1[IT_LPB];   // table byte offsets of this block's two rows
+#pragma unroll
+      for (int i = 0; i < IT_LPB; i++) { a0[i] = (c[i] & 0xFFFFu) * 8u; a1[i] = (c[i] >> 16) * 8u; }
+      fetch(c, fut);
+      next(fut);
+      l2_prefetch(pf);
+      next(pf);
+      mbar_wait_spin(&v_empty[s], par);
+      const uint32_t vb = vring + s * IT_V_BYTES;
+      if (!(p.dbg & 2))
+#pragma unroll
+      for (int cc = 0; cc < 8; cc++) {
+        uint32_t x0, x1, x2, x3;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a0[2 * cc]));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a0[2 * cc + 1]));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)cc ^ sw) << 4)), "r"(x0),
+                     "r"(x1), "r"(x2), "r"(x3)
+                     : "memory");
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a1[2 * cc]));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a1[2 * cc + 1]));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)cc ^ sw) << 4)), "r"(x0),
+                     "r"(x1), "r"(x2), "r"(x3)
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      mbar_arrive(&v_full[s]);
+      if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
+    };
+    constexpr int IT_PF = 8;
+    Pos cur = {(long long)blockIdx.x, 0}, fut = cur, pf = cur;
+    uint32_t cA[IT_LPB], cB[IT_LPB];
+    fetch(cA, fut); next(fut);
+    fetch(cB, fut); next(fut);
+    for (int i = 0; i < IT_PF; i++) { if (i >= 2) l2_prefetch(pf); next(pf); }
+    while (cur.u < n_units) {
+      step(cA, fut, pf);
+      next(cur);
+      if (cur.u >= n_units) break;
+      step(cB, fut, pf);
+      next(cur);
     }
   } else {
     // ======================= epilogue =======================
@@ -306,7 +324,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         mbar_wait(acc_full, full_par);
         full_par ^= 1;
         tc_fence_after();
-        if (!live) {
+        if (!live || (p.dbg & 16)) {
           if (lane == 0) mbar_arrive(acc_free);
           continue;
         }
@@ -408,13 +426,15 @@ __global__ void int_prep_kernel(const IntPrepParams p) {
   }
 }
 
-// codes [T][stride] (int16 / int32 / int64) -> layer-major int16 [L][T_pad]; out-of-range codes and the
-// padding tokens map to K (the zero row of the lookup table)
+// codes [T][stride] (int16 / int32 / int64) -> tile-major int16 pairs [T_pad/256][L][128][2]: within a tile of 256
+// tokens the codes of token b and token b+128 at one layer share a 32-bit word (the two rows one builder thread
+// writes), and a tile's layers are contiguous (one bulk L2 prefetch per K-block).  Out-of-range codes and the
+// padding tokens map to K (the zero row of the lookup table).
 template <typename CT>
 __global__ void int_transpose_kernel(const CT* __restrict__ codes, long long stride, long long T, int L, int K,
                                      short* __restrict__ out, long long T_pad) {
   __shared__ short tile[64][65];
-  const long long t0 = (long long)blockIdx.x * 64;
+  const long long t0 = (long long)blockIdx.x * 64;   // 64 | 256: the block's tokens lie inside one token tile
   const int l0 = blockIdx.y * 64;
   for (int i = threadIdx.y; i < 64; i += blockDim.y) {   // token i, layer threadIdx.x (+32)
     for (int j = threadIdx.x; j < 64; j += 32) {
@@ -429,12 +449,15 @@ __global__ void int_transpose_kernel(const CT* __restrict__ codes, long long str
     }
   }
   __syncthreads();
+  const long long tt = t0 / IT_TOK;
+  const int i0 = (int)(t0 % IT_TOK);
   for (int j = threadIdx.y; j < 64; j += blockDim.y) {   // layer j, token threadIdx.x (+32)
     const int l = l0 + j;
     if (l >= L) continue;
+    short* row = out + ((size_t)tt * L + l) * IT_TOK;
     for (int i = threadIdx.x; i < 64; i += 32) {
-      const long long t = t0 + i;
-      if (t < T_pad) out[(size_t)l * T_pad + t] = tile[i][j];
+      const int it = i0 + i;   // token within the tile
+      row[(it & 127) * 2 + (it >> 7)] = tile[i][j];
     }
   }
 }

@@ -744,7 +744,7 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   });
   RQ_CUDA(attr_err);
   rq::IntParams ip;
-  ip.codes_t = (const short*)(ws + L.off_codes); ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
+  ip.codes_p = (const uint32_t*)(ws + L.off_codes); ip.L = L.L; ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
   ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
