@@ -431,34 +431,53 @@ __global__ void int_prep_kernel(const IntPrepParams p) {
 // writes), and a tile's layers are contiguous (one bulk L2 prefetch per K-block).  Out-of-range codes and the
 // padding tokens map to K (the zero row of the lookup table).
 template <typename CT>
-__global__ void int_transpose_kernel(const CT* __restrict__ codes, long long stride, long long T, int L, int K,
-                                     short* __restrict__ out, long long T_pad) {
-  __shared__ short tile[64][65];
-  const long long t0 = (long long)blockIdx.x * 64;   // 64 | 256: the block's tokens lie inside one token tile
-  const int l0 = blockIdx.y * 64;
-  for (int i = threadIdx.y; i < 64; i += blockDim.y) {   // token i, layer threadIdx.x (+32)
-    for (int j = threadIdx.x; j < 64; j += 32) {
-      short v = (short)K;
-      const long long t = t0 + i;
-      const int l = l0 + j;
-      if (t < T && l < L) {
-        const long long c = (long long)codes[t * stride + l];
-        if (c >= 0 && c < K) v = (short)c;
+__global__ void __launch_bounds__(256) int_transpose_kernel(const CT* __restrict__ codes, long long stride, long long T, int L,
+                                                            int K, uint32_t* __restrict__ out) {
+  // block = one token tile (256 tokens) x 32 layers, staged in shared memory as [token][layer] with an 80-byte pitch
+  __shared__ __align__(16) unsigned char tile[IT_TOK * 80];
+  const long long tt = blockIdx.x;
+  const long long t0 = tt * IT_TOK;
+  const int l0 = blockIdx.y * 32;
+  const int tid = threadIdx.x;
+  const bool vec = sizeof(CT) == 2 && (stride % 8) == 0 && ((uintptr_t)codes % 16) == 0 && l0 + 32 <= L;
+  if (vec) {   // int16 codes: 16-byte loads (8 layers of one token), four per thread
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int idx = tid + it * 256;
+      const int i = idx >> 2, c = idx & 3;   // token, 16-byte chunk of its 32 layers
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      const bool live = t0 + i < T;
+      if (live) v = __ldg(reinterpret_cast<const uint4*>(codes + (t0 + i) * stride + l0) + c);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+        // as signed 16-bit: negative or >= K -> K
+        lo = (!live || lo >= (uint32_t)K) ? (uint32_t)K : lo;
+        hi = (!live || hi >= (uint32_t)K) ? (uint32_t)K : hi;
+        w[k] = lo | (hi << 16);
       }
-      tile[i][j] = v;
+      *reinterpret_cast<uint4*>(tile + i * 80 + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    for (int idx = tid; idx < IT_TOK * 32; idx += 256) {
+      const int i = idx >> 5, j = idx & 31;
+      unsigned short v = (unsigned short)K;
+      if (t0 + i < T && l0 + j < L) {
+        const long long c = (long long)codes[(t0 + i) * stride + l0 + j];
+        if (c >= 0 && c < K) v = (unsigned short)c;
+      }
+      *reinterpret_cast<unsigned short*>(tile + i * 80 + j * 2) = v;
     }
   }
   __syncthreads();
-  const long long tt = t0 / IT_TOK;
-  const int i0 = (int)(t0 % IT_TOK);
-  for (int j = threadIdx.y; j < 64; j += blockDim.y) {   // layer j, token threadIdx.x (+32)
-    const int l = l0 + j;
-    if (l >= L) continue;
-    short* row = out + ((size_t)tt * L + l) * IT_TOK;
-    for (int i = threadIdx.x; i < 64; i += 32) {
-      const int it = i0 + i;   // token within the tile
-      row[(it & 127) * 2 + (it >> 7)] = tile[i][j];
-    }
+  // word b of (tile, layer) = code(token b) | code(token b + 128) << 16: a warp writes 128 contiguous bytes
+  for (int idx = tid; idx < 32 * 128; idx += 256) {
+    const int j = idx >> 7, b = idx & 127;
+    if (l0 + j >= L) continue;
+    const uint32_t lo = *reinterpret_cast<const unsigned short*>(tile + b * 80 + j * 2);
+    const uint32_t hi = *reinterpret_cast<const unsigned short*>(tile + (b + 128) * 80 + j * 2);
+    out[((size_t)tt * L + l0 + j) * 128 + b] = lo | (hi << 16);
   }
 }
 

@@ -721,11 +721,11 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   RQ_CUDA(cudaGetLastError());
   // 2. codes -> layer-major int16
   {
-    dim3 grid((unsigned)(L.T_pad / 64), (unsigned)((L.L + 63) / 64)), block(32, 8);
-    short* ct = (short*)(ws + L.off_codes);
-    if (code_dtype == 2) rq::int_transpose_kernel<long long><<<grid, block, 0, st>>>((const long long*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
-    else if (code_dtype == 1) rq::int_transpose_kernel<int><<<grid, block, 0, st>>>((const int*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
-    else rq::int_transpose_kernel<short><<<grid, block, 0, st>>>((const short*)codes, code_stride, n_tokens, L.L, K, ct, L.T_pad);
+    dim3 grid((unsigned)(L.T_pad / rq::IT_TOK), (unsigned)((L.L + 31) / 32)), block(256);
+    uint32_t* ct = (uint32_t*)(ws + L.off_codes);
+    if (code_dtype == 2) rq::int_transpose_kernel<long long><<<grid, block, 0, st>>>((const long long*)codes, code_stride, n_tokens, L.L, K, ct);
+    else if (code_dtype == 1) rq::int_transpose_kernel<int><<<grid, block, 0, st>>>((const int*)codes, code_stride, n_tokens, L.L, K, ct);
+    else rq::int_transpose_kernel<short><<<grid, block, 0, st>>>((const short*)codes, code_stride, n_tokens, L.L, K, ct);
     RQ_CUDA(cudaGetLastError());
   }
   // 3. feature operand tiles
