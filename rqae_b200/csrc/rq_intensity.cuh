@@ -68,7 +68,7 @@ struct IntParams {
   __half* out;                   // [F][n_cuts][out_stride]
   long long out_stride;
   long long n_tok_tiles;
-  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start
 };
 
 struct IntSmem {
@@ -181,6 +181,13 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 
   const int n_pairs = (p.F_tiles + 1) / 2;
   const long long n_units = p.n_tok_tiles * n_pairs;
+  if (p.dbg & 32) {   // experiment: de-phase the CTAs so that their store-bound early cuts do not coincide
+    const long long t0 = clock64();
+    const long long d = (long long)(blockIdx.x % 4) * 80000;
+    while (clock64() - t0 < d) {
+    }
+    __syncthreads();
+  }
   const uint32_t vring = smem_u32(smem + IntSmem::VRING), uring = smem_u32(smem + IntSmem::URING);
   if (vring & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
 

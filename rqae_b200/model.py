@@ -426,9 +426,27 @@ class RQAE(nn.Module):
 
     @property
     def subfeature_sims(self):
+        """model.py:157-167: cosine similarities of the rows of ``subfeatures`` per layer, fp16 (nq, K, K).
+        The reference materialises ``subfeatures`` (nq, K, D) fp32 -- 5.9 GB at the 2B shape -- to get them.
+        A subfeature is the affine image ``W_out[l] c + b_out[l]``, so all K*K inner products of a layer follow
+        from the 5x5 Gram matrix of ``[W_out[l] | b_out[l]]``: ``<s_a, s_b> = [c_a;1]^T M_l [c_b;1]``.
+        Same values up to fp32 rounding of a different summation order (a few fp16 ulps in rare entries)."""
         if "_subfeature_sims" not in self.__dict__:
-            n = F.normalize(self.subfeatures, dim=-1)
-            self.__dict__["_subfeature_sims"] = (n @ n.transpose(-1, -2)).to(torch.float16)
+            with torch.no_grad():
+                w = torch.stack([l[1].weight.detach() for l in self.layers]).float()          # (nq, D, cd)
+                b = torch.stack([l[1].bias.detach() for l in self.layers]).float()            # (nq, D)
+                a = torch.cat([w, b.unsqueeze(-1)], dim=-1)                                   # (nq, D, cd+1)
+                m = a.transpose(1, 2) @ a                                                      # (nq, cd+1, cd+1)
+                cb = self.codebook.detach().float()                                            # (nq, K, cd)
+                x = torch.cat([cb, torch.ones_like(cb[..., :1])], dim=-1)                      # (nq, K, cd+1)
+                out = torch.empty(cb.shape[0], cb.shape[1], cb.shape[1], dtype=torch.float16, device=cb.device)
+                step = 64
+                for l0 in range(0, cb.shape[0], step):
+                    xs, ms = x[l0:l0 + step], m[l0:l0 + step]
+                    g = xs @ ms @ xs.transpose(1, 2)                                           # (s, K, K) inner products
+                    n = g.diagonal(dim1=1, dim2=2).clamp_min(0).sqrt().clamp_min(1e-12)         # F.normalize eps
+                    out[l0:l0 + step] = (g / (n.unsqueeze(2) * n.unsqueeze(1))).to(torch.float16)
+            self.__dict__["_subfeature_sims"] = out
         return self.__dict__["_subfeature_sims"]
 
     @property

@@ -99,3 +99,11 @@ def test_derived_tables_match_reference_formulas():
     assert m.subfeature_sims.shape == (3, 625, 625) and m.subfeature_sims.dtype == torch.float16
     ln = torch.tensor([l[1].weight.data.norm(dim=0).mean().item() for l in m.layers])
     assert torch.equal(m.layer_norms, ln)
+    # subfeature_sims comes from the 5x5 Gram of [W_out | b_out], not from the (nq, K, D) subfeatures
+    # tensor the reference materialises (model.py:145-167): same table within one fp16 ulp
+    import torch.nn.functional as F
+    with torch.no_grad():
+        n = F.normalize(m.subfeatures, dim=-1)
+        ref = (n @ n.transpose(-1, -2)).to(torch.float16)
+    assert float((m.subfeature_sims.float() - ref.float()).abs().max()) <= 2 ** -10
+    assert float((m.subfeature_sims == ref).float().mean()) > 0.99
