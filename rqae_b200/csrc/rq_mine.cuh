@@ -37,7 +37,10 @@ __device__ __forceinline__ uint32_t mn_bits(uint32_t d) { return (d & 0x8000u) ?
 
 struct MineSmem {
   uint32_t hist1[MN_BINS];                 // counts, then exclusive prefix
-  uint32_t hist2[4][MN_WARPS][MN_SUB];
+  union {
+    uint32_t hist1b[2][MN_BINS];           // pass 1 only: private copies of the counts (warp % 3 picks hist1 / copy 0 / copy 1)
+    uint32_t hist2[4][MN_WARPS][MN_SUB];   // pass 2
+  };
   uint32_t scan[MN_WARPS];
   uint32_t bin[4], rem[4], key[4], less[4];
   uint32_t base[4][MN_WARPS];
@@ -59,8 +62,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
 
   for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
     const uint4* src = reinterpret_cast<const uint4*>(p.vals + row * p.row_stride);
-    for (int i = tid; i < MN_BINS; i += MN_THREADS) sm.hist1[i] = 0;
-    for (int i = tid; i < 4 * MN_WARPS * MN_SUB; i += MN_THREADS) (&sm.hist2[0][0][0])[i] = 0;
+    for (int i = tid; i < 3 * MN_BINS; i += MN_THREADS) sm.hist1[i] = 0;   // hist1 and its two copies are contiguous
     if (tid < 3) sm.cnt[tid] = 0;
     __syncthreads();
 
@@ -72,14 +74,15 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
       for (int e = 0; e < 8; e++) {
         if (i0 + e < w_hi) {
           const uint32_t d = mn_dkey((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-          atomicAdd(&sm.hist1[d >> 5], 1u);
+          atomicAdd(&sm.hist1[(warp % 3) * MN_BINS + (d >> 5)], 1u);
         }
       }
     }
     __syncthreads();
     // exclusive prefix over the 2048 bins (2 per thread)
     {
-      const uint32_t a = sm.hist1[2 * tid], b = sm.hist1[2 * tid + 1];
+      const uint32_t a = sm.hist1[2 * tid] + sm.hist1b[0][2 * tid] + sm.hist1b[1][2 * tid];
+      const uint32_t b = sm.hist1[2 * tid + 1] + sm.hist1b[0][2 * tid + 1] + sm.hist1b[1][2 * tid + 1];
       uint32_t x = a + b;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
       sm.hist1[2 * tid + 1] = excl + a;
     }
     __syncthreads();
+    for (int i = tid; i < 4 * MN_WARPS * MN_SUB; i += MN_THREADS) (&sm.hist2[0][0][0])[i] = 0;   // the copies' space is reused
     if (tid < 4) {   // last bin whose exclusive prefix is <= rank
       const uint32_t r = (uint32_t)rank[tid];
       int lo = 0, hi = MN_BINS - 1;
@@ -177,7 +181,6 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
       for (long long i0 = w_lo + lane * 8; i0 - lane * 8 < w_hi; i0 += 256) {   // whole warp iterates together
         uint32_t d[8];
         bool live[8];
-        uint32_t neq[4] = {0, 0, 0, 0};
         bool cand = false;
         if (i0 < w_hi) {
           const uint4 v = __ldg(src + i0 / 8);
@@ -186,16 +189,19 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
           for (int e = 0; e < 8; e++) {
             live[e] = i0 + e < w_hi;
             d[e] = mn_dkey((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-            if (live[e]) {
-              neq[0] += d[e] == K0; neq[1] += d[e] == K1; neq[2] += d[e] == K2; neq[3] += d[e] == K3;
-              cand |= d[e] <= K0 || d[e] >= K3 || (d[e] >= K1 && d[e] <= K2);
-            }
+            // inside or on the edge of a window (an element equal to a boundary key always is)
+            cand |= live[e] && (d[e] <= K0 || d[e] >= K3 || (d[e] >= K1 && d[e] <= K2));
           }
         } else {
 #pragma unroll
           for (int e = 0; e < 8; e++) { live[e] = false; d[e] = 0; }
         }
         if (!__any_sync(0xffffffffu, cand)) continue;
+        uint32_t neq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          if (live[e]) { neq[0] += d[e] == K0; neq[1] += d[e] == K1; neq[2] += d[e] == K2; neq[3] += d[e] == K3; }
+        }
         // tie ranks: exclusive prefix over the lanes of the per-lane tie counts, per boundary key
         uint32_t ex[4];
 #pragma unroll

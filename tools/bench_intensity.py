@@ -4,7 +4,7 @@ usage: python tools/bench_intensity.py [--tokens N] [--features F] [--reps R]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from rqae_b200.feature import intensity_many
+from rqae_b200.feature import intensity_many, select_top_middle_bottom
 
 CUTS = [2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1023]
 
@@ -43,6 +43,17 @@ def main():
     ms = e0.elapsed_time(e1) / a.reps
     flop = 2.0 * a.tokens * a.features * 4096
     byts = a.tokens * 2048 + a.features * len(CUTS) * a.tokens * 2
+    res = intensity_many(m, codes, centers, CUTS, layer_weights=lw, out=out)
+    select_top_middle_bottom(res, 100)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.reps):
+        idx, val = select_top_middle_bottom(res, 100)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_sel = e0.elapsed_time(e1) / a.reps
+    print(json.dumps({"select_ms": ms_sel, "select_gbs": a.features * len(CUTS) * a.tokens * 2 / ms_sel / 1e6,
+                      "rows": a.features * len(CUTS)}))
     print(json.dumps({"tokens": a.tokens, "features": a.features, "ms": ms, "tokens_per_s": a.tokens / ms * 1e3,
                       "tflops": flop / ms / 1e9, "out_gbs": byts / ms / 1e6,
                       "note": "whole call: schedule + code transpose + feature operand + GEMM"}))
