@@ -13,6 +13,9 @@
 #include <thread>
 #include <vector>
 #include <math.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/rqae_b200.h"
 #include "rq_decode.cuh"
@@ -545,11 +548,20 @@ struct HostPipe {
 };
 static thread_local HostPipe g_pipe;
 
-// int16 -> int32 / int64 on `threads` host threads (codes cross PCIe as int16 and are widened here)
+// int16 -> int32 / int64 on `threads` host threads (codes cross PCIe as int16 and are widened here).  The wide
+// result is written once and not read again by this library: streaming stores keep it out of the caches and
+// spare the read-for-ownership of every destination line (with 8 ranks widening at once the host's memory
+// bandwidth, not PCIe, bounds the end-to-end path).
 static void widen_codes(const int16_t* src, void* dst, size_t n, int code_dtype, int threads) {
   auto work = [=](size_t lo, size_t hi) {
+#if defined(__x86_64__)
+    if (code_dtype == 2) { long long* d = (long long*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si64(d + i, (long long)src[i]); }
+    else { int* d = (int*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si32(d + i, (int)src[i]); }
+    _mm_sfence();
+#else
     if (code_dtype == 2) { int64_t* d = (int64_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
     else { int32_t* d = (int32_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
+#endif
   };
   if (threads <= 1 || n < (1u << 16)) { work(0, n); return; }
   std::vector<std::thread> pool;
