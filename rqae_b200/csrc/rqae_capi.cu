@@ -13,7 +13,7 @@
 #include <thread>
 #include <vector>
 #include <math.h>
-#if defined(__x86_64__)
+#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
 #include <emmintrin.h>
 #endif
 
@@ -554,7 +554,7 @@ static thread_local HostPipe g_pipe;
 // bandwidth, not PCIe, bounds the end-to-end path).
 static void widen_codes(const int16_t* src, void* dst, size_t n, int code_dtype, int threads) {
   auto work = [=](size_t lo, size_t hi) {
-#if defined(__x86_64__)
+#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
     if (code_dtype == 2) { long long* d = (long long*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si64(d + i, (long long)src[i]); }
     else { int* d = (int*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si32(d + i, (int)src[i]); }
     _mm_sfence();
