@@ -1,0 +1,14 @@
+#!/bin/bash
+# compute-sanitizer over small cases of every kernel (memcheck, then racecheck on the shared-memory heavy ones).
+#   usage: gpurun --timeout 900 -- 'bash tools/sanitize.sh'
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+CS=/usr/local/cuda/bin/compute-sanitizer
+echo "=== memcheck: mining path (intensity GEMM, transpose, pack, radix select) ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x \
+  -k "small or dtypes or api_shapes or 5000 or 4097 or 257 or 100-100" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_mining.log
+echo "=== memcheck: forward / decode small cases ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -x -k "small_forward or decode" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_fwd.log
+echo "=== racecheck: radix select ==="
+timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "5000 or 4097 or 257" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine.log
