@@ -409,9 +409,21 @@ def run_b200(args, rank, local_rank, world):
             b.record(); torch.cuda.synchronize(dev)
             return out, Ts * reps / (a.elapsed_time(b) * 1e-3)
         codes_s, enc_rate = timed(lambda: model.encode(xs, out_dtype=torch.int16))
-        _, dec_rate = timed(lambda: model.decode(codes_s))
+        dec_exact, dec_rate = timed(lambda: model.decode(codes_s))
         extra = {"encode_only_int16_tokens_per_s": enc_rate, "decode_only_tokens_per_s": dec_rate, "tokens": Ts,
                  "decode_frac_of_fp32_peak": None}
+        if not args.no_extras:
+            try:   # opt-in tensor-core decode (tcgen05 GEMM over the codes), not bit-exact: rate and error vs the exact kernel
+                tc = {}
+                for prec, npass in (("f16", 1), ("f16x3", 3)):
+                    dq, rate = timed(lambda: model.decode(codes_s, precision=prec))
+                    tc[prec] = {"tokens_per_s": rate, "tflops": rate * npass * 2 * 4 * NQ * D / 1e12,
+                                "max_err_over_max_abs": float(((dq - dec_exact).abs().max() / dec_exact.abs().max()).item())}
+                    del dq
+                extra["decode_tensor_core_opt_in"] = tc
+            except Exception as e:
+                extra["decode_tensor_core_opt_in"] = {"error": repr(e)}
+        del dec_exact
         if not args.no_extras and world == 1:
             try:
                 extra["mining"] = mining_extras(torch, model, codes_s[0, : 1 << 17], dev)

@@ -114,7 +114,7 @@ int rqae_forward_host_release(void);
  * Computed as one tcgen05 GEMM over the rank-4 factors of sims; the sum is accumulated in
  * fp32 from fp16 factors, so values agree with the reference within the tolerance DESIGN.md states,
  * not bitwise.  The roundings after the sum are the reference's.
- *   cb_norm            [K][4] fp32 = F.normalize(codebook[0], dim=-1)            (K + 1 <= 1024)
+ *   cb_norm            [K][4] fp32 = F.normalize(codebook[0], dim=-1)            (K + 1 <= 640)
  *   codes              [n_tokens][code_stride] of code_dtype (codes outside [0,K) contribute 0)
  *   centers            int32 [n_features][center_stride]
  *   layer_weights_f16  fp16 [>= max cut + 1]
@@ -140,6 +140,22 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
  * top_k <= 256, top_k <= n < 2^31. */
 int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t row_stride, int64_t n, int top_k,
                                       int32_t* idx_out, void* val_out, void* stream);
+
+/* Opt-in tensor-core variant of RQAE.decode (rqae/model.py:232-252): the same sum as rqae_decode_f32,
+ * evaluated as one tcgen05 GEMM  q[t][d] = sum_{l,j} V[t][4l+j] * U[d][4l+j] + sum_l b_out[l][d]  with
+ * V = codebook[0][codes] and U = W_out, fp16 operands and fp32 accumulation.  NOT bit-exact (the default
+ * rqae_decode_f32 is): `passes` = 1 rounds both operands to fp16 (relative error of q about 3e-4),
+ * `passes` = 3 adds the fp16 remainders of both operands (V_hi U_hi + V_hi U_lo + V_lo U_hi: about 2e-5,
+ * which is the tensor core's own fp32 accumulation over 12 288 terms, no longer the operand rounding).
+ *   w_out [nq][dim][4] and b_out [nq][dim]: the reference parameters stacked over layers (layers.{l}.1.*)
+ *   codebook0 [K][4], K + 1 <= 640; codes / code_dtype / code_stride / layer_mask / nq_codes as in rqae_decode_f32
+ *   workspace: device scratch of rqae_decode_tc_workspace_bytes(...) bytes, 1024-byte aligned
+ * nq_codes * passes <= 3200 layers-passes (200 K-blocks of 16 layers). */
+size_t rqae_decode_tc_workspace_bytes(int nq_codes, int dim, int64_t n_tokens, int passes);
+int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* codebook0, int nq, int nq_codes, int dim,
+                       int codebook_dim, int K, const void* codes, int code_dtype, int64_t code_stride,
+                       const uint8_t* layer_mask, int64_t n_tokens, float* q_out, int passes, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Measurement helpers used by bench.py for the roofline denominators (no model semantics):
  * sustained rate of the FP32 pipe, in FLOP per call; time it with CUDA events on `stream`.

@@ -43,8 +43,8 @@ constexpr int IT_V_BYTES = IT_TOK * 128;        // 32 KB
 constexpr int IT_U_TILE = IT_FT * 128;          // 16 KB
 constexpr int IT_U_BYTES = 2 * IT_U_TILE;       // both feature tiles of the pair
 constexpr int IT_MAX_CUTS = 64;
-constexpr int IT_MAX_KB = 192;
-constexpr int IT_LUT_ROWS = 1024;               // codebook rows + the zero row must fit
+constexpr int IT_MAX_KB = 200;                  // nq = 1024 in three passes (decode, f16x3) is 192 K-blocks
+constexpr int IT_LUT_ROWS = 640;                // codebook rows + the zero row must fit (5^4 + 1); two tables
 constexpr int IT_STG_PITCH = 80;                // bytes per staged row: 32 tokens fp16 + 16 (conflict-free 128-bit access)
 constexpr int IT_STG_WARP = 32 * IT_STG_PITCH;  // per epilogue warp
 constexpr int IT_THREADS = 448;
@@ -52,7 +52,8 @@ constexpr int IT_EPI_WARPS = 8;
 constexpr int IT_BUILDERS = 128;
 
 struct IntKBlock {   // one K-block of the schedule: layers l0 .. l0+n-1 (n <= 16), the rest of the 16 slots zero
-  int l0, n, cut, pad;   // cut >= 0: this block ends the segment of that cut (the epilogue emits it)
+  int l0, n, cut, tab;   // cut >= 0: this block ends the segment of that cut (the epilogue emits it);
+                         // tab: which of the two lookup tables the token operand is built from (decode: 0 hi, 1 lo)
 };
 
 struct IntParams {
@@ -63,11 +64,16 @@ struct IntParams {
   const unsigned char* u_tiles;  // [F_tiles][NKB][16 KB]
   const IntKBlock* sched;        // [NKB]
   const float* wcum;             // [n_cuts] float(fp16(sum_{l<=cut} w_l)), then [n_cuts] its fp32 reciprocal
-  const uint2* lut;              // [K+1] fp16x4 normalised codebook rows, row K = 0
+  const uint2* lut;              // [2][IT_LUT_ROWS] fp16x4 codebook rows (table 0; table 1 only in decode f16x3), row K = 0
   int K, NKB, n_cuts, F, F_tiles;
   __half* out;                   // [F][n_cuts][out_stride]
   long long out_stride;
   long long n_tok_tiles;
+  // decode epilogue (EPI = 1): q_out[t][d] = accumulator + bias[d], fp32, rows of `D` floats, t < T
+  float* q_out;
+  const float* bias;
+  long long T;
+  int D;
   int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start
 };
 
@@ -75,7 +81,7 @@ struct IntSmem {
   static constexpr int VRING = 0;
   static constexpr int URING = IT_VSTAGES * IT_V_BYTES;
   static constexpr int LUT = URING + IT_USTAGES * IT_U_BYTES;
-  static constexpr int SCHED = LUT + IT_LUT_ROWS * 8;
+  static constexpr int SCHED = LUT + 2 * IT_LUT_ROWS * 8;
   static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
   static constexpr int STG = WCUM + 2 * IT_MAX_CUTS * 4;
   static constexpr int BARS = STG + IT_EPI_WARPS * IT_STG_WARP;
@@ -143,6 +149,10 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// EPI = 0: feature intensities (fp16 out[f][cut][t] with the reference's roundings).
+// EPI = 1: tensor-core decode -- "features" are the D output dimensions, U holds W_out, one cut at the last layer,
+//          out is q_out[t][d] fp32 (+ the summed out-projection biases); opt-in, not bit-exact (rq_decode.cuh is).
+template <int EPI>
 __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,7 +168,10 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   const float* wcum_s = reinterpret_cast<const float*>(smem + IntSmem::WCUM);
 
   // ---- one-time setup ----
-  for (int i = threadIdx.x; i <= p.K; i += IT_THREADS) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
+  for (int i = threadIdx.x; i <= p.K; i += IT_THREADS) {
+    reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
+    if (EPI == 1) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
+  }
   for (int i = threadIdx.x; i < p.NKB * 4; i += IT_THREADS)
     reinterpret_cast<int*>(smem + IntSmem::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
   for (int i = threadIdx.x; i < 2 * p.n_cuts; i += IT_THREADS)
@@ -272,10 +285,11 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 512) : "memory");
       }
     };
-    auto step = [&](uint32_t (&c)[IT_LPB], Pos& fut, Pos& pf) {
+    auto step = [&](uint32_t (&c)[IT_LPB], const Pos& now, Pos& fut, Pos& pf) {
       uint32_t a0[IT_LPB], a1[IT_LPB];   // table byte offsets of this block's two rows
+      const uint32_t tsel = (EPI == 1) ? (uint32_t)(sched[now.kb].tab & 1) * (IT_LUT_ROWS * 8u) : 0u;
 #pragma unroll
-      for (int i = 0; i < IT_LPB; i++) { a0[i] = (c[i] & 0xFFFFu) * 8u; a1[i] = (c[i] >> 16) * 8u; }
+      for (int i = 0; i < IT_LPB; i++) { a0[i] = (c[i] & 0xFFFFu) * 8u + tsel; a1[i] = (c[i] >> 16) * 8u + tsel; }
       fetch(c, fut);
       next(fut);
       l2_prefetch(pf);
@@ -308,10 +322,10 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     fetch(cB, fut); next(fut);
     for (int i = 0; i < IT_PF; i++) { if (i >= 2) l2_prefetch(pf); next(pf); }
     while (cur.u < n_units) {
-      step(cA, fut, pf);
+      step(cA, cur, fut, pf);
       next(cur);
       if (cur.u >= n_units) break;
-      step(cB, fut, pf);
+      step(cB, cur, fut, pf);
       next(cur);
     }
   } else {
@@ -335,8 +349,31 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           if (lane == 0) mbar_arrive(acc_free);
           continue;
         }
-        const float inv = wcum_s[p.n_cuts + cut];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * IT_TOK;
+        if (EPI == 1) {
+          // decode: lane = output dimension d, columns = tokens; a store instruction covers 32 consecutive floats
+          const int d = (2 * pr + acc) * IT_FT + q * 32 + lane;
+          const float bsum = d < p.D ? __ldg(p.bias + d) : 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < IT_TOK / 32; ch++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == IT_TOK / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_free);
+            }
+            float* o = p.q_out + (size_t)(tok0 + ch * 32) * p.D + d;
+            if (d < p.D && !(p.dbg & 1)) {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (tok0 + ch * 32 + j < p.T) __stcs(o + (size_t)j * p.D, __uint_as_float(v[j]) + bsum);
+            }
+          }
+          continue;
+        }
+        const float inv = wcum_s[p.n_cuts + cut];
         // After the reference's roundings the warp's 32 features x 32 tokens go through a private staging
         // tile so that a store instruction writes 8 rows x 64 contiguous bytes instead of 32 rows x 16.
         const int frow0 = (2 * pr + acc) * IT_FT + q * 32;
@@ -422,7 +459,7 @@ __global__ void int_prep_kernel(const IntPrepParams p) {
     for (int l0 = prev + 1; l0 <= cut; l0 += IT_LPB) {
       const int n = min(IT_LPB, cut - l0 + 1);
       IntKBlock b;
-      b.l0 = l0; b.n = n; b.cut = (l0 + n - 1 == cut) ? c : -1; b.pad = 0;
+      b.l0 = l0; b.n = n; b.cut = (l0 + n - 1 == cut) ? c : -1; b.tab = 0;
       p.sched[kb++] = b;
     }
     for (; l <= cut; l++) run = __fadd_rn(run, __half2float(p.w[l]));
@@ -516,6 +553,91 @@ __global__ void int_pack_u_kernel(const int* __restrict__ centers, long long cen
   unsigned char* tile = u_tiles + ((size_t)ft * NKB + kb) * (size_t)IT_U_TILE;
   const int chunk = s >> 1;
   *reinterpret_cast<uint2*>(tile + r * 128 + (((chunk ^ (r & 7)) << 4) | ((s & 1) << 3))) = val;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tensor-core decode (EPI = 1): preparation kernels
+// ---------------------------------------------------------------------------------------------------
+// q[t][d] = sum_l sum_j c[t][l][j] * W_out[l][d][j] + sum_l b_out[l][d]  (rqae/model.py:232-252) as the same GEMM:
+// V[t][4l+j] = codebook[0][code_t[l]][j], U[d][4l+j] = W_out[l][d][j].  One pass rounds both factors to fp16
+// (relative error of q ~2e-4); three passes add the fp16 remainders: V_hi U_hi + V_hi U_lo + V_lo U_hi (~2e-5: what is
+// left is the tensor core's fp32 accumulation over 3 x 4096 terms).
+// K-block tab: bit 0 = token operand from the remainder table, bit 1 = weight operand is the remainder.
+struct DecPrepParams {
+  int L, K, passes;
+  const float* codebook0;   // [K][4]
+  IntKBlock* sched;
+  float* wcum;
+  uint2* lut;               // [2][IT_LUT_ROWS]
+};
+
+__device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d) {
+  const __half2 x = __floats2half2_rn(a, b), y = __floats2half2_rn(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&x), *reinterpret_cast<const uint32_t*>(&y));
+}
+__device__ __forceinline__ float h_rem(float v) { return v - __half2float(__float2half_rn(v)); }
+
+__global__ void dec_prep_kernel(const DecPrepParams p) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int c = gid; c <= p.K; c += gridDim.x * blockDim.x) {
+    uint2 hi = make_uint2(0u, 0u), lo = hi;
+    if (c < p.K) {
+      const float4 v = reinterpret_cast<const float4*>(p.codebook0)[c];
+      hi = pack_h4(v.x, v.y, v.z, v.w);
+      lo = pack_h4(h_rem(v.x), h_rem(v.y), h_rem(v.z), h_rem(v.w));
+    }
+    p.lut[c] = hi;
+    p.lut[IT_LUT_ROWS + c] = lo;
+  }
+  if (gid != 0) return;
+  int kb = 0;
+  for (int ps = 0; ps < p.passes; ps++) {
+    for (int l0 = 0; l0 < p.L; l0 += IT_LPB) {
+      IntKBlock b;
+      b.l0 = l0; b.n = min(IT_LPB, p.L - l0); b.cut = -1; b.tab = ps == 0 ? 0 : (ps == 1 ? 2 : 1);
+      p.sched[kb++] = b;
+    }
+  }
+  p.sched[kb - 1].cut = 0;
+  p.wcum[0] = 1.0f;
+  p.wcum[1] = 1.0f;
+}
+
+// weight operand tiles: [F_tiles][NKB] tiles of 128 output dimensions x 64 k, same swizzled layout as the feature tiles
+__global__ void dec_pack_u_kernel(const float* __restrict__ w_out, int D, int F_tiles, int NKB,
+                                  const IntKBlock* __restrict__ sched, const unsigned char* __restrict__ layer_mask,
+                                  unsigned char* __restrict__ u_tiles) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)F_tiles * NKB * IT_FT * IT_LPB;
+  if (gid >= total) return;
+  const int s = (int)(gid % IT_LPB);
+  const int r = (int)((gid / IT_LPB) % IT_FT);
+  const int kb = (int)((gid / (IT_LPB * IT_FT)) % NKB);
+  const int ft = (int)(gid / ((long long)IT_LPB * IT_FT * NKB));
+  const IntKBlock b = sched[kb];
+  const int d = ft * IT_FT + r;
+  uint2 val = make_uint2(0u, 0u);
+  if (d < D && s < b.n) {
+    const int l = b.l0 + s;
+    if (layer_mask == nullptr || layer_mask[l]) {
+      const float4 w = reinterpret_cast<const float4*>(w_out)[(size_t)l * D + d];
+      val = (b.tab & 2) ? pack_h4(h_rem(w.x), h_rem(w.y), h_rem(w.z), h_rem(w.w)) : pack_h4(w.x, w.y, w.z, w.w);
+    }
+  }
+  unsigned char* tile = u_tiles + ((size_t)ft * NKB + kb) * (size_t)IT_U_TILE;
+  const int chunk = s >> 1;
+  *reinterpret_cast<uint2*>(tile + r * 128 + (((chunk ^ (r & 7)) << 4) | ((s & 1) << 3))) = val;
+}
+
+// bias[d] = sum over the selected layers of b_out[l][d], in layer order
+__global__ void dec_bias_kernel(const float* __restrict__ b_out, int L, int D, const unsigned char* __restrict__ layer_mask,
+                                float* __restrict__ bias) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int l = 0; l < L; l++)
+    if (layer_mask == nullptr || layer_mask[l]) acc = __fadd_rn(acc, b_out[(size_t)l * D + d]);
+  bias[d] = acc;
 }
 
 }  // namespace rq

@@ -47,6 +47,22 @@ thread_local int64_t g_launches = 0;
     }                                    \
   } while (0)
 
+// Opt a kernel in to its dynamic shared-memory size, once per (kernel, device): the attribute is per device, and a
+// process may drive more than one.
+cudaError_t ensure_dynamic_smem(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, cudaError_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({kern, dev});
+  if (it != done.end()) return it->second;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done[{kern, dev}] = e;
+  return e;
+}
+
 int device_sm_count(int* sms) {
   int dev = 0;
   RQ_CUDA(cudaGetDevice(&dev));
@@ -327,10 +343,7 @@ template <int E, int EC, int CH, int NSLOT, int TG, bool DBG>
 int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   using C = rq::FwdCfg<E, EC, CH, NSLOT, TG>;
   auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG, DBG>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL); });
-  RQ_CUDA(attr_err);
+  RQ_CUDA(ensure_dynamic_smem((const void*)kern, C::SM_TOTAL));
   const long long n_units = (prm.n_tokens + 2 * TG - 1) / (2 * TG);
   const int grid = (int)(n_units < sms ? n_units : sms);
   rq::FwdParams p2 = prm;
@@ -369,7 +382,7 @@ const char* rqae_strerror(int code) {
   switch (code) {
     case RQAE_OK: return "ok";
     case RQAE_EINVAL: return "invalid argument";
-    case RQAE_EUNSUPPORTED: return "unsupported shape (codebook_dim must be 4, dim <= 3584, K <= 65535; intensity: K < 1024, <= 64 cuts; selection: top_k <= 256)";
+    case RQAE_EUNSUPPORTED: return "unsupported shape (codebook_dim must be 4, dim <= 3584, K <= 65535; intensity and tensor-core decode: K < 640, <= 64 cuts; selection: top_k <= 256)";
     case RQAE_ECUDA: return "CUDA runtime error";
     case RQAE_ENODEVICE: return "current device is not an sm_100 (B200) GPU";
     case RQAE_ESIZE: return "buffer too small";
@@ -691,7 +704,7 @@ static int int_layout(const int32_t* cuts, int n_cuts, int F, int64_t n_tokens, 
   size_t off = 0;
   o->off_sched = off; off = up(off + (size_t)rq::IT_MAX_KB * sizeof(rq::IntKBlock));
   o->off_wcum = off;  off = up(off + 2 * (size_t)rq::IT_MAX_CUTS * 4);
-  o->off_lut = off;   off = up(off + (size_t)rq::IT_LUT_ROWS * 8);
+  o->off_lut = off;   off = up(off + 2 * (size_t)rq::IT_LUT_ROWS * 8);
   o->off_u = off;     off = up(off + (size_t)o->F_tiles * nkb * rq::IT_U_TILE);
   o->off_codes = off; off = up(off + (size_t)o->L * (size_t)o->T_pad * 2);
   o->total = off;
@@ -749,21 +762,17 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
     RQ_CUDA(cudaGetLastError());
   }
   // 4. the GEMM
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(rq::rq_intensity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rq::IntSmem::TOTAL);
-  });
-  RQ_CUDA(attr_err);
+  RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_intensity_kernel<0>, rq::IntSmem::TOTAL));
   rq::IntParams ip;
   ip.codes_p = (const uint32_t*)(ws + L.off_codes); ip.L = L.L; ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
   ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
+  ip.q_out = nullptr; ip.bias = nullptr; ip.T = n_tokens; ip.D = 0;
   ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
   const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
-  rq::rq_intensity_kernel<<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
+  rq::rq_intensity_kernel<0><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
   RQ_CUDA(cudaGetLastError());
   g_launches += 4;
   return RQAE_OK;
@@ -785,6 +794,95 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
   rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
   RQ_CUDA(cudaGetLastError());
   g_launches++;
+  return RQAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core decode (opt-in; rq_decode.cuh is the bit-exact default)
+// ---------------------------------------------------------------------------------------------
+struct DecTcLayout {
+  int NKB, F_tiles;
+  long long T_pad;
+  size_t off_sched, off_wcum, off_lut, off_bias, off_u, off_codes, total;
+};
+
+static int dec_tc_layout(int nq_codes, int dim, int64_t n_tokens, int passes, DecTcLayout* o) {
+  if (nq_codes <= 0 || dim <= 0 || n_tokens < 0 || (passes != 1 && passes != 3)) return RQAE_EINVAL;
+  o->NKB = passes * ((nq_codes + rq::IT_LPB - 1) / rq::IT_LPB);
+  if (o->NKB > rq::IT_MAX_KB) return RQAE_EUNSUPPORTED;
+  o->F_tiles = (dim + rq::IT_FT - 1) / rq::IT_FT;
+  o->T_pad = (n_tokens + rq::IT_TOK - 1) / rq::IT_TOK * rq::IT_TOK;
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  size_t off = 0;
+  o->off_sched = off; off = up(off + (size_t)rq::IT_MAX_KB * sizeof(rq::IntKBlock));
+  o->off_wcum = off;  off = up(off + 2 * (size_t)rq::IT_MAX_CUTS * 4);
+  o->off_lut = off;   off = up(off + 2 * (size_t)rq::IT_LUT_ROWS * 8);
+  o->off_bias = off;  off = up(off + (size_t)o->F_tiles * rq::IT_FT * 4);
+  o->off_u = off;     off = up(off + (size_t)o->F_tiles * o->NKB * rq::IT_U_TILE);
+  o->off_codes = off; off = up(off + (size_t)nq_codes * (size_t)o->T_pad * 2);
+  o->total = off;
+  return RQAE_OK;
+}
+
+size_t rqae_decode_tc_workspace_bytes(int nq_codes, int dim, int64_t n_tokens, int passes) {
+  DecTcLayout L;
+  if (dec_tc_layout(nq_codes, dim, n_tokens, passes, &L)) return 0;
+  return L.total;
+}
+
+int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* codebook0, int nq, int nq_codes, int dim,
+                       int codebook_dim, int K, const void* codes, int code_dtype, int64_t code_stride,
+                       const uint8_t* layer_mask, int64_t n_tokens, float* q_out, int passes, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!w_out || !b_out || !codebook0 || !codes || !q_out || !workspace || nq <= 0 || nq_codes <= 0 || nq_codes > nq || K <= 0)
+    return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2 || code_stride < nq_codes) return RQAE_EINVAL;
+  if (codebook_dim != 4 || K + 1 > rq::IT_LUT_ROWS) return RQAE_EUNSUPPORTED;
+  DecTcLayout L;
+  int rc = dec_tc_layout(nq_codes, dim, n_tokens, passes, &L);
+  if (rc) return rc;
+  if (((uintptr_t)workspace & 1023) || workspace_bytes < L.total) return RQAE_ESIZE;
+  if (n_tokens == 0) return RQAE_OK;
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  rq::DecPrepParams pp;
+  pp.L = nq_codes; pp.K = K; pp.passes = passes; pp.codebook0 = codebook0;
+  pp.sched = (rq::IntKBlock*)(ws + L.off_sched); pp.wcum = (float*)(ws + L.off_wcum); pp.lut = (uint2*)(ws + L.off_lut);
+  rq::dec_prep_kernel<<<4, 256, 0, st>>>(pp);
+  RQ_CUDA(cudaGetLastError());
+  {
+    dim3 grid((unsigned)(L.T_pad / rq::IT_TOK), (unsigned)((nq_codes + 31) / 32)), block(256);
+    uint32_t* ct = (uint32_t*)(ws + L.off_codes);
+    if (code_dtype == 2) rq::int_transpose_kernel<long long><<<grid, block, 0, st>>>((const long long*)codes, code_stride, n_tokens, nq_codes, K, ct);
+    else if (code_dtype == 1) rq::int_transpose_kernel<int><<<grid, block, 0, st>>>((const int*)codes, code_stride, n_tokens, nq_codes, K, ct);
+    else rq::int_transpose_kernel<short><<<grid, block, 0, st>>>((const short*)codes, code_stride, n_tokens, nq_codes, K, ct);
+    RQ_CUDA(cudaGetLastError());
+  }
+  {
+    const long long total = (long long)L.F_tiles * L.NKB * rq::IT_FT * rq::IT_LPB;
+    rq::dec_pack_u_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_out, dim, L.F_tiles, L.NKB,
+                                                                          (const rq::IntKBlock*)(ws + L.off_sched), layer_mask,
+                                                                          ws + L.off_u);
+    RQ_CUDA(cudaGetLastError());
+    rq::dec_bias_kernel<<<(dim + 127) / 128, 128, 0, st>>>(b_out, nq_codes, dim, layer_mask, (float*)(ws + L.off_bias));
+    RQ_CUDA(cudaGetLastError());
+  }
+  RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_intensity_kernel<1>, rq::IntSmem::TOTAL));
+  rq::IntParams ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.codes_p = (const uint32_t*)(ws + L.off_codes); ip.L = nq_codes; ip.T_pad = L.T_pad; ip.u_tiles = ws + L.off_u;
+  ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
+  ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = 1; ip.F = dim; ip.F_tiles = L.F_tiles;
+  ip.n_tok_tiles = L.T_pad / rq::IT_TOK; ip.q_out = q_out; ip.bias = (const float*)(ws + L.off_bias); ip.T = n_tokens; ip.D = dim;
+  { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
+  const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
+  const int grid = (int)(units < sms ? units : sms);
+  rq::rq_intensity_kernel<1><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
+  RQ_CUDA(cudaGetLastError());
+  g_launches += 5;
   return RQAE_OK;
 }
 

@@ -121,6 +121,7 @@ class RQAE(nn.Module):
     # ------------------------------------------------------------------ packed weights
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
+        self.__dict__.pop("_tc_weights", None)
         for k in ("_codebook_sims", "_subfeatures", "_subfeature_sims", "_layer_norms"):
             self.__dict__.pop(k, None)
         return super()._apply(fn, *args, **kwargs)
@@ -323,10 +324,60 @@ class RQAE(nn.Module):
         """model.py:236-248."""
         return self._run_decode(None, codebook_values, layers)
 
-    def decode(self, indices, layers=None):
+    def decode(self, indices, layers=None, precision: str = "fp32"):
         """model.py:250-252: gather from codebook[0] + sum of the selected layers' out-projections, fused
-        (the (B,S,nq,4) intermediate of the reference is never materialised)."""
-        return self._run_decode(indices, None, layers)
+        (the (B,S,nq,4) intermediate of the reference is never materialised).
+
+        ``precision="fp32"`` (default) is bit-identical to the reference.  ``"f16"`` / ``"f16x3"`` opt in to the
+        tensor-core path (one tcgen05 GEMM over the codes; fp16 operands, fp32 accumulation): relative error of
+        the result about 2e-4 / 2e-5 (measured, max error over max |q|), 15x / 8x faster.  Not the default because it is not bit-exact."""
+        if precision == "fp32":
+            return self._run_decode(indices, None, layers)
+        if precision not in ("f16", "f16x3"):
+            raise ValueError("precision must be 'fp32', 'f16' or 'f16x3'")
+        return self._run_decode_tc(indices, layers, 1 if precision == "f16" else 3)
+
+    def _run_decode_tc(self, codes: torch.Tensor, layers, passes: int):
+        if not codes.is_cuda:
+            raise RuntimeError("rqae_b200.RQAE.decode needs CUDA tensors; there is no CPU fallback")
+        lib = _lib.load()
+        dev = codes.device
+        if codes.dtype not in (torch.int16, torch.int32, torch.int64):
+            codes = codes.to(torch.int64)
+        codes = codes.contiguous()
+        lead, nq_codes = codes.shape[:-1], min(codes.shape[-1], self.num_quantizers)
+        mask, any_sel = self._layer_mask(layers, nq_codes, dev)
+        if not any_sel:
+            return None
+        n = int(math.prod(lead)) if len(lead) else 1
+        q = torch.empty(*lead, self.dim, dtype=torch.float32, device=dev)
+        if n == 0:
+            return q
+        key = self._weights_key()
+        cache = self.__dict__.get("_tc_weights")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                w_out = torch.stack([l[1].weight.detach() for l in self.layers]).float().contiguous()   # (nq, D, 4)
+                b_out = torch.stack([l[1].bias.detach() for l in self.layers]).float().contiguous()     # (nq, D)
+            cache = (key, w_out, b_out)
+            self.__dict__["_tc_weights"] = cache
+        _, w_out, b_out = cache
+        cb0 = self.codebook.detach()[0].float().contiguous()
+        nbytes = lib.rqae_decode_tc_workspace_bytes(nq_codes, self.dim, n, passes)
+        if nbytes == 0:
+            raise NotImplementedError("tensor-core decode supports at most 3200 layer-passes (nq * passes)")
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        with torch.cuda.device(dev):
+            rc = lib.rqae_decode_tc_f32(
+                w_out.data_ptr(), b_out.data_ptr(), cb0.data_ptr(), self.num_quantizers, nq_codes, self.dim,
+                self.codebook_dim, self.codebook.shape[1], codes.data_ptr(),
+                _lib.CODE_DTYPE[str(codes.dtype).split(".")[-1]], codes.shape[-1], 0 if mask is None else mask.data_ptr(),
+                n, q.data_ptr(), passes, ws_ptr, nbytes, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "rqae_decode_tc_f32")
+        for t in (ws, cb0, codes):
+            t.record_stream(torch.cuda.current_stream(dev))
+        return q
 
     def forward_host(self, x_host: torch.Tensor, max_layers=float("inf"), want_q: bool = True,
                      out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 33152, device=None,

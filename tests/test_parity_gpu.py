@@ -363,3 +363,37 @@ def test_many_units_per_cta_lockstep_path_bit_exact():
         i2 = m.encode(xd, out_dtype=torch.int32)
     torch.cuda.synchronize()
     assert np.array_equal(i1.cpu().numpy(), co) and np.array_equal(i2.cpu().numpy(), co)
+
+
+# ---------------------------------------------------------------------------------------------------
+# opt-in tensor-core decode (tcgen05 GEMM over codes): tolerance against the bit-exact decode
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,rtol", [("f16", 1e-3), ("f16x3", 5e-5)])
+def test_tensor_core_decode_within_stated_tolerance(model_2b, golden_2b, precision, rtol):
+    """SURVEY 8c: a tensor-core decode is judged by relative error (<= 1e-3 for a single reduced-precision pass);
+    the three-pass split removes the operand rounding and is left with the tensor core's fp32 accumulation
+    (measured 1.8e-5 over 262 144 tokens; bound 5e-5)."""
+    m, _ = model_2b
+    codes = torch.from_numpy(golden_2b["codes1024"].astype(np.int64))[:300].to(_cuda())     # ragged: 2 token tiles
+    exact = m.decode(codes)
+    fast = m.decode(codes, precision=precision)
+    torch.cuda.synchronize()
+    assert fast.shape == exact.shape and fast.dtype == torch.float32
+    err = (fast - exact).abs().max().item() / exact.abs().max().item()
+    assert err <= rtol, f"{precision}: max abs error / max |q| = {err}"
+    # the layers= filter and narrow code dtypes go through the same path
+    sub = list(range(0, 1024, 3))
+    a = m.decode(codes.to(torch.int16), layers=sub, precision=precision)
+    b = m.decode(codes, layers=sub)
+    assert (a - b).abs().max().item() / b.abs().max().item() <= rtol
+    with pytest.raises(ValueError):
+        m.decode(codes, precision="bf16")
+
+
+def test_tensor_core_decode_small_shapes(golden_small):
+    d = util.small_case(golden_small, "round_fsq_d200_ragged")      # D = 200: one partial feature tile
+    m = util.module_from_case(d, _cuda())
+    codes = torch.from_numpy(d["codes"].astype(np.int64)).to(_cuda())
+    exact = m.decode(codes)
+    fast = m.decode(codes, precision="f16x3")
+    assert (fast - exact).abs().max().item() <= 5e-5 * exact.abs().max().item()

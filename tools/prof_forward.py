@@ -26,3 +26,8 @@ print("forward ms", e0.elapsed_time(e1), "tokens", a.tokens, "tok/s", a.tokens /
 if a.decode:
     e0.record(); d = m.decode(idx); e1.record(); torch.cuda.synchronize()
     print("decode ms", e0.elapsed_time(e1), "tok/s", a.tokens / e0.elapsed_time(e1) * 1e3)
+    for prec in ("f16", "f16x3"):
+        d2 = m.decode(idx, precision=prec); torch.cuda.synchronize()
+        e0.record(); d2 = m.decode(idx, precision=prec); e1.record(); torch.cuda.synchronize()
+        err = ((d2 - d).abs().max() / d.abs().max()).item()
+        print("decode", prec, "ms", e0.elapsed_time(e1), "tok/s", a.tokens / e0.elapsed_time(e1) * 1e3, "rel err", err)
