@@ -39,3 +39,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_d
   -o $OUT/prof_dec_$TAG python tools/prof_forward.py --tokens 9472 --reps 1 --decode > $OUT/ncu_dec_$TAG.log 2>&1
 tail -3 $OUT/ncu_dec_$TAG.log
 ls -la $OUT
+echo "=== ncu full capture of the tensor-core decode (rq_intensity_kernel<1>) ==="
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_intensity -s 2 -c 1 -f \
+  -o $OUT/prof_dectc_$TAG python tools/prof_forward.py --tokens 65536 --reps 1 --decode > $OUT/ncu_dectc_$TAG.log 2>&1
+tail -3 $OUT/ncu_dectc_$TAG.log
