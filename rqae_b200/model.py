@@ -330,7 +330,7 @@ class RQAE(nn.Module):
 
         ``precision="fp32"`` (default) is bit-identical to the reference.  ``"f16"`` / ``"f16x3"`` opt in to the
         tensor-core path (one tcgen05 GEMM over the codes; fp16 operands, fp32 accumulation): relative error of
-        the result about 2e-4 / 2e-5 (measured, max error over max |q|), 15x / 8x faster.  Not the default because it is not bit-exact."""
+        the result about 2e-4 / 2e-5 (measured, max error over max |q|), 29x / 11x faster (1.0-1.15 PFLOP/s).  Not the default because it is not bit-exact."""
         if precision == "fp32":
             return self._run_decode(indices, None, layers)
         if precision not in ("f16", "f16x3"):
