@@ -141,6 +141,35 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
 int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t row_stride, int64_t n, int top_k,
                                       int32_t* idx_out, void* val_out, void* stream);
 
+/* Nearest-example search over a code store: the inner loops of IntensityEngine.find_examples
+ * (demo/server/server.py:159-325), split at the points where the reference hands data between steps.
+ * `sims_f16` is the engine's table (server.py:104-115): fp16 [nq][K][K] = subfeature_sims * layer_norms, indexed
+ * [layer][query code][dataset code].  All roundings are the reference's (fp16 table values, fp32 sum inside a chunk
+ * of <= 64 layers rounded to fp16, fp16 adds between chunks and between layer ranges); the only freedom is the order
+ * of the fp32 additions inside a chunk (ascending layer order here).
+ *
+ * rqae_search_build_table_f16 -- server.py:176-196: the query's rows of the table for layers [0, n_layers),
+ *   table[l][c][q] = sims[l][query[q][l]][c], fp16 [n_layers][K][128], q >= n_query zero-filled (one 256-byte row
+ *   per (layer, dataset code)).   query: int32 [n_query][query_stride], n_query <= 128; a query code outside [0,K)
+ *   gives a zero row.  table_bytes >= rqae_search_table_bytes(n_layers, K); 16-byte aligned.
+ * rqae_search_accumulate_f16 -- server.py:41-68 (get_intensities), :204-263: for every dataset token t,
+ *   acc[t][q] (+)= sum over layers [layer_begin, layer_end) of table[l][codes[t][l]][q]   (one layer range of the
+ *   reference's `layers` list per call; `first` != 0 stores instead of adding: the reference's first range).
+ *   codes [n_tokens][code_stride] of code_dtype, tokens sequence-major (token = sequence * seq_len + position);
+ *   acc fp16 [n_tokens][128] = the reference's intensity_accumulation (N, S, Sq) with Sq padded to 128.
+ *   A dataset code outside [0,K) contributes 0 (the reference would raise an indexing error).
+ * rqae_search_position_max_f16 -- server.py:265-267: out[q][n] = max over the seq_len positions of sequence n of
+ *   acc[n*seq_len + s][q] (a NaN wins, as in torch.max), fp16 [n_query][out_stride], out_stride % 8 == 0,
+ *   out_stride >= n_seq, columns >= n_seq zero-filled: the row layout rqae_select_top_middle_bottom_f16 reads, which
+ *   then replaces the argsort + slices of server.py:268-287. */
+size_t rqae_search_table_bytes(int n_layers, int K);
+int rqae_search_build_table_f16(const void* sims_f16, int K, const int32_t* query, int64_t query_stride, int n_query,
+                                int n_layers, void* table, size_t table_bytes, void* stream);
+int rqae_search_accumulate_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride,
+                               int64_t n_tokens, int layer_begin, int layer_end, int first, void* acc, void* stream);
+int rqae_search_position_max_f16(const void* acc, int64_t n_seq, int seq_len, int n_query, void* out,
+                                 int64_t out_stride, void* stream);
+
 /* Opt-in tensor-core variant of RQAE.decode (rqae/model.py:232-252): the same sum as rqae_decode_f32,
  * evaluated as one tcgen05 GEMM  q[t][d] = sum_{l,j} V[t][4l+j] * U[d][4l+j] + sum_l b_out[l][d]  with
  * V = codebook[0][codes] and U = W_out, fp16 operands and fp32 accumulation.  NOT bit-exact (the default

@@ -19,6 +19,7 @@ SYMBOLS = [
     "rqae_forward_f32", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_release", "rqae_fp32_peak_probe",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
+    "rqae_search_table_bytes", "rqae_search_build_table_f16", "rqae_search_accumulate_f16", "rqae_search_position_max_f16",
 ]
 
 CODE_DTYPE = {"int16": 0, "int32": 1, "int64": 2}
@@ -68,6 +69,14 @@ def load() -> ctypes.CDLL:
     lib.rqae_decode_tc_workspace_bytes.argtypes = [i, i, i64, i]
     lib.rqae_decode_tc_f32.restype = i
     lib.rqae_decode_tc_f32.argtypes = [vp, vp, vp, i, i, i, i, i, vp, i, i64, vp, i64, vp, i, vp, sz, vp]
+    lib.rqae_search_table_bytes.restype = sz
+    lib.rqae_search_table_bytes.argtypes = [i, i]
+    lib.rqae_search_build_table_f16.restype = i
+    lib.rqae_search_build_table_f16.argtypes = [vp, i, vp, i64, i, i, vp, sz, vp]
+    lib.rqae_search_accumulate_f16.restype = i
+    lib.rqae_search_accumulate_f16.argtypes = [vp, i, vp, i, i64, i64, i, i, i, vp, vp]
+    lib.rqae_search_position_max_f16.restype = i
+    lib.rqae_search_position_max_f16.argtypes = [vp, i64, i, i, vp, i64, vp]
     lib.rqae_launch_count.restype = i64
     lib.rqae_launch_count.argtypes = [i]
     _lib = lib

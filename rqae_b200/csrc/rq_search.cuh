@@ -1,0 +1,198 @@
+// Nearest-example search over a code store (sm_100a) -- SURVEY 8f-3.
+//
+// Replaces the inner loops of IntensityEngine.find_examples (reference harish-kamath/rqae,
+// demo/server/server.py:159-325).  For a query of Sq <= 128 positions and a dataset of N sequences of S
+// positions, the reference keeps  intensity_accumulation[n][s][q] (fp16)  and, for every layer range
+// [a, b) of its `layers` list, adds
+//     sum_{l in [a,b)} sims[l][ q_code[q][l] ][ d_code[n][s][l] ]                 (server.py:41-68, 204-263)
+// where sims = subfeature_sims * layer_norms is an fp16 table (server.py:104-115).  The reference
+// materialises the gathered values as a (1024, 127, 127, <=64) fp16 tensor per shard and chunk (2.1 GB) and
+// reduces it with `sum(dim=-1)`; here the gather, the sum and the accumulation are one pass:
+//
+//   search_table_kernel       Qt[l][c][q] = sims[l][q_code[q][l]][c], q padded to 128 with zeros: the
+//                             query's rows of the table, transposed so that everything one dataset token
+//                             needs at one layer is ONE contiguous 256-byte row (server.py:183-196 builds
+//                             the same rows untransposed)
+//   search_accumulate_kernel  a warp owns 8 dataset tokens; lane j owns query positions 4j..4j+3; per
+//                             (token, layer) one coalesced 256-byte row load from L1/L2 and four fp32 adds
+//                             per lane.  Roundings are the reference's: fp32 running sum inside a chunk of
+//                             <= 64 layers (ascending layer order), one rounding to fp16 per chunk, chunks
+//                             of a range added in fp16 (server.py:216-234), ranges added in fp16 (:256-259)
+//   search_posmax_kernel      max over the S positions of every dataset sequence (server.py:265-267),
+//                             written query-position-major so that rq_mine_kernel (rq_mine.cuh) can rank the
+//                             sequences of every query position without the reference's full argsort
+//
+// Bound: the table rows.  A token-layer reads 256 B of table against 2-4 B of code store, and a layer's slab
+// (K x 256 B = 160 KB at K = 625) is as large as an SM's L1, so the row loads are served by L2: this first
+// version is L2-bandwidth-bound, not HBM-bound (DESIGN.md 4.6 has the arithmetic and the plan).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "rq_common.cuh"
+
+namespace rq {
+
+constexpr int SR_Q = 128;            // padded query positions (row = 128 fp16 = 256 B)
+constexpr int SR_THREADS = 256;      // accumulate kernel: 8 warps
+constexpr int SR_TOK_PER_WARP = 8;
+constexpr int SR_TILE = (SR_THREADS / 32) * SR_TOK_PER_WARP;   // 64 tokens per CTA pass
+constexpr int SR_CHUNK = 64;         // server.py:219-222: a range longer than 64 layers is summed in chunks of 64
+
+// ---------------------------------------------------------------------------------------------------------
+// Qt[l][c][q] = sims[l][qcode[q][l]][c]
+// ---------------------------------------------------------------------------------------------------------
+struct SearchTableParams {
+  const __half* sims;       // [>= n_layers][K][K]
+  const int* query;         // [n_query][query_stride] int32 codes
+  long long query_stride;
+  int n_query, n_layers, K;
+  __half* table;            // [n_layers][K][SR_Q]
+};
+
+__global__ void __launch_bounds__(256) search_table_kernel(const SearchTableParams p) {
+  __shared__ __half tile[SR_Q][34];
+  const int l = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int K = p.K;
+  {
+    const int cc = tid & 31, qq = tid >> 5;
+    for (int q = qq; q < SR_Q; q += 8) {
+      __half v = __float2half(0.f);
+      if (q < p.n_query && c0 + cc < K) {
+        const int qc = p.query[(long long)q * p.query_stride + l];
+        if (qc >= 0 && qc < K) v = p.sims[((size_t)l * K + qc) * K + c0 + cc];
+      }
+      tile[q][cc] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int q = tid & (SR_Q - 1), ch = tid >> 7;
+    for (int cc = ch; cc < 32; cc += 2)
+      if (c0 + cc < K) p.table[((size_t)l * K + c0 + cc) * SR_Q + q] = tile[q][cc];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// acc[t][q] (+)= range sum
+// ---------------------------------------------------------------------------------------------------------
+struct SearchAccParams {
+  const __half* table;      // [.. layer_end][K][SR_Q]
+  const void* codes;        // [n_tokens][code_stride] of CodeT
+  long long code_stride, n_tokens;
+  int K, layer_begin, layer_end, first;
+  __half* acc;              // [n_tokens][SR_Q]
+};
+
+__device__ __forceinline__ float sr_round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+template <typename CodeT>
+__global__ void __launch_bounds__(SR_THREADS) search_accumulate_kernel(const SearchAccParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const CodeT* __restrict__ codes = (const CodeT*)p.codes;
+  const long long n_tiles = (p.n_tokens + SR_TILE - 1) / SR_TILE;
+  const int K = p.K;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tok0 = tile * SR_TILE + warp * SR_TOK_PER_WARP;
+    if (tok0 >= p.n_tokens) continue;
+    float rng[SR_TOK_PER_WARP][4];          // the range's value so far, already fp16-representable
+    for (int c0 = p.layer_begin; c0 < p.layer_end; c0 += SR_CHUNK) {
+      const int c1 = (c0 + SR_CHUNK < p.layer_end) ? c0 + SR_CHUNK : p.layer_end;
+      float cs[SR_TOK_PER_WARP][4];
+#pragma unroll
+      for (int j = 0; j < SR_TOK_PER_WARP; ++j) cs[j][0] = cs[j][1] = cs[j][2] = cs[j][3] = 0.f;
+      for (int l0 = c0; l0 < c1; l0 += 32) {
+        const int nl = (c1 - l0 < 32) ? c1 - l0 : 32;
+        int mine[SR_TOK_PER_WARP];          // lane i holds the codes of layer l0 + i
+#pragma unroll
+        for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
+          mine[j] = -1;
+          if (lane < nl && tok0 + j < p.n_tokens) {
+            const long long v = (long long)codes[(tok0 + j) * p.code_stride + l0 + lane];
+            mine[j] = (v >= 0 && v < K) ? (int)v : -1;
+          }
+        }
+        for (int i = 0; i < nl; ++i) {
+          const __half* slab = p.table + (size_t)(l0 + i) * K * SR_Q + 4 * lane;
+          uint2 w[SR_TOK_PER_WARP];          // all eight row loads are issued before the first add
+#pragma unroll
+          for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
+            const int c = __shfl_sync(0xffffffffu, mine[j], i);     // warp-uniform
+            w[j] = make_uint2(0u, 0u);       // a code outside [0, K) or a token past the end adds +0
+            if (c >= 0) w[j] = __ldg(reinterpret_cast<const uint2*>(slab + (size_t)c * SR_Q));
+          }
+#pragma unroll
+          for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w[j].x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j].y));
+            cs[j][0] += lo.x; cs[j][1] += lo.y; cs[j][2] += hi.x; cs[j][3] += hi.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < SR_TOK_PER_WARP; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float h = sr_round_h(cs[j][e]);                       // sum(dim=-1) of an fp16 tensor
+          rng[j][e] = (c0 == p.layer_begin) ? h : sr_round_h(rng[j][e] + h);   // intensities += chunk (fp16)
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
+      if (tok0 + j >= p.n_tokens) break;
+      uint2* dst = reinterpret_cast<uint2*>(p.acc + (size_t)(tok0 + j) * SR_Q + 4 * lane);
+      float r0 = rng[j][0], r1 = rng[j][1], r2 = rng[j][2], r3 = rng[j][3];
+      if (!p.first) {                                                  // intensity_accumulation += range (fp16)
+        const uint2 o = *dst;
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&o.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&o.y));
+        r0 = lo.x + r0; r1 = lo.y + r1; r2 = hi.x + r2; r3 = hi.y + r3;
+      }
+      const __half2 a = __floats2half2_rn(r0, r1), b = __floats2half2_rn(r2, r3);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&a);
+      w.y = *reinterpret_cast<const uint32_t*>(&b);
+      *dst = w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out[q][n] = max_s acc[n * S + s][q]
+// ---------------------------------------------------------------------------------------------------------
+struct SearchMaxParams {
+  const __half* acc;        // [n_seq * seq_len][SR_Q]
+  long long n_seq, out_stride;
+  int seq_len, n_query;
+  __half* out;              // [n_query][out_stride]; columns n_seq..out_stride-1 are zero-filled
+};
+
+__global__ void __launch_bounds__(256) search_posmax_kernel(const SearchMaxParams p) {
+  __shared__ __half tile[32][SR_Q + 2];
+  const int tid = threadIdx.x;
+  const long long n0 = (long long)blockIdx.x * 32;
+  {
+    const int q = tid & (SR_Q - 1), half_id = tid >> 7;
+    for (int nl = half_id; nl < 32; nl += 2) {
+      const long long n = n0 + nl;
+      float m = 0.f;
+      if (n < p.n_seq) {
+        const __half* src = p.acc + (size_t)n * p.seq_len * SR_Q + q;
+        m = __half2float(src[0]);
+        for (int s = 1; s < p.seq_len; ++s) {
+          const float v = __half2float(src[(size_t)s * SR_Q]);
+          m = (v > m || v != v) ? v : m;          // torch.max: a NaN wins and stays
+        }
+      }
+      tile[nl][q] = __float2half_rn(m);
+    }
+  }
+  __syncthreads();
+  {
+    const int nl = tid & 31, qq = tid >> 5;
+    const long long n = n0 + nl;
+    if (n < p.out_stride)
+      for (int q = qq; q < p.n_query; q += 8) p.out[(size_t)q * p.out_stride + n] = tile[nl][q];
+  }
+}
+
+}  // namespace rq

@@ -22,6 +22,7 @@
 #include "rq_forward.cuh"
 #include "rq_intensity.cuh"
 #include "rq_mine.cuh"
+#include "rq_search.cuh"
 #include "rq_layout.h"
 
 #ifndef RQ_L2_HOT_DEFAULT
@@ -792,6 +793,77 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
   mp.idx_out = idx_out; mp.val_out = (__half*)val_out;
   const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
   rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest-example search over a code store (rq_search.cuh; demo/server/server.py:159-325)
+// ---------------------------------------------------------------------------------------------
+size_t rqae_search_table_bytes(int n_layers, int K) {
+  if (n_layers <= 0 || K <= 0) return 0;
+  return (size_t)n_layers * (size_t)K * rq::SR_Q * sizeof(__half);
+}
+
+int rqae_search_build_table_f16(const void* sims_f16, int K, const int32_t* query, int64_t query_stride, int n_query,
+                                int n_layers, void* table, size_t table_bytes, void* stream) {
+  if (!sims_f16 || !query || !table || K <= 0 || n_layers <= 0 || n_query <= 0 || query_stride < n_layers) return RQAE_EINVAL;
+  if (n_query > rq::SR_Q || n_layers > 65535) return RQAE_EUNSUPPORTED;
+  if (((uintptr_t)table & 15)) return RQAE_EINVAL;
+  if (table_bytes < rqae_search_table_bytes(n_layers, K)) return RQAE_ESIZE;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  rq::SearchTableParams tp;
+  tp.sims = (const __half*)sims_f16; tp.query = query; tp.query_stride = query_stride;
+  tp.n_query = n_query; tp.n_layers = n_layers; tp.K = K; tp.table = (__half*)table;
+  dim3 grid((unsigned)((K + 31) / 32), (unsigned)n_layers);
+  rq::search_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
+int rqae_search_accumulate_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride,
+                               int64_t n_tokens, int layer_begin, int layer_end, int first, void* acc, void* stream) {
+  if (!table || !codes || !acc || K <= 0 || n_tokens < 0) return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
+  if (layer_begin < 0 || layer_end <= layer_begin || code_stride < layer_end) return RQAE_EINVAL;
+  if (((uintptr_t)table & 7) || ((uintptr_t)acc & 7)) return RQAE_EINVAL;     // 8-byte lane accesses
+  if (n_tokens == 0) return RQAE_OK;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  rq::SearchAccParams ap;
+  ap.table = (const __half*)table; ap.codes = codes; ap.code_stride = code_stride; ap.n_tokens = n_tokens;
+  ap.K = K; ap.layer_begin = layer_begin; ap.layer_end = layer_end; ap.first = first ? 1 : 0; ap.acc = (__half*)acc;
+  const long long tiles = (n_tokens + rq::SR_TILE - 1) / rq::SR_TILE;
+  const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (code_dtype == RQAE_CODE_I64) rq::search_accumulate_kernel<long long><<<grid, rq::SR_THREADS, 0, st>>>(ap);
+  else if (code_dtype == RQAE_CODE_I32) rq::search_accumulate_kernel<int><<<grid, rq::SR_THREADS, 0, st>>>(ap);
+  else rq::search_accumulate_kernel<short><<<grid, rq::SR_THREADS, 0, st>>>(ap);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
+int rqae_search_position_max_f16(const void* acc, int64_t n_seq, int seq_len, int n_query, void* out,
+                                 int64_t out_stride, void* stream) {
+  if (!acc || !out || n_seq < 0 || seq_len <= 0 || n_query <= 0) return RQAE_EINVAL;
+  if (n_query > rq::SR_Q) return RQAE_EUNSUPPORTED;
+  if (out_stride < n_seq || (out_stride & 7) || ((uintptr_t)out & 15)) return RQAE_EINVAL;   // the layout rq_mine_kernel reads
+  if (out_stride == 0) return RQAE_OK;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  rq::SearchMaxParams mp;
+  mp.acc = (const __half*)acc; mp.n_seq = n_seq; mp.out_stride = out_stride; mp.seq_len = seq_len; mp.n_query = n_query;
+  mp.out = (__half*)out;
+  const long long blocks = (out_stride + 31) / 32;
+  if (blocks >= (1LL << 31)) return RQAE_EUNSUPPORTED;
+  rq::search_posmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mp);
   RQ_CUDA(cudaGetLastError());
   g_launches++;
   return RQAE_OK;

@@ -1,0 +1,159 @@
+"""``IntensityEngine`` -- host-side mirror of the nearest-example search of the reference's demo server
+(harish-kamath/rqae, ``demo/server/server.py:71-325``) without the Modal plumbing.
+
+Kept as in the reference: what ``setup()`` leaves on the object (``sims`` = ``subfeature_sims * layer_norms`` in
+fp16, server.py:104-115; ``activations`` = the code store with the BOS position dropped, :118-139) and
+``find_examples(idx=None, activation=None, top_examples=30, middle_examples=10, bottom_examples=10, layers=[...])``
+as a generator that yields, after every layer of ``layers``, ``({"top"|"middle"|"bottom": {"indices": int32
+(Sq, k) CPU, "intensities": fp16 (Sq, k, S) CPU}}, layer)`` (:159-325), with the same ``ValueError`` for a missing
+or doubled query (:174-182).
+
+Different by design: the code store is ONE resident CUDA tensor (N, S, nq) instead of a Python list of CPU
+shards copied to the GPU range by range (a B200 holds the whole 36 864 x 127 x 1024 store: 9.6 GB as int16); the
+gather + sum + accumulate of :204-263 is one kernel per layer range (``rqae_search_accumulate_f16``) that never
+materialises the (1024, 127, 127, 64) gathered tensor; the ``argsort`` over sequences of :268 is the exact radix
+select of the mining path (``rqae_select_top_middle_bottom_f16``).  Order among equal maxima: value descending,
+sequence index ascending (the reference's unstable ``argsort`` leaves it unspecified).
+
+There is no CPU path: model and code store must be on the GPU.
+"""
+from __future__ import annotations
+
+from typing import Iterator, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib, store
+
+SQ_PAD = 128          # rq_search.cuh SR_Q: query positions are padded to one 256-byte row
+SELECT_KMAX = 256     # rq_mine.cuh MN_KMAX
+SERVER_LAYERS = [4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1023]   # server.py:167
+
+_CODE_DTYPE = {torch.int16: 0, torch.int32: 1, torch.int64: 2}
+
+
+def engine_sims(model, mode: str = "projected") -> torch.Tensor:
+    """server.py:103-115: the (nq, K, K) fp16 table of the engine."""
+    if mode == "original":
+        sims = model.codebook_sims.unsqueeze(0).repeat(model.num_quantizers, 1, 1)
+    elif mode == "projected":
+        sims = model.subfeature_sims.clone()
+    else:
+        raise ValueError(f"Invalid mode: {mode}")
+    sims *= model.layer_norms.to(sims.device).unsqueeze(-1).unsqueeze(-1)
+    return sims.detach().contiguous()
+
+
+class IntensityEngine:
+    """server.py:71-325.  ``activations``: (N, S, nq) integer CUDA tensor, or a list of such shards (they are
+    concatenated once; the reference keeps the list).  ``sims``: the fp16 table, or ``model`` to build it."""
+
+    def __init__(self, model=None, activations: Union[torch.Tensor, Sequence[torch.Tensor], None] = None, *,
+                 sims: Optional[torch.Tensor] = None, mode: str = "projected", dataset: str = "monology_pile",
+                 model_id: str = "rqae-rqae-round_fsq-cbd4-cbs5-nq1024"):
+        self.dataset = dataset
+        self.model_id = model_id
+        if sims is None:
+            if model is None:
+                raise ValueError("Must specify either model or sims")
+            sims = engine_sims(model, mode)
+        if not sims.is_cuda:
+            raise RuntimeError("IntensityEngine needs CUDA tensors; there is no CPU fallback")
+        if sims.dim() != 3 or sims.shape[1] != sims.shape[2]:
+            raise ValueError(f"sims must be (num_quantizers, K, K), got {tuple(sims.shape)}")
+        self.sims = sims.to(torch.float16).contiguous()
+        if activations is None:
+            raise ValueError("Must specify activations")
+        if not isinstance(activations, torch.Tensor):
+            activations = torch.cat([a.to(self.sims.device) for a in activations], dim=0)
+        if not activations.is_cuda:
+            raise RuntimeError("IntensityEngine needs the code store on the GPU; there is no CPU fallback")
+        if activations.dim() != 3 or activations.dtype not in _CODE_DTYPE:
+            raise ValueError("activations must be an int16/int32/int64 tensor (sequences, positions, num_quantizers)")
+        self.activations = activations.contiguous()
+
+    @classmethod
+    def from_store(cls, model, folder: str, model_name: Optional[str] = None, dtype: torch.dtype = torch.int16, **kw):
+        """server.py:117-139: every shard of the store, BOS position dropped, resident on the model's device."""
+        dev = next(model.parameters()).device
+        name = model.name if model_name is None else model_name
+        codes = store.load_code_shards(folder, name, skip_bos=True, dtype=dtype, device=dev)
+        return cls(model, codes, **kw)
+
+    # ------------------------------------------------------------------------------------------------
+    def _query(self, idx, activation, n_layers: int) -> torch.Tensor:
+        if activation is not None and idx is not None:
+            raise ValueError("Cannot specify both idx and activation")
+        elif idx is not None:
+            q = self.activations[int(idx)]
+        elif activation is not None:
+            q = torch.as_tensor(activation)
+        else:
+            raise ValueError("Must specify either idx or activation")
+        if q.dim() != 2 or q.shape[1] < n_layers:
+            raise ValueError(f"query must be (positions, >= {n_layers} layers), got {tuple(q.shape)}")
+        if q.shape[0] > SQ_PAD:
+            raise NotImplementedError(f"at most {SQ_PAD} query positions (got {q.shape[0]})")
+        return q[:, :n_layers].to(device=self.sims.device, dtype=torch.int32).contiguous()
+
+    def accumulate(self, query: torch.Tensor, layers: Sequence[int]) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """After every layer range of ``layers`` (server.py:198-263): (``intensity_accumulation`` as a view
+        (N, S, Sq) of the padded fp16 buffer, per-position maxima (Sq, N) fp16 = ``max_values.T`` of :267).
+        The buffers are reused from one step to the next, as in the reference."""
+        layers = [int(l) for l in layers]
+        if not layers or any(b <= a for a, b in zip([0] + layers[:-1], layers)):
+            raise ValueError("layers must be strictly ascending positive layer indices")
+        L = layers[-1]
+        nq, K = self.sims.shape[0], self.sims.shape[1]
+        N, S, nq_codes = self.activations.shape
+        if L > nq or L > nq_codes:
+            raise ValueError(f"max(layers)={L} exceeds the {min(nq, nq_codes)} layers of the table / code store")
+        dev = self.sims.device
+        Sq = query.shape[0]
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            tbytes = lib.rqae_search_table_bytes(L, K)
+            table = torch.empty(tbytes // 2, dtype=torch.float16, device=dev)
+            _lib.check(lib.rqae_search_build_table_f16(self.sims.data_ptr(), K, query.data_ptr(), query.stride(0), Sq, L,
+                                                      table.data_ptr(), tbytes, st), "rqae_search_build_table_f16")
+            acc = torch.empty(N * S, SQ_PAD, dtype=torch.float16, device=dev)
+            n_pad = (N + 7) // 8 * 8
+            maxv = torch.empty(Sq, n_pad, dtype=torch.float16, device=dev)
+            a = 0
+            for b in layers:
+                _lib.check(lib.rqae_search_accumulate_f16(table.data_ptr(), K, self.activations.data_ptr(),
+                                                         _CODE_DTYPE[self.activations.dtype], nq_codes, N * S, a, b,
+                                                         1 if a == 0 else 0, acc.data_ptr(), st), "rqae_search_accumulate_f16")
+                _lib.check(lib.rqae_search_position_max_f16(acc.data_ptr(), N, S, Sq, maxv.data_ptr(), n_pad, st),
+                           "rqae_search_position_max_f16")
+                yield acc.view(N, S, SQ_PAD)[:, :, :Sq], maxv[:, :N]
+                a = b
+
+    def find_examples(self, idx: int = None, activation: torch.Tensor = None, top_examples: int = 30,
+                      middle_examples: int = 10, bottom_examples: int = 10,
+                      layers: List[int] = SERVER_LAYERS):
+        """server.py:159-325."""
+        layers = list(layers)
+        query = self._query(idx, activation, max(layers))
+        N, S, _ = self.activations.shape
+        Sq = query.shape[0]
+        top, mid, bot = int(top_examples), int(middle_examples), int(bottom_examples)
+        k = max(top, mid, bot, 1)
+        if k > SELECT_KMAX:
+            raise NotImplementedError(f"at most {SELECT_KMAX} examples per window")
+        k = min(k, N)
+        kh, mh = k // 2, mid // 2
+        if mh > kh:
+            raise ValueError(f"middle_examples={mid} needs at least {2 * mh} sequences, the store has {N}")
+        from .feature import select_top_middle_bottom
+        qpos = torch.arange(Sq, device=self.sims.device).unsqueeze(-1)
+        for layer, (acc, maxv) in zip(layers, self.accumulate(query, layers)):
+            sel, _ = select_top_middle_bottom(maxv, k, n=N)                  # (Sq, 3, k) int32
+            lists = {"top": sel[:, 0, :min(top, k)], "middle": sel[:, 1, kh - mh: kh + mh],
+                     "bottom": sel[:, 2, k - min(bot, k):]}
+            out = {}
+            for name, lst in lists.items():
+                inten = acc[lst.long(), :, qpos]                              # (Sq, k', S): intensity_accumulation[lst[i], :, i]
+                out[name] = {"indices": lst.cpu().int(), "intensities": inten.cpu().to(torch.float16)}
+            yield out, layer

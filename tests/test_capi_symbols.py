@@ -60,3 +60,23 @@ def test_mining_entry_points_validate_before_touching_the_gpu():
     assert lib.rqae_select_top_middle_bottom_f16(one, 4, 512, 400, 300, one, None, None) == 2      # k > 256
     assert lib.rqae_select_top_middle_bottom_f16(one, 4, 250, 250, 10, one, None, None) == 1       # rows not 16-byte aligned
     assert lib.rqae_select_top_middle_bottom_f16(one, 0, 256, 250, 10, one, None, None) == 0       # nothing to do
+
+
+def test_search_entry_points_validate_before_touching_the_gpu():
+    import ctypes
+    lib = _lib.load()
+    assert lib.rqae_search_table_bytes(1023, 625) == 1023 * 625 * 128 * 2
+    assert lib.rqae_search_table_bytes(0, 625) == 0
+    one = ctypes.c_void_p(4096)
+    tb = lib.rqae_search_table_bytes(16, 625)
+    assert lib.rqae_search_build_table_f16(None, 625, one, 16, 7, 16, one, tb, None) == 1
+    assert lib.rqae_search_build_table_f16(one, 625, one, 8, 7, 16, one, tb, None) == 1        # query rows shorter than n_layers
+    assert lib.rqae_search_build_table_f16(one, 625, one, 16, 129, 16, one, tb, None) == 2     # more than 128 query positions
+    assert lib.rqae_search_build_table_f16(one, 625, one, 16, 7, 16, one, tb - 1, None) == 5   # table too small
+    assert lib.rqae_search_accumulate_f16(one, 625, one, 3, 16, 8, 0, 4, 1, one, None) == 1    # unknown code dtype
+    assert lib.rqae_search_accumulate_f16(one, 625, one, 1, 16, 8, 4, 4, 0, one, None) == 1    # empty layer range
+    assert lib.rqae_search_accumulate_f16(one, 625, one, 1, 16, 8, 4, 24, 0, one, None) == 1   # range beyond the code rows
+    assert lib.rqae_search_accumulate_f16(one, 625, one, 1, 16, 0, 0, 4, 1, one, None) == 0    # no tokens: nothing to do
+    assert lib.rqae_search_position_max_f16(one, 24, 7, 7, one, 20, None) == 1                 # rows shorter than n_seq
+    assert lib.rqae_search_position_max_f16(one, 24, 7, 7, one, 28, None) == 1                 # row stride not a multiple of 8
+    assert lib.rqae_search_position_max_f16(one, 24, 7, 200, one, 24, None) == 2               # more than 128 query positions

@@ -1,0 +1,79 @@
+"""The search oracle (oracle/search_oracle.py) against outputs of the unmodified reference server code
+(tests/golden/kat_search.npz; demo/server/server.py:159-325 run by tests/golden/make_golden_search.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import search_oracle as so
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "kat_search.npz")
+CASES = [("k81", "idx5"), ("k81", "ext"), ("k625", "idx3")]
+
+
+def load_case(kat, case, tag):
+    sims = torch.from_numpy(kat[f"{case}/sims"])
+    shards = [torch.from_numpy(s.astype(np.int32)) for s in kat[f"{case}/shards"]]
+    if tag.startswith("idx"):
+        i = int(tag[3:])
+        n_per = shards[0].shape[0]
+        query = shards[i // n_per][i % n_per]
+    else:
+        query = torch.from_numpy(kat[f"{case}/{tag}"].astype(np.int32))
+    layers = [int(v) for v in kat[f"{case}/{tag}/layers"]]
+    top, mid, bot = (int(v) for v in kat[f"{case}/args"])
+    return sims, shards, query, layers, (top, mid, bot)
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(GOLD)
+
+
+@pytest.mark.parametrize("case,tag", CASES)
+def test_find_examples_bit_identical_to_reference(kat, case, tag):
+    sims, shards, query, layers, (top, mid, bot) = load_case(kat, case, tag)
+    n = 0
+    for res, layer in so.find_examples(shards, sims, query, top, mid, bot, layers):
+        for part in ("top", "middle", "bottom"):
+            assert np.array_equal(res[part]["indices"].numpy(), kat[f"{case}/{tag}/{layer}/{part}/indices"]), (layer, part)
+            a = res[part]["intensities"].numpy()
+            b = kat[f"{case}/{tag}/{layer}/{part}/intensities"]
+            assert a.dtype == np.float16 and np.array_equal(a.view(np.uint16), b.view(np.uint16)), (layer, part)
+        n += 1
+    assert n == len(layers)
+
+
+@pytest.mark.parametrize("case,tag", CASES)
+def test_written_out_roundings_match_the_aten_form(kat, case, tag):
+    """accumulate_steps (the kernel's order of operations) against the ATen form: identical except where the
+    order of the fp32 additions inside a chunk moves a sum across an fp16 rounding boundary."""
+    sims, shards, query, layers, _ = load_case(kat, case, tag)
+    codes = torch.cat(shards).reshape(-1, shards[0].shape[-1])
+    worst_ulps, differing, total = 0, 0, 0
+    for ref, mine in zip(so.accumulate(shards, sims, query, layers), so.accumulate_steps(codes, sims, query, layers)):
+        r = ref.reshape(-1, ref.shape[-1])
+        d = (r.view(torch.int16).int() - mine.view(torch.int16).int()).abs()
+        same_sign = (r.float() * mine.float()) >= 0
+        assert bool(same_sign.all())
+        worst_ulps = max(worst_ulps, int(d.max()))
+        differing += int((d != 0).sum())
+        total += d.numel()
+    assert worst_ulps <= 2, worst_ulps                 # fp16 steps, accumulated over the ranges
+    assert differing <= 0.01 * total, (differing, total)
+
+
+def test_layer_ranges_and_chunks():
+    assert so.layer_ranges([4, 6, 150]) == [(0, 4), (4, 6), (6, 150)]
+    # the chunked branch (server.py:216-234): a range of 144 layers is 64 + 64 + 16
+    sims = torch.randn(150, 9, 9).half()
+    q = torch.randint(0, 9, (3, 150), dtype=torch.int32)
+    sh = torch.randint(0, 9, (2, 4, 150), dtype=torch.int32)
+    qt = so.query_table(sims, q, 150)
+    whole = so.range_intensities(sh, qt, 6, 150)
+    parts = [so.get_intensities(sh[..., a:b], qt[a:b].transpose(0, 1)).sum(-1) for a, b in [(6, 70), (70, 134), (134, 150)]]
+    manual = parts[0].clone()
+    manual += parts[1]
+    manual += parts[2]
+    assert torch.equal(whole, manual)
