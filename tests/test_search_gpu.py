@@ -1,0 +1,183 @@
+"""GPU parity tests of the nearest-example search (rq_search.cuh through the C ABI via rqae_b200.search)
+against outputs of the unmodified reference server code (tests/golden/kat_search.npz) and the oracle.
+
+Bars: the running accumulation is BIT-EXACT against the oracle's written-out form (same fp16 table values, fp32
+sum in ascending layer order inside a chunk of <= 64 layers, the reference's fp16 roundings) and within
+ULPS fp16 steps of the reference's own ATen result (whose fp32 summation order inside `sum` is torch's; on the
+goldens the two are identical).  The selected sequences equal a stable descending argsort of the per-position
+maxima index for index; against the reference's (unstable) argsort they are compared through the selected VALUES,
+which are order-independent."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import search_oracle as so
+from tests.test_search_oracle import CASES, GOLD, load_case
+
+pytestmark = pytest.mark.gpu
+ULPS = 2
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(GOLD)
+
+
+def _ulps(a: torch.Tensor, b: torch.Tensor) -> int:
+    """largest distance in fp16 steps between two fp16 tensors (+0 and -0 coincide)."""
+    def key(t):
+        i = t.contiguous().view(torch.int16).int()
+        return torch.where(i < 0, -(i & 0x7FFF), i)
+    return int((key(a) - key(b)).abs().max()) if a.numel() else 0
+
+
+def _engine(sims, shards, dtype=torch.int32):
+    from rqae_b200.search import IntensityEngine
+    dev = _dev()
+    return IntensityEngine(sims=sims.to(dev), activations=[s.to(dev).to(dtype) for s in shards])
+
+
+@pytest.mark.parametrize("case,tag", CASES)
+def test_accumulation_bit_exact_vs_oracle_and_reference_form(kat, case, tag):
+    sims, shards, query, layers, _ = load_case(kat, case, tag)
+    eng = _engine(sims, shards)
+    q = eng._query(None, query, max(layers))
+    codes = torch.cat(shards).reshape(-1, shards[0].shape[-1])
+    N, S = eng.activations.shape[:2]
+    steps = so.accumulate_steps(codes, sims, query, layers)
+    aten = so.accumulate(shards, sims, query, layers)
+    for (acc, maxv), want, ref in zip(eng.accumulate(q, layers), steps, aten):
+        got = acc.cpu()
+        assert torch.equal(got.reshape(N * S, -1).float(), want.float())
+        assert _ulps(got, ref) <= ULPS
+        assert torch.equal(maxv.cpu().float(), want.reshape(N, S, -1).max(dim=1).values.T.float())
+
+
+@pytest.mark.parametrize("case,tag", CASES)
+def test_find_examples_matches_reference_golden(kat, case, tag):
+    sims, shards, query, layers, (top, mid, bot) = load_case(kat, case, tag)
+    eng = _engine(sims, shards, torch.int16)
+    kw = dict(idx=int(tag[3:])) if tag.startswith("idx") else dict(activation=query)
+    accs = so.accumulate(shards, sims, query, layers)
+    n = 0
+    for (res, layer), acc in zip(eng.find_examples(top_examples=top, middle_examples=mid, bottom_examples=bot,
+                                                   layers=layers, **kw), accs):
+        maxv = acc.max(dim=1).values                                   # (N, Sq), the reference's max_values
+        order = torch.sort(maxv.float(), dim=0, descending=True, stable=True).indices
+        N = order.shape[0]
+        want = {"top": order[:top].T, "middle": order[N // 2 - mid // 2: N // 2 + mid // 2].T, "bottom": order[-bot:].T}
+        for part in ("top", "middle", "bottom"):
+            idx = res[part]["indices"]
+            gold_idx = torch.from_numpy(kat[f"{case}/{tag}/{layer}/{part}/indices"])
+            gold_int = torch.from_numpy(kat[f"{case}/{tag}/{layer}/{part}/intensities"])
+            assert idx.dtype == torch.int32 and idx.shape == gold_idx.shape
+            assert res[part]["intensities"].dtype == torch.float16 and res[part]["intensities"].shape == gold_int.shape
+            assert torch.equal(idx.long(), want[part]), (layer, part)                 # stable order, index for index
+            # against the reference's own selection: the same values at every rank (ties may name other sequences)
+            qpos = torch.arange(idx.shape[0]).unsqueeze(-1)
+            assert torch.equal(maxv[idx.long(), qpos].float(), maxv[gold_idx.long(), qpos].float()), (layer, part)
+            # intensities of the selected sequences = the reference's accumulation rows
+            assert torch.equal(res[part]["intensities"].float(), acc[idx.long(), :, qpos].float()), (layer, part)
+            same = (idx == gold_idx).all(dim=1)
+            assert torch.equal(res[part]["intensities"][same].float(), gold_int[same].float())
+        n += 1
+    assert n == len(layers)
+
+
+@pytest.mark.parametrize("dtype", [torch.int16, torch.int32, torch.int64])
+def test_random_table_ragged_sizes_and_code_dtypes(dtype):
+    """K = 625, 127 query positions, a token count that is no multiple of the 64-token tile, ranges of 1, 63, 64,
+    65 and 130 layers (chunk boundaries, server.py:216-234), a few codes outside [0, K) (contribute 0)."""
+    g = torch.Generator().manual_seed(5)
+    nq, K, N, S, Sq = 330, 625, 13, 21, 127
+    sims = (torch.randn(nq, K, K, generator=g) * 0.7).half()
+    codes = torch.randint(0, K, (N, S, nq), generator=g, dtype=torch.int32)
+    codes[3, 5, 7] = -1
+    codes[4, 0, 100] = K
+    query = torch.randint(0, K, (Sq, nq), generator=g, dtype=torch.int32)
+    query[9, 2] = K + 3                                                # a zero row of the query table
+    layers = [1, 64, 128, 193, 323]
+    eng = _engine(sims, [codes], dtype)
+    q = eng._query(None, query, max(layers))
+    # oracle with the out-of-range codes mapped to an appended all-zero row / column
+    sims_z = torch.zeros(nq, K + 1, K + 1, dtype=torch.float16)
+    sims_z[:, :K, :K] = sims
+    codes_z = codes.clone().reshape(-1, nq)
+    codes_z[(codes_z < 0) | (codes_z >= K)] = K
+    query_z = query.clone()
+    query_z[(query_z < 0) | (query_z >= K)] = K
+    for (acc, maxv), want in zip(eng.accumulate(q, layers), so.accumulate_steps(codes_z, sims_z, query_z, layers)):
+        assert torch.equal(acc.cpu().reshape(N * S, Sq).float(), want.float())
+        assert torch.equal(maxv.cpu().float(), want.reshape(N, S, Sq).max(dim=1).values.T.float())
+
+
+def test_single_query_position_and_full_128():
+    g = torch.Generator().manual_seed(6)
+    nq, K, N, S = 40, 81, 70, 9
+    sims = torch.randn(nq, K, K, generator=g).half()
+    codes = torch.randint(0, K, (N, S, nq), generator=g, dtype=torch.int32)
+    eng = _engine(sims, [codes], torch.int16)
+    for Sq in (1, 128):
+        query = torch.randint(0, K, (Sq, nq), generator=g, dtype=torch.int32)
+        layers = [3, 40]
+        got = list(eng.find_examples(activation=query, top_examples=7, middle_examples=5, bottom_examples=2, layers=layers))
+        for (res, layer), want in zip(got, so.accumulate_steps(codes.reshape(-1, nq), sims, query, layers)):
+            maxv = want.reshape(N, S, Sq).max(dim=1).values
+            order = torch.sort(maxv.float(), dim=0, descending=True, stable=True).indices
+            assert torch.equal(res["top"]["indices"].long(), order[:7].T)
+            assert torch.equal(res["middle"]["indices"].long(), order[N // 2 - 2: N // 2 + 2].T)   # 2 * (5 // 2) entries
+            assert torch.equal(res["bottom"]["indices"].long(), order[-2:].T)
+            assert res["top"]["intensities"].shape == (Sq, 7, S)
+
+
+def test_argument_errors_are_the_reference_s():
+    g = torch.Generator().manual_seed(7)
+    sims = torch.randn(8, 9, 9, generator=g).half()
+    codes = torch.randint(0, 9, (6, 4, 8), generator=g, dtype=torch.int32)
+    eng = _engine(sims, [codes])
+    with pytest.raises(ValueError, match="Cannot specify both idx and activation"):      # server.py:174-175
+        next(eng.find_examples(idx=1, activation=codes[0], layers=[2, 4]))
+    with pytest.raises(ValueError, match="Must specify either idx or activation"):        # server.py:181-182
+        next(eng.find_examples(layers=[2, 4]))
+    with pytest.raises(ValueError):
+        next(eng.find_examples(idx=1, layers=[4, 2]))
+    with pytest.raises(ValueError):
+        next(eng.find_examples(idx=1, layers=[2, 9]))                                     # deeper than the store
+    from rqae_b200.search import IntensityEngine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        IntensityEngine(sims=sims, activations=codes)
+
+
+def test_engine_from_model_and_store(tmp_path):
+    """End to end on a real (random-init) model: codes from RQAE.encode, the store's file format, the engine's table
+    from the model's own derived tables (server.py:103-115), query by idx; checked against the oracle run on the same
+    table."""
+    from rqae_b200 import RQAE, store
+    from rqae_b200.search import IntensityEngine
+    dev = _dev()
+    torch.manual_seed(0)
+    m = RQAE(dim=256, num_quantizers=24, name="t").eval().to(dev)
+    x = torch.randn(12, 8, 256, generator=torch.Generator().manual_seed(2)).to(dev)
+    codes = m.encode(x, out_dtype=torch.int32)                         # (12, 8, 24), BOS position included
+    store.save_code_shard(str(tmp_path), m.name, 0, codes[:6])
+    store.save_code_shard(str(tmp_path), m.name, 1, codes[6:])
+    eng = IntensityEngine.from_store(m, str(tmp_path))
+    assert tuple(eng.activations.shape) == (12, 7, 24) and eng.activations.dtype == torch.int16
+    layers = [4, 6, 8, 12, 23]
+    sims_cpu, act_cpu = eng.sims.cpu(), eng.activations.cpu().int()
+    want = so.find_examples([act_cpu], sims_cpu, act_cpu[5], 4, 2, 2, layers)
+    for (res, layer), (ref, rlayer) in zip(eng.find_examples(idx=5, top_examples=4, middle_examples=2, bottom_examples=2,
+                                                             layers=layers), want):
+        assert layer == rlayer
+        # the query sequence itself is its own best match at every position's own slot
+        for part in ("top", "middle", "bottom"):
+            assert res[part]["indices"].shape == ref[part]["indices"].shape
+            same = (res[part]["indices"] == ref[part]["indices"]).all(dim=1)
+            assert _ulps(res[part]["intensities"][same], ref[part]["intensities"][same]) <= ULPS
