@@ -275,6 +275,47 @@ def mining_extras(torch, model, codes, dev):
     return res
 
 
+def search_extras(torch, model, dev, sequences=36864, positions=127):
+    """nearest-example search (demo/server/server.py:159-325) over a code store of the reference's shape
+    (36 864 sequences x 127 positions x 1024 layers, server.py:139; synthetic uniform codes, int16, resident in HBM) with
+    the engine table of THIS model (subfeature_sims * layer_norms), one 127-position query, the server's 13 layer cuts,
+    top-30 / middle-10 / bottom-10 after every cut.  Side measurement, CUDA events, outside the timed region."""
+    from rqae_b200 import _lib
+    from rqae_b200.search import IntensityEngine, SERVER_LAYERS, engine_sims
+    nq, K = model.num_quantizers, model.codebook.shape[1]
+    g = torch.Generator(device=dev).manual_seed(77)
+    codes = torch.randint(0, K, (sequences, positions, nq), generator=g, device=dev, dtype=torch.int16)
+    eng = IntensityEngine(sims=engine_sims(model), activations=codes)
+    lib = _lib.load()
+    idx = sequences // 3
+
+    def one():
+        last = None
+        for res, layer in eng.find_examples(idx=idx):
+            last = res
+        return last
+    n0 = int(lib.rqae_launch_count(0))
+    res, ms = _event_ms(torch, dev, one, reps=2)                   # one warm-up pass + two timed
+    launches = (int(lib.rqae_launch_count(0)) - n0) // 3
+    L = max(SERVER_LAYERS)
+    rows = sequences * positions * L
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    # algorithmic HBM bytes: the code store once + the fp16 accumulation written once per cut and re-read by the next cut
+    # and by the per-position max
+    acc_bytes = sequences * positions * 128 * 2
+    hbm = rows * 2 + acc_bytes * (3 * len(SERVER_LAYERS) - 1)
+    return {
+        "sequences": sequences, "positions": positions, "layers": L, "query_positions": positions, "cuts": len(SERVER_LAYERS),
+        "find_examples_ms": ms, "sequences_per_s": sequences / ms * 1e3, "launches_per_query": launches,
+        "table_row_tbps": rows * 256 / ms / 1e9, "hbm_gbs": hbm / ms / 1e6, "hbm_frac_of_peak": hbm / ms / 1e6 / hbm_peak,
+        "bound": "L2 -> SM delivery of 256-byte table rows (DESIGN.md 4.6); HBM fraction shown for scale",
+        "self_match_top1": bool((res["top"]["indices"][:, 0] == idx).all().item()),
+        "includes": "query table build, 13 x (accumulate + per-position max + radix select), gather of the selected rows and "
+                    "their device->host copies (the reference's .cpu() calls)",
+    }
+
+
 def encode_9b_extra(torch, dev, tokens=1 << 16):
     """BASELINE configs[3]: Gemma-2-9B width (d=3584), deeper stack (nq=2048), encode-only code extraction."""
     from rqae_b200 import RQAE
@@ -435,6 +476,11 @@ def run_b200(args, rank, local_rank, world):
                 extra["config4_9b_encode_only"] = encode_9b_extra(torch, dev)
             except Exception as e:
                 extra["config4_9b_encode_only"] = {"error": repr(e)}
+        if not args.no_extras and world == 1:
+            try:
+                extra["example_search"] = search_extras(torch, model, dev)
+            except Exception as e:
+                extra["example_search"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:

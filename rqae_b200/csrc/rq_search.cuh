@@ -23,8 +23,9 @@
 //                             sequences of every query position without the reference's full argsort
 //
 // Bound: the table rows.  A token-layer reads 256 B of table against 2-4 B of code store, and a layer's slab
-// (K x 256 B = 160 KB at K = 625) is as large as an SM's L1, so the row loads are served by L2: this first
-// version is L2-bandwidth-bound, not HBM-bound (DESIGN.md 4.6 has the arithmetic and the plan).
+// (K x 256 B = 160 KB at K = 625) is as large as an SM's L1 (hit rate 9 %), so the rows come from L2: the kernel
+// runs at the rate L2 delivers 256-byte rows to the SMs (6.2-7.6 TB/s measured), not at the HBM rate of the code
+// store (DESIGN.md 4.6 has the arithmetic, the measurements and the plan).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -83,10 +84,17 @@ struct SearchAccParams {
   __half* acc;              // [n_tokens][SR_Q]
 };
 
-__device__ __forceinline__ float sr_round_h(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ uint32_t sr_pack(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 sr_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 
-template <typename CodeT>
-__global__ void __launch_bounds__(SR_THREADS) search_accumulate_kernel(const SearchAccParams p) {
+// DEPTH = row loads kept in flight per token: the loads of layer i + DEPTH are issued as soon as layer i has been
+// consumed, so a warp has DEPTH x 8 independent 256-byte row loads outstanding instead of 8 (the first version waited
+// for every layer's rows before asking for the next: 17 B/clk/SM, r1s ncu).
+template <typename CodeT, int DEPTH>
+__global__ void __launch_bounds__(SR_THREADS, 2) search_accumulate_kernel(const SearchAccParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const CodeT* __restrict__ codes = (const CodeT*)p.codes;
   const long long n_tiles = (p.n_tokens + SR_TILE - 1) / SR_TILE;
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(SR_THREADS) search_accumulate_kernel(const Sea
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tok0 = tile * SR_TILE + warp * SR_TOK_PER_WARP;
     if (tok0 >= p.n_tokens) continue;
-    float rng[SR_TOK_PER_WARP][4];          // the range's value so far, already fp16-representable
+    uint32_t rng[SR_TOK_PER_WARP][2];       // the range's value so far: four fp16 per token, packed
     for (int c0 = p.layer_begin; c0 < p.layer_end; c0 += SR_CHUNK) {
       const int c1 = (c0 + SR_CHUNK < p.layer_end) ? c0 + SR_CHUNK : p.layer_end;
       float cs[SR_TOK_PER_WARP][4];
@@ -111,47 +119,61 @@ __global__ void __launch_bounds__(SR_THREADS) search_accumulate_kernel(const Sea
             mine[j] = (v >= 0 && v < K) ? (int)v : -1;
           }
         }
-        for (int i = 0; i < nl; ++i) {
-          const __half* slab = p.table + (size_t)(l0 + i) * K * SR_Q + 4 * lane;
-          uint2 w[SR_TOK_PER_WARP];          // all eight row loads are issued before the first add
+        const __half* slab0 = p.table + (size_t)l0 * K * SR_Q + 4 * lane;
+        uint2 w[DEPTH][SR_TOK_PER_WARP];
+        // issue the eight row loads of layer l0 + i into buffer b
+#define SR_ISSUE(b, i)                                                                              \
+  {                                                                                                 \
+    const __half* slab = slab0 + (size_t)(i) * K * SR_Q;                                            \
+    _Pragma("unroll") for (int j = 0; j < SR_TOK_PER_WARP; ++j) {                                   \
+      const int c = __shfl_sync(0xffffffffu, mine[j], (i)); /* warp-uniform */                      \
+      w[b][j] = make_uint2(0u, 0u); /* a code outside [0, K) or a token past the end adds +0 */     \
+      if (c >= 0) w[b][j] = __ldg(reinterpret_cast<const uint2*>(slab + (size_t)c * SR_Q));         \
+    }                                                                                               \
+  }
 #pragma unroll
-          for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
-            const int c = __shfl_sync(0xffffffffu, mine[j], i);     // warp-uniform
-            w[j] = make_uint2(0u, 0u);       // a code outside [0, K) or a token past the end adds +0
-            if (c >= 0) w[j] = __ldg(reinterpret_cast<const uint2*>(slab + (size_t)c * SR_Q));
-          }
+        for (int d = 0; d < DEPTH; ++d)
+          if (d < nl) SR_ISSUE(d, d)
+        for (int i = 0; i < nl; i += DEPTH) {
 #pragma unroll
-          for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w[j].x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j].y));
-            cs[j][0] += lo.x; cs[j][1] += lo.y; cs[j][2] += hi.x; cs[j][3] += hi.y;
+          for (int d = 0; d < DEPTH; ++d) {
+            if (i + d < nl) {
+#pragma unroll
+              for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
+                const float2 lo = sr_unpack(w[d][j].x), hi = sr_unpack(w[d][j].y);
+                cs[j][0] += lo.x; cs[j][1] += lo.y; cs[j][2] += hi.x; cs[j][3] += hi.y;   // ascending layer order
+              }
+              if (i + d + DEPTH < nl) SR_ISSUE(d, i + d + DEPTH)
+            }
           }
         }
+#undef SR_ISSUE
       }
 #pragma unroll
       for (int j = 0; j < SR_TOK_PER_WARP; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float h = sr_round_h(cs[j][e]);                       // sum(dim=-1) of an fp16 tensor
-          rng[j][e] = (c0 == p.layer_begin) ? h : sr_round_h(rng[j][e] + h);   // intensities += chunk (fp16)
+        for (int e = 0; e < 2; ++e) {
+          const uint32_t h = sr_pack(cs[j][2 * e], cs[j][2 * e + 1]);              // sum(dim=-1) of an fp16 tensor
+          if (c0 == p.layer_begin) {
+            rng[j][e] = h;
+          } else {                                                                 // intensities += chunk (fp16)
+            const float2 a = sr_unpack(rng[j][e]), b = sr_unpack(h);
+            rng[j][e] = sr_pack(a.x + b.x, a.y + b.y);
+          }
         }
     }
 #pragma unroll
     for (int j = 0; j < SR_TOK_PER_WARP; ++j) {
       if (tok0 + j >= p.n_tokens) break;
       uint2* dst = reinterpret_cast<uint2*>(p.acc + (size_t)(tok0 + j) * SR_Q + 4 * lane);
-      float r0 = rng[j][0], r1 = rng[j][1], r2 = rng[j][2], r3 = rng[j][3];
-      if (!p.first) {                                                  // intensity_accumulation += range (fp16)
+      uint2 r = make_uint2(rng[j][0], rng[j][1]);
+      if (!p.first) {                                                              // intensity_accumulation += range (fp16)
         const uint2 o = *dst;
-        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&o.x));
-        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&o.y));
-        r0 = lo.x + r0; r1 = lo.y + r1; r2 = hi.x + r2; r3 = hi.y + r3;
+        const float2 a0 = sr_unpack(o.x), b0 = sr_unpack(r.x), a1 = sr_unpack(o.y), b1 = sr_unpack(r.y);
+        r.x = sr_pack(a0.x + b0.x, a0.y + b0.y);
+        r.y = sr_pack(a1.x + b1.x, a1.y + b1.y);
       }
-      const __half2 a = __floats2half2_rn(r0, r1), b = __floats2half2_rn(r2, r3);
-      uint2 w;
-      w.x = *reinterpret_cast<const uint32_t*>(&a);
-      w.y = *reinterpret_cast<const uint32_t*>(&b);
-      *dst = w;
+      *dst = r;
     }
   }
 }
@@ -166,25 +188,35 @@ struct SearchMaxParams {
   __half* out;              // [n_query][out_stride]; columns n_seq..out_stride-1 are zero-filled
 };
 
+__device__ __forceinline__ float sr_max_nan(float m, float v) { return (v > m || v != v) ? v : m; }   // torch.max: a NaN wins and stays
+
+// 32 sequences per CTA; a warp takes four of them in turn and reads whole 256-byte rows (lane = 4 query positions).
 __global__ void __launch_bounds__(256) search_posmax_kernel(const SearchMaxParams p) {
   __shared__ __half tile[32][SR_Q + 2];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n0 = (long long)blockIdx.x * 32;
-  {
-    const int q = tid & (SR_Q - 1), half_id = tid >> 7;
-    for (int nl = half_id; nl < 32; nl += 2) {
-      const long long n = n0 + nl;
-      float m = 0.f;
-      if (n < p.n_seq) {
-        const __half* src = p.acc + (size_t)n * p.seq_len * SR_Q + q;
-        m = __half2float(src[0]);
-        for (int s = 1; s < p.seq_len; ++s) {
-          const float v = __half2float(src[(size_t)s * SR_Q]);
-          m = (v > m || v != v) ? v : m;          // torch.max: a NaN wins and stays
-        }
+  for (int k = 0; k < 4; ++k) {
+    const int nl = warp * 4 + k;
+    const long long n = n0 + nl;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    if (n < p.n_seq) {
+      const uint2* src = reinterpret_cast<const uint2*>(p.acc + (size_t)n * p.seq_len * SR_Q) + lane;
+      {
+        const uint2 w = src[0];
+        const float2 lo = sr_unpack(w.x), hi = sr_unpack(w.y);
+        m0 = lo.x; m1 = lo.y; m2 = hi.x; m3 = hi.y;
       }
-      tile[nl][q] = __float2half_rn(m);
+#pragma unroll 4
+      for (int s = 1; s < p.seq_len; ++s) {
+        const uint2 w = src[(size_t)s * (SR_Q / 4)];
+        const float2 lo = sr_unpack(w.x), hi = sr_unpack(w.y);
+        m0 = sr_max_nan(m0, lo.x); m1 = sr_max_nan(m1, lo.y); m2 = sr_max_nan(m2, hi.x); m3 = sr_max_nan(m3, hi.y);
+      }
     }
+    tile[nl][4 * lane + 0] = __float2half_rn(m0);
+    tile[nl][4 * lane + 1] = __float2half_rn(m1);
+    tile[nl][4 * lane + 2] = __float2half_rn(m2);
+    tile[nl][4 * lane + 3] = __float2half_rn(m3);
   }
   __syncthreads();
   {

@@ -841,9 +841,19 @@ int rqae_search_accumulate_f16(const void* table, int K, const void* codes, int 
   const long long tiles = (n_tokens + rq::SR_TILE - 1) / rq::SR_TILE;
   const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);
   cudaStream_t st = (cudaStream_t)stream;
-  if (code_dtype == RQAE_CODE_I64) rq::search_accumulate_kernel<long long><<<grid, rq::SR_THREADS, 0, st>>>(ap);
-  else if (code_dtype == RQAE_CODE_I32) rq::search_accumulate_kernel<int><<<grid, rq::SR_THREADS, 0, st>>>(ap);
-  else rq::search_accumulate_kernel<short><<<grid, rq::SR_THREADS, 0, st>>>(ap);
+  // RQAE_SEARCH_DEPTH = 1 / 2 / 3 selects how many layers of row loads a warp keeps in flight (A/B timing knob;
+  // measured on the full store: 197 / 196 / 275 ms, profiles/r1s_search_ab.jsonl)
+  static const int depth = [] { const char* e = getenv("RQAE_SEARCH_DEPTH"); const int d = e ? atoi(e) : 2; return d < 1 ? 1 : (d > 3 ? 3 : d); }();
+#define RQ_SR_LAUNCH(T)                                                                                   \
+  do {                                                                                                    \
+    if (depth == 1) rq::search_accumulate_kernel<T, 1><<<grid, rq::SR_THREADS, 0, st>>>(ap);              \
+    else if (depth == 2) rq::search_accumulate_kernel<T, 2><<<grid, rq::SR_THREADS, 0, st>>>(ap);         \
+    else rq::search_accumulate_kernel<T, 3><<<grid, rq::SR_THREADS, 0, st>>>(ap);                         \
+  } while (0)
+  if (code_dtype == RQAE_CODE_I64) RQ_SR_LAUNCH(long long);
+  else if (code_dtype == RQAE_CODE_I32) RQ_SR_LAUNCH(int);
+  else RQ_SR_LAUNCH(short);
+#undef RQ_SR_LAUNCH
   RQ_CUDA(cudaGetLastError());
   g_launches++;
   return RQAE_OK;
@@ -854,6 +864,7 @@ int rqae_search_position_max_f16(const void* acc, int64_t n_seq, int seq_len, in
   if (!acc || !out || n_seq < 0 || seq_len <= 0 || n_query <= 0) return RQAE_EINVAL;
   if (n_query > rq::SR_Q) return RQAE_EUNSUPPORTED;
   if (out_stride < n_seq || (out_stride & 7) || ((uintptr_t)out & 15)) return RQAE_EINVAL;   // the layout rq_mine_kernel reads
+  if ((uintptr_t)acc & 7) return RQAE_EINVAL;                                                // 8-byte lane loads
   if (out_stride == 0) return RQAE_OK;
   int sms = 0;
   int rc = device_sm_count(&sms);
