@@ -91,3 +91,27 @@ def select_top_middle_bottom(values: torch.Tensor, top_k: int = 100):
     bottom = order[-top_k:]
     middle = order[n // 2 - top_k // 2: n // 2 + top_k // 2]
     return top, middle, bottom
+
+
+def get_activations(all_intensities: torch.Tensor, layers: Sequence[int], top_k: int, seq_len: int, stable: bool = False):
+    """scripts/3_make_rqae_features.py:115-149 after the intensities are known.  all_intensities (T, len(layers)),
+    tokens sequence-major.  Per layer: the sequence numbers of the selected tokens (top, then middle, then bottom),
+    de-duplicated in order of first appearance (:133-139), and each such sequence's activations at all of its
+    positions (:143-147).  ``stable=True`` orders equal values by index, as the CUDA selection does; the reference's
+    ``torch.argsort`` (stable=False) leaves that order unspecified.  Returns {layer: (sequences list, (n, seq_len) array)}."""
+    out = {}
+    for j, l in enumerate(layers):
+        col = all_intensities[:, j]
+        if stable:
+            order = torch.sort(col.float(), descending=True, stable=True).indices
+            n = len(order)
+            picked = torch.cat([order[:top_k], order[n // 2 - top_k // 2: n // 2 + top_k // 2], order[-top_k:]])
+        else:
+            picked = torch.cat(select_top_middle_bottom(col, top_k))
+        seqs = []
+        for k in picked.tolist():
+            if k // seq_len not in seqs:
+                seqs.append(k // seq_len)
+        acts = torch.stack([col[s * seq_len:(s + 1) * seq_len] for s in seqs]).numpy()
+        out[l] = (seqs, acts)
+    return out

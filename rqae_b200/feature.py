@@ -231,3 +231,83 @@ class RQAEFeature:
             except Exception:
                 pass
         return cls(**params)
+
+
+def _sequences_in_order(picked: Sequence[int], seq_len: int) -> List[int]:
+    """scripts/3:129-139: sequence numbers of the picked token positions, first appearance kept."""
+    seen, out = set(), []
+    for k in picked:
+        s = int(k) // seq_len
+        if s not in seen:
+            seen.add(s)
+            out.append(s)
+    return out
+
+
+class FeatureHelper:
+    """``scripts/3_make_rqae_features.py:33-162`` without the Modal decorators: ``tokens`` (sequences, positions),
+    ``texts`` (per sequence) and ``indices`` = the code store (sequences, positions, num_quantizers), here resident on
+    the GPU.  ``get_activations`` keeps the reference's signature and result
+    (``{layer: [{"text": ..., "activations": fp16 ndarray (positions,)}, ...]}``, sequences of the top / middle /
+    bottom-k tokens in order of first appearance); ``get_activations_many`` does the same for a list of features with
+    ONE intensity GEMM and ONE selection launch instead of one container per feature (scripts/3:189-191).  Equal
+    intensities are ordered by token index (the reference's unstable argsort leaves them unspecified)."""
+
+    FEATURE_FOLDER = "/data/datasets/monology_pile/features/rqae-rqae-round_fsq-cbd4-cbs5-nq1024"   # scripts/3:152-158
+
+    def __init__(self, tokens: torch.Tensor, texts: Sequence, indices: torch.Tensor, feature_folder: Optional[str] = None):
+        if not indices.is_cuda:
+            raise RuntimeError("FeatureHelper needs the code store on the GPU; there is no CPU fallback")
+        if indices.dim() != 3 or tuple(indices.shape[:2]) != tuple(tokens.shape[:2]):
+            raise ValueError("indices must be (sequences, positions, num_quantizers) matching tokens (sequences, positions)")
+        self.tokens = tokens
+        self.texts = texts
+        self.indices = indices
+        self.feature_folder = feature_folder or self.FEATURE_FOLDER
+
+    def get_token_indices(self, index: torch.Tensor):
+        """scripts/3:84-89."""
+        if len(index.shape) == 1:
+            return self.indices[index[0], index[1]]
+        return self.indices[index[:, 0], index[:, 1]]
+
+    def get_text(self, index: torch.Tensor):
+        """scripts/3:91-96."""
+        if index.shape[0] == 1:
+            return self.texts[index[0].item()]
+        return self.texts[index[0].item()][index[1].item()]
+
+    def get_activations_many(self, features: Sequence["RQAEFeature"], layers: list = None, top_k: int = 100) -> List[dict]:
+        if not features:
+            return []
+        if layers is None:
+            layers = features[0].layers
+        rqae = features[0].rqae
+        if rqae is None:
+            raise ValueError("Model not loaded. Needed for intensity calculation.")
+        n_seq, seq_len = self.indices.shape[:2]
+        centers = torch.stack([f.center.reshape(-1) for f in features])
+        inten = intensity_many(rqae, self.indices, centers, layers, layer_weights=features[0].layer_weights)   # (F, C, T)
+        sel, _ = select_top_middle_bottom(inten, top_k)                                                        # (F, C, 3, k)
+        sel = sel.cpu()
+        mid = 2 * (top_k // 2)
+        results = []
+        for f in range(len(features)):
+            activations = {}
+            for j, l in enumerate(layers):
+                picked = sel[f, j, 0].tolist() + sel[f, j, 1, :mid].tolist() + sel[f, j, 2].tolist()
+                seqs = _sequences_in_order(picked, seq_len)
+                rows = inten[f, j].reshape(n_seq, seq_len)[torch.tensor(seqs, device=inten.device)].cpu().numpy()
+                activations[l] = [{"text": self.texts[s], "activations": rows[i]} for i, s in enumerate(seqs)]
+            results.append(activations)
+        return results
+
+    def get_activations(self, rqae: "RQAEFeature", layers: list = None, top_k: int = 100, index=None):
+        """scripts/3:98-162."""
+        import os
+        activations = self.get_activations_many([rqae], layers=layers, top_k=top_k)[0]
+        if index is not None:
+            rqae.activations = activations
+            os.makedirs(self.feature_folder, exist_ok=True)
+            rqae.save(os.path.join(self.feature_folder, f"{index:06d}.npz"))
+        return activations

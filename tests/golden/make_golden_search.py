@@ -3,7 +3,8 @@
 Run in the build container only (needs /root/reference):  python tests/golden/make_golden_search.py
 
 server.py imports ``modal`` at module level and that package is not in this image, so a stub module whose
-decorators return the decorated object is put into ``sys.modules`` first; nothing of the reference is edited.
+decorators return the decorated object is put into ``sys.modules`` first (tests/golden/_ref_loader.py); nothing of
+the reference is edited.
 ``IntensityEngine.find_examples`` (server.py:159-325) calls ``.cuda()`` on its tensors; there is no GPU in the
 build container, so ``torch.Tensor.cuda`` is an identity for the duration of the script and the reference's
 torch code runs on the CPU.  The engine object is created without ``setup()`` (which reads a Modal volume)
@@ -20,10 +21,8 @@ Writes tests/golden/kat_search.npz with two cases:
 Each case holds the scaled fp16 table, the code shards, the query and, per yielded layer, the reference's
 top / middle / bottom ``indices`` and ``intensities``.
 """
-import importlib.util
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -33,34 +32,12 @@ REF = "/root/reference"
 sys.path.insert(0, REF)
 
 
-class _Stub:
-    """Stands in for every attribute of ``modal``: calling it with one plain callable (a decorator use)
-    returns that callable, anything else returns another stub; usable as a context manager."""
-
-    def __getattr__(self, k):
-        return _Stub()
-
-    def __call__(self, *a, **k):
-        if len(a) == 1 and callable(a[0]) and not k and not isinstance(a[0], _Stub):
-            return a[0]
-        return _Stub()
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
+sys.path.insert(0, HERE)
+from _ref_loader import load_reference_file  # noqa: E402
 
 
 def load_reference_server():
-    modal = types.ModuleType("modal")
-    for n in ["App", "Volume", "Image", "build", "enter", "method", "asgi_app"]:
-        setattr(modal, n, _Stub())
-    sys.modules["modal"] = modal
-    spec = importlib.util.spec_from_file_location("ref_server", os.path.join(REF, "demo", "server", "server.py"))
-    srv = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(srv)
-    return srv
+    return load_reference_file("demo/server/server.py", "ref_server")
 
 
 def run(engine, out, prefix, tag, **kw):

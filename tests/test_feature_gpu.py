@@ -175,3 +175,45 @@ def test_mining_pipeline_intensity_then_selection(kat):
             assert torch.equal(o[f, c][idx[f, c, 0].cpu().long()].float(), o[f, c][top].float())
             assert torch.equal(o[f, c][idx[f, c, 1].cpu().long()].float(), o[f, c][mid].float())
             assert torch.equal(o[f, c][idx[f, c, 2].cpu().long()].float(), o[f, c][bot].float())
+
+
+@pytest.mark.parametrize("top_k", [7, 100])
+def test_feature_helper_get_activations(top_k):
+    """FeatureHelper (scripts/3_make_rqae_features.py:33-162): the result dict equals the oracle's restatement of
+    scripts/3:115-149 applied to the kernel's own intensities with index-ordered ties, and sits within ATOL of what the
+    unmodified reference returned for the same store (tests/golden/kat_mining.npz)."""
+    from rqae_b200.feature import FeatureHelper, RQAEFeature, intensity_many
+    kat = np.load(os.path.join(ROOT, "tests", "golden", "kat_mining.npz"))
+    dev = _dev()
+    model = _Stub(torch.from_numpy(kat["cb0"]), dev)
+    model.num_quantizers, model.codebook_dim = 64, 4
+    codes = torch.from_numpy(kat["codes"].astype(np.int64))
+    N, S, _ = codes.shape
+    layers = [int(l) for l in kat["layers"]]
+    lw = torch.from_numpy(kat["lw"])
+    feats = []
+    for c in kat["centers"]:
+        f = RQAEFeature(num_quantizers=64, dim=4, center=c, layers=layers)
+        f.rqae, f.layer_weights = model, lw
+        feats.append(f)
+    helper = FeatureHelper(torch.zeros(N, S, dtype=torch.int64), list(range(N)), codes.to(dev).to(torch.int16))
+    many = helper.get_activations_many(feats, top_k=top_k)
+    inten = intensity_many(model, helper.indices, torch.from_numpy(kat["centers"]), layers, layer_weights=lw).cpu()
+    for fi, acts in enumerate(many):
+        want = fo.get_activations(inten[fi].T.contiguous(), layers, top_k, S, stable=True)
+        for l in layers:
+            seqs, rows = want[l]
+            assert [a["text"] for a in acts[l]] == seqs, (fi, l)
+            got_rows = np.stack([a["activations"] for a in acts[l]])
+            assert got_rows.dtype == np.float16 and np.array_equal(got_rows, rows), (fi, l)
+            gold_seqs = [int(s) for s in kat[f"f{fi}/k{top_k}/{l}/sequences"]]
+            gold_rows = kat[f"f{fi}/k{top_k}/{l}/activations"].astype(np.float32)
+            pos = {s: i for i, s in enumerate(seqs)}
+            common = [s for s in gold_seqs if s in pos]
+            assert len(common) >= 0.5 * len(gold_seqs), (fi, l, len(common), len(gold_seqs))
+            for s in common:
+                assert np.abs(got_rows[pos[s]].astype(np.float32) - gold_rows[gold_seqs.index(s)]).max() <= ATOL
+            # the extreme values agree within the intensity tolerance whatever the tie order
+            assert abs(float(got_rows.max()) - float(gold_rows.max())) <= ATOL and abs(float(got_rows.min()) - float(gold_rows.min())) <= ATOL
+    one = helper.get_activations(feats[0], top_k=top_k)
+    assert [a["text"] for a in one[layers[-1]]] == [a["text"] for a in many[0][layers[-1]]]

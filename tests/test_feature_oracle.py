@@ -84,3 +84,22 @@ def test_feature_save_load_roundtrip(tmp_path):
     f.save(path)
     g = RQAEFeature.load(path)
     assert g.id == "7" and list(g.layers) == [1, 7] and torch.equal(g.center, f.center)
+
+
+@pytest.mark.parametrize("f", [0, 1])
+@pytest.mark.parametrize("top_k", [7, 100])
+def test_mining_selection_bit_identical_to_reference_get_activations(f, top_k):
+    """scripts/3_make_rqae_features.py:98-149 run unmodified (tests/golden/make_golden_mining.py): intensities, argsort,
+    the three slices, de-duplication by sequence and the per-sequence activation rows."""
+    kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat_mining.npz"))
+    codes = torch.from_numpy(kat["codes"].astype(np.int64))                  # (N, S, nq)
+    N, S, _ = codes.shape
+    layers = [int(l) for l in kat["layers"]]
+    sims = fo.codebook_sims(torch.from_numpy(kat["cb0"]))
+    inten = fo.intensity(sims, torch.from_numpy(kat["centers"][f]), codes, torch.from_numpy(kat["lw"]), layers)
+    got = fo.get_activations(inten.flatten(0, 1), layers, top_k, S)
+    for l in layers:
+        seqs, acts = got[l]
+        assert seqs == [int(s) for s in kat[f"f{f}/k{top_k}/{l}/sequences"]], l
+        want = kat[f"f{f}/k{top_k}/{l}/activations"]
+        assert acts.dtype == want.dtype and np.array_equal(acts.view(np.uint16), want.view(np.uint16)), l
