@@ -275,6 +275,25 @@ def mining_extras(torch, model, codes, dev):
     return res
 
 
+def search_cpu_port(torch, sims_cpu, sequences=256, positions=127, seed=78):
+    """The reference's CPU path for the example search (oracle port of demo/server/server.py:159-325, same ATen calls),
+    on a bounded sample of the store: `sequences` synthetic sequences, one 127-position query, the server's 13 cuts."""
+    from oracle import search_oracle as so
+    import time as _t
+    nq, K = sims_cpu.shape[0], sims_cpu.shape[1]
+    g = torch.Generator().manual_seed(seed)
+    codes = torch.randint(0, K, (sequences, positions, nq), generator=g, dtype=torch.int32)
+    k = min(10, sequences)
+    t0 = _t.perf_counter()
+    n = 0
+    for _res, _layer in so.find_examples([codes], sims_cpu, codes[sequences // 3], k, k, k, so.SERVER_LAYERS):
+        n += 1
+    dt = _t.perf_counter() - t0
+    return {"sequences_per_s": sequences / dt, "seconds": dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sequences} sequences x {positions} positions x {max(so.SERVER_LAYERS)} layers, 127-position query, "
+                      f"{n} cuts, torch CPU (oracle port of server.py find_examples)"}
+
+
 def search_extras(torch, model, dev, sequences=36864, positions=127):
     """nearest-example search (demo/server/server.py:159-325) over a code store of the reference's shape
     (36 864 sequences x 127 positions x 1024 layers, server.py:139; synthetic uniform codes, int16, resident in HBM) with
@@ -305,7 +324,12 @@ def search_extras(torch, model, dev, sequences=36864, positions=127):
     # and by the per-position max
     acc_bytes = sequences * positions * 128 * 2
     hbm = rows * 2 + acc_bytes * (3 * len(SERVER_LAYERS) - 1)
+    try:
+        cpu = search_cpu_port(torch, eng.sims.cpu())
+    except Exception as e:
+        cpu = {"error": repr(e)}
     return {
+        "cpu_port": cpu,
         "sequences": sequences, "positions": positions, "layers": L, "query_positions": positions, "cuts": len(SERVER_LAYERS),
         "find_examples_ms": ms, "sequences_per_s": sequences / ms * 1e3, "launches_per_query": launches,
         "table_row_tbps": rows * 256 / ms / 1e9, "hbm_gbs": hbm / ms / 1e6, "hbm_frac_of_peak": hbm / ms / 1e6 / hbm_peak,
