@@ -136,24 +136,37 @@ class IntensityEngine:
         """server.py:159-325."""
         layers = list(layers)
         query = self._query(idx, activation, max(layers))
-        N, S, _ = self.activations.shape
+        N = self.activations.shape[0]
         Sq = query.shape[0]
-        top, mid, bot = int(top_examples), int(middle_examples), int(bottom_examples)
-        k = max(top, mid, bot, 1)
-        if k > SELECT_KMAX:
-            raise NotImplementedError(f"at most {SELECT_KMAX} examples per window")
-        k = min(k, N)
-        kh, mh = k // 2, mid // 2
-        if mh > kh:
-            raise ValueError(f"middle_examples={mid} needs at least {2 * mh} sequences, the store has {N}")
+        k = window_k(top_examples, middle_examples, bottom_examples, N)
         from .feature import select_top_middle_bottom
         qpos = torch.arange(Sq, device=self.sims.device).unsqueeze(-1)
         for layer, (acc, maxv) in zip(layers, self.accumulate(query, layers)):
             sel, _ = select_top_middle_bottom(maxv, k, n=N)                  # (Sq, 3, k) int32
-            lists = {"top": sel[:, 0, :min(top, k)], "middle": sel[:, 1, kh - mh: kh + mh],
-                     "bottom": sel[:, 2, k - min(bot, k):]}
             out = {}
-            for name, lst in lists.items():
+            for name, lst in window_lists(sel, top_examples, middle_examples, bottom_examples).items():
                 inten = acc[lst.long(), :, qpos]                              # (Sq, k', S): intensity_accumulation[lst[i], :, i]
                 out[name] = {"indices": lst.cpu().int(), "intensities": inten.cpu().to(torch.float16)}
             yield out, layer
+
+
+def window_k(top_examples: int, middle_examples: int, bottom_examples: int, n_sequences: int) -> int:
+    """The single window size the radix select is asked for: it returns argsort[:k], argsort[n//2 - k//2 : n//2 + k//2]
+    and argsort[-k:]; the three lists of server.py:271-287 are sub-slices of those (``window_lists``)."""
+    top, mid, bot = int(top_examples), int(middle_examples), int(bottom_examples)
+    k = max(top, mid, bot, 1)
+    if k > SELECT_KMAX:
+        raise NotImplementedError(f"at most {SELECT_KMAX} examples per window")
+    k = min(k, int(n_sequences))
+    if mid // 2 > k // 2:
+        raise ValueError(f"middle_examples={mid} needs at least {2 * (mid // 2)} sequences, the store has {n_sequences}")
+    return k
+
+
+def window_lists(sel: torch.Tensor, top_examples: int, middle_examples: int, bottom_examples: int) -> dict:
+    """sel (Sq, 3, k) from the select -> {"top": (Sq, top), "middle": (Sq, 2*(mid//2)), "bottom": (Sq, bottom)},
+    i.e. sorted[:top], sorted[n//2 - mid//2 : n//2 + mid//2], sorted[-bottom:] of server.py:271-287."""
+    k = sel.shape[-1]
+    top, mh, bot = min(int(top_examples), k), int(middle_examples) // 2, min(int(bottom_examples), k)
+    kh = k // 2
+    return {"top": sel[:, 0, :top], "middle": sel[:, 1, kh - mh: kh + mh], "bottom": sel[:, 2, k - bot:]}

@@ -131,3 +131,68 @@ def mine_sharded(intens_local: torch.Tensor, n_tokens: int, top_k: int = 100, se
     rows, frange = exchange_to_feature_shards(intens_local, n_tokens, group=group)
     idx, val = select_fn(rows, top_k)
     return idx, val, frange
+
+
+# ---------------------------------------------------------------------------------------------------
+# nearest-example search across GPUs: sequences shard, the ranking is global
+# ---------------------------------------------------------------------------------------------------
+def find_examples_sharded(engine, n_sequences: int, idx: Optional[int] = None, activation: Optional[torch.Tensor] = None,
+                          top_examples: int = 30, middle_examples: int = 10, bottom_examples: int = 10,
+                          layers=None, group: Optional[dist.ProcessGroup] = None, select_fn=None):
+    """``IntensityEngine.find_examples`` (demo/server/server.py:159-325) over a code store whose SEQUENCES are split
+    across ranks: ``engine`` is this rank's ``rqae_b200.search.IntensityEngine`` over the contiguous range
+    ``token_range(n_sequences, rank, world)``.  The accumulation has no cross-sequence term, so each rank runs the
+    kernels on its shard; per layer cut the only exchange is an all_gather of the per-position maxima (Sq x N fp16:
+    9.4 MB for the reference's 36 864 sequences) -- every rank then ranks all sequences with the radix select -- and
+    an all_reduce that collects the (Sq, k, S) intensity rows of the selected sequences from their owners.  Yields
+    the reference's ``(result dict, layer)`` on every rank, equal to the single-GPU result.  ``idx`` is a GLOBAL
+    sequence number; its owner broadcasts the query codes.  ``select_fn(rows (Sq, N) fp16, k) -> (idx (Sq, 3, k), val)``
+    defaults to the CUDA radix select."""
+    from .search import SERVER_LAYERS, window_k, window_lists
+    if select_fn is None:
+        from .feature import select_top_middle_bottom as select_fn
+    layers = list(SERVER_LAYERS if layers is None else layers)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = token_range(n_sequences, rank, world)
+    n_local, seq_len = engine.activations.shape[:2]
+    if n_local != hi - lo:
+        raise ValueError(f"rank {rank} must hold sequences [{lo}, {hi}), its engine holds {n_local}")
+    if activation is not None and idx is not None:
+        raise ValueError("Cannot specify both idx and activation")                 # server.py:174-175
+    if activation is None and idx is None:
+        raise ValueError("Must specify either idx or activation")                  # server.py:181-182
+    L = max(layers)
+    dev = engine.sims.device
+    if idx is not None:
+        if not 0 <= int(idx) < n_sequences:
+            raise IndexError(f"idx {idx} outside the {n_sequences} sequences of the store")
+        owner = next(r for r in range(world) if token_range(n_sequences, r, world)[0] <= int(idx) < token_range(n_sequences, r, world)[1])
+        query = engine._query(int(idx) - lo, None, L) if rank == owner else torch.empty(seq_len, L, dtype=torch.int32, device=dev)
+        dist.broadcast(query, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    else:
+        query = engine._query(None, activation, L)
+    Sq = query.shape[0]
+    k = window_k(top_examples, middle_examples, bottom_examples, n_sequences)
+    sizes = [token_range(n_sequences, r, world)[1] - token_range(n_sequences, r, world)[0] for r in range(world)]
+    widest = max(sizes)
+    qpos = torch.arange(Sq, device=dev).unsqueeze(-1)
+    n_pad = (n_sequences + 7) // 8 * 8
+    for layer, (acc, maxv) in zip(layers, engine.accumulate(query, layers)):
+        mine = torch.zeros(Sq, widest, dtype=torch.float16, device=dev)
+        mine[:, :n_local] = maxv
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        rows = torch.zeros(Sq, n_pad, dtype=torch.float16, device=dev)             # row layout of the radix select
+        rows[:, :n_sequences] = torch.cat([p[:, :sizes[r]] for r, p in enumerate(parts)], dim=1)
+        sel, _ = select_fn(rows[:, :n_sequences], k)
+        out = {}
+        for name, lst in window_lists(sel, top_examples, middle_examples, bottom_examples).items():
+            g = lst.long()
+            own = (g >= lo) & (g < hi)
+            inten = torch.zeros(Sq, g.shape[1], seq_len, dtype=torch.float32, device=dev)
+            if bool(own.any()):
+                qq = qpos.expand_as(g)
+                inten[own] = acc[g[own] - lo, :, qq[own]].float()
+            dist.all_reduce(inten, group=group)                                    # one owner per row: the sum is exact
+            out[name] = {"indices": lst.cpu().int(), "intensities": inten.cpu().to(torch.float16)}
+        yield out, layer

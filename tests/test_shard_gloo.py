@@ -121,3 +121,88 @@ def test_two_rank_mining_exchange_equals_single_process(tmp_path):
         got[fa:fb] = torch.from_numpy(np.load(os.path.join(str(tmp_path), f"mine_{r}.npy")))
         seen += fb - fa
     assert seen == n_feat and torch.equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# example search: sequence-sharded store, global ranking (shard.find_examples_sharded)
+# ---------------------------------------------------------------------------------------------------
+class _OracleEngine:
+    """Stand-in for rqae_b200.search.IntensityEngine on CPU ranks: the search ORACLE produces the accumulation and
+    the per-position maxima the kernels would (there is no CPU compute path in the product)."""
+
+    def __init__(self, sims, activations):
+        self.sims, self.activations = sims, activations
+
+    def _query(self, idx, activation, n_layers):
+        q = self.activations[int(idx)] if idx is not None else torch.as_tensor(activation)
+        return q[:, :n_layers].to(torch.int32).contiguous()
+
+    def accumulate(self, query, layers):
+        from oracle import search_oracle as so
+        N, S, nq = self.activations.shape
+        for acc in so.accumulate_steps(self.activations.reshape(N * S, nq), self.sims, query, layers):
+            a3 = acc.reshape(N, S, -1)
+            yield a3, a3.max(dim=1).values.T.contiguous()
+
+
+def _select_rows(rows, k, n=None):
+    idx, _ = _oracle_select(rows.unsqueeze(0), k)
+    return idx[0], None
+
+
+SEARCH_CASE = dict(nq=40, K=27, N=13, S=5, layers=[3, 8, 40], top=4, mid=3, bot=2)
+
+
+def _search_inputs():
+    c = SEARCH_CASE
+    g = torch.Generator().manual_seed(13)
+    sims = torch.randn(c["nq"], c["K"], c["K"], generator=g).half()
+    codes = torch.randint(0, c["K"], (c["N"], c["S"], c["nq"]), generator=g, dtype=torch.int32)
+    ext = torch.randint(0, c["K"], (4, c["nq"]), generator=g, dtype=torch.int32)
+    return sims, codes, ext
+
+
+def _search_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = SEARCH_CASE
+        sims, codes, ext = _search_inputs()
+        a, b = shard.token_range(c["N"], rank, world)
+        eng = _OracleEngine(sims, codes[a:b])
+        res = {}
+        for tag, kw in (("idx", dict(idx=9)), ("ext", dict(activation=ext))):      # sequence 9 lives on rank 1
+            for out, layer in shard.find_examples_sharded(eng, c["N"], top_examples=c["top"], middle_examples=c["mid"],
+                                                          bottom_examples=c["bot"], layers=c["layers"],
+                                                          select_fn=_select_rows, **kw):
+                for part in ("top", "middle", "bottom"):
+                    res[f"{tag}/{layer}/{part}/indices"] = out[part]["indices"].numpy()
+                    res[f"{tag}/{layer}/{part}/intensities"] = out[part]["intensities"].numpy()
+        with pytest.raises(ValueError, match="Cannot specify both"):
+            next(shard.find_examples_sharded(eng, c["N"], idx=1, activation=ext, layers=c["layers"], select_fn=_select_rows))
+        np.savez(os.path.join(out_dir, f"search_{rank}.npz"), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_example_search_equals_single_process(tmp_path):
+    from rqae_b200.search import window_k, window_lists
+    world = 2
+    port = _free_port()
+    mp.spawn(_search_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    c = SEARCH_CASE
+    sims, codes, ext = _search_inputs()
+    eng = _OracleEngine(sims, codes)
+    k = window_k(c["top"], c["mid"], c["bot"], c["N"])
+    got = [np.load(os.path.join(str(tmp_path), f"search_{r}.npz")) for r in range(world)]
+    for tag, query in (("idx", eng._query(9, None, 40)), ("ext", eng._query(None, ext, 40))):
+        qpos = torch.arange(query.shape[0]).unsqueeze(-1)
+        for layer, (acc, maxv) in zip(c["layers"], eng.accumulate(query, c["layers"])):
+            sel, _ = _select_rows(maxv, k)
+            for part, lst in window_lists(sel, c["top"], c["mid"], c["bot"]).items():
+                want_i = lst.int().numpy()
+                want_v = acc[lst.long(), :, qpos].numpy()
+                for r in range(world):
+                    assert np.array_equal(got[r][f"{tag}/{layer}/{part}/indices"], want_i), (tag, layer, part, r)
+                    assert np.array_equal(got[r][f"{tag}/{layer}/{part}/intensities"], want_v), (tag, layer, part, r)
