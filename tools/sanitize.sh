@@ -12,3 +12,6 @@ echo "=== memcheck: forward / decode small cases ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -x -k "small_forward or decode" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_fwd.log
 echo "=== racecheck: radix select ==="
 timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "5000 or 4097 or 257" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine.log
+echo "=== memcheck + racecheck: example search (table transpose, accumulate, per-position max) ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "golden or single_query or argument or int16" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_search.log
+timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "single_query" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_search.log
