@@ -133,3 +133,49 @@ def accumulate_steps(codes: torch.Tensor, sims_h: torch.Tensor, query: torch.Ten
         acc = rng if acc is None else (acc.float() + rng.float()).to(torch.float16)
         assert L >= b
         yield acc
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the rank-5 form of the table (groundwork for a tensor-core variant of the search)
+# ---------------------------------------------------------------------------------------------------------------
+def rank5_factors(w_out: torch.Tensor, b_out: torch.Tensor, codebook: torch.Tensor):
+    """subfeature_sims[l][a][b] (rqae/model.py:145-167) is the cosine of the affine images W_out[l] c + b_out[l] of two
+    codewords, i.e. u_l(a) . u_l(b) with the unit 5-vectors u_l(c) = R_l [c; 1] / |R_l [c; 1]|, R_l^T R_l = [W|b]^T [W|b].
+    w_out (nq, D, cd), b_out (nq, D), codebook (nq, K, cd) -> (nq, K, cd + 1) float64 (zero rows for a zero image)."""
+    g = torch.cat([w_out.double(), b_out.double().unsqueeze(-1)], dim=-1)          # (nq, D, 5)
+    m = g.transpose(1, 2) @ g                                                      # (nq, 5, 5) Gram
+    evals, evecs = torch.linalg.eigh(m)
+    r = evals.clamp_min(0).sqrt().unsqueeze(-1) * evecs.transpose(1, 2)            # R = sqrt(L) V^T, R^T R = M
+    x = torch.cat([codebook.double(), torch.ones_like(codebook[..., :1]).double()], dim=-1)   # (nq, K, 5)
+    u = x @ r.transpose(1, 2)                                                      # rows R [c; 1]
+    n = u.norm(dim=-1, keepdim=True)
+    return torch.where(n > 1e-12, u / n.clamp_min(1e-12), torch.zeros_like(u))
+
+
+def accumulate_rank5(codes: torch.Tensor, factors: torch.Tensor, layer_norms: torch.Tensor, query: torch.Tensor,
+                     layers: Sequence[int], passes: int = 1) -> Iterator[torch.Tensor]:
+    """What a tensor-core form of the search would compute: per layer the 5-term dot product of the dataset token's
+    factor (fp16) with the query position's factor times the layer norm (fp16), exact products accumulated in fp32,
+    with the reference's chunk / range roundings (as in ``accumulate_steps``).  ``passes = 3`` adds the fp16 remainders
+    of both operands (hi*hi + hi*lo + lo*hi, the split the tensor-core decode uses).  codes (T, nq) -> (T, Sq) fp16."""
+    def split(v):
+        hi = v.to(torch.float16)
+        lo = (v - hi.double()).to(torch.float16)
+        return hi.float(), lo.float()
+    d_hi, d_lo = split(factors)                                                    # dataset side
+    q_hi, q_lo = split(factors * layer_norms.double().reshape(-1, 1, 1))           # query side carries the layer norm
+    T, Sq = codes.shape[0], query.shape[0]
+    acc = None
+    for a, b in layer_ranges(layers):
+        rng = None
+        for c0 in range(a, b, CHUNK):
+            run = torch.zeros(T, Sq, dtype=torch.float32)
+            for l in range(c0, min(c0 + CHUNK, b)):
+                dc, qc = codes[:, l].long(), query[:, l].long()
+                run = run + d_hi[l][dc] @ q_hi[l][qc].T
+                if passes == 3:
+                    run = run + d_hi[l][dc] @ q_lo[l][qc].T + d_lo[l][dc] @ q_hi[l][qc].T
+            h = run.to(torch.float16)
+            rng = h if rng is None else (rng.float() + h.float()).to(torch.float16)
+        acc = rng if acc is None else (acc.float() + rng.float()).to(torch.float16)
+        yield acc

@@ -77,3 +77,35 @@ def test_layer_ranges_and_chunks():
     manual += parts[1]
     manual += parts[2]
     assert torch.equal(whole, manual)
+
+
+def test_rank5_form_of_the_table_and_its_distance_from_the_reference():
+    """Groundwork for the tensor-core variant: the engine table is a rank-5 Gram matrix per layer, and
+    a search computed from fp16 factors lands within a few fp16 steps of the reference's table-gather form -- it cannot
+    be bit-exact, because the reference sums fp16-ROUNDED table entries."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import engine_sims
+    torch.manual_seed(3)
+    m = RQAE(dim=96, num_quantizers=160).eval()                       # host-side tables only, no kernel
+    sims = engine_sims(m)                                             # (nq, K, K) fp16 = subfeature_sims * layer_norms
+    w = torch.stack([l[1].weight.detach() for l in m.layers])
+    b = torch.stack([l[1].bias.detach() for l in m.layers])
+    fac = so.rank5_factors(w, b, m.codebook.detach())
+    # 1. the factorisation reproduces the table up to its own fp16 roundings
+    exact = (fac @ fac.transpose(1, 2)) * m.layer_norms.double().reshape(-1, 1, 1)
+    assert float((exact - sims.double()).abs().max()) <= 2 ** -9 * float(m.layer_norms.max())
+    # 2. accumulated over the server's ranges: distance in fp16 steps of the running value
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, 625, (6 * 9, 160), generator=g, dtype=torch.int32)
+    query = codes[:9].clone()
+    layers = [4, 6, 8, 12, 16, 24, 32, 48, 64, 150]
+
+    def steps(t):
+        i = t.contiguous().view(torch.int16).int()
+        return torch.where(i < 0, -(i & 0x7FFF), i)
+    for passes, bar in ((1, 4), (3, 3)):
+        worst = 0
+        for ref, alt in zip(so.accumulate_steps(codes, sims, query, layers),
+                            so.accumulate_rank5(codes, fac, m.layer_norms, query, layers, passes=passes)):
+            worst = max(worst, int((steps(ref) - steps(alt)).abs().max()))
+        assert worst <= bar, (passes, worst)
