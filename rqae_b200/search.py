@@ -70,6 +70,8 @@ class IntensityEngine:
             raise RuntimeError("IntensityEngine needs the code store on the GPU; there is no CPU fallback")
         if activations.dim() != 3 or activations.dtype not in _CODE_DTYPE:
             raise ValueError("activations must be an int16/int32/int64 tensor (sequences, positions, num_quantizers)")
+        if activations.shape[0] == 0 or activations.shape[1] == 0:
+            raise ValueError("the code store is empty")
         self.activations = activations.contiguous()
 
     @classmethod
