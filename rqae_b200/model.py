@@ -432,7 +432,15 @@ class RQAE(nn.Module):
             llm = kwargs.pop("llm")
             assert hasattr(llm, "norm") and hasattr(llm, "denorm"), "RQAE hook requires norm and denorm from LLM"
             return self.hook(norm=llm.norm, denorm=llm.denorm, **kwargs)
-        store = kwargs.get("store", lambda name, value: None)
+        user_store = kwargs.get("store")
+        if user_store is None:
+            # the reference clones five full tensors per call even for its default no-op store (model.py:258,278-288);
+            # without a consumer the clones are skipped ("zero clones when store is the default no-op")
+            def store(name, value):
+                return None
+        else:
+            def store(name, value):
+                return user_store(name, value.detach().clone())
         skip_bos = kwargs.get("skip_bos", True)
         replace = kwargs.get("replace", True)
         if "norm" not in kwargs:
@@ -443,16 +451,16 @@ class RQAE(nn.Module):
 
         def hook_fn(module, input, output):
             hs = output[0].float()                      # (B, S, dim)
-            store("original", hs.detach().clone())
+            store("original", hs)
             rms_hs = norm(hs)
-            store("normed", rms_hs.detach().clone())
+            store("normed", rms_hs)
             q_out, indices = self(rms_hs)               # one fused kernel on the current stream, no sync
-            store("quantized", q_out.detach().clone())
-            store("indices", indices.detach().clone())
+            store("quantized", q_out)
+            store("indices", indices)
             q_out = denorm(q_out, hs)
             if skip_bos:
                 q_out[:, 0] = hs[:, 0]
-            store("new", q_out.detach().clone())
+            store("new", q_out)
             if replace:
                 output[0].data.copy_(q_out)
 

@@ -84,6 +84,23 @@ def test_hook_argument_contract_and_wiring(monkeypatch):
     expect = hs.float() * 2 * 0.5 + 1
     expect[:, 0] = hs.float()[:, 0]
     assert torch.equal(out[0], expect.half())
+    # stored tensors are clones taken at the time of the call (model.py:278-288): the later denorm / BOS overwrite
+    # of q_out must not show in "quantized"
+    assert torch.equal(stash["quantized"], hs.float() * 2 * 0.5)
+    assert stash["quantized"].data_ptr() != stash["new"].data_ptr()
+    # without a store the five clones are skipped
+    clones = {"n": 0}
+    real_clone = torch.Tensor.clone
+
+    def counting_clone(self, *a, **k):
+        clones["n"] += 1
+        return real_clone(self, *a, **k)
+    monkeypatch.setattr(torch.Tensor, "clone", counting_clone)
+    m.hook(norm=lambda h: h, denorm=lambda q, h: q)(None, None, (real_clone(hs),))
+    assert clones["n"] == 0
+    m.hook(norm=lambda h: h, denorm=lambda q, h: q, store=lambda k, v: None)(None, None, (real_clone(hs),))
+    assert clones["n"] == 5
+    monkeypatch.setattr(torch.Tensor, "clone", real_clone)
     out2 = (hs.clone(),)
     m.hook(norm=lambda h: h, denorm=lambda q, h: q, replace=False, skip_bos=False)(None, None, out2)
     assert torch.equal(out2[0], hs)
