@@ -109,3 +109,23 @@ def test_rank5_form_of_the_table_and_its_distance_from_the_reference():
                             so.accumulate_rank5(codes, fac, m.layer_norms, query, layers, passes=passes)):
             worst = max(worst, int((steps(ref) - steps(alt)).abs().max()))
         assert worst <= bar, (passes, worst)
+
+
+def test_engine_table_modes_follow_the_server_setup():
+    """server.py:103-115: 'projected' = subfeature_sims * layer_norms, 'original' = codebook_sims repeated per layer
+    * layer_norms, both multiplied IN fp16; anything else is the reference's ValueError."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import engine_sims
+    torch.manual_seed(5)
+    m = RQAE(dim=48, num_quantizers=5).eval()
+    ln = m.layer_norms
+    proj = engine_sims(m)
+    assert proj.dtype == torch.float16 and proj.shape == (5, 625, 625)
+    assert torch.equal(proj, so.scaled_sims(m.subfeature_sims, ln))
+    assert torch.equal(m.subfeature_sims, so.scaled_sims(m.subfeature_sims, torch.ones(5)))   # the cached table is not scaled in place
+    orig = engine_sims(m, "original")
+    want = m.codebook_sims.unsqueeze(0).repeat(5, 1, 1)
+    want *= ln.unsqueeze(-1).unsqueeze(-1)
+    assert torch.equal(orig, want)
+    with pytest.raises(ValueError, match="Invalid mode"):
+        engine_sims(m, "other")
