@@ -90,9 +90,10 @@ __device__ __forceinline__ uint32_t sr_pack(float a, float b) {
 }
 __device__ __forceinline__ float2 sr_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 
-// DEPTH = row loads kept in flight per token: the loads of layer i + DEPTH are issued as soon as layer i has been
-// consumed, so a warp has DEPTH x 8 independent 256-byte row loads outstanding instead of 8 (the first version waited
-// for every layer's rows before asking for the next: 17 B/clk/SM, r1s ncu).
+// DEPTH = layers of row loads kept in flight per token: the loads of layer i + DEPTH are issued as soon as layer i has
+// been consumed (DEPTH x 8 independent 256-byte rows outstanding per warp).  Measured on the whole store, DEPTH 1 / 2 / 3
+// = 197 / 196 / 275 ms: the kernel is bound by what L2 delivers, not by the latency a warp sees, so 2 is the default
+// (it rides out the DRAM misses of the longest range) and 3 only adds queueing.
 template <typename CodeT, int DEPTH>
 __global__ void __launch_bounds__(SR_THREADS, 2) search_accumulate_kernel(const SearchAccParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
