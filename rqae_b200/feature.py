@@ -244,6 +244,20 @@ def _sequences_in_order(picked: Sequence[int], seq_len: int) -> List[int]:
     return out
 
 
+def unique_token_indices(tokens: torch.Tensor) -> torch.Tensor:
+    """scripts/3:53-82: for every distinct token id (ascending), the (sequence, position) of ONE occurrence chosen
+    uniformly at random -- the first occurrence under a random permutation of all positions.  Draws exactly one
+    ``torch.randperm(tokens.numel())`` from the global generator, as the reference does, so the same seed gives the same
+    result.  Returns int32 (n_unique, 2)."""
+    n, seq_len = tokens.numel(), tokens.shape[1]
+    perm = torch.randperm(n)
+    shuffled = tokens.flatten()[perm]
+    uniq, inverse = torch.unique(shuffled, return_inverse=True)
+    first = torch.full((uniq.numel(),), n, dtype=torch.int64).scatter_reduce(0, inverse, torch.arange(n), reduce="amin")
+    where = perm[first]
+    return torch.stack([where // seq_len, where % seq_len], dim=1).to(torch.int32)
+
+
 class FeatureHelper:
     """``scripts/3_make_rqae_features.py:33-162`` without the Modal decorators: ``tokens`` (sequences, positions),
     ``texts`` (per sequence) and ``indices`` = the code store (sequences, positions, num_quantizers), here resident on
@@ -264,6 +278,10 @@ class FeatureHelper:
         self.texts = texts
         self.indices = indices
         self.feature_folder = feature_folder or self.FEATURE_FOLDER
+
+    def get_unique_token_indices(self):
+        """scripts/3:53-82."""
+        return unique_token_indices(self.tokens)
 
     def get_token_indices(self, index: torch.Tensor):
         """scripts/3:84-89."""

@@ -49,6 +49,13 @@ def main():
             for l in layers:
                 out[f"f{f}/k{top_k}/{l}/sequences"] = np.array([a["text"] for a in acts[l]], np.int32)
                 out[f"f{f}/k{top_k}/{l}/activations"] = np.stack([a["activations"] for a in acts[l]])
+    # get_unique_token_indices (scripts/3:53-82) under a fixed seed: a small vocabulary with repeats
+    vocab_tokens = torch.randint(0, 50, (40, 9), generator=g)
+    helper.tokens = vocab_tokens
+    torch.manual_seed(1234)
+    out["unique/tokens"] = vocab_tokens.numpy()
+    out["unique/seed"] = np.array([1234])
+    out["unique/indices"] = helper.get_unique_token_indices().numpy()
     path = os.path.join(HERE, "kat_mining.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

@@ -103,3 +103,17 @@ def test_mining_selection_bit_identical_to_reference_get_activations(f, top_k):
         assert seqs == [int(s) for s in kat[f"f{f}/k{top_k}/{l}/sequences"]], l
         want = kat[f"f{f}/k{top_k}/{l}/activations"]
         assert acts.dtype == want.dtype and np.array_equal(acts.view(np.uint16), want.view(np.uint16)), l
+
+
+def test_unique_token_indices_equal_the_reference_under_the_same_seed():
+    """FeatureHelper.get_unique_token_indices (scripts/3:53-82, run unmodified by make_golden_mining.py): one random
+    occurrence per distinct token; the mirror draws the same single randperm, so the same seed gives the same picks."""
+    from rqae_b200.feature import unique_token_indices
+    kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat_mining.npz"))
+    tokens = torch.from_numpy(kat["unique/tokens"])
+    torch.manual_seed(int(kat["unique/seed"][0]))
+    got = unique_token_indices(tokens)
+    assert got.dtype == torch.int32 and np.array_equal(got.numpy(), kat["unique/indices"])
+    # every pick is an occurrence of its token, tokens ascending
+    picked = tokens[got[:, 0].long(), got[:, 1].long()]
+    assert torch.equal(picked, torch.unique(tokens))
