@@ -329,3 +329,33 @@ class FeatureHelper:
             os.makedirs(self.feature_folder, exist_ok=True)
             rqae.save(os.path.join(self.feature_folder, f"{index:06d}.npz"))
         return activations
+
+
+SCRIPT3_LAYERS = [2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1023]   # scripts/3:178
+
+
+def make_feature(rqae, feature_helper: "FeatureHelper", num_tokens: int = 1024, layers: Optional[List[int]] = None,
+                 top_k: int = 100, features_per_launch: int = 64, save: bool = True) -> List["RQAEFeature"]:
+    """The driver of ``scripts/3_make_rqae_features.py:164-200`` on one GPU: one random occurrence per distinct token
+    (``get_unique_token_indices``), the 200 lowest and highest token ids dropped, shuffled, the first ``num_tokens``
+    kept (:167-172; two draws from the global generator, as in the reference); each becomes an ``RQAEFeature`` centred
+    on that token's codes (:184-188) whose activations are mined over the whole store and saved as
+    ``<feature_folder>/{i:06d}.npz`` (:150-158).  Where the reference spawns one container per feature (:189-191),
+    ``features_per_launch`` features share one intensity GEMM and one selection launch (64 features x 14 cuts x
+    4.7 M tokens of fp16 intensities = 8.4 GB)."""
+    import os
+    layers = list(SCRIPT3_LAYERS if layers is None else layers)
+    picks = feature_helper.get_unique_token_indices()
+    picks = picks[200:-200]
+    picks = picks[torch.randperm(picks.shape[0])]
+    picks = picks[:num_tokens]
+    centers = feature_helper.get_token_indices(picks)
+    features = [RQAEFeature.from_quantizer(rqae, center=centers[i].cpu().numpy(), layers=layers) for i in range(picks.shape[0])]
+    for f0 in range(0, len(features), features_per_launch):
+        group = features[f0:f0 + features_per_launch]
+        for j, acts in enumerate(feature_helper.get_activations_many(group, layers=layers, top_k=top_k)):
+            group[j].activations = acts
+            if save:
+                os.makedirs(feature_helper.feature_folder, exist_ok=True)
+                group[j].save(os.path.join(feature_helper.feature_folder, f"{f0 + j:06d}.npz"))
+    return features

@@ -124,3 +124,34 @@ def test_derived_tables_match_reference_formulas():
         ref = (n @ n.transpose(-1, -2)).to(torch.float16)
     assert float((m.subfeature_sims.float() - ref.float()).abs().max()) <= 2 ** -10
     assert float((m.subfeature_sims == ref).float().mean()) > 0.99
+
+
+def test_make_feature_driver_follows_scripts3(tmp_path, monkeypatch):
+    """scripts/3_make_rqae_features.py:164-200 as rqae_b200.feature.make_feature: which tokens become features, their
+    centers, batching over features and the saved files -- with the GPU step (get_activations_many) stubbed out."""
+    from rqae_b200 import feature as ft
+    torch.manual_seed(0)
+    m = RQAE(dim=64, num_quantizers=6).eval()
+    g = torch.Generator().manual_seed(1)
+    tokens = torch.randint(0, 450, (300, 7), generator=g)
+    codes = torch.randint(0, 625, (300, 7, 6), generator=g, dtype=torch.int32)
+    helper = ft.FeatureHelper.__new__(ft.FeatureHelper)          # the constructor insists on a CUDA store
+    helper.tokens, helper.texts, helper.indices, helper.feature_folder = tokens, list(range(300)), codes, str(tmp_path / "features")
+    launches = []
+
+    def fake_many(features, layers=None, top_k=100):
+        launches.append(len(features))
+        return [{l: [{"text": 0, "activations": np.zeros(7, np.float16)}] for l in layers} for _ in features]
+    helper.get_activations_many = fake_many
+    torch.manual_seed(7)
+    feats = ft.make_feature(m, helper, num_tokens=10, layers=[1, 3, 5], top_k=4, features_per_launch=4)
+    # the same two draws by hand: unique picks, [200:-200], shuffle, first 10
+    torch.manual_seed(7)
+    picks = ft.unique_token_indices(tokens)[200:-200]
+    picks = picks[torch.randperm(picks.shape[0])][:10]
+    assert len(feats) == 10 and launches == [4, 4, 2]
+    for i, f in enumerate(feats):
+        assert torch.equal(f.center, codes[picks[i, 0], picks[i, 1]]) and f.layers == [1, 3, 5]
+        assert f.layer_weights.dtype == torch.float16 and f.rqae is m
+        back = ft.RQAEFeature.load(str(tmp_path / "features" / f"{i:06d}.npz"))
+        assert torch.equal(back.center, f.center) and list(back.layers) == [1, 3, 5]
