@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step")
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (mining stage, 9B encode)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 4096-token KAT parity block")
+    ap.add_argument("--tokens-9b", type=int, default=1 << 20, help="tokens per GPU of the configs[3] extra")
+    ap.add_argument("--tokens-mining", type=int, default=1 << 21, help="tokens per GPU of the configs[4] extra")
     return ap.parse_args()
 
 
@@ -340,17 +343,246 @@ def search_extras(torch, model, dev, sequences=36864, positions=127):
     }
 
 
-def encode_9b_extra(torch, dev, tokens=1 << 16):
-    """BASELINE configs[3]: Gemma-2-9B width (d=3584), deeper stack (nq=2048), encode-only code extraction."""
+def parity_block(torch, model, dev):
+    """BASELINE configs[0] through the SAME model object that is timed below: the 4096 KAT tokens
+    (torch.manual_seed(0) weights, x = randn(32,128,2304) from CPU seed 1) against the codes of the unmodified
+    reference (tests/golden/kat_2b_codes4096.npz) under the near-tie protocol of SURVEY 8c (tests/parity.py):
+    a token whose first differing layer has an fp64 margin (teacher-forced along the reference's trajectory,
+    C oracle) below eps is a near-tie flip, anything else a failure."""
+    import hashlib
+    import numpy as np
+    from oracle import c_oracle
+    from oracle import rqae_oracle as orc
+    from tests import parity
+    gdir = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(gdir, "kat_2b.npz"))
+    ref = np.load(os.path.join(gdir, "kat_2b_codes4096.npz"))["codes4096"]
+    x = torch.randn(32, 128, D, generator=torch.Generator().manual_seed(1))
+    if hashlib.sha256(x.numpy().tobytes()).hexdigest()[:16] != str(g["fp_x"]):
+        return {"error": "KAT input does not reproduce on this torch build"}
+    q, codes = model(x.to(dev))
+    codes = codes.cpu().numpy().reshape(4096, NQ)
+    q = q.cpu().numpy().reshape(4096, D)
+    bad = np.flatnonzero((codes != ref).any(axis=1))
+    margins = np.full(ref.shape, np.inf, np.float32)
+    if len(bad):
+        w = orc.StackedWeights.from_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        cw = c_oracle.CWeights.from_stacked(w)
+        _, _, mb = c_oracle.forward_f64(cw, x.view(-1, D).numpy()[bad], teacher=ref[bad])
+        margins[bad] = mb
+    rep = parity.compare_codes(codes, ref, margins)
+    ok128 = parity.exact_token_mask(codes[:128], ref[:128])
+    rel = float(np.abs(q[:128][ok128] - g["q128"][ok128]).max() / np.abs(g["q128"]).max())
+    flips = [{"token": int(t), "layer": int(np.argmax(codes[t] != ref[t])),
+              "fp64_margin": float(margins[t, int(np.argmax(codes[t] != ref[t]))])} for t in bad[:32]]
+    return {"tokens": rep.tokens, "exact": rep.exact, "near_tie": rep.near_tie, "failures": rep.failures,
+            "eps": parity.EPS, "worst_accepted_margin": rep.worst_margin, "flips": flips,
+            "recon_max_rel_err_first128": rel, "recon_tolerance": 2e-5,
+            "reference": "unmodified rqae.model.RQAE on BASELINE configs[0] (tests/golden/kat_2b_codes4096.npz, "
+                         "sha %s); margins: fp64 C oracle teacher-forced along the reference's codes" % str(g["fp_codes_i16"])}
+
+
+class GemmaStub:
+    """The two methods RQAE.hook needs from rqae/llm.py:65-73 (Gemma2.norm = the model's final RMSNorm,
+    x * rsqrt(mean(x^2) + eps) * (1 + w); denorm inverts it) with a synthetic norm weight."""
+
+    def __init__(self, torch, dim, dev, eps=1e-6):
+        self.torch = torch
+        self.eps = eps
+        self.weight = (0.1 * torch.randn(dim, generator=torch.Generator().manual_seed(5))).to(dev)
+        self.rms_weight, self.rms_eps = self.weight, eps      # what the fused hook path reads
+
+    def norm(self, hs):
+        t = self.torch
+        x = hs.float()
+        return (x * t.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps) * (1.0 + self.weight.float())).type_as(hs)
+
+    def denorm(self, hs, orig):
+        t = self.torch
+        hs = hs / (1.0 + self.weight.float())
+        return hs.float() / t.rsqrt(orig.float().pow(2).mean(-1, keepdim=True) + 1e-6)
+
+
+def hook_extra(torch, model, dev, batch=4, seq=128, reps=20):
+    """The production caller's operating point (scripts/1_create_activations.py:152: 4 sequences x 128 tokens of
+    fp16 hidden states through hook_fn, model.py:276-289): microseconds per hook call, generic path (torch
+    norm / denorm around the fused layer loop) and fused path (one launch), CUDA events."""
+    stub = GemmaStub(torch, D, dev)
+    hs = (3.0 * torch.randn(batch, seq, D, generator=torch.Generator().manual_seed(6))).to(dev).half()
+    out = {"batch": batch, "seq": seq, "tokens": batch * seq, "dtype": "fp16"}
+    results = {}
+    for name, kw in (("generic", dict(norm=stub.norm, denorm=stub.denorm, fused=False)),
+                     ("fused", dict(norm=stub.norm, denorm=stub.denorm, rms_weight=stub.rms_weight, rms_eps=stub.rms_eps))):
+        try:
+            fn = model.hook(**kw)
+        except TypeError:
+            continue
+        buf = hs.clone()
+        fn(None, None, (buf,))
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            buf.copy_(hs)
+            fn(None, None, (buf,))
+        b.record()
+        torch.cuda.synchronize(dev)
+        results[name] = buf.float()
+        out[name + "_us_per_call"] = a.elapsed_time(b) / reps * 1e3
+        out[name + "_tokens_per_s"] = batch * seq / (a.elapsed_time(b) / reps * 1e-3)
+    if "generic" in results and "fused" in results:
+        d = (results["generic"] - results["fused"]).abs()
+        tok_same = (d.amax(-1) <= 2e-3 * results["generic"].abs().amax()).float().mean().item()
+        out["fused_vs_generic_tokens_within_fp16_rounding"] = tok_same
+    return out
+
+
+def stock_pytorch_gpu_extra(torch, model, dev, sizes=(512, 4096, 65536)):
+    """The bar on the same box: the reference's own ATen op sequence with the
+    weights on the GPU (what scripts/1:144 does with .to("cuda"); the op-for-op port, ~13 launches per layer) next
+    to this repo's fused kernel on the same tokens.  tokens/s for forward (encode + reconstruction)."""
+    from oracle import rqae_oracle as orc
+    w = orc.StackedWeights.from_state_dict({k: v.detach() for k, v in model.state_dict().items()})
+    res = {}
+    for n in sizes:
+        x = torch.randn(1, n, D, device=dev, generator=torch.Generator(device=dev).manual_seed(4321 + n))
+        (_, ci), ms_ref = _event_ms(torch, dev, lambda: orc.forward(w, x), reps=1)
+        (_, ck), ms_ours = _event_ms(torch, dev, lambda: model(x), reps=3)
+        res[str(n)] = {"stock_pytorch_tokens_per_s": n / ms_ref * 1e3, "stock_pytorch_ms": ms_ref,
+                       "rqae_b200_tokens_per_s": n / ms_ours * 1e3, "rqae_b200_ms": ms_ours,
+                       "speedup": ms_ref / ms_ours,
+                       "tokens_with_identical_codes": float((ci == ck).all(-1).float().mean().item())}
+        del x, ci, ck
+    res["note"] = ("stock PyTorch = oracle/rqae_oracle.forward (the reference's ATen calls, op for op) on cuda tensors, "
+                   "torch %s; both on the same B200, CUDA events; code disagreements are near-tie flips of a different "
+                   "fp32 summation order (cuBLAS vs the fused kernel), see `parity`" % torch.__version__)
+    return res
+
+
+def config3_9b_extra(torch, dist, dev, rank, world, tokens):
+    """BASELINE configs[3]: Gemma-2-9B width (d=3584), deeper stack (nq=2048), encode-only code extraction;
+    every rank encodes its own `tokens` tokens (weak scaling), time = max over ranks."""
     from rqae_b200 import RQAE
     torch.manual_seed(0)
     m = RQAE(dim=3584, num_quantizers=2048).eval().to(dev)
     m.freeze_packed()
-    x = torch.randn(1, tokens, 3584, device=dev, generator=torch.Generator(device=dev).manual_seed(99))
-    _, ms = _event_ms(torch, dev, lambda: m.encode(x, out_dtype=torch.int16))
+    x = torch.empty(1, tokens, 3584, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    for c0 in range(0, tokens, 1 << 16):
+        c1 = min(tokens, c0 + (1 << 16))
+        x[0, c0:c1] = torch.randn(c1 - c0, 3584, generator=gen, device=dev)
+    m.encode(x[:, : min(tokens, 1 << 15)], out_dtype=torch.int16)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    codes = m.encode(x, out_dtype=torch.int16)
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     flop_tok = 2048 * (2 * 2 * 4 * 3584 + 5000 + 3584)
-    return {"tokens": tokens, "dim": 3584, "num_quantizers": 2048, "tokens_per_s": tokens / ms * 1e3,
-            "tflops_fp32": flop_tok * tokens / ms / 1e9, "flop_per_token": flop_tok}
+    res = {"tokens_per_gpu": tokens, "n_gpus": world, "dim": 3584, "num_quantizers": 2048, "code_dtype": "int16",
+           "tokens_per_s": world * tokens / ms * 1e3, "tokens_per_s_per_gpu": tokens / ms * 1e3, "ms": ms,
+           "tflops_fp32_per_gpu": flop_tok * tokens / ms / 1e9, "flop_per_token": flop_tok,
+           "checksum_codes": int(codes[0, :4096].long().sum().item())}
+    del m, x, codes
+    torch.cuda.empty_cache()
+    return res
+
+
+def config3_9b_cpu_port(torch, tokens=32):
+    from oracle import rqae_oracle as orc
+    w = orc.random_init(dim=3584, num_quantizers=2048)
+    x = torch.randn(1, tokens, 3584, generator=torch.Generator().manual_seed(3))
+    orc.forward(w, x[:, :4])
+    t0 = time.perf_counter()
+    orc.forward(w, x)
+    dt = time.perf_counter() - t0
+    return {"tokens_per_s": tokens / dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{tokens} tokens, full depth (nq=2048), forward incl. reconstruction, torch CPU fp32, {dt:.1f} s"}
+
+
+def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_features=1024, group=128, top_k=100):
+    """BASELINE configs[4] (scripts/3_make_rqae_features.py pattern) at its stated scale: every rank encodes its
+    `tokens` tokens (2 Mi per GPU = 16 Mi on 8 GPUs), then for feature groups of `group`: intensities of the group over
+    the rank's tokens at the 14 cuts of scripts/3:178 (tcgen05 GEMM), all_to_all so that every (feature, cut) row is
+    whole on one rank (shard.exchange_to_feature_shards), top / middle / bottom-100 of every row over ALL tokens
+    (radix select).  Wall clock from a barrier to the last kernel, max over ranks; stage times are CUDA events."""
+    from rqae_b200.feature import intensity_many, select_top_middle_bottom, layer_weights_f16
+    from rqae_b200 import shard
+    T_x = x.shape[1]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    codes = torch.empty(tokens, NQ, dtype=torch.int16, device=dev)
+    lw = layer_weights_f16(model).to(dev)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t_wall0 = time.perf_counter()
+    e0, e1 = ev(), ev()
+    e0.record()
+    gen = torch.Generator(device=dev).manual_seed(777 + rank)
+    for c0 in range(0, tokens, T_x):
+        n = min(T_x, tokens - c0)
+        if c0 > 0:   # fresh activations for every pass over the staging buffer
+            for k0 in range(0, n, 1 << 16):
+                k1 = min(n, k0 + (1 << 16))
+                x[0, k0:k1] = torch.randn(k1 - k0, D, generator=gen, device=dev)
+        codes[c0:c0 + n] = model.encode(x[:, :n], out_dtype=torch.int16)[0]
+    e1.record()
+    # feature centers = the codes of n_features tokens (of rank 0's shard), the same on every rank
+    pick = torch.randperm(tokens, generator=torch.Generator().manual_seed(5))[:n_features].to(dev)
+    centers = codes[pick].to(torch.int32)
+    if world > 1:
+        dist.broadcast(centers, src=0)
+    n_total = world * tokens
+    ms_int = ms_x = ms_sel = 0.0
+    checksum = 0
+    buf = torch.empty(group, len(SCRIPT3_CUTS), (tokens + 255) // 256 * 256, dtype=torch.float16, device=dev)
+    for f0 in range(0, n_features, group):
+        a, b, c, d = ev(), ev(), ev(), ev()
+        a.record()
+        inten = intensity_many(model, codes, centers[f0:f0 + group], SCRIPT3_CUTS, layer_weights=lw, out=buf)
+        b.record()
+        if world > 1:
+            rows, _ = shard.exchange_to_feature_shards(inten, n_total)
+        else:
+            rows = inten
+        c.record()
+        idx, val = select_top_middle_bottom(rows, top_k)
+        d.record()
+        torch.cuda.synchronize(dev)
+        ms_int += a.elapsed_time(b); ms_x += b.elapsed_time(c); ms_sel += c.elapsed_time(d)
+        checksum += int(idx[:, :, 0, 0].sum().item())
+        del rows, idx, val
+    t_wall = time.perf_counter() - t_wall0
+    ms_enc = e0.elapsed_time(e1)
+    stats = torch.tensor([t_wall, ms_enc, ms_int, ms_x, ms_sel], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    t_wall, ms_enc, ms_int, ms_x, ms_sel = [float(v) for v in stats.tolist()]
+    rows_per_rank = (n_features // world) * len(SCRIPT3_CUTS)
+    peaks = measured_peaks()
+    res = {"tokens_per_gpu": tokens, "tokens_total": n_total, "n_gpus": world, "features": n_features, "cuts": len(SCRIPT3_CUTS),
+           "top_k": top_k, "feature_group": group,
+           "tokens_per_s": n_total / t_wall, "seconds": t_wall,
+           "stage_ms_max_over_ranks": {"encode": ms_enc, "intensity_gemm": ms_int, "all_to_all_and_repack": ms_x, "select": ms_sel},
+           "encode_tokens_per_s": n_total / ms_enc * 1e3,
+           "intensity_tflops_per_gpu": 2.0 * tokens * n_features * 4 * (SCRIPT3_CUTS[-1] + 1) / ms_int / 1e9,
+           "intensity_frac_of_tensor_peak": 2.0 * tokens * n_features * 4 * (SCRIPT3_CUTS[-1] + 1) / ms_int / 1e9
+                                            / (peaks["bf16_tflops"] if peaks else 1590.0),
+           "select_gbs_per_gpu": rows_per_rank * n_total * 2 / ms_sel / 1e6,
+           "exchange_gbs_per_gpu": (n_features * len(SCRIPT3_CUTS) * tokens * 2 * (world - 1) / world) / ms_x / 1e6 if world > 1 else None,
+           "checksum_top_idx": checksum,
+           "timing": "host wall clock barrier -> last kernel done (encode + 8 feature groups x (GEMM, all_to_all, select)), "
+                     "max over ranks"}
+    del codes, buf
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_b200(args, rank, local_rank, world):
@@ -393,6 +625,11 @@ def run_b200(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
+    # ---- parity gate: the reference's 4096-token KAT through this very model object ----
+    par = None
+    if rank == 0 and not args.no_parity:
+        par = parity_block(torch, model, dev)
+
     for _ in range(max(args.warmup, 3)):
         q, codes = model(xv)
     torch.cuda.synchronize(dev)
@@ -426,41 +663,50 @@ def run_b200(args, rank, local_rank, world):
     if not args.no_e2e:
         import psutil
         Te = args.e2e_tokens or T
-        need = Te * (4 * D * 2 + 8 * NQ)
+        need = Te * (4 * D * 2 + 8 * NQ + 4 * NQ)
         avail = psutil.virtual_memory().available / max(1, world)
         while need > 0.25 * avail and Te > (1 << 16):
             Te //= 2
-            need = Te * (4 * D * 2 + 8 * NQ)
+            need = Te * (4 * D * 2 + 8 * NQ + 4 * NQ)
         xh = torch.empty(Te, D, dtype=torch.float32, pin_memory=True)
         for c0 in range(0, Te, 1 << 16):
             c1 = min(Te, c0 + (1 << 16))
             xh[c0:c1].copy_(x[c0 % T:c0 % T + (c1 - c0)] if c0 % T + (c1 - c0) <= T else torch.randn(c1 - c0, D))
         # result buffers are allocated (page-locked) once, as a caller that loops over shards would
         qh = torch.empty(Te, D, dtype=torch.float32, pin_memory=True)
-        ch = torch.empty(Te, NQ, dtype=torch.int64, pin_memory=True)
         steps_e = args.e2e_steps or min(args.steps, 3)
-        model.forward_host(xh[: 1 << 15], out=(qh[: 1 << 15], ch[: 1 << 15]))  # warm-up of the host path
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps_e):
-            model.forward_host(xh, out=(qh, ch))
-        t_e = time.perf_counter() - t0    # forward_host returns after the last D2H copy completed
-        barrier()
-        if world > 1:
-            t = torch.tensor([t_e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e = float(t.item())
-        e2e = {"value": world * Te * steps_e / t_e, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4,
+
+        def e2e_run(dt):
+            ch = torch.empty(Te, NQ, dtype=dt, pin_memory=True)
+            model.forward_host(xh[: 1 << 15], out=(qh[: 1 << 15], ch[: 1 << 15]), out_dtype=dt)  # warm-up of the host path
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps_e):
+                model.forward_host(xh, out=(qh, ch), out_dtype=dt)
+            t_e = time.perf_counter() - t0    # forward_host returns after the last D2H copy completed
+            barrier()
+            if world > 1:
+                t = torch.tensor([t_e], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_e = float(t.item())
+            return world * Te * steps_e / t_e, int(ch[: 1 << 12].long().sum().item())
+
+        v64, ck64 = e2e_run(torch.int64)
+        v32, ck32 = e2e_run(torch.int32)
+        e2e = {"value": v64, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4,
                "d2h_bytes_per_step": Te * (NQ * 8 + D * 4), "tokens_per_step_per_gpu": Te, "steps": steps_e,
                "timing": "host wall clock around RQAE.forward_host (pinned host buffers in and out; H2D, kernel and "
-                         "D2H of 33152-token chunks pipelined inside the C library; codes cross PCIe as int16 and "
-                         "are widened to the int64 result by host threads; returns after the last D2H), "
-                         "max over ranks",
-               "pcie_bytes_per_step": {"h2d": Te * D * 4, "d2h": Te * (NQ * 2 + D * 4)},
-               "checksum_codes": int(ch[: 1 << 12].sum().item())}
-        del xh, qh, ch
+                         "D2H of 9472-token chunks on three streams inside the C library; int64 codes written by the "
+                         "kernel and copied straight into the caller's tensor, no host threads; returns after the "
+                         "last D2H), max over ranks",
+               "checksum_codes": ck64,
+               "int32_codes": {"value": v32, "unit": UNIT, "d2h_bytes_per_step": Te * (NQ * 4 + D * 4),
+                               "checksum_codes": ck32,
+                               "note": "same call with out_dtype=int32, the dtype the reference's code store keeps "
+                                       "(scripts/1_create_activations.py:184-186)"}}
+        del xh, qh
 
-    # ---- side measurements (outside the timed region): encode-only and decode-only throughput ----
+    # ---- side measurements (outside the timed region) ----
     extra = None
     if rank == 0:
         Ts = min(T, 1 << 18)
@@ -477,12 +723,13 @@ def run_b200(args, rank, local_rank, world):
         dec_exact, dec_rate = timed(lambda: model.decode(codes_s))
         extra = {"encode_only_int16_tokens_per_s": enc_rate, "decode_only_tokens_per_s": dec_rate, "tokens": Ts,
                  "decode_frac_of_fp32_peak": None}
-        if not args.no_extras:
+        if not args.no_extras and world == 1:
             try:   # opt-in tensor-core decode (tcgen05 GEMM over the codes), not bit-exact: rate and error vs the exact kernel
                 tc = {}
                 for prec, npass in (("f16", 1), ("f16x3", 3)):
                     dq, rate = timed(lambda: model.decode(codes_s, precision=prec))
-                    tc[prec] = {"tokens_per_s": rate, "tflops": rate * npass * 2 * 4 * NQ * D / 1e12,
+                    tc[prec] = {"tokens_per_s": rate, "algorithmic_tflops": rate * 2 * 4 * NQ * D / 1e12,
+                                "issued_tflops": rate * npass * 2 * 4 * NQ * D / 1e12, "passes": npass,
                                 "max_err_over_max_abs": float(((dq - dec_exact).abs().max() / dec_exact.abs().max()).item())}
                     del dq
                 extra["decode_tensor_core_opt_in"] = tc
@@ -490,21 +737,36 @@ def run_b200(args, rank, local_rank, world):
                 extra["decode_tensor_core_opt_in"] = {"error": repr(e)}
         del dec_exact
         if not args.no_extras and world == 1:
-            try:
-                extra["mining"] = mining_extras(torch, model, codes_s[0, : 1 << 17], dev)
-            except Exception as e:   # side measurement only: never lose the bench line over it
-                extra["mining"] = {"error": repr(e)}
+            for name, fn in (("mining", lambda: mining_extras(torch, model, codes_s[0, : 1 << 17], dev)),
+                             ("hook_512", lambda: hook_extra(torch, model, dev)),
+                             ("stock_pytorch_gpu", lambda: stock_pytorch_gpu_extra(torch, model, dev)),
+                             ("example_search", lambda: search_extras(torch, model, dev))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:   # side measurement only: never lose the bench line over it
+                    extra[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
         del codes_s
-        if not args.no_extras and world == 1:
-            try:
-                extra["config4_9b_encode_only"] = encode_9b_extra(torch, dev)
-            except Exception as e:
-                extra["config4_9b_encode_only"] = {"error": repr(e)}
-        if not args.no_extras and world == 1:
-            try:
-                extra["example_search"] = search_extras(torch, model, dev)
-            except Exception as e:
-                extra["example_search"] = {"error": repr(e)}
+    # configs[3] and configs[4] run on EVERY rank (weak scaling, max over ranks)
+    if not args.no_extras:
+        try:
+            c4 = config4_mining_extra(torch, dist, model, xv, dev, rank, world, args.tokens_mining)
+        except Exception as e:
+            c4 = {"error": repr(e)}
+        del x, xv
+        torch.cuda.empty_cache()
+        try:
+            c3 = config3_9b_extra(torch, dist, dev, rank, world, args.tokens_9b)
+        except Exception as e:
+            c3 = {"error": repr(e)}
+        if rank == 0:
+            extra["config3_9b"] = c3
+            extra["config4_mining"] = c4
+            if world == 1:
+                try:
+                    extra["config3_9b"]["cpu_port"] = config3_9b_cpu_port(torch)
+                except Exception as e:
+                    extra["config3_9b"]["cpu_port"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -524,10 +786,17 @@ def run_b200(args, rank, local_rank, world):
     except Exception:
         pass
     if extra is not None:
-        extra["decode_frac_of_fp32_peak"] = extra["decode_only_tokens_per_s"] * NQ * (6 * D) * 2 / 1e12 / fp32_peak
-        c4 = extra.get("config4_9b_encode_only")
-        if isinstance(c4, dict) and "tflops_fp32" in c4:
-            c4["frac_of_fp32_peak"] = c4["tflops_fp32"] / fp32_peak
+        # algorithmic flops of decode: 2*4*D + D = 20 736 per layer-token; the kernel issues 12*D
+        extra["decode_frac_of_fp32_peak"] = extra["decode_only_tokens_per_s"] * NQ * (2 * 4 * D + D) / 1e12 / fp32_peak
+        extra["decode_fp32_pipe_busy_frac"] = extra["decode_only_tokens_per_s"] * NQ * (6 * D) * 2 / 1e12 / fp32_peak
+        tcx = extra.get("decode_tensor_core_opt_in")
+        if isinstance(tcx, dict) and peaks:
+            for v in tcx.values():
+                if isinstance(v, dict) and "algorithmic_tflops" in v:
+                    v["algorithmic_frac_of_tensor_peak"] = v["algorithmic_tflops"] / peaks["bf16_tflops"]
+        c3 = extra.get("config3_9b")
+        if isinstance(c3, dict) and "tflops_fp32_per_gpu" in c3:
+            c3["frac_of_fp32_peak"] = c3["tflops_fp32_per_gpu"] / fp32_peak
     roofline = {
         "kernel": "rq::rq_forward_kernel (E=9 instantiation for d=2304; one cooperative launch per step)",
         "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak,
@@ -562,13 +831,15 @@ def run_b200(args, rank, local_rank, world):
                    "l2": "per-step inputs+outputs (%.1f GB) exceed the 126 MB L2; the 85 MB of weights are L2-resident by design"
                          % (HBM_BYTES_PER_TOKEN_FWD * T / 1e9)},
         "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "checksum_codes": checksum,
-        "extra": extra,
+        "parity": par, "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if par is not None and (par.get("failures", 0) > 0 or "error" in par):
+        raise SystemExit("parity gate failed: %s" % json.dumps(par)[:400])
 
 
 def main():

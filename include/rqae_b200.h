@@ -95,14 +95,28 @@ int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_c
 /* Host-buffer front end of rqae_forward_f32 (the end-to-end path bench.py times as `e2e`):
  * x_host / codes_host / q_host are HOST pointers (pinned for full speed).  The call stages
  * chunks of `chunk_tokens` tokens through internal device buffers on three internal streams
- * (H2D, compute, D2H double-buffered) and returns after the last D2H copy has completed.
- * int32 / int64 codes cross PCIe as int16 and are widened into `codes_host` by host threads while
- * the next chunk is in flight.  The staging buffers, streams and events are cached per calling
- * thread between calls; rqae_forward_host_release() frees them. */
+ * (H2D, compute, D2H; three buffer sets) and returns after the last D2H copy has completed.
+ * Every CUDA call on the way is checked; after a failure the streams are drained and RQAE_ECUDA
+ * is returned.  The staging buffers, streams, events and worker threads are cached per calling
+ * thread between calls; rqae_forward_host_release() frees them.
+ *
+ * rqae_forward_host_config selects how int32 / int64 codes reach `codes_host` (process-wide;
+ * -1 keeps a setting):
+ *   code_transfer  0 auto (= direct), 1 narrow: int16 over PCIe into a pinned staging buffer, widened
+ *                  into the caller's tensor by `widen_threads` host threads (a quarter of the PCIe
+ *                  bytes, 12 KB of extra host memory traffic per token); 2 direct: the kernel emits
+ *                  the caller's dtype and the copy lands in the caller's tensor (no host threads)
+ *   widen_threads  0 auto = cores / (2 * LOCAL_WORLD_SIZE), clamped to [1, 8]
+ * Environment defaults: RQAE_HOST_CODES = auto | narrow | direct, RQAE_HOST_THREADS = n. */
 int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq,
                           int nq_run, int dim, int codebook_dim, int K, const float* x_host,
                           int64_t n_tokens, void* codes_host, int code_dtype, float* q_host,
                           int64_t chunk_tokens);
+int rqae_forward_host_config(int code_transfer, int widen_threads);
+/* The widening step of the narrow mode on its own: int16 -> int32 / int64 with streaming stores on `threads`
+ * host threads (0 = auto).  Host pointers; no CUDA call.  (scripts/1_create_activations.py:184-186 stores
+ * int32: a caller that keeps int16 on the wire widens with this.) */
+int rqae_widen_codes_host(const int16_t* src_host, void* dst_host, int64_t n, int code_dtype, int threads);
 int rqae_forward_host_release(void);
 
 /* RQAEFeature.intensity (rqae/feature.py:102-129) for `n_features` features at once -- the inner

@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.
 # every symbol include/rqae_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
-    "rqae_forward_f32", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_release", "rqae_fp32_peak_probe",
+    "rqae_forward_f32", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_widen_codes_host", "rqae_forward_host_release",
+    "rqae_fp32_peak_probe",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
     "rqae_search_table_bytes", "rqae_search_build_table_f16", "rqae_search_accumulate_f16", "rqae_search_position_max_f16",
@@ -55,6 +56,10 @@ def load() -> ctypes.CDLL:
     lib.rqae_decode_f32.argtypes = [vp, vp, i, i, i, i, i, vp, i, i64, vp, vp, i64, vp, vp]
     lib.rqae_forward_host_f32.restype = i
     lib.rqae_forward_host_f32.argtypes = [vp, vp, i, i, i, i, i, i, vp, i64, vp, i, vp, i64]
+    lib.rqae_forward_host_config.restype = i
+    lib.rqae_forward_host_config.argtypes = [i, i]
+    lib.rqae_widen_codes_host.restype = i
+    lib.rqae_widen_codes_host.argtypes = [vp, vp, i64, i, i]
     lib.rqae_forward_host_release.restype = i
     lib.rqae_forward_host_release.argtypes = []
     lib.rqae_fp32_peak_probe.restype = i

@@ -8,13 +8,14 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
 #include <math.h>
 #if defined(__x86_64__) && !defined(RQ_NO_STREAM)
-#include <emmintrin.h>
+#include <immintrin.h>
 #endif
 
 #include "../../include/rqae_b200.h"
@@ -447,6 +448,7 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
                      int64_t code_stride, float* q_out, const int32_t* teacher, float* z_out, void* stream) {
   if (!packed || !codebook || nq <= 0 || nq_run <= 0 || nq_run > nq || dim <= 0 || K <= 0 || n_tokens < 0) return RQAE_EINVAL;
   if (code_dtype < 0 || code_dtype > 2 || (codes && code_stride < nq_run)) return RQAE_EINVAL;
+  if (codes && code_dtype == RQAE_CODE_I16 && K > 32768) return RQAE_EINVAL;   // int16 cannot hold codes >= 32768
   if (n_tokens > 0 && !x) return RQAE_EINVAL;
   RqShape s;
   if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
@@ -530,19 +532,181 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
   return RQAE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host-buffer front end (the end-to-end path)
+// ---------------------------------------------------------------------------------------------
+// Pipeline options (rqae_forward_host_config; environment defaults RQAE_HOST_CODES = auto|narrow|direct,
+// RQAE_HOST_THREADS = n).  Two ways to deliver int32 / int64 codes to a host tensor:
+//   narrow  the kernel emits int16 (every code is < K <= 32767), a quarter of the int64 bytes cross PCIe into a
+//           pinned staging buffer, and a pool of host threads widens them into the caller's tensor with streaming
+//           stores while the next chunk is in flight.  Least PCIe traffic, most host work: per token 2 KB of DMA
+//           writes + 2 KB of reads + 8 KB of stores on the host.
+//   direct  the kernel emits the caller's dtype and the D2H copy lands in the caller's tensor.  No host threads,
+//           no staging; per token 8 KB of DMA writes and nothing else.
+// `auto` = direct: with one rank per GPU on a shared host the end-to-end rate is bounded by host memory traffic and
+// host cores long before PCIe, and direct removes a third of the former and all of the latter.
+static std::atomic<int> g_host_code_transfer{-1};   // -1: not initialised; 0 auto, 1 narrow, 2 direct
+static std::atomic<int> g_host_threads{-1};         // -1: not initialised; 0 auto
+
+static void host_config_init() {
+  if (g_host_code_transfer.load() < 0) {
+    const char* e = getenv("RQAE_HOST_CODES");
+    int v = 0;
+    if (e && !strcmp(e, "narrow")) v = 1;
+    else if (e && !strcmp(e, "direct")) v = 2;
+    g_host_code_transfer.store(v);
+  }
+  if (g_host_threads.load() < 0) {
+    const char* e = getenv("RQAE_HOST_THREADS");
+    const int v = e ? atoi(e) : 0;
+    g_host_threads.store(v < 0 ? 0 : (v > 64 ? 64 : v));
+  }
+}
+
+// Widening threads per rank when not given: the host's cores are shared by all ranks of the node
+// (LOCAL_WORLD_SIZE, set by torchrun), and half of a rank's share is left to the framework's own threads.
+static int host_auto_threads() {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  int lws = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) lws = atoi(e) > 0 ? atoi(e) : 1;
+  int t = (int)hw / (2 * lws);
+  return t < 1 ? 1 : (t > 8 ? 8 : t);
+}
+
+// int16 -> int32 / int64.  The wide result is written once and not read again by this library: streaming stores
+// keep it out of the caches and spare the read-for-ownership of every destination line.
+static void widen_range_scalar(const int16_t* src, void* dst, size_t lo, size_t hi, int code_dtype) {
+#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
+  if (code_dtype == 2) { long long* d = (long long*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si64(d + i, (long long)src[i]); }
+  else { int* d = (int*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si32(d + i, (int)src[i]); }
+  _mm_sfence();
+#else
+  if (code_dtype == 2) { int64_t* d = (int64_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
+  else { int32_t* d = (int32_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
+#endif
+}
+
+#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
+__attribute__((target("avx2"))) static void widen_range_avx2(const int16_t* src, void* dst, size_t lo, size_t hi, int code_dtype) {
+  size_t i = lo;
+  if (code_dtype == 2) {
+    long long* d = (long long*)dst;
+    for (; i < hi && ((uintptr_t)(d + i) & 31); i++) d[i] = src[i];
+    for (; i + 16 <= hi; i += 16) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+      const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 8));
+      _mm256_stream_si256((__m256i*)(d + i), _mm256_cvtepi16_epi64(a));
+      _mm256_stream_si256((__m256i*)(d + i + 4), _mm256_cvtepi16_epi64(_mm_srli_si128(a, 8)));
+      _mm256_stream_si256((__m256i*)(d + i + 8), _mm256_cvtepi16_epi64(b));
+      _mm256_stream_si256((__m256i*)(d + i + 12), _mm256_cvtepi16_epi64(_mm_srli_si128(b, 8)));
+    }
+    for (; i < hi; i++) d[i] = src[i];
+  } else {
+    int* d = (int*)dst;
+    for (; i < hi && ((uintptr_t)(d + i) & 31); i++) d[i] = src[i];
+    for (; i + 16 <= hi; i += 16) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+      const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 8));
+      _mm256_stream_si256((__m256i*)(d + i), _mm256_cvtepi16_epi32(a));
+      _mm256_stream_si256((__m256i*)(d + i + 8), _mm256_cvtepi16_epi32(b));
+    }
+    for (; i < hi; i++) d[i] = src[i];
+  }
+  _mm_sfence();
+}
+#endif
+
+static void widen_range(const int16_t* src, void* dst, size_t lo, size_t hi, int code_dtype) {
+#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) { widen_range_avx2(src, dst, lo, hi, code_dtype); return; }
+#endif
+  widen_range_scalar(src, dst, lo, hi, code_dtype);
+}
+
+// Persistent worker pool of the calling thread's pipeline (the first version spawned threads per chunk).
+class WidenPool {
+ public:
+  ~WidenPool() { stop(); }
+  void resize(int workers) {
+    if ((int)th_.size() == workers) return;
+    stop();
+    stop_ = false;
+    for (int i = 0; i < workers; i++) th_.emplace_back([this, i] { loop(i + 1); });
+  }
+  int workers() const { return (int)th_.size(); }
+  // splits [0, n) over the workers and the caller; returns when all parts are done
+  void run(const int16_t* src, void* dst, size_t n, int code_dtype) {
+    const int parts = (int)th_.size() + 1;
+    if (parts == 1 || n < (1u << 16)) { widen_range(src, dst, 0, n, code_dtype); return; }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      src_ = src; dst_ = dst; n_ = n; dtype_ = code_dtype; parts_ = parts;
+      pending_ = (int)th_.size();
+      gen_++;
+    }
+    go_.notify_all();
+    part(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void part(int id) {
+    const size_t per = ((n_ + parts_ - 1) / parts_ + 15) & ~(size_t)15;
+    const size_t lo = per * id, hi = lo + per < n_ ? lo + per : n_;
+    if (lo < hi) widen_range(src_, dst_, lo, hi, dtype_);
+  }
+  void loop(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        go_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      part(id);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    go_.notify_all();
+    for (auto& t : th_) t.join();
+    th_.clear();
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable go_, done_;
+  unsigned long long gen_ = 0;
+  int pending_ = 0, parts_ = 1, dtype_ = 2;
+  bool stop_ = false;
+  const int16_t* src_ = nullptr;
+  void* dst_ = nullptr;
+  size_t n_ = 0;
+};
+
 // Cached resources of the host pipeline (per calling thread): device staging buffers, a pinned staging
 // area for narrow codes, streams and events.  Re-created when a call needs more room or another device.
+constexpr int kHostBufs = 3;
 struct HostPipe {
   int dev = -1;
   size_t x_bytes = 0, q_bytes = 0, c_bytes = 0, h_bytes = 0;
-  float* dx[2] = {nullptr, nullptr};
-  float* dq[2] = {nullptr, nullptr};
-  void* dc[2] = {nullptr, nullptr};
-  void* hc[2] = {nullptr, nullptr};   // pinned
+  float* dx[kHostBufs] = {};
+  float* dq[kHostBufs] = {};
+  void* dc[kHostBufs] = {};
+  void* hc[kHostBufs] = {};   // pinned
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[kHostBufs] = {}, ev_cmp[kHostBufs] = {}, ev_out[kHostBufs] = {};
+  WidenPool pool;
   void release() {
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kHostBufs; b++) {
       if (dx[b]) cudaFree(dx[b]);
       if (dq[b]) cudaFree(dq[b]);
       if (dc[b]) cudaFree(dc[b]);
@@ -562,34 +726,26 @@ struct HostPipe {
 };
 static thread_local HostPipe g_pipe;
 
-// int16 -> int32 / int64 on `threads` host threads (codes cross PCIe as int16 and are widened here).  The wide
-// result is written once and not read again by this library: streaming stores keep it out of the caches and
-// spare the read-for-ownership of every destination line (with 8 ranks widening at once the host's memory
-// bandwidth, not PCIe, bounds the end-to-end path).
-static void widen_codes(const int16_t* src, void* dst, size_t n, int code_dtype, int threads) {
-  auto work = [=](size_t lo, size_t hi) {
-#if defined(__x86_64__) && !defined(RQ_NO_STREAM)
-    if (code_dtype == 2) { long long* d = (long long*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si64(d + i, (long long)src[i]); }
-    else { int* d = (int*)dst; for (size_t i = lo; i < hi; i++) _mm_stream_si32(d + i, (int)src[i]); }
-    _mm_sfence();
-#else
-    if (code_dtype == 2) { int64_t* d = (int64_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
-    else { int32_t* d = (int32_t*)dst; for (size_t i = lo; i < hi; i++) d[i] = src[i]; }
-#endif
-  };
-  if (threads <= 1 || n < (1u << 16)) { work(0, n); return; }
-  std::vector<std::thread> pool;
-  const size_t per = (n + threads - 1) / threads;
-  for (int t = 1; t < threads; t++) {
-    const size_t lo = per * t, hi = lo + per < n ? lo + per : n;
-    if (lo < hi) pool.emplace_back(work, lo, hi);
-  }
-  work(0, per < n ? per : n);
-  for (auto& th : pool) th.join();
-}
-
 int rqae_forward_host_release(void) {
   g_pipe.release();
+  g_pipe.pool.resize(0);
+  return RQAE_OK;
+}
+
+int rqae_widen_codes_host(const int16_t* src_host, void* dst_host, int64_t n, int code_dtype, int threads) {
+  if ((!src_host || !dst_host) && n > 0) return RQAE_EINVAL;
+  if (n < 0 || (code_dtype != RQAE_CODE_I32 && code_dtype != RQAE_CODE_I64) || threads < 0 || threads > 64) return RQAE_EINVAL;
+  static thread_local WidenPool pool;
+  pool.resize((threads > 0 ? threads : host_auto_threads()) - 1);
+  pool.run(src_host, dst_host, (size_t)n, code_dtype);
+  return RQAE_OK;
+}
+
+int rqae_forward_host_config(int code_transfer, int widen_threads) {
+  host_config_init();
+  if (code_transfer > 2 || widen_threads > 64) return RQAE_EINVAL;
+  if (code_transfer >= 0) g_host_code_transfer.store(code_transfer);
+  if (widen_threads >= 0) g_host_threads.store(widen_threads);
   return RQAE_OK;
 }
 
@@ -598,16 +754,15 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
                           int code_dtype, float* q_host, int64_t chunk_tokens) {
   if (!packed || !codebook || !x_host || n_tokens < 0 || chunk_tokens <= 0 || code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
   if (nq_run <= 0 || nq_run > nq) return RQAE_EINVAL;
+  if (code_dtype == RQAE_CODE_I16 && K > 32768) return RQAE_EINVAL;   // int16 cannot hold the codes
   if (n_tokens == 0) return RQAE_OK;
   if (chunk_tokens > n_tokens) chunk_tokens = n_tokens;
-  // Codes are < K <= 32767 in every supported model, so they cross PCIe as int16 (a quarter of the int64 bytes)
-  // and host threads widen them into the caller's tensor while the next chunk is in flight.
-  const bool narrow = codes_host != nullptr && code_dtype != RQAE_CODE_I16 && K <= 32767;
+  host_config_init();
+  const int mode = g_host_code_transfer.load();
+  const bool narrow = codes_host != nullptr && code_dtype != RQAE_CODE_I16 && K <= 32767 && mode == 1;
   const int dev_dtype = narrow ? RQAE_CODE_I16 : code_dtype;
   const size_t dsz = dev_dtype == 2 ? 8 : (dev_dtype == 1 ? 4 : 2);     // code size on the device / on the wire
   const size_t usz = code_dtype == 2 ? 8 : (code_dtype == 1 ? 4 : 2);   // code size in the caller's tensor
-  int rc = RQAE_OK;
-  auto fail = [&](cudaError_t e) { g_last_cuda = e; rc = RQAE_ECUDA; };
 
   HostPipe& P = g_pipe;
   int dev = 0;
@@ -620,7 +775,7 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
     RQ_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
     RQ_CUDA(cudaStreamCreateWithFlags(&P.s_cmp, cudaStreamNonBlocking));
     RQ_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kHostBufs; b++) {
       RQ_CUDA(cudaMalloc(&P.dx[b], need_x));
       if (need_q) RQ_CUDA(cudaMalloc(&P.dq[b], need_q));
       if (need_c) RQ_CUDA(cudaMalloc(&P.dc[b], need_c));
@@ -631,51 +786,62 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
     }
     P.x_bytes = need_x; P.q_bytes = need_q; P.c_bytes = need_c; P.h_bytes = need_h;
   }
-  unsigned hw = std::thread::hardware_concurrency();
-  const int wthreads = (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+  if (narrow) {
+    const int t = g_host_threads.load() > 0 ? g_host_threads.load() : host_auto_threads();
+    P.pool.resize(t - 1);   // the calling thread is one of them
+  }
 
+  int rc = RQAE_OK;
+  cudaError_t err = cudaSuccess;
+#define RQ_TRY(call)                                        \
+  do {                                                      \
+    if (rc == RQAE_OK && err == cudaSuccess) err = (call);  \
+  } while (0)
   const int64_t n_chunks = (n_tokens + chunk_tokens - 1) / chunk_tokens;
   auto chunk_len = [&](int64_t c) { const int64_t t0 = c * chunk_tokens; return (n_tokens - t0 < chunk_tokens) ? (n_tokens - t0) : chunk_tokens; };
   auto finish_chunk = [&](int64_t c) {   // host side of chunk c: wait for its D2H copies, widen the codes
-    const int b = (int)(c & 1);
-    cudaError_t e = cudaEventSynchronize(P.ev_out[b]);
-    if (e != cudaSuccess) { fail(e); return; }
-    widen_codes((const int16_t*)P.hc[b], (char*)codes_host + (size_t)c * chunk_tokens * nq_run * usz,
-                (size_t)chunk_len(c) * nq_run, code_dtype, wthreads);
+    const int b = (int)(c % kHostBufs);
+    RQ_TRY(cudaEventSynchronize(P.ev_out[b]));
+    if (rc == RQAE_OK && err == cudaSuccess)
+      P.pool.run((const int16_t*)P.hc[b], (char*)codes_host + (size_t)c * chunk_tokens * nq_run * usz,
+                 (size_t)chunk_len(c) * nq_run, code_dtype);
   };
-  for (int64_t c = 0; c < n_chunks && rc == 0; c++) {
-    const int b = (int)(c & 1);
+  for (int64_t c = 0; c < n_chunks && rc == RQAE_OK && err == cudaSuccess; c++) {
+    const int b = (int)(c % kHostBufs);
     const int64_t t0 = c * chunk_tokens;
     const int64_t nt = chunk_len(c);
-    // the input buffer b is free once the kernel of chunk c-2 has run; the output buffers once the D2H copies
-    // of chunk c-2 are done (waited for by the compute stream below)
-    if (c >= 2) cudaStreamWaitEvent(P.s_in, P.ev_cmp[b], 0);
-    cudaError_t e = cudaMemcpyAsync(P.dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, P.s_in);
-    if (e != cudaSuccess) { fail(e); break; }
-    cudaEventRecord(P.ev_in[b], P.s_in);
-    cudaStreamWaitEvent(P.s_cmp, P.ev_in[b], 0);
-    if (c >= 2) cudaStreamWaitEvent(P.s_cmp, P.ev_out[b], 0);
+    // buffer set b was last used by chunk c - kHostBufs: its input is free once that kernel has run, its outputs
+    // once their D2H copies are done -- and, in narrow mode, once the host has widened the staged codes, which
+    // finish_chunk(c - kHostBufs) did before this iteration (it runs kHostBufs - 1 chunks behind the enqueue)
+    if (c >= kHostBufs) RQ_TRY(cudaStreamWaitEvent(P.s_in, P.ev_cmp[b], 0));
+    RQ_TRY(cudaMemcpyAsync(P.dx[b], x_host + (size_t)t0 * dim, (size_t)nt * dim * 4, cudaMemcpyHostToDevice, P.s_in));
+    RQ_TRY(cudaEventRecord(P.ev_in[b], P.s_in));
+    RQ_TRY(cudaStreamWaitEvent(P.s_cmp, P.ev_in[b], 0));
+    if (c >= kHostBufs) RQ_TRY(cudaStreamWaitEvent(P.s_cmp, P.ev_out[b], 0));
+    if (err != cudaSuccess) break;
     rc = rqae_forward_f32(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, P.dx[b], nt,
                           codes_host ? P.dc[b] : nullptr, dev_dtype, nq_run, q_host ? P.dq[b] : nullptr, nullptr, nullptr,
                           (void*)P.s_cmp);
     if (rc) break;
-    cudaEventRecord(P.ev_cmp[b], P.s_cmp);
-    cudaStreamWaitEvent(P.s_out, P.ev_cmp[b], 0);
+    RQ_TRY(cudaEventRecord(P.ev_cmp[b], P.s_cmp));
+    RQ_TRY(cudaStreamWaitEvent(P.s_out, P.ev_cmp[b], 0));
     if (codes_host) {
       void* dst = narrow ? P.hc[b] : (void*)((char*)codes_host + (size_t)t0 * nq_run * usz);
-      cudaMemcpyAsync(dst, P.dc[b], (size_t)nt * nq_run * dsz, cudaMemcpyDeviceToHost, P.s_out);
+      RQ_TRY(cudaMemcpyAsync(dst, P.dc[b], (size_t)nt * nq_run * dsz, cudaMemcpyDeviceToHost, P.s_out));
     }
-    if (q_host) cudaMemcpyAsync(q_host + (size_t)t0 * dim, P.dq[b], (size_t)nt * dim * 4, cudaMemcpyDeviceToHost, P.s_out);
-    cudaEventRecord(P.ev_out[b], P.s_out);
-    // chunk c is queued; while the GPU works on it, finish chunk c-1 on the host.  (Its staging buffer is
-    // reused by chunk c+1, which is enqueued only after this returns.)
-    if (narrow && c >= 1) finish_chunk(c - 1);
+    if (q_host) RQ_TRY(cudaMemcpyAsync(q_host + (size_t)t0 * dim, P.dq[b], (size_t)nt * dim * 4, cudaMemcpyDeviceToHost, P.s_out));
+    RQ_TRY(cudaEventRecord(P.ev_out[b], P.s_out));
+    // chunk c is queued; while the GPU works on it, finish an earlier chunk on the host.  Its staging buffer is
+    // reused by chunk c + 1, which is enqueued only after this returns.
+    if (narrow && c >= kHostBufs - 1) finish_chunk(c - (kHostBufs - 1));
   }
-  if (rc == 0 && narrow) finish_chunk(n_chunks - 1);
-  cudaError_t e1 = cudaStreamSynchronize(P.s_in), e2 = cudaStreamSynchronize(P.s_cmp), e3 = cudaStreamSynchronize(P.s_out);
-  if (rc == 0 && e1 != cudaSuccess) fail(e1);
-  if (rc == 0 && e2 != cudaSuccess) fail(e2);
-  if (rc == 0 && e3 != cudaSuccess) fail(e3);
+  if (narrow)
+    for (int64_t c = (n_chunks > kHostBufs - 1 ? n_chunks - (kHostBufs - 1) : 0); c < n_chunks; c++) finish_chunk(c);
+#undef RQ_TRY
+  // drain every stream even after a failure: the buffers may be re-used by the next call
+  const cudaError_t e1 = cudaStreamSynchronize(P.s_in), e2 = cudaStreamSynchronize(P.s_cmp), e3 = cudaStreamSynchronize(P.s_out);
+  if (err == cudaSuccess) err = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  if (rc == RQAE_OK && err != cudaSuccess) { g_last_cuda = err; rc = RQAE_ECUDA; }
   return rc;
 }
 

@@ -263,6 +263,8 @@ class RQAE(nn.Module):
     def encode(self, x, max_layers: int = float("inf"), out_dtype: torch.dtype = torch.int64):
         """Codes only (forward without the reconstruction write).  ``out_dtype`` may be int16 / int32 / int64;
         every code is < codebook rows <= 65535."""
+        if out_dtype == torch.int16 and self.codebook.shape[1] > 32768:
+            raise ValueError(f"int16 cannot hold the codes of a {self.codebook.shape[1]}-row codebook; use int32")
         _, codes, _ = self._run_forward(x, max_layers, 0.0, False, out_dtype)
         return codes
 
@@ -380,14 +382,21 @@ class RQAE(nn.Module):
         return q
 
     def forward_host(self, x_host: torch.Tensor, max_layers=float("inf"), want_q: bool = True,
-                     out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 33152, device=None,
-                     out: Optional[tuple] = None):
+                     out_dtype: torch.dtype = torch.int64, chunk_tokens: int = 9472, device=None,
+                     out: Optional[tuple] = None, code_transfer: Optional[str] = None,
+                     widen_threads: Optional[int] = None):
         """End-to-end variant for host-resident activations: ``x_host`` is a CPU tensor (pinned for full
         copy speed); codes and reconstruction come back in (pinned) CPU tensors.  H2D copy, kernel and D2H
         copies of consecutive chunks overlap inside ``rqae_forward_host_f32``.  ``out=(q, codes)`` reuses
         caller-owned (pinned) result tensors -- page-locking fresh result buffers costs more than the whole
-        computation, so a caller that loops should allocate them once.  The default chunk is 14 full waves of
-        the forward kernel (148 SMs x 16 tokens)."""
+        computation, so a caller that loops should allocate them once.  The default chunk is 4 full waves of
+        the forward kernel (148 SMs x 16 tokens): the first H2D and the last D2H, which nothing overlaps, are
+        1 % of a 1 Mi-token call.  ``code_transfer`` = "direct" | "narrow" | "auto" and ``widen_threads`` set the
+        process-wide pipeline options of ``rqae_forward_host_config`` (see include/rqae_b200.h)."""
+        if code_transfer is not None or widen_threads is not None:
+            mode = {None: -1, "auto": 0, "narrow": 1, "direct": 2}[code_transfer]
+            _lib.check(_lib.load().rqae_forward_host_config(mode, -1 if widen_threads is None else int(widen_threads)),
+                       "rqae_forward_host_config")
         if x_host.is_cuda or x_host.dtype != torch.float32:
             raise RuntimeError("forward_host expects a float32 CPU tensor")
         if x_host.shape[-1] != self.dim:

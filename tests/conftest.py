@@ -22,3 +22,9 @@ def golden_small():
 def golden_2b():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "kat_2b.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_9b():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "kat_9b.npz"))

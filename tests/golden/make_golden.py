@@ -14,6 +14,14 @@ pinned on outputs of the reference itself.  Two files are written:
   kat_small.npz  small configs with the weights stored in full: round_fsq, fsq,
                  a learned-codebook method, max_layers, decode(layers=...),
                  zero rows (NaN rule), duplicate-codeword tie rule.
+  kat_2b_codes4096.npz  the reference's int16 codes of ALL 4096 tokens of the 2B KAT
+                 (BASELINE configs[0]); sha-checked against kat_2b.npz's fp_codes_i16.
+  kat_9b.npz     Gemma-2-9B width with the deeper stack of BASELINE configs[3]
+                 (torch.manual_seed(0); RQAE(dim=3584, num_quantizers=2048)), 64 tokens:
+                 reference codes, reconstruction, decode, fp64 margins teacher-forced
+                 along the reference's trajectory, weight fingerprints.
+
+`--only NAME` (small | 2b | codes4096 | 9b) regenerates one file.
 """
 import hashlib
 import os
@@ -154,7 +162,56 @@ def make_small():
     np.savez_compressed(os.path.join(HERE, "kat_small.npz"), **out)
 
 
+def make_codes4096():
+    """All 4096 tokens of the 2B KAT through the unmodified reference (about two minutes on 8 cores)."""
+    torch.manual_seed(0)
+    ref = RefRQAE().eval()
+    x = torch.randn(32, 128, 2304, generator=torch.Generator().manual_seed(1))
+    t0 = time.time()
+    with torch.inference_mode():
+        _, idx = ref(x)
+    idx16 = idx.contiguous().to(torch.int16)
+    g = np.load(os.path.join(HERE, "kat_2b.npz"))
+    assert sha16(idx16) == str(g["fp_codes_i16"]), "codes differ from the committed fingerprint"
+    np.savez_compressed(os.path.join(HERE, "kat_2b_codes4096.npz"), codes4096=idx16.view(-1, 1024).numpy(),
+                        fp_codes_i16=sha16(idx16), fp_x=sha16(x))
+    print("codes4096:", sha16(idx16), "fwd s", time.time() - t0)
+
+
+def make_9b(tokens=64):
+    torch.manual_seed(0)
+    ref = RefRQAE(dim=3584, num_quantizers=2048).eval()
+    sd = ref.state_dict()
+    x = torch.randn(1, tokens, 3584, generator=torch.Generator().manual_seed(3))
+    t0 = time.time()
+    with torch.inference_mode():
+        q, idx = ref(x)
+        idx = idx.contiguous()
+        dec = ref.decode(idx[:, :8])
+    t_fwd = time.time() - t0
+    w = orc.StackedWeights.from_state_dict(sd)
+    _, idx64_tf, margins_tf = orc.forward(w, x, dtype=torch.float64, want_margins=True, teacher_codes=idx)
+    out = dict(
+        x=x[0].numpy(), codes=idx[0].to(torch.int16).numpy(), q=q[0].numpy(), dec8=dec[0].numpy(),
+        margins_fp64=margins_tf[0].numpy().astype(np.float32), codes_fp64=idx64_tf[0].to(torch.int16).numpy(),
+        fp_layers=layers_fingerprint(sd), fp_codebook0=sha16(sd["codebook"][0]), fp_x=sha16(x),
+        fp_codes_i16=sha16(idx.to(torch.int16)), codes_sum=np.int64(idx.sum().item()),
+        ref_forward_seconds=np.float64(t_fwd), ref_threads=np.int64(torch.get_num_threads()),
+        torch_version=torch.__version__,
+    )
+    np.savez_compressed(os.path.join(HERE, "kat_9b.npz"), **out)
+    print("9b:", {k: out[k] for k in ("fp_layers", "fp_x", "fp_codes_i16", "codes_sum")}, "fwd s", t_fwd)
+    print("   fp64 teacher-forced argmax identical to fp32 reference at",
+          float((idx64_tf[0] == idx[0]).float().mean()), "of (token, layer) pairs")
+
+
 if __name__ == "__main__":
-    make_small()
-    if "--small-only" not in sys.argv:
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only in (None, "small"):
+        make_small()
+    if only in (None, "2b") and "--small-only" not in sys.argv:
         make_2b()
+    if only in (None, "codes4096") and "--small-only" not in sys.argv:
+        make_codes4096()
+    if only in (None, "9b") and "--small-only" not in sys.argv:
+        make_9b()

@@ -80,3 +80,27 @@ def test_search_entry_points_validate_before_touching_the_gpu():
     assert lib.rqae_search_position_max_f16(one, 24, 7, 7, one, 20, None) == 1                 # rows shorter than n_seq
     assert lib.rqae_search_position_max_f16(one, 24, 7, 7, one, 28, None) == 1                 # row stride not a multiple of 8
     assert lib.rqae_search_position_max_f16(one, 24, 7, 200, one, 24, None) == 2               # more than 128 query positions
+
+
+def test_host_widening_pool_matches_numpy():
+    """The widening step of the narrow host pipeline (int16 -> int32 / int64, AVX2 streaming stores, persistent worker
+    pool) on its own: every thread count, unaligned destinations, sizes around the split and vector widths."""
+    import numpy as np
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 16, 17, 65535, 65536, 65537, 300001, 1 << 20):
+        src = rng.integers(0, 625, size=n + 8, dtype=np.int16)
+        for dtype, code in ((np.int32, 1), (np.int64, 2)):
+            for threads in (1, 2, 3, 8):
+                for off in (0, 1):
+                    dst = np.full(n + 8, -7, dtype=dtype)
+                    rc = lib.rqae_widen_codes_host(src[off:].ctypes.data, dst[off:].ctypes.data, n, code, threads)
+                    assert rc == 0
+                    assert np.array_equal(dst[off:off + n], src[off:off + n].astype(dtype))
+                    assert (dst[:off] == -7).all() and (dst[off + n:] == -7).all()
+    assert lib.rqae_widen_codes_host(None, None, 4, 2, 1) == 1
+    assert lib.rqae_widen_codes_host(None, None, 0, 0, 1) == 1      # int16 is not a widening target
+    assert lib.rqae_forward_host_config(3, 0) == 1 and lib.rqae_forward_host_config(-1, -1) == 0
+    # int16 codes cannot hold a 40000-row codebook: refused before any CUDA call
+    one = ctypes.c_void_p(4096)
+    assert lib.rqae_forward_f32(one, one, 0, 8, 8, 256, 4, 40000, one, 4, one, 0, 8, None, None, None, None) == 1

@@ -105,3 +105,35 @@ def test_2b_fingerprints_and_first_tokens(golden_2b):
     assert rep.failures == 0, str(rep)
     dec = c_oracle.decode_f32(cw, codes=g["codes1024"][:8])
     assert np.array_equal(dec, g["dec128"][:8])
+
+
+def test_9b_width_oracles_pinned_on_reference(golden_9b):
+    """BASELINE configs[3] shape (d=3584, nq=2048): both oracles against the golden of the unmodified reference
+    (tests/golden/kat_9b.npz) -- the torch port reproduces the reference's codes on the same tokens, the C oracle
+    in the CUDA kernel's summation order passes the near-tie protocol at full depth and reproduces the reference's
+    decode bit for bit.  This is what pins the kernel-order C oracle (the GPU tests' bit-exact comparator) at 9B
+    width."""
+    g = golden_9b
+    w = orc.random_init(dim=3584, num_quantizers=2048)
+    h = hashlib.sha256()
+    for l in range(w.nq):
+        for t in (w.w_in[l], w.b_in[l], w.w_out[l], w.b_out[l]):
+            h.update(t.numpy().tobytes())
+    assert h.hexdigest()[:16] == str(g["fp_layers"])
+    assert hashlib.sha256(g["x"].tobytes()).hexdigest()[:16] == str(g["fp_x"])
+    x = torch.from_numpy(g["x"])
+    q, idx = orc.forward(w, x[None, :8])
+    assert np.array_equal(idx[0].numpy(), g["codes"][:8].astype(np.int64))
+    cw = c_oracle.CWeights.from_stacked(w)
+    qc, codes = c_oracle.forward_f32(cw, g["x"], **c_oracle.KERNEL_ORDER)
+    rep = parity.compare_codes(codes, g["codes"], g["margins_fp64"])
+    assert rep.failures == 0, str(rep)
+    ok = parity.exact_token_mask(codes, g["codes"])
+    assert ok.sum() >= len(ok) - 8
+    assert np.abs(qc[ok] - g["q"][ok]).max() <= 2e-5 * np.abs(g["q"]).max()
+    assert np.array_equal(c_oracle.decode_f32(cw, codes=g["codes"][:8]), g["dec8"])
+    # the fp64 C oracle, teacher-forced along the reference's codes, agrees with the committed margins
+    _, c64, m64 = c_oracle.forward_f64(cw, g["x"][:8], teacher=g["codes"][:8])
+    big = g["margins_fp64"][:8] > 1e-4
+    assert np.array_equal(c64[big], g["codes"][:8].astype(np.int32)[big])
+    assert np.abs(m64 - g["margins_fp64"][:8])[big].max() < 1e-5

@@ -119,6 +119,72 @@ def test_2b_1024_tokens_vs_reference_codes(model_2b, golden_2b):
     assert rep.near_tie <= 32   # expected ~0.2-1 % of tokens at nq=1024
 
 
+def test_2b_all_4096_tokens_of_config0_vs_reference_codes(model_2b, golden_2b):
+    """BASELINE configs[0] in full: every one of the 4096 KAT tokens against the reference's codes
+    (tests/golden/kat_2b_codes4096.npz, sha-checked against the per-token fingerprints in kat_2b.npz)."""
+    import os
+    m, cw = model_2b
+    g = golden_2b
+    g4 = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat_2b_codes4096.npz"))
+    ref = g4["codes4096"]
+    assert ref.shape == (4096, 1024) and str(g4["fp_codes_i16"]) == str(g["fp_codes_i16"])
+    assert hashlib.sha256(ref.tobytes()).hexdigest()[:16] == str(g["fp_codes_i16"])
+    tok_sha = np.frombuffer(b"".join(hashlib.sha256(r.tobytes()).digest()[:8] for r in ref), dtype=np.uint64)
+    assert np.array_equal(tok_sha, g["tok_sha4096"])
+    x = util.x_2b()
+    codes = m.encode(x.to(_cuda()), out_dtype=torch.int16).cpu().numpy().reshape(4096, 1024)
+    got_sha = np.frombuffer(b"".join(hashlib.sha256(r.tobytes()).digest()[:8] for r in codes), dtype=np.uint64)
+    bad = np.flatnonzero(got_sha != g["tok_sha4096"])
+    assert np.array_equal(bad, np.flatnonzero((codes != ref).any(axis=1)))
+    margins = np.full(ref.shape, np.inf, np.float32)
+    if len(bad):
+        _, _, mb = c_oracle.forward_f64(cw, x.view(-1, 2304).numpy()[bad], teacher=ref[bad])
+        margins[bad] = mb
+    rep = parity.compare_codes(codes, ref, margins)
+    print("2B, all 4096 tokens of configs[0] vs reference:", rep)
+    assert rep.failures == 0, str(rep)
+    assert rep.near_tie <= 128   # expected ~0.2-1 % of tokens at nq=1024 (SURVEY 8c)
+
+
+def test_9b_kat_full_depth_vs_reference(golden_9b):
+    """BASELINE configs[3] shape (d=3584, nq=2048) pinned on the UNMODIFIED reference: codes under the near-tie
+    protocol with fp64 margins along the reference's trajectory, reconstruction within the stated tolerance,
+    decode bit-exact; and bit-exact against the C oracle in kernel order at full depth."""
+    from rqae_b200 import RQAE
+    g = golden_9b
+    torch.manual_seed(0)
+    m = RQAE(dim=3584, num_quantizers=2048).eval()
+    h = hashlib.sha256()
+    for k, v in m.state_dict().items():
+        if k.startswith("layers."):
+            h.update(v.numpy().tobytes())
+    assert h.hexdigest()[:16] == str(g["fp_layers"])
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    m = m.to(_cuda())
+    x = torch.from_numpy(g["x"])
+    assert hashlib.sha256(x.numpy().tobytes()).hexdigest()[:16] == str(g["fp_x"])
+    n = x.shape[0]
+    q, idx = m(x.to(_cuda()).view(1, n, 3584))
+    codes = idx[0].cpu().numpy()
+    qo, co = c_oracle.forward_f32(cw, g["x"], **KERNEL_ORDER)
+    assert np.array_equal(codes, co.astype(np.int64)) and np.array_equal(q[0].cpu().numpy(), qo)
+    rep = parity.compare_codes(codes, g["codes"], g["margins_fp64"])
+    print("9B-width KAT (d=3584, nq=2048), %d tokens vs reference:" % n, rep)
+    assert rep.failures == 0, str(rep)
+    assert rep.exact >= n - 8
+    ok = parity.exact_token_mask(codes, g["codes"])
+    rel = np.abs(q[0].cpu().numpy()[ok] - g["q"][ok]).max() / np.abs(g["q"]).max()
+    print("   reconstruction max rel err on exact tokens:", rel)
+    assert rel <= 2e-5
+    # teacher-forced: every (token, layer) of the reference trajectory checked independently
+    teacher = torch.from_numpy(g["codes"].astype(np.int32)).to(_cuda()).view(1, n, 2048)
+    _, tf, _ = m._run_forward(x.to(_cuda()).view(1, n, 3584), float("inf"), 0.0, False, torch.int32, teacher=teacher)
+    mism = tf[0].cpu().numpy() != g["codes"]
+    assert (g["margins_fp64"][mism] < parity.EPS).all() and mism.mean() < 1e-4
+    dec = m.decode(torch.from_numpy(g["codes"][:8].astype(np.int64)).to(_cuda()).view(1, 8, 2048))
+    assert np.array_equal(dec[0].cpu().numpy(), g["dec8"])
+
+
 def test_2b_decode_bit_exact(model_2b, golden_2b):
     m, _ = model_2b
     g = golden_2b
