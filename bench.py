@@ -442,7 +442,7 @@ def stock_pytorch_gpu_extra(torch, model, dev, sizes=(512, 4096, 65536)):
     weights on the GPU (what scripts/1:144 does with .to("cuda"); the op-for-op port, ~13 launches per layer) next
     to this repo's fused kernel on the same tokens.  tokens/s for forward (encode + reconstruction)."""
     from oracle import rqae_oracle as orc
-    w = orc.StackedWeights.from_state_dict({k: v.detach() for k, v in model.state_dict().items()})
+    w = orc.StackedWeights.from_state_dict({k: v.detach() for k, v in model.state_dict().items()}).to(dev)
     res = {}
     for n in sizes:
         x = torch.randn(1, n, D, device=dev, generator=torch.Generator(device=dev).manual_seed(4321 + n))

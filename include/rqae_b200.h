@@ -79,6 +79,24 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
                      int code_dtype, int64_t code_stride, float* q_out, const int32_t* teacher,
                      float* z_out, void* stream);
 
+/* The body of RQAE.hook's hook_fn (rqae/model.py:276-289) for the Gemma-2 adapter (rqae/llm.py:60-73) in ONE launch:
+ *     hs = hidden.float(); x = hs * rsqrt(mean(hs^2) + rms_eps) * (1 + rms_weight)          (llm.py:65-66)
+ *     q, codes = forward(x)                                                                  (model.py:281)
+ *     q = q / (1 + rms_weight) / rsqrt(mean(hs^2) + 1e-6)                                    (llm.py:68-73)
+ *     q[:, 0] = hs[:, 0] when skip_bos (token t with t % seq_len == 0 is left untouched)     (model.py:285-286)
+ *     hidden <- q in hidden's own dtype when replace                                         (model.py:289)
+ * The normalisation, the de-normalisation, the BOS rule and the cast are fused into the load and the epilogue of
+ * the forward kernel; no fp32 copy of the hidden states, no normalised copy and no fp32 reconstruction exist.
+ *   hidden        [n_tokens][dim] of hidden_dtype (0 fp32, 1 fp16, 2 bf16), read and (replace != 0) overwritten
+ *   rms_weight    fp32 [dim], the RMSNorm weight w (NOT 1 + w)
+ *   codes         nullable, as in rqae_forward_f32
+ * Arithmetic is fp32 with the reference's operation order; the sum of squares is accumulated in a different order
+ * than torch's reduction, so results agree with the unfused path to fp32 rounding (codes: near-tie protocol). */
+int rqae_hook_rmsnorm(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                      int codebook_dim, int K, void* hidden, int hidden_dtype, int64_t n_tokens, int seq_len,
+                      const float* rms_weight, float rms_eps, int skip_bos, int replace, void* codes, int code_dtype,
+                      int64_t code_stride, void* stream);
+
 /* RQAE.decode / decode_from_codebook_values (rqae/model.py:232-252): sum over the selected layers,
  * in ascending order, of W_out[l] c_l + b_out[l], with the reference's fp32 arithmetic
  * (o = fma(c3,w3,fma(c2,w2,fma(c1,w1,c0*w0))) + b; q = o_first, then q += o).

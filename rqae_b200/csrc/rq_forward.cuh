@@ -32,6 +32,9 @@
 // the tile a token lands in, on the grid size or on timing.  The reconstruction is emitted as
 // q = x - r_final (one extra read of x) instead of a second register-resident accumulator.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "rq_common.cuh"
 #include "rq_layout.h"
 
@@ -55,7 +58,25 @@ struct FwdParams {
   float* z_out;                 // nullable debug: [n_tokens][nq_run][4] in-projection values
   float l2_hot;                 // fraction of the weight stream pinned in L2 with evict_last (rest evict_first)
   unsigned int* sync_ctr;       // nullable: grid lock-step counter of this launch (zeroed before the launch)
+  // ---- hook mode (HOOK instantiation; rqae/model.py:276-289 with the Gemma-2 norm / denorm of rqae/llm.py:65-73) ----
+  const void* hs;               // hidden states [n_tokens][D] of hs_dtype; the kernel normalises them itself (x unused)
+  void* hs_out;                 // nullable: denormalised reconstruction in hs_dtype (may alias hs: same thread, same element)
+  const float* rms_w;           // [D] RMSNorm weight w; the norm multiplies by (1 + w)
+  float rms_eps;                // eps of the norm (the reference's denorm uses 1e-6, llm.py:71)
+  int hs_dtype;                 // 0: fp32, 1: fp16, 2: bf16
+  int seq_len, skip_bos;        // token t is left untouched when skip_bos && t % seq_len == 0 (model.py:285-286)
 };
+
+__device__ __forceinline__ float hook_load(const void* base, long long i, int dt) {
+  if (dt == 1) return __half2float(reinterpret_cast<const __half*>(base)[i]);
+  if (dt == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+  return reinterpret_cast<const float*>(base)[i];
+}
+__device__ __forceinline__ void hook_store(void* base, long long i, int dt, float v) {
+  if (dt == 1) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+  else if (dt == 2) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(base)[i] = v;
+}
 
 #ifndef RQ_SKEW_CLK
 #define RQ_SKEW_CLK 350
@@ -87,7 +108,8 @@ struct FwdCfg {
   static constexpr int SM_CPR = SM_PART + 2 * kComputeWarps * 32 * 4;       // u64[2][4][4] (pairs padded to 4)
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
   static constexpr int SM_THR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // float[4] search thresholds
-  static constexpr int SM_BAR = SM_THR + 16;                                // mbarriers
+  static constexpr int SM_HOOK = SM_THR + 16;                               // float[8][16] warp partials + float[2][16] scales (hook mode)
+  static constexpr int SM_BAR = SM_HOOK + (kComputeWarps * 16 + 32) * 4;    // mbarriers
   static constexpr int N_BAR = 2 * NSLOT + 4;
   static constexpr int SM_TOTAL = SM_BAR + N_BAR * 8;
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -205,7 +227,7 @@ __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4]
 
 // Register budget: ptxas compiles the kernel for 384 threads/CTA at 168 registers, so the CTA owns a pool
 // of 384*168 = 64512 registers; setmaxnreg can only re-split THAT pool (an .inc beyond it spins forever).
-template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, int REG_COMPUTE = RQ_REGC, int REG_HELPER = RQ_REGH>
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, bool HOOK = false, int REG_COMPUTE = RQ_REGC, int REG_HELPER = RQ_REGH>
 __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams p) {
   static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= kThreads * 168, "register pool budget");
   using C = FwdCfg<E, EC, CH, NSLOT, TG>;
@@ -266,17 +288,68 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       const long long tok0 = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG);
       // ---- load the unit's activations into registers (zeros outside [0,n_tokens) x [0,D)) ----
       u64 r2[TG][E];   // [phase * NP + pair][element]
+      if constexpr (!HOOK) {
 #pragma unroll
-      for (int pi = 0; pi < TG; pi++) {
-        const long long ta = tok0 + 2 * pi, tb = ta + 1;
-        const float* xa = p.x + ta * (long long)p.D;
-        const float* xb = p.x + tb * (long long)p.D;
+        for (int pi = 0; pi < TG; pi++) {
+          const long long ta = tok0 + 2 * pi, tb = ta + 1;
+          const float* xa = p.x + ta * (long long)p.D;
+          const float* xb = p.x + tb * (long long)p.D;
+#pragma unroll
+          for (int j = 0; j < E; j++) {
+            const int d = j * RQ_GROUP_THREADS + ct;
+            const float a = (ta < p.n_tokens && d < p.D) ? __ldcs(xa + d) : 0.0f;
+            const float b = (tb < p.n_tokens && d < p.D) ? __ldcs(xb + d) : 0.0f;
+            r2[pi][j] = pack2(a, b);
+          }
+        }
+      } else {
+        // Hook mode: the unit's hidden states are RMS-normalised on the way in (rqae/llm.py:65-66 = Gemma2RMSNorm:
+        // x * rsqrt(mean(x^2) + eps) * (1 + w), all in fp32 as the hook's .float() makes it).  Sum of squares: per
+        // thread over its E elements, xor-shuffle tree over the warp, the 8 warps as a pairwise tree.
+        float ss[2 * TG];
+#pragma unroll
+        for (int i = 0; i < 2 * TG; i++) ss[i] = 0.0f;
+#pragma unroll
+        for (int pi = 0; pi < TG; pi++) {
+          const long long ta = tok0 + 2 * pi, tb = ta + 1;
+#pragma unroll
+          for (int j = 0; j < E; j++) {
+            const int d = j * RQ_GROUP_THREADS + ct;
+            const float a = (ta < p.n_tokens && d < p.D) ? hook_load(p.hs, ta * (long long)p.D + d, p.hs_dtype) : 0.0f;
+            const float b = (tb < p.n_tokens && d < p.D) ? hook_load(p.hs, tb * (long long)p.D + d, p.hs_dtype) : 0.0f;
+            r2[pi][j] = pack2(a, b);
+            ss[2 * pi] = __fmaf_rn(a, a, ss[2 * pi]);
+            ss[2 * pi + 1] = __fmaf_rn(b, b, ss[2 * pi + 1]);
+          }
+        }
+        float* hk = reinterpret_cast<float*>(smem + C::SM_HOOK);
+#pragma unroll
+        for (int i = 0; i < 2 * TG; i++) {
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) ss[i] = __fadd_rn(ss[i], __shfl_xor_sync(0xffffffffu, ss[i], o));
+          if (lane == 0) hk[warp * 16 + i] = ss[i];
+        }
+        named_bar_sync(1, RQ_GROUP_THREADS);
+        if (ct < 2 * TG) {
+          const float t = __fadd_rn(__fadd_rn(__fadd_rn(hk[ct], hk[16 + ct]), __fadd_rn(hk[32 + ct], hk[48 + ct])),
+                                    __fadd_rn(__fadd_rn(hk[64 + ct], hk[80 + ct]), __fadd_rn(hk[96 + ct], hk[112 + ct])));
+          const float ms = __fdiv_rn(t, (float)p.D);
+          hk[kComputeWarps * 16 + ct] = rsqrtf(__fadd_rn(ms, p.rms_eps));        // norm
+          hk[kComputeWarps * 16 + 16 + ct] = rsqrtf(__fadd_rn(ms, 1e-6f));       // denorm (llm.py:71)
+        }
+        named_bar_sync(1, RQ_GROUP_THREADS);
 #pragma unroll
         for (int j = 0; j < E; j++) {
           const int d = j * RQ_GROUP_THREADS + ct;
-          const float a = (ta < p.n_tokens && d < p.D) ? __ldcs(xa + d) : 0.0f;
-          const float b = (tb < p.n_tokens && d < p.D) ? __ldcs(xb + d) : 0.0f;
-          r2[pi][j] = pack2(a, b);
+          const float w1 = d < p.D ? __fadd_rn(1.0f, __ldg(p.rms_w + d)) : 0.0f;
+#pragma unroll
+          for (int pi = 0; pi < TG; pi++) {
+            float a, b;
+            unpack2(r2[pi][j], a, b);
+            a = __fmul_rn(__fmul_rn(a, hk[kComputeWarps * 16 + 2 * pi]), w1);
+            b = __fmul_rn(__fmul_rn(b, hk[kComputeWarps * 16 + 2 * pi + 1]), w1);
+            r2[pi][j] = pack2(a, b);
+          }
         }
       }
 
@@ -329,7 +402,37 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       }
 
       // ---- reconstruction q = x - r_final ----
-      if (p.q_out != nullptr) {
+      if constexpr (HOOK) {
+        // q is denormalised (llm.py:68-73: / (1 + w), then / rsqrt(mean(hs^2) + 1e-6)), the BOS position keeps its
+        // hidden state (model.py:285-286) and the result replaces the hidden states in their own dtype (model.py:289).
+        // x is recomputed from hs with the operations of the way in, so it is the same value bit for bit.
+        if (p.hs_out != nullptr) {
+          const float* hk = reinterpret_cast<const float*>(smem + C::SM_HOOK) + kComputeWarps * 16;
+#pragma unroll
+          for (int j = 0; j < E; j++) {
+            const int d = j * RQ_GROUP_THREADS + ct;
+            const float w1 = d < p.D ? __fadd_rn(1.0f, __ldg(p.rms_w + d)) : 1.0f;
+#pragma unroll
+            for (int pi = 0; pi < TG; pi++) {
+              const long long ta = tok0 + 2 * pi, tb = ta + 1;
+              float ra, rb;
+              unpack2(r2[pi][j], ra, rb);
+              if (d < p.D) {
+                if (ta < p.n_tokens && !(p.skip_bos && ta % p.seq_len == 0)) {
+                  const float x = __fmul_rn(__fmul_rn(hook_load(p.hs, ta * (long long)p.D + d, p.hs_dtype), hk[2 * pi]), w1);
+                  hook_store(p.hs_out, ta * (long long)p.D + d, p.hs_dtype,
+                             __fdiv_rn(__fdiv_rn(__fsub_rn(x, ra), w1), hk[16 + 2 * pi]));
+                }
+                if (tb < p.n_tokens && !(p.skip_bos && tb % p.seq_len == 0)) {
+                  const float x = __fmul_rn(__fmul_rn(hook_load(p.hs, tb * (long long)p.D + d, p.hs_dtype), hk[2 * pi + 1]), w1);
+                  hook_store(p.hs_out, tb * (long long)p.D + d, p.hs_dtype,
+                             __fdiv_rn(__fdiv_rn(__fsub_rn(x, rb), w1), hk[16 + 2 * pi + 1]));
+                }
+              }
+            }
+          }
+        }
+      } else if (p.q_out != nullptr) {
 #pragma unroll
         for (int pi = 0; pi < TG; pi++) {
           const long long ta = tok0 + 2 * pi, tb = ta + 1;

@@ -341,10 +341,10 @@ __global__ void __launch_bounds__(256, 1) fma_pattern_probe_kernel(int iters, fl
 // ---------------------------------------------------------------------------------------------
 // forward launch
 // ---------------------------------------------------------------------------------------------
-template <int E, int EC, int CH, int NSLOT, int TG, bool DBG>
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG, bool HOOK = false>
 int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   using C = rq::FwdCfg<E, EC, CH, NSLOT, TG>;
-  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG, DBG>;
+  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG, DBG, HOOK>;
   RQ_CUDA(ensure_dynamic_smem((const void*)kern, C::SM_TOTAL));
   const long long n_units = (prm.n_tokens + 2 * TG - 1) / (2 * TG);
   const int grid = (int)(n_units < sms ? n_units : sms);
@@ -370,6 +370,7 @@ int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
 
 template <int E, int EC, int CH, int NSLOT, int TG>
 int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+  if (prm.hs != nullptr) return launch_forward_t<E, EC, CH, NSLOT, TG, false, true>(prm, sms, st);
   if (prm.teacher != nullptr || prm.z_out != nullptr) return launch_forward_t<E, EC, CH, NSLOT, TG, true>(prm, sms, st);
   return launch_forward_t<E, EC, CH, NSLOT, TG, false>(prm, sms, st);
 }
@@ -443,13 +444,12 @@ int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, 
   return RQAE_OK;
 }
 
-int rqae_forward_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
-                     int codebook_dim, int K, const float* x, int64_t n_tokens, void* codes, int code_dtype,
-                     int64_t code_stride, float* q_out, const int32_t* teacher, float* z_out, void* stream) {
+static int forward_common(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                          int codebook_dim, int K, int64_t n_tokens, void* codes, int code_dtype, int64_t code_stride,
+                          rq::FwdParams& prm, void* stream) {
   if (!packed || !codebook || nq <= 0 || nq_run <= 0 || nq_run > nq || dim <= 0 || K <= 0 || n_tokens < 0) return RQAE_EINVAL;
   if (code_dtype < 0 || code_dtype > 2 || (codes && code_stride < nq_run)) return RQAE_EINVAL;
   if (codes && code_dtype == RQAE_CODE_I16 && K > 32768) return RQAE_EINVAL;   // int16 cannot hold codes >= 32768
-  if (n_tokens > 0 && !x) return RQAE_EINVAL;
   RqShape s;
   if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
   if (n_tokens == 0) return RQAE_OK;
@@ -458,13 +458,11 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
   if (rc) return rc;
   RqLayout L;
   rq_layout(nq, K, &s, &L);
-  rq::FwdParams prm;
   prm.packed = (const unsigned char*)packed;
   prm.off_bin = L.off_bin; prm.off_cbt = L.off_cbt; prm.off_map = L.off_map; prm.off_stage = L.off_stage;
   prm.off_tp = L.off_tp; prm.off_map3 = L.off_map3;
   prm.codebook = codebook; prm.cb_shared = codebook_shared ? 1 : 0; prm.K = K; prm.nq_run = nq_run; prm.D = dim;
-  prm.x = x; prm.n_tokens = n_tokens; prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride;
-  prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
+  prm.n_tokens = n_tokens; prm.codes = codes; prm.code_dtype = code_dtype; prm.code_stride = code_stride;
   {
     static const float l2_hot = [] {   // tuning knob ("L2 residency of the weight stream")
       const char* e = getenv("RQAE_L2_HOT");
@@ -482,6 +480,31 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
     case 14: return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
     default: return RQAE_EUNSUPPORTED;
   }
+}
+
+int rqae_forward_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                     int codebook_dim, int K, const float* x, int64_t n_tokens, void* codes, int code_dtype,
+                     int64_t code_stride, float* q_out, const int32_t* teacher, float* z_out, void* stream) {
+  if (n_tokens > 0 && !x) return RQAE_EINVAL;
+  rq::FwdParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.x = x; prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
+  return forward_common(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, n_tokens, codes, code_dtype,
+                        code_stride, prm, stream);
+}
+
+int rqae_hook_rmsnorm(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
+                      int codebook_dim, int K, void* hidden, int hidden_dtype, int64_t n_tokens, int seq_len,
+                      const float* rms_weight, float rms_eps, int skip_bos, int replace, void* codes, int code_dtype,
+                      int64_t code_stride, void* stream) {
+  if (!hidden && n_tokens > 0) return RQAE_EINVAL;
+  if (!rms_weight || hidden_dtype < 0 || hidden_dtype > 2 || seq_len <= 0 || !(rms_eps >= 0.0f)) return RQAE_EINVAL;
+  rq::FwdParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.hs = hidden; prm.hs_out = replace ? hidden : nullptr; prm.hs_dtype = hidden_dtype; prm.rms_w = rms_weight;
+  prm.rms_eps = rms_eps; prm.seq_len = seq_len; prm.skip_bos = skip_bos ? 1 : 0;
+  return forward_common(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, n_tokens, codes, code_dtype,
+                        code_stride, prm, stream);
 }
 
 int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_codes, int dim, int codebook_dim, int K,

@@ -436,10 +436,72 @@ class RQAE(nn.Module):
         return q, codes
 
     # ------------------------------------------------------------------ hook (model.py:254-291)
+    @staticmethod
+    def _gemma_rmsnorm(llm):
+        """The final RMSNorm of the reference's Gemma-2 adapter (rqae/llm.py:60-73: ``norm`` = ``model.model.norm``,
+        ``denorm`` divides by ``1 + norm.weight`` and by ``rsqrt(mean(hs^2) + 1e-6)``), when ``llm`` is that adapter:
+        (weight, eps) or None.  Only the (1 + w) RMSNorm of the Gemma family qualifies for the fused hook."""
+        try:
+            norm = llm.model.model.norm
+        except AttributeError:
+            return None
+        if "Gemma" not in type(norm).__name__ or not hasattr(norm, "weight") or not hasattr(norm, "eps"):
+            return None
+        if type(llm).__name__ != "Gemma2":         # another adapter may define norm / denorm differently
+            return None
+        return norm.weight, float(norm.eps)
+
+    def hook_rmsnorm_(self, hidden: torch.Tensor, rms_weight: torch.Tensor, rms_eps: float = 1e-6, skip_bos: bool = True,
+                      replace: bool = True, return_codes: bool = False, out_dtype: torch.dtype = torch.int64):
+        """The body of ``hook_fn`` (model.py:276-289) for the Gemma-2 RMSNorm (llm.py:65-73) as ONE kernel launch on the
+        current stream (``rqae_hook_rmsnorm``): ``hidden`` (B, S, dim) fp16 / bf16 / fp32, contiguous, is normalised on
+        the way into the layer loop and -- when ``replace`` -- overwritten in place with the de-normalised
+        reconstruction (position 0 of every sequence untouched when ``skip_bos``).  Returns the codes (B, S, nq) when
+        ``return_codes``, else None."""
+        hd = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}.get(hidden.dtype)
+        if hd is None or not hidden.is_cuda or hidden.dim() != 3 or hidden.shape[-1] != self.dim or not hidden.is_contiguous():
+            raise RuntimeError("hook_rmsnorm_ needs a contiguous CUDA tensor (B, S, dim) of fp16 / bf16 / fp32")
+        if self.training:
+            raise NotImplementedError("the fused hook is an inference path (eval mode)")
+        _, packed, shared, cb_arg = self._ensure_packed()
+        if not shared or self.quantization_method not in _FSQ:
+            raise NotImplementedError("the fused hook supports the shared fsq / round_fsq codebook")
+        dev = hidden.device
+        cache = self.__dict__.get("_rms_w")
+        if cache is None or cache[0] is not rms_weight or cache[1].device != dev or cache[2] != rms_weight._version:
+            cache = (rms_weight, rms_weight.detach().to(device=dev, dtype=torch.float32).contiguous(), rms_weight._version)
+            self.__dict__["_rms_w"] = cache
+        w = cache[1]
+        if w.numel() != self.dim:
+            raise RuntimeError(f"rms_weight must have {self.dim} elements")
+        B, S, _ = hidden.shape
+        n = B * S
+        codes = torch.empty(B, S, self.num_quantizers, dtype=out_dtype, device=dev) if return_codes else None
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = _lib.load().rqae_hook_rmsnorm(
+                    packed.data_ptr(), cb_arg.data_ptr(), int(shared), self.num_quantizers, self.num_quantizers, self.dim,
+                    self.codebook_dim, self.codebook.shape[1], hidden.data_ptr(), hd, n, S, w.data_ptr(), float(rms_eps),
+                    int(bool(skip_bos)), int(bool(replace)), 0 if codes is None else codes.data_ptr(),
+                    _lib.CODE_DTYPE[str(out_dtype).split(".")[-1]], self.num_quantizers,
+                    torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "rqae_hook_rmsnorm")
+        return codes
+
     def hook(self, **kwargs) -> Callable:
+        """model.py:254-291.  Same kwargs (``llm=`` or ``norm=`` / ``denorm=``, ``store``, ``skip_bos``, ``replace``).
+
+        Fused fast path: when the norm is the Gemma-2 RMSNorm -- ``llm`` is the reference's ``Gemma2``
+        adapter, or ``rms_weight=`` / ``rms_eps=`` are passed -- and no ``store`` consumer is given, the whole body of
+        ``hook_fn`` (float cast, norm, forward, denorm, BOS passthrough, cast back, in-place replace) is ONE kernel
+        launch (``rqae_hook_rmsnorm``) on the current stream.  ``fused=False`` forces the generic path."""
         if "llm" in kwargs:
             llm = kwargs.pop("llm")
             assert hasattr(llm, "norm") and hasattr(llm, "denorm"), "RQAE hook requires norm and denorm from LLM"
+            if "rms_weight" not in kwargs:
+                g = self._gemma_rmsnorm(llm)
+                if g is not None:
+                    kwargs["rms_weight"], kwargs["rms_eps"] = g
             return self.hook(norm=llm.norm, denorm=llm.denorm, **kwargs)
         user_store = kwargs.get("store")
         if user_store is None:
@@ -457,8 +519,23 @@ class RQAE(nn.Module):
         if "denorm" not in kwargs:
             raise ValueError("RQAE hook requires denorm from LLM")
         norm, denorm = kwargs["norm"], kwargs["denorm"]
+        rms_weight = kwargs.get("rms_weight")
+        rms_eps = float(kwargs.get("rms_eps", 1e-6))
+        want_fused = kwargs.get("fused", True) and user_store is None and rms_weight is not None
+
+        def hook_fused(out0) -> bool:
+            """One launch for the whole hook body; False when this call does not qualify."""
+            if out0.dtype not in (torch.float32, torch.float16, torch.bfloat16) or not out0.is_cuda or out0.dim() != 3 \
+                    or out0.shape[-1] != self.dim or not out0.is_contiguous():
+                return False
+            if self.training or self.quantization_method not in _FSQ or not self._ensure_packed()[2]:
+                return False
+            self.hook_rmsnorm_(out0, rms_weight, rms_eps, skip_bos=skip_bos, replace=replace)
+            return True
 
         def hook_fn(module, input, output):
+            if want_fused and hook_fused(output[0].data):
+                return
             hs = output[0].float()                      # (B, S, dim)
             store("original", hs)
             rms_hs = norm(hs)

@@ -366,6 +366,69 @@ def test_hook_with_stub_llm(model_2b):
     assert torch.equal(idx, stash["indices"]) and torch.equal(q, stash["quantized"])
 
 
+class _GemmaStub:
+    """rqae/llm.py:60-73 with a synthetic RMSNorm weight: norm = Gemma2RMSNorm (x * rsqrt(mean(x^2) + eps) * (1 + w)),
+    denorm = its inverse with the reference's hard-coded 1e-6."""
+
+    def __init__(self, dim, eps=1e-6, seed=5):
+        self.eps = eps
+        self.weight = (0.1 * torch.randn(dim, generator=torch.Generator().manual_seed(seed))).cuda()
+
+    def norm(self, hs):
+        x = hs.float()
+        return (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps) * (1.0 + self.weight.float())).type_as(hs)
+
+    def denorm(self, hs, orig):
+        hs = hs / (1.0 + self.weight.float())
+        return hs.float() / torch.rsqrt(orig.float().pow(2).mean(-1, keepdim=True) + 1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_fused_hook_equals_generic_hook(model_2b, dtype):
+    """hook_fn (model.py:276-289) as one launch (rqae_hook_rmsnorm) against the generic path (torch
+    .float / norm / denorm / BOS / copy_ around the forward kernel) with the arithmetic of llm.py:65-73.  The two sum
+    the squares in a different order, so the normalised input differs in the last fp32 bit: codes are compared under
+    the near-tie protocol (margins from the fp64 C oracle along the generic path's codes), replaced hidden states on
+    tokens with identical codes within one rounding step of the output dtype."""
+    m, cw = model_2b
+    stub = _GemmaStub(2304)
+    B, S = 4, 37
+    hs = (3.0 * torch.randn(B, S, 2304, generator=torch.Generator().manual_seed(14))).to(_cuda()).to(dtype)
+    stash = {}
+    ref_out = (hs.clone(),)
+    m.hook(norm=stub.norm, denorm=stub.denorm, store=lambda k, v: stash.__setitem__(k, v))(None, None, ref_out)
+    fused = hs.clone()
+    codes = m.hook_rmsnorm_(fused, stub.weight, stub.eps, return_codes=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fused[:, 0], hs[:, 0])                                      # BOS passthrough, bit for bit
+    ref_codes = stash["indices"].cpu().numpy().reshape(B * S, -1)
+    got = codes.cpu().numpy().reshape(B * S, -1)
+    bad = np.flatnonzero((got != ref_codes).any(axis=1))
+    margins = np.full(ref_codes.shape, np.inf, np.float32)
+    if len(bad):
+        xn = stash["normed"].cpu().numpy().reshape(B * S, -1)
+        _, _, mb = c_oracle.forward_f64(cw, xn[bad], teacher=ref_codes[bad])
+        margins[bad] = mb
+    rep = parity.compare_codes(got, ref_codes, margins)
+    print(f"fused hook ({dtype}) vs generic hook:", rep)
+    assert rep.failures == 0, str(rep)
+    same = torch.from_numpy(parity.exact_token_mask(got, ref_codes)).view(B, S).to(_cuda())
+    a, b = fused.float()[same], ref_out[0].float()[same]
+    step = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7, torch.float32: 2e-5}[dtype]
+    assert ((a - b).abs() <= step * b.abs().clamp_min(b.abs().max() * 1e-3)).all()
+    # the hook object takes the fused path on its own when it is told the norm weight, and leaves the input alone
+    # with replace=False
+    via_hook = hs.clone()
+    m.hook(norm=stub.norm, denorm=stub.denorm, rms_weight=stub.weight, rms_eps=stub.eps)(None, None, (via_hook,))
+    assert torch.equal(via_hook, fused)
+    untouched = hs.clone()
+    m.hook(norm=stub.norm, denorm=stub.denorm, rms_weight=stub.weight, replace=False)(None, None, (untouched,))
+    assert torch.equal(untouched, hs)
+    no_bos = hs.clone()
+    m.hook_rmsnorm_(no_bos, stub.weight, stub.eps, skip_bos=False)
+    assert not torch.equal(no_bos[:, 0], hs[:, 0]) and torch.equal(no_bos[:, 1:], fused[:, 1:])
+
+
 def test_forward_host_matches_device_path(model_2b):
     m, _ = model_2b
     x = torch.randn(3000, 2304, generator=torch.Generator().manual_seed(17))
@@ -383,6 +446,12 @@ def test_forward_host_matches_device_path(model_2b):
             assert torch.equal(co.to(torch.int64), idx_d[0].cpu()) and torch.equal(qo, q_d[0].cpu())
     _, c3 = m.forward_host(x.pin_memory(), max_layers=32, want_q=False, chunk_tokens=999)
     assert torch.equal(c3, idx_d[0].cpu())
+    # both code-transfer modes of the host pipeline, every widening thread count
+    for mode, thr in (("narrow", 1), ("narrow", 3), ("direct", 0), ("auto", 0)):
+        for dt in (torch.int64, torch.int32):
+            q4, c4 = m.forward_host(x.pin_memory(), max_layers=32, chunk_tokens=500, out_dtype=dt, code_transfer=mode,
+                                    widen_threads=thr)
+            assert torch.equal(c4.to(torch.int64), idx_d[0].cpu()) and torch.equal(q4, q_d[0].cpu()), (mode, thr, dt)
 
 
 def test_gemma9b_width_bit_exact_vs_c_oracle():

@@ -63,6 +63,13 @@ def main():
         dt = (time.perf_counter() - t0) / reps
         return maxr(dt)
 
+    import faulthandler
+    faulthandler.enable()
+
+    def note(msg):
+        if rank == 0:
+            print("[probe]", msg, file=sys.stderr, flush=True)
+
     lib = _lib.load()
     res = {"world": world, "cores": os.cpu_count(), "tokens_per_rank": args.tokens}
     try:
@@ -76,6 +83,7 @@ def main():
     except Exception:
         pass
 
+    note("raw copies")
     # ---- raw copies ----
     nb = 1 << 31
     hp = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
@@ -102,6 +110,7 @@ def main():
     res["bidir_gbs_per_rank_each_way"] = nb / t / 1e9
     del dv, dv2
 
+    note("host memory")
     # ---- host memory ----
     a = torch.empty(1 << 30, dtype=torch.uint8); b = torch.empty(1 << 30, dtype=torch.uint8)
     a.fill_(3); b.copy_(a)
@@ -117,6 +126,7 @@ def main():
         res[f"widen_gcodes_per_rank_{th}thr"] = n / timed(lambda: lib.rqae_widen_codes_host(src.ctypes.data, dst.ctypes.data, n, 2, th), 2) / 1e9
     del src, dst, hp, hp2
 
+    note("model")
     # ---- the model ----
     torch.manual_seed(0)
     model = RQAE().eval().to(dev)
@@ -141,6 +151,7 @@ def main():
     fh = {}
     ref_sum = None
     for mode, thr, dt, chunk in cases:
+        note(f"forward_host {mode} {thr} {dt} {chunk}")
         ch = outs[dt]
         ch.zero_()
 
