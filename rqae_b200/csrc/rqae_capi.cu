@@ -472,12 +472,22 @@ static int forward_common(const void* packed, const float* codebook, int codeboo
     prm.l2_hot = l2_hot;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // Few tokens (the hook's operating point is 4 x 128, scripts/1_create_activations.py:152): units of 2 x 4 tokens
+  // instead of 2 x 8 put twice as many SMs to work and halve the time of a pass; a token's arithmetic does not
+  // depend on the unit size, so the codes are the same bit for bit.  (Units of 2 x 2 would ask the L2 for more
+  // weight bytes per layer than it delivers.)  RQAE_SMALL_UNITS=0 switches it off (A/B timing).
+  static const bool small_units = [] { const char* e = getenv("RQAE_SMALL_UNITS"); return e ? atoi(e) != 0 : true; }();
+  const bool few = small_units && n_tokens <= (int64_t)sms * 8;
   switch (s.E) {
     case 1: return launch_forward<1, 1, 1, 4, 8>(prm, sms, st);
     case 3: return launch_forward<3, 3, 1, 4, 8>(prm, sms, st);
     case 6: return launch_forward<6, 3, 2, 6, 8>(prm, sms, st);
-    case 9: return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 8>(prm, sms, st);
-    case 14: return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
+    case 9:
+      if (few) return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 4>(prm, sms, st);
+      return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 8>(prm, sms, st);
+    case 14:
+      if (few) return launch_forward<14, 2, 7, 10, 4>(prm, sms, st);
+      return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
     default: return RQAE_EUNSUPPORTED;
   }
 }
@@ -656,7 +666,8 @@ class WidenPool {
     if ((int)th_.size() == workers) return;
     stop();
     stop_ = false;
-    for (int i = 0; i < workers; i++) th_.emplace_back([this, i] { loop(i + 1); });
+    const unsigned long long g0 = gen_;   // a new worker must not mistake an old generation for a job
+    for (int i = 0; i < workers; i++) th_.emplace_back([this, i, g0] { loop(i + 1, g0); });
   }
   int workers() const { return (int)th_.size(); }
   // splits [0, n) over the workers and the caller; returns when all parts are done
@@ -681,8 +692,7 @@ class WidenPool {
     const size_t lo = per * id, hi = lo + per < n_ ? lo + per : n_;
     if (lo < hi) widen_range(src_, dst_, lo, hi, dtype_);
   }
-  void loop(int id) {
-    unsigned long long seen = 0;
+  void loop(int id, unsigned long long seen) {
     for (;;) {
       {
         std::unique_lock<std::mutex> lk(mu_);

@@ -98,6 +98,13 @@ def test_host_widening_pool_matches_numpy():
                     assert rc == 0
                     assert np.array_equal(dst[off:off + n], src[off:off + n].astype(dtype))
                     assert (dst[:off] == -7).all() and (dst[off + n:] == -7).all()
+    # changing the thread count between calls re-creates the pool: new workers must wait for a NEW job
+    big = rng.integers(0, 625, size=1 << 18, dtype=np.int16)
+    for threads in (8, 2, 5, 1, 8, 3):
+        dst = np.empty(1 << 18, np.int64)
+        assert lib.rqae_widen_codes_host(big.ctypes.data, dst.ctypes.data, 1 << 18, 2, threads) == 0
+        assert np.array_equal(dst, big.astype(np.int64))
+        del dst
     assert lib.rqae_widen_codes_host(None, None, 4, 2, 1) == 1
     assert lib.rqae_widen_codes_host(None, None, 0, 0, 1) == 1      # int16 is not a widening target
     assert lib.rqae_forward_host_config(3, 0) == 1 and lib.rqae_forward_host_config(-1, -1) == 0

@@ -415,7 +415,7 @@ def test_fused_hook_equals_generic_hook(model_2b, dtype):
     same = torch.from_numpy(parity.exact_token_mask(got, ref_codes)).view(B, S).to(_cuda())
     a, b = fused.float()[same], ref_out[0].float()[same]
     step = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7, torch.float32: 2e-5}[dtype]
-    assert ((a - b).abs() <= step * b.abs().clamp_min(b.abs().max() * 1e-3)).all()
+    assert ((a - b).abs() <= step * b.abs() + 2e-5 * b.abs().max()).all()   # one output rounding step + the fp32 tolerance
     # the hook object takes the fused path on its own when it is told the norm weight, and leaves the input alone
     # with replace=False
     via_hook = hs.clone()
