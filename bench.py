@@ -519,6 +519,9 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
     ev = lambda: torch.cuda.Event(enable_timing=True)
     codes = torch.empty(tokens, NQ, dtype=torch.int16, device=dev)
     lw = layer_weights_f16(model).to(dev)
+    if world > 1:   # bring up NCCL's point-to-point channels (lazy, seconds on first use) outside the timed region
+        wu = torch.zeros(world * 1024, dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(torch.empty_like(wu), wu)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -541,6 +544,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
         dist.broadcast(centers, src=0)
     n_total = world * tokens
     ms_int = ms_x = ms_sel = 0.0
+    ms_x_groups = []
     checksum = 0
     buf = torch.empty(group, len(SCRIPT3_CUTS), (tokens + 255) // 256 * 256, dtype=torch.float16, device=dev)
     for f0 in range(0, n_features, group):
@@ -557,6 +561,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
         d.record()
         torch.cuda.synchronize(dev)
         ms_int += a.elapsed_time(b); ms_x += b.elapsed_time(c); ms_sel += c.elapsed_time(d)
+        ms_x_groups.append(round(b.elapsed_time(c), 2))
         checksum += int(idx[:, :, 0, 0].sum().item())
         del rows, idx, val
     t_wall = time.perf_counter() - t_wall0
@@ -577,7 +582,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
                                             / (peaks["bf16_tflops"] if peaks else 1590.0),
            "select_gbs_per_gpu": rows_per_rank * n_total * 2 / ms_sel / 1e6,
            "exchange_gbs_per_gpu": (n_features * len(SCRIPT3_CUTS) * tokens * 2 * (world - 1) / world) / ms_x / 1e6 if world > 1 else None,
-           "checksum_top_idx": checksum,
+           "exchange_ms_per_group_rank0": ms_x_groups, "checksum_top_idx": checksum,
            "timing": "host wall clock barrier -> last kernel done (encode + 8 feature groups x (GEMM, all_to_all, select)), "
                      "max over ranks"}
     del codes, buf
@@ -691,16 +696,24 @@ def run_b200(args, rank, local_rank, world):
                 t_e = float(t.item())
             return world * Te * steps_e / t_e, int(ch[: 1 << 12].long().sum().item())
 
+        import ctypes
         v64, ck64 = e2e_run(torch.int64)
         v32, ck32 = e2e_run(torch.int32)
+        m_, t_ = ctypes.c_int(0), ctypes.c_int(0)
+        lib.rqae_forward_host_mode(ctypes.byref(m_), ctypes.byref(t_))
+        narrow = m_.value == 1
         e2e = {"value": v64, "unit": UNIT, "h2d_bytes_per_step": Te * D * 4,
-               "d2h_bytes_per_step": Te * (NQ * 8 + D * 4), "tokens_per_step_per_gpu": Te, "steps": steps_e,
+               "d2h_bytes_per_step": Te * ((NQ * 2 if narrow else NQ * 8) + D * 4), "tokens_per_step_per_gpu": Te,
+               "steps": steps_e, "result_bytes_per_step": Te * (NQ * 8 + D * 4),
+               "code_transfer": "narrow" if narrow else "direct", "widen_threads": t_.value if narrow else 0,
                "timing": "host wall clock around RQAE.forward_host (pinned host buffers in and out; H2D, kernel and "
-                         "D2H of 9472-token chunks on three streams inside the C library; int64 codes written by the "
-                         "kernel and copied straight into the caller's tensor, no host threads; returns after the "
-                         "last D2H), max over ranks",
+                         "D2H of 9472-token chunks on three streams inside the C library; "
+                         + ("codes cross PCIe as int16 and are widened into the caller's int64 tensor by %d host "
+                            "thread(s) while the next chunk is in flight; " % t_.value if narrow else
+                            "int64 codes written by the kernel and copied straight into the caller's tensor; ")
+                         + "returns after the last D2H), max over ranks",
                "checksum_codes": ck64,
-               "int32_codes": {"value": v32, "unit": UNIT, "d2h_bytes_per_step": Te * (NQ * 4 + D * 4),
+               "int32_codes": {"value": v32, "unit": UNIT, "d2h_bytes_per_step": Te * ((NQ * 2 if narrow else NQ * 4) + D * 4),
                                "checksum_codes": ck32,
                                "note": "same call with out_dtype=int32, the dtype the reference's code store keeps "
                                        "(scripts/1_create_activations.py:184-186)"}}

@@ -120,10 +120,11 @@ int rqae_decode_f32(const void* packed, const float* codebook0, int nq, int nq_c
  *
  * rqae_forward_host_config selects how int32 / int64 codes reach `codes_host` (process-wide;
  * -1 keeps a setting):
- *   code_transfer  0 auto (= direct), 1 narrow: int16 over PCIe into a pinned staging buffer, widened
+ *   code_transfer  0 auto (= narrow), 1 narrow: int16 over PCIe into a pinned staging buffer, widened
  *                  into the caller's tensor by `widen_threads` host threads (a quarter of the PCIe
- *                  bytes, 12 KB of extra host memory traffic per token); 2 direct: the kernel emits
- *                  the caller's dtype and the copy lands in the caller's tensor (no host threads)
+ *                  bytes; with 8 ranks on one host the device -> host bytes bound the rate);
+ *                  2 direct: the kernel emits the caller's dtype and the copy lands in the caller's
+ *                  tensor (no host threads, no staging)
  *   widen_threads  0 auto = cores / (2 * LOCAL_WORLD_SIZE), clamped to [1, 8]
  * Environment defaults: RQAE_HOST_CODES = auto | narrow | direct, RQAE_HOST_THREADS = n. */
 int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq,
@@ -131,6 +132,8 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
                           int64_t n_tokens, void* codes_host, int code_dtype, float* q_host,
                           int64_t chunk_tokens);
 int rqae_forward_host_config(int code_transfer, int widen_threads);
+/* The settings in effect: *code_transfer = 1 narrow | 2 direct, *widen_threads = the resolved thread count. */
+int rqae_forward_host_mode(int* code_transfer, int* widen_threads);
 /* The widening step of the narrow mode on its own: int16 -> int32 / int64 with streaming stores on `threads`
  * host threads (0 = auto).  Host pointers; no CUDA call.  (scripts/1_create_activations.py:184-186 stores
  * int32: a caller that keeps int16 on the wire widens with this.) */

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.
 # every symbol include/rqae_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
-    "rqae_forward_f32", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_widen_codes_host", "rqae_forward_host_release",
+    "rqae_forward_f32", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_forward_host_mode", "rqae_widen_codes_host", "rqae_forward_host_release",
     "rqae_fp32_peak_probe",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
@@ -60,6 +60,8 @@ def load() -> ctypes.CDLL:
     lib.rqae_forward_host_f32.argtypes = [vp, vp, i, i, i, i, i, i, vp, i64, vp, i, vp, i64]
     lib.rqae_forward_host_config.restype = i
     lib.rqae_forward_host_config.argtypes = [i, i]
+    lib.rqae_forward_host_mode.restype = i
+    lib.rqae_forward_host_mode.argtypes = [c.POINTER(c.c_int), c.POINTER(c.c_int)]
     lib.rqae_widen_codes_host.restype = i
     lib.rqae_widen_codes_host.argtypes = [vp, vp, i64, i, i]
     lib.rqae_forward_host_release.restype = i

@@ -572,12 +572,14 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
 // RQAE_HOST_THREADS = n).  Two ways to deliver int32 / int64 codes to a host tensor:
 //   narrow  the kernel emits int16 (every code is < K <= 32767), a quarter of the int64 bytes cross PCIe into a
 //           pinned staging buffer, and a pool of host threads widens them into the caller's tensor with streaming
-//           stores while the next chunk is in flight.  Least PCIe traffic, most host work: per token 2 KB of DMA
-//           writes + 2 KB of reads + 8 KB of stores on the host.
+//           stores while the next chunk is in flight.  Least PCIe traffic: 11.3 KB per token device -> host.
 //   direct  the kernel emits the caller's dtype and the D2H copy lands in the caller's tensor.  No host threads,
-//           no staging; per token 8 KB of DMA writes and nothing else.
-// `auto` = direct: with one rank per GPU on a shared host the end-to-end rate is bounded by host memory traffic and
-// host cores long before PCIe, and direct removes a third of the former and all of the latter.
+//           no staging; 17.4 KB per token device -> host for int64.
+// `auto` = narrow.  Measured with one rank per GPU on an 8 x B200 host (tools/e2e_probe.py, profiles/r2c_*): the
+// ranks share a host I/O fabric that delivers 185 GB/s host -> device alone, 90 GB/s device -> host alone and
+// 64 + 64 GB/s when both directions run, so at 8 ranks the end-to-end rate is bounded by the device -> host
+// bytes per token, not by the host cores (one AVX2 widening thread does 1.9 G codes/s; a rank needs 1.2):
+// narrow 617 k tokens/s per rank against 549 k direct.  With one or two ranks the two modes tie.
 static std::atomic<int> g_host_code_transfer{-1};   // -1: not initialised; 0 auto, 1 narrow, 2 direct
 static std::atomic<int> g_host_threads{-1};         // -1: not initialised; 0 auto
 
@@ -782,6 +784,13 @@ int rqae_forward_host_config(int code_transfer, int widen_threads) {
   return RQAE_OK;
 }
 
+int rqae_forward_host_mode(int* code_transfer, int* widen_threads) {
+  host_config_init();
+  if (code_transfer) *code_transfer = g_host_code_transfer.load() == 2 ? 2 : 1;
+  if (widen_threads) *widen_threads = g_host_threads.load() > 0 ? g_host_threads.load() : host_auto_threads();
+  return RQAE_OK;
+}
+
 int rqae_forward_host_f32(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
                           int codebook_dim, int K, const float* x_host, int64_t n_tokens, void* codes_host,
                           int code_dtype, float* q_host, int64_t chunk_tokens) {
@@ -792,7 +801,7 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
   if (chunk_tokens > n_tokens) chunk_tokens = n_tokens;
   host_config_init();
   const int mode = g_host_code_transfer.load();
-  const bool narrow = codes_host != nullptr && code_dtype != RQAE_CODE_I16 && K <= 32767 && mode == 1;
+  const bool narrow = codes_host != nullptr && code_dtype != RQAE_CODE_I16 && K <= 32767 && mode != 2;
   const int dev_dtype = narrow ? RQAE_CODE_I16 : code_dtype;
   const size_t dsz = dev_dtype == 2 ? 8 : (dev_dtype == 1 ? 4 : 2);     // code size on the device / on the wire
   const size_t usz = code_dtype == 2 ? 8 : (code_dtype == 1 ? 4 : 2);   // code size in the caller's tensor
@@ -990,8 +999,18 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
   rq::MineParams mp;
   mp.vals = (const __half*)vals; mp.rows = rows; mp.row_stride = row_stride; mp.n = n; mp.k = top_k;
   mp.idx_out = idx_out; mp.val_out = (__half*)val_out;
-  const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
-  rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
+  // RQAE_MINE_V1=1 selects the first version of the kernel (shared-memory atomics per element; A/B timing)
+  static const bool v1 = [] { const char* e = getenv("RQAE_MINE_V1"); return e && atoi(e) != 0; }();
+  if (v1) {
+    const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
+    rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
+  } else {
+    constexpr int smem = rq::M2_SMEM_BYTES_PAD + rq::M2_LP_BYTES + (int)sizeof(rq::Mine2Smem);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_mine2_kernel, smem));
+    const int grid = (int)(rows < (long long)sms ? rows : (long long)sms);
+    rq::rq_mine2_kernel<<<grid, rq::M2_THREADS, smem, (cudaStream_t)stream>>>(mp);
+  }
   RQ_CUDA(cudaGetLastError());
   g_launches++;
   return RQAE_OK;

@@ -155,6 +155,66 @@ def test_select_top_middle_bottom_matches_stable_argsort(T, k, quant):
             assert torch.equal(v[a, b][m2].float(), val[a, b, 1, :len(m2)].float())
 
 
+def _key_windows(bits: np.ndarray, k: int):
+    """The kernel's total order written out: key = the fp16 bit pattern mapped so that it ascends when the value
+    descends (+0 before -0, NaN patterns by their bits), ties by index ascending."""
+    u = bits.astype(np.uint32)
+    dkey = np.where(u & 0x8000, u, ~u & 0x7FFF)
+    order = np.argsort(dkey, kind="stable")
+    n = len(order)
+    return order[:k], order[n // 2 - k // 2: n // 2 + k // 2], order[n - k:]
+
+
+@pytest.mark.parametrize("case", ["constant_131072", "two_values", "one_bin", "straddle", "specials", "ragged_131077",
+                                  "long_2M", "tiny"])
+def test_select_adversarial_rows_against_key_order(case):
+    """Rows built to hit the corners of the lane-private-counter kernel: 8-bit counters that wrap (a lane sees 256
+    equal high bytes), every boundary inside one histogram bin, the median window straddling two bins, dense tail
+    bins (the atomics path), inf / -0 / NaN bit patterns, partial last vectors, several fold blocks per lane."""
+    from rqae_b200.feature import select_top_middle_bottom
+    dev = _dev()
+    rng = np.random.default_rng(sum(map(ord, case)))
+    k = 100
+    if case == "constant_131072":
+        rows = np.full((2, 131072), np.float16(0.4375).view(np.uint16), np.uint16)
+        rows[1, ::3] = np.float16(-0.25).view(np.uint16)
+    elif case == "two_values":
+        rows = np.where(rng.random((2, 70000)) < 0.5, np.float16(0.5).view(np.uint16), np.float16(0.50048828125).view(np.uint16)).astype(np.uint16)
+    elif case == "one_bin":
+        rows = (rng.uniform(0.5, 0.53, size=(2, 150001))).astype(np.float16).view(np.uint16)
+    elif case == "straddle":     # half of the row just below a high-byte boundary, half just above it
+        lo = np.float16(0.4990234375).view(np.uint16)    # 0x37FC
+        rows = (lo + rng.integers(0, 8, size=(2, 131072))).astype(np.uint16)
+    elif case == "specials":
+        rows = (rng.normal(0, 0.3, size=(2, 40000))).astype(np.float16).view(np.uint16)
+        for r in rows:
+            r[rng.integers(0, 40000, 60)] = 0x7C00      # +inf
+            r[rng.integers(0, 40000, 60)] = 0xFC00      # -inf
+            r[rng.integers(0, 40000, 300)] = 0x8000     # -0
+            r[rng.integers(0, 40000, 300)] = 0x0000     # +0
+            r[rng.integers(0, 40000, 20)] = 0x7E00      # NaN
+            r[rng.integers(0, 40000, 20)] = 0xFE01      # NaN, sign set
+    elif case == "ragged_131077":
+        rows = (rng.normal(0.02, 0.05, size=(3, 131077))).astype(np.float16).view(np.uint16)
+    elif case == "long_2M":
+        rows = (rng.normal(0.0, 0.04, size=(1, (1 << 21) + 3))).astype(np.float16).view(np.uint16)
+    else:
+        rows = (rng.normal(0, 1, size=(4, 100))).astype(np.float16).view(np.uint16)
+    n = rows.shape[1]
+    v = torch.from_numpy(rows.view(np.float16).copy())
+    idx, val = select_top_middle_bottom(v.to(dev), k)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy().astype(np.int64)
+    valb = val.cpu().numpy().view(np.uint16)
+    for r in range(rows.shape[0]):
+        top, mid, bot = _key_windows(rows[r], k)
+        assert np.array_equal(idx[r, 0], top), (case, r, "top")
+        assert np.array_equal(idx[r, 1, :len(mid)], mid), (case, r, "middle")
+        assert np.array_equal(idx[r, 2], bot), (case, r, "bottom")
+        assert np.array_equal(valb[r, 0], rows[r][top]) and np.array_equal(valb[r, 2], rows[r][bot])
+        assert np.array_equal(valb[r, 1, :len(mid)], rows[r][mid])
+
+
 def test_mining_pipeline_intensity_then_selection(kat):
     """intensity_many -> select_top_middle_bottom on the kernel's own output layout (rows of T_pad)."""
     from rqae_b200.feature import intensity_many, select_top_middle_bottom
