@@ -273,8 +273,11 @@ __global__ void __launch_bounds__(MN_THREADS, 1) rq_mine_kernel(const MineParams
 //           that hold the top / bottom boundaries are tails with few members and use per-warp atomics
 //   pass 3  collects the members of the three windows (identical to the first version)
 // One CTA of 512 threads per row, 200 KB of shared memory, one CTA per SM.
-constexpr int M2_THREADS = 512;
-constexpr int M2_WARPS = 16;
+#ifndef RQ_M2_WARPS
+#define RQ_M2_WARPS 8   /* 8: two CTAs per SM (one row's serial steps run under the other's streaming); 16: one CTA per SM */
+#endif
+constexpr int M2_WARPS = RQ_M2_WARPS;
+constexpr int M2_THREADS = 32 * M2_WARPS;
 constexpr int M2_BLOCK_IT = 32;   // 8-element vectors per lane between two folds: 256 elements, see above
 
 constexpr int M2_LP_BYTES = M2_WARPS * 256 * 32;   // lane-private 8-bit counters lp[warp][bin][lane], 8 KB-aligned
@@ -288,6 +291,7 @@ struct Mine2Smem {
   uint32_t bin[4], rem[4], key[4], less[4], slot[4];
   uint32_t base[4][M2_WARPS];
   uint32_t cnt[3];
+  uint32_t special, simple, thr[3];      // row flags and the packed-compare thresholds of the pass-2 shortcut
   uint32_t bufk[3][MN_KMAX];
   uint32_t bufi[3][MN_KMAX];
   unsigned char lut[256];                // raw high byte -> 0: not a boundary bin, 1: the dense bin, 2..4: ah[slot - 2]
@@ -296,7 +300,16 @@ struct Mine2Smem {
 __device__ __forceinline__ void m2_bump(uint32_t addr) {   // lane-private: no other thread touches this byte
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v + 1u) : "memory");
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v + 1u));   // ordered against the other volatile accesses only:
+}                                                                   // the folds sit behind __syncwarp / __syncthreads
+// two counters of the same lane at once: both loads are in flight together (one trip through shared memory for
+// two values); if they are the SAME counter the second store carries both increments
+__device__ __forceinline__ void m2_bump2(uint32_t a0, uint32_t a1) {
+  uint32_t v0, v1;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v0) : "r"(a0));
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v1) : "r"(a1));
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a0), "r"(v0 + 1u));
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a1), "r"(v1 + 1u + (a0 == a1 ? 1u : 0u)));
 }
 __device__ __forceinline__ uint32_t m2_peek(uint32_t addr) {
   uint32_t v;
@@ -324,7 +337,7 @@ __device__ __forceinline__ void m2_fold(Mine2Smem& sm, unsigned char* lp, int wa
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParams p) {
+__global__ void __launch_bounds__(M2_THREADS, 16 / M2_WARPS) rq_mine2_kernel(const MineParams p) {
   extern __shared__ __align__(16) unsigned char m2_raw[];
   // the counters sit on an 8 KB boundary so that the address of a counter is (bin << 5) OR-ed into the lane's base
   const uint32_t raw32 = smem_u32(m2_raw);
@@ -351,29 +364,43 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
     for (int i = tid; i < 3 * M2_WARPS * 256; i += M2_THREADS) (&sm.ah[0][0][0])[i] = 0;
     if (tid < 3) sm.cnt[tid] = 0;
     if (tid < 256) sm.lut[tid] = 0;
+    if (tid == 3) sm.special = 0;
     __syncthreads();
 
     // ---- pass 1: high byte ----
     for (long long ib = w_lo; ib < w_hi; ib += 256LL * M2_BLOCK_IT) {
       uint32_t last = 0;
-#pragma unroll 2
-      for (int b = 0; b < M2_BLOCK_IT; b++) {
-        const long long i0 = ib + (long long)b * 256 + lane * 8;
+      // two vectors per step, and the next step's two loads are issued before this step's updates (the update chain
+      // of a step is about as long as a trip to L2 / HBM)
+      uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
+      {
+        const long long j0 = ib + lane * 8, j1 = j0 + 256;
+        if (j0 < w_hi) na = __ldg(src + j0 / 8);
+        if (j1 < w_hi) nb = __ldg(src + j1 / 8);
+      }
+      for (int b = 0; b < M2_BLOCK_IT; b += 2) {
+        const long long i0 = ib + (long long)b * 256 + lane * 8, i1 = i0 + 256;
         if (i0 >= w_hi) break;
-        const uint4 v = __ldg(src + i0 / 8);
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-        if (i0 + 8 <= w_hi) {
+        const bool two = i1 < w_hi;
+        const uint4 va = na, vb = nb;
+        if (b + 2 < M2_BLOCK_IT) {
+          const long long j0 = i0 + 512, j1 = i0 + 768;
+          if (j0 < w_hi) na = __ldg(src + j0 / 8);
+          if (j1 < w_hi) nb = __ldg(src + j1 / 8);
+        }
+        const uint32_t w8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        if (two && i1 + 8 <= w_hi) {
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            m2_bump(((w4[e] >> 3) & 0x1FE0u) | my);       // ((bits >> 8) & 0xFF) * 32
-            last = ((w4[e] >> 19) & 0x1FE0u) | my;
-            m2_bump(last);
+          for (int e = 0; e < 8; e++) {
+            last = ((w8[e] >> 19) & 0x1FE0u) | my;
+            m2_bump2(((w8[e] >> 3) & 0x1FE0u) | my, last);       // ((bits >> 8) & 0xFF) * 32
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            if (i0 + e < w_hi) {
-              last = ((((w4[e >> 1] >> ((e & 1) * 16)) >> 8) & 0xFFu) << 5) | my;
+          for (int e = 0; e < 16; e++) {
+            const long long pos = (e < 8 ? i0 + e : i1 + (e - 8));
+            if ((e < 8 || two) && pos < w_hi) {
+              last = ((((w8[e >> 1] >> ((e & 1) * 16)) >> 8) & 0xFFu) << 5) | my;
               m2_bump(last);
             }
           }
@@ -391,6 +418,8 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
         const int raw = (tid & 0x80) ? tid : (~tid & 0x7F);
 #pragma unroll
         for (int w = 0; w < M2_WARPS; w++) c += sm.wtot[w][raw];
+        // inf / NaN patterns (exponent 31) anywhere in the row: the packed-compare shortcuts of passes 2 and 3 are off
+        if ((raw & 0x7C) == 0x7C && c != 0) sm.special = 1;
       }
       uint32_t x = c;
 #pragma unroll
@@ -411,7 +440,7 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
       }
       __syncthreads();
       if (tid < 256) sm.pre[tid] = x - c + (warp > 0 ? sm.scan[warp - 1] : 0u);
-      if (tid == 256) sm.pre[256] = (uint32_t)n;
+      if (tid == 0) sm.pre[256] = (uint32_t)n;
     }
     __syncthreads();
     for (int i = tid; i < M2_WARPS * 256; i += M2_THREADS) (&sm.wtot[0][0])[i] = 0;   // reused by pass 2
@@ -439,29 +468,85 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
         const int d = (int)sm.bin[j];
         sm.lut[(d & 0x80) ? d : (~d & 0x7F)] = (unsigned char)s;
       }
+      // Shortcut of pass 2: besides the dense bin only TAIL bins are boundary bins (both median ranks in one bin) and
+      // the row holds no inf / NaN.  A value can then only belong to a tail bin if it is >= the smallest value of the
+      // top boundary bin or <= the largest value of the bottom one -- one packed fp16 compare per pair of values.
+      sm.simple = (sm.special == 0 && sm.slot[2] == 1) ? 1u : 0u;
+      const int d0 = (int)sm.bin[0], d3 = (int)sm.bin[3];
+      const uint32_t r0 = (d0 & 0x80) ? d0 : (~d0 & 0x7F), r3 = (d3 & 0x80) ? d3 : (~d3 & 0x7F);
+      // bit patterns of the smallest value of bin r0 / the largest value of bin r3 (negative: larger pattern = smaller value)
+      const uint32_t lo0 = (r0 & 0x80) ? ((r0 << 8) | 0xFFu) : (r0 << 8);
+      const uint32_t hi3 = (r3 & 0x80) ? (r3 << 8) : ((r3 << 8) | 0xFFu);
+      sm.thr[0] = sm.slot[0] == 1 ? 0x7C00u : lo0;    // +inf: never reached in a simple row
+      sm.thr[1] = sm.slot[3] == 1 ? 0xFC00u : hi3;    // -inf
+      const int dd = (int)sm.bin[1];
+      sm.thr[2] = (dd & 0x80) ? dd : (~dd & 0x7F);   // raw high byte of the dense bin
     }
     __syncthreads();
 
     // ---- pass 2: low byte inside the boundary bins ----
+    const bool simple = sm.simple != 0;
     for (long long ib = w_lo; ib < w_hi; ib += 256LL * M2_BLOCK_IT) {
       uint32_t last = 0;
-#pragma unroll 2
-      for (int b = 0; b < M2_BLOCK_IT; b++) {
-        const long long i0 = ib + (long long)b * 256 + lane * 8;
-        if (i0 >= w_hi) break;
-        const uint4 v = __ldg(src + i0 / 8);
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-        const bool full = i0 + 8 <= w_hi;
+      if (simple) {
+        const uint32_t dlo = sm.thr[2] << 8, dhi = sm.thr[2] << 24;
+        const uint32_t ttop = sm.thr[0] * 0x10001u, tbot = sm.thr[1] * 0x10001u;
+        const __half2 htop = *reinterpret_cast<const __half2*>(&ttop), hbot = *reinterpret_cast<const __half2*>(&tbot);
+        uint4 nv = make_uint4(0u, 0u, 0u, 0u);
+        if (ib + lane * 8 < w_hi) nv = __ldg(src + (ib + lane * 8) / 8);
+        for (int b = 0; b < M2_BLOCK_IT; b++) {
+          const long long i0 = ib + (long long)b * 256 + lane * 8;
+          if (i0 >= w_hi) break;
+          const uint4 v = nv;
+          if (b + 1 < M2_BLOCK_IT && i0 + 256 < w_hi) nv = __ldg(src + (i0 + 256) / 8);
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+          if (i0 + 8 <= w_hi) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          if (full || i0 + e < w_hi) {
-            const uint32_t u = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-            const uint32_t s = sm.lut[u >> 8];
-            if (s == 1) {
-              last = ((u & 0xFFu) << 5) | my;
-              m2_bump(last);
-            } else if (s != 0) {
-              atomicAdd(&sm.ah[s - 2][warp][u & 0xFFu], 1u);
+            for (int e = 0; e < 4; e++) {
+              const uint32_t w = w4[e];
+              const __half2 h = *reinterpret_cast<const __half2*>(&w);
+              const uint32_t tm = __hge2_mask(h, htop) | __hle2_mask(h, hbot);
+              if ((w & 0xFF00u) == dlo) { last = ((w << 5) & 0x1FE0u) | my; m2_bump(last); }
+              if ((w & 0xFF000000u) == dhi) { last = ((w >> 11) & 0x1FE0u) | my; m2_bump(last); }
+              if (tm != 0) {   // a value in (or beyond) a tail boundary bin: a few hundred per row
+                if (tm & 0xFFFFu) {
+                  const uint32_t s = sm.lut[(w >> 8) & 0xFFu];
+                  if (s >= 2) atomicAdd(&sm.ah[s - 2][warp][w & 0xFFu], 1u);
+                }
+                if (tm >> 16) {
+                  const uint32_t s = sm.lut[w >> 24];
+                  if (s >= 2) atomicAdd(&sm.ah[s - 2][warp][(w >> 16) & 0xFFu], 1u);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              if (i0 + e < w_hi) {
+                const uint32_t u = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                const uint32_t s = sm.lut[u >> 8];
+                if (s == 1) { last = ((u & 0xFFu) << 5) | my; m2_bump(last); }
+                else if (s != 0) atomicAdd(&sm.ah[s - 2][warp][u & 0xFFu], 1u);
+              }
+            }
+          }
+        }
+      } else {
+        for (int b = 0; b < M2_BLOCK_IT; b++) {
+          const long long i0 = ib + (long long)b * 256 + lane * 8;
+          if (i0 >= w_hi) break;
+          const uint4 v = __ldg(src + i0 / 8);
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+          const bool full = i0 + 8 <= w_hi;
+          uint32_t sl[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) sl[e] = sm.lut[((w4[e >> 1] >> ((e & 1) * 16)) >> 8) & 0xFFu];
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            if (full || i0 + e < w_hi) {
+              const uint32_t u = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+              if (sl[e] == 1) { last = ((u & 0xFFu) << 5) | my; m2_bump(last); }
+              else if (sl[e] != 0) atomicAdd(&sm.ah[sl[e] - 2][warp][u & 0xFFu], 1u);
             }
           }
         }
@@ -528,29 +613,57 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
       const uint32_t mid_take = (uint32_t)m1 - sm.less[2];                   // tie ranks < mid_take are in middle
       const uint32_t bot_skip = (uint32_t)(n - k) - sm.less[3];              // tie ranks >= bot_skip are in bottom
       uint32_t tc[4] = {sm.base[0][warp], sm.base[1][warp], sm.base[2][warp], sm.base[3][warp]};
+      // Rows without inf / NaN: a value is a candidate only if it is >= value(K0), <= value(K3) or inside
+      // [value(K2), value(K1)] -- packed fp16 compares (a superset where +0 / -0 are concerned; the exact key test
+      // follows for the values that pass).
+      const bool quick = sm.special == 0;
+      const uint32_t b0 = mn_bits(K0) * 0x10001u, b1 = mn_bits(K1) * 0x10001u, b2 = mn_bits(K2) * 0x10001u, b3 = mn_bits(K3) * 0x10001u;
+      const __half2 h0 = *reinterpret_cast<const __half2*>(&b0), h1 = *reinterpret_cast<const __half2*>(&b1);
+      const __half2 h2 = *reinterpret_cast<const __half2*>(&b2), h3 = *reinterpret_cast<const __half2*>(&b3);
+      auto append = [&](int wdw, uint32_t dd, uint32_t index) {
+        const uint32_t s = atomicAdd(&sm.cnt[wdw], 1u);
+        if (s < MN_KMAX) { sm.bufk[wdw][s] = dd; sm.bufi[wdw][s] = index; }
+      };
+      uint4 nv = make_uint4(0u, 0u, 0u, 0u);
+      if (w_lo + lane * 8 < w_hi) nv = __ldg(src + (w_lo + lane * 8) / 8);
       for (long long i0 = w_lo + lane * 8; i0 - lane * 8 < w_hi; i0 += 256) {   // whole warp iterates together
-        uint32_t d[8];
-        bool live[8];
-        bool cand = false;
-        if (i0 < w_hi) {
-          const uint4 v = __ldg(src + i0 / 8);
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        const uint4 v = nv;
+        nv = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + 256 < w_hi) nv = __ldg(src + (i0 + 256) / 8);   // the next vector is in flight while this one is examined
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        // per pair of values: which halves can be candidates at all
+        uint32_t qm[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (quick) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const __half2 h = *reinterpret_cast<const __half2*>(&w4[e]);
+            qm[e] = __hge2_mask(h, h0) | __hle2_mask(h, h3) | (__hle2_mask(h, h1) & __hge2_mask(h, h2));
+          }
+        }
+        const bool lane_any = i0 < w_hi && (qm[0] | qm[1] | qm[2] | qm[3]) != 0;
+        if (!__any_sync(0xffffffffu, lane_any)) continue;
+        // Values strictly inside a window are appended at once; values EQUAL to a boundary key are ties whose
+        // membership depends on their rank among the equal values (index order): counted here, ranked below.
+        uint32_t neq[4] = {0, 0, 0, 0};
+        if (lane_any) {
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            live[e] = i0 + e < w_hi;
-            d[e] = mn_dkey((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-            cand |= live[e] && (d[e] <= K0 || d[e] >= K3 || (d[e] >= K1 && d[e] <= K2));
+            if (((qm[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) != 0 && i0 + e < w_hi) {
+              const uint32_t dd = mn_dkey((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
+              const bool e0 = dd == K0, e1 = dd == K1, e2 = dd == K2, e3 = dd == K3;
+              if (e0 | e1 | e2 | e3) {
+                neq[0] += e0; neq[1] += e1; neq[2] += e2; neq[3] += e3;
+              } else {
+                const uint32_t index = (uint32_t)(i0 + e);
+                if (dd < K0) append(0, dd, index);
+                if (kh > 0 && dd > K1 && dd < K2) append(1, dd, index);
+                if (dd > K3) append(2, dd, index);
+              }
+            }
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; e++) { live[e] = false; d[e] = 0; }
         }
-        if (!__any_sync(0xffffffffu, cand)) continue;
-        uint32_t neq[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          if (live[e]) { neq[0] += d[e] == K0; neq[1] += d[e] == K1; neq[2] += d[e] == K2; neq[3] += d[e] == K3; }
-        }
+        const bool lane_tie = (neq[0] | neq[1] | neq[2] | neq[3]) != 0;
+        if (!__any_sync(0xffffffffu, lane_tie)) continue;
         uint32_t ex[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -563,20 +676,23 @@ __global__ void __launch_bounds__(M2_THREADS, 1) rq_mine2_kernel(const MineParam
           ex[j] = tc[j] + x - neq[j];
           tc[j] += __shfl_sync(0xffffffffu, x, 31);
         }
-        if (cand) {
+        if (lane_tie) {
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            if (!live[e]) continue;
-            const uint32_t dd = d[e];
-            const uint32_t t0 = ex[0], t1 = ex[1], t2 = ex[2], t3 = ex[3];
-            ex[0] += dd == K0; ex[1] += dd == K1; ex[2] += dd == K2; ex[3] += dd == K3;
-            const bool in_top = dd < K0 || (dd == K0 && t0 < top_take);
-            const bool in_mid = kh > 0 && (dd > K1 || (dd == K1 && t1 >= mid_skip)) && (dd < K2 || (dd == K2 && t2 < mid_take));
-            const bool in_bot = dd > K3 || (dd == K3 && t3 >= bot_skip);
-            const uint32_t index = (uint32_t)(i0 + e);
-            if (in_top) { const uint32_t s = atomicAdd(&sm.cnt[0], 1u); if (s < MN_KMAX) { sm.bufk[0][s] = dd; sm.bufi[0][s] = index; } }
-            if (in_mid) { const uint32_t s = atomicAdd(&sm.cnt[1], 1u); if (s < MN_KMAX) { sm.bufk[1][s] = dd; sm.bufi[1][s] = index; } }
-            if (in_bot) { const uint32_t s = atomicAdd(&sm.cnt[2], 1u); if (s < MN_KMAX) { sm.bufk[2][s] = dd; sm.bufi[2][s] = index; } }
+            if (i0 + e < w_hi) {
+              const uint32_t dd = mn_dkey((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
+              if (dd == K0 || dd == K1 || dd == K2 || dd == K3) {
+                const uint32_t t0 = ex[0], t1 = ex[1], t2 = ex[2], t3 = ex[3];
+                ex[0] += dd == K0; ex[1] += dd == K1; ex[2] += dd == K2; ex[3] += dd == K3;
+                const bool in_top = dd < K0 || (dd == K0 && t0 < top_take);
+                const bool in_mid = kh > 0 && (dd > K1 || (dd == K1 && t1 >= mid_skip)) && (dd < K2 || (dd == K2 && t2 < mid_take));
+                const bool in_bot = dd > K3 || (dd == K3 && t3 >= bot_skip);
+                const uint32_t index = (uint32_t)(i0 + e);
+                if (in_top) append(0, dd, index);
+                if (in_mid) append(1, dd, index);
+                if (in_bot) append(2, dd, index);
+              }
+            }
           }
         }
       }

@@ -1006,9 +1006,10 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
     rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
   } else {
     constexpr int smem = rq::M2_SMEM_BYTES_PAD + rq::M2_LP_BYTES + (int)sizeof(rq::Mine2Smem);
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+    constexpr int per_sm = 16 / rq::M2_WARPS;
+    static_assert(smem <= (228 * 1024 - per_sm * 1024) / per_sm, "shared memory budget");
     RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_mine2_kernel, smem));
-    const int grid = (int)(rows < (long long)sms ? rows : (long long)sms);
+    const int grid = (int)(rows < (long long)sms * per_sm ? rows : (long long)sms * per_sm);
     rq::rq_mine2_kernel<<<grid, rq::M2_THREADS, smem, (cudaStream_t)stream>>>(mp);
   }
   RQ_CUDA(cudaGetLastError());

@@ -350,7 +350,12 @@ def make_feature(rqae, feature_helper: "FeatureHelper", num_tokens: int = 1024, 
     picks = picks[torch.randperm(picks.shape[0])]
     picks = picks[:num_tokens]
     centers = feature_helper.get_token_indices(picks)
-    features = [RQAEFeature.from_quantizer(rqae, center=centers[i].cpu().numpy(), layers=layers) for i in range(picks.shape[0])]
+    lw = layer_weights_f16(rqae)          # once: from_quantizer would recompute it (num_quantizers host syncs) per feature
+    features = []
+    for i in range(picks.shape[0]):
+        f = RQAEFeature(num_quantizers=rqae.num_quantizers, dim=rqae.codebook_dim, center=centers[i].cpu().numpy(), layers=layers)
+        f.rqae, f.layer_weights = rqae, lw
+        features.append(f)
     for f0 in range(0, len(features), features_per_launch):
         group = features[f0:f0 + features_per_launch]
         for j, acts in enumerate(feature_helper.get_activations_many(group, layers=layers, top_k=top_k)):

@@ -39,9 +39,11 @@ _FSQ = ("fsq", "round_fsq")
 def _fsq_grid(codebook_size: int, codebook_dim: int, normalise: bool) -> torch.Tensor:
     """linspace(-1, 1, cbs)^cd, first coordinate slowest (itertools.product order), rows divided by
     their float64 norm for round_fsq with the zero row left untouched, then cast to fp32
-    (model.py:63-72).  sqrt and divide are correctly rounded in float64 both here and in numpy, so
-    the table is bit-identical to the reference's."""
-    axis = torch.linspace(-1, 1, codebook_size, dtype=torch.float64)
+    (model.py:63-72).  The axis is numpy's linspace, as in the reference (torch.linspace can differ from it
+    in the last bit of a middle value, which changes a row of the normalised table).  sqrt and divide are correctly rounded in float64 both here and in numpy, so the table is
+    bit-identical to the reference's (tests/test_model_host.py checks sizes 2..9)."""
+    import numpy as np
+    axis = torch.from_numpy(np.linspace(-1, 1, codebook_size))
     grid = torch.cartesian_prod(*([axis] * codebook_dim)).reshape(-1, codebook_dim)
     if normalise:
         n = grid.pow(2).sum(-1, keepdim=True).sqrt()
@@ -143,8 +145,11 @@ class RQAE(nn.Module):
         w = self.layers[0][0].weight
         key = [w.device, w.data_ptr(), self.codebook.data_ptr()]
         if not self._static_weights:
+            # learned codebooks are re-normalised in place by every forward (model.py:126-131): their version is
+            # not part of the key, the per-layer tables are handed to the kernel separately (_learned_tables)
+            learned = self.quantization_method not in _FSQ
             try:
-                key.append(sum(p._version for p in self.parameters()))
+                key.append(sum(p._version for p in self.parameters() if not (learned and p is self.codebook)))
             except RuntimeError:  # inference tensors carry no version counter
                 pass
         return tuple(key)

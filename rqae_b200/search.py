@@ -113,24 +113,36 @@ class IntensityEngine:
         dev = self.sims.device
         Sq = query.shape[0]
         lib = _lib.load()
+        # The device guard and the stream are taken around every group of C calls, never across a `yield`: the
+        # consumer may switch device or stream between steps, and its own indexing of the yielded buffers runs on
+        # whatever stream is current then.
+        tbytes = lib.rqae_search_table_bytes(L, K)
+        table = torch.empty(tbytes // 2, dtype=torch.float16, device=dev)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            tbytes = lib.rqae_search_table_bytes(L, K)
-            table = torch.empty(tbytes // 2, dtype=torch.float16, device=dev)
             _lib.check(lib.rqae_search_build_table_f16(self.sims.data_ptr(), K, query.data_ptr(), query.stride(0), Sq, L,
                                                       table.data_ptr(), tbytes, st), "rqae_search_build_table_f16")
-            acc = torch.empty(N * S, SQ_PAD, dtype=torch.float16, device=dev)
-            n_pad = (N + 7) // 8 * 8
-            maxv = torch.empty(Sq, n_pad, dtype=torch.float16, device=dev)
-            a = 0
-            for b in layers:
+        last = torch.cuda.current_stream(dev)
+        acc = torch.empty(N * S, SQ_PAD, dtype=torch.float16, device=dev)
+        n_pad = (N + 7) // 8 * 8
+        maxv = torch.empty(Sq, n_pad, dtype=torch.float16, device=dev)
+        a = 0
+        for b in layers:
+            with torch.cuda.device(dev):
+                cur = torch.cuda.current_stream(dev)
+                if cur != last:          # the consumer changed streams: order this step after the previous one
+                    cur.wait_stream(last)
+                    for t in (table, acc, maxv, query):
+                        t.record_stream(cur)
+                    last = cur
+                st = cur.cuda_stream
                 _lib.check(lib.rqae_search_accumulate_f16(table.data_ptr(), K, self.activations.data_ptr(),
                                                          _CODE_DTYPE[self.activations.dtype], nq_codes, N * S, a, b,
                                                          1 if a == 0 else 0, acc.data_ptr(), st), "rqae_search_accumulate_f16")
                 _lib.check(lib.rqae_search_position_max_f16(acc.data_ptr(), N, S, Sq, maxv.data_ptr(), n_pad, st),
                            "rqae_search_position_max_f16")
-                yield acc.view(N, S, SQ_PAD)[:, :, :Sq], maxv[:, :N]
-                a = b
+            yield acc.view(N, S, SQ_PAD)[:, :, :Sq], maxv[:, :N]
+            a = b
 
     def find_examples(self, idx: int = None, activation: torch.Tensor = None, top_examples: int = 30,
                       middle_examples: int = 10, bottom_examples: int = 10,

@@ -60,8 +60,9 @@ def gather_codes(codes_local: torch.Tensor, n_tokens: int, group: Optional[dist.
         bufs = [torch.empty_like(send) for _ in range(world)]
         dist.all_gather(bufs, send, group=group)
     else:
+        # `dst` is a rank of `group`; dist.gather wants the global rank
         bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-        dist.gather(send, bufs, dst=dst, group=group)
+        dist.gather(send, bufs, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
         if rank != dst:
             return None
     return torch.cat([buf.view(codes_local.dtype)[:n] for buf, n in zip(bufs, sizes)], dim=0)
@@ -103,14 +104,17 @@ def exchange_to_feature_shards(intens_local: torch.Tensor, n_tokens: int,
     if T_r != b - a:
         raise ValueError(f"rank {rank} must pass its {b - a} tokens, got {T_r}")
     fa, fb = token_range(F, rank, world)
-    send = [intens_local[token_range(F, d, world)[0]:token_range(F, d, world)[1]].contiguous().view(torch.uint8).reshape(-1)
-            for d in range(world)]
     sizes = [token_range(n_tokens, s, world)[1] - token_range(n_tokens, s, world)[0] for s in range(world)]
     esz = intens_local.element_size()
+    in_splits = [(token_range(F, d, world)[1] - token_range(F, d, world)[0]) * C * T_r * esz for d in range(world)]
+    if intens_local.is_contiguous():   # the feature ranges are consecutive slabs of the buffer: send it as it is
+        send_flat = intens_local.view(torch.uint8).reshape(-1)
+    else:
+        send_flat = torch.cat([intens_local[token_range(F, d, world)[0]:token_range(F, d, world)[1]].contiguous()
+                               .view(torch.uint8).reshape(-1) for d in range(world)])
     out_splits = [(fb - fa) * C * sizes[s] * esz for s in range(world)]
     recv_flat = torch.empty(sum(out_splits), dtype=torch.uint8, device=intens_local.device)
-    dist.all_to_all_single(recv_flat, torch.cat(send), output_split_sizes=out_splits,
-                           input_split_sizes=[t.numel() for t in send], group=group)
+    dist.all_to_all_single(recv_flat, send_flat, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
     recv = list(torch.split(recv_flat, out_splits))
     stride = (n_tokens + 7) // 8 * 8
     full = torch.zeros(fb - fa, C, stride, dtype=intens_local.dtype, device=intens_local.device)

@@ -55,6 +55,8 @@ def load_code_shards(folder: str, model_name: str, shards: Optional[Iterable[int
         t = torch.load(p)
         if skip_bos:
             t = t[:, 1:]
+        if dtype == torch.int16 and t.numel() and int(t.max()) > 32767:
+            raise ValueError(f"{p}: codes up to {int(t.max())} do not fit int16; load the store as int32")
         parts.append(t.to(dtype))
     out = torch.cat(parts, dim=0) if parts else torch.empty(0, 0, 0, dtype=dtype)
     return out if device is None else out.to(device)

@@ -155,3 +155,22 @@ def test_make_feature_driver_follows_scripts3(tmp_path, monkeypatch):
         assert f.layer_weights.dtype == torch.float16 and f.rqae is m
         back = ft.RQAEFeature.load(str(tmp_path / "features" / f"{i:06d}.npz"))
         assert torch.equal(back.center, f.center) and list(back.layers) == [1, 3, 5]
+
+
+@pytest.mark.parametrize("method", ["round_fsq", "fsq"])
+def test_fsq_grid_equals_reference_construction_for_every_size(method):
+    """model.py:63-72 (numpy linspace ^ codebook_dim in itertools.product order, float64 row norms, zero row kept):
+    the oracle restates it with numpy, the module builds it with torch -- equal bit for bit for sizes 2..9 (the
+    axis comes from numpy's linspace in both, so any size whose middle value is not exactly 0 there agrees too)."""
+    from oracle import rqae_oracle as orc
+    from rqae_b200.model import _fsq_grid
+    for cbs in range(2, 10):
+        want = orc.fsq_codebook(cbs, 4, method == "round_fsq")
+        got = _fsq_grid(cbs, 4, method == "round_fsq")
+        assert got.dtype == torch.float32 and torch.equal(got, want), cbs
+
+
+def test_int16_codes_are_range_checked():
+    m = RQAE(dim=64, num_quantizers=2, quantization_method="vq", codebook_size=40000).eval()
+    with pytest.raises(ValueError, match="int16"):
+        m.encode(torch.zeros(1, 1, 64), out_dtype=torch.int16)
