@@ -10,8 +10,12 @@ timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_f
   -k "small or dtypes or api_shapes or 5000 or 4097 or 257 or 100-100" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_mining.log
 echo "=== memcheck: forward / decode small cases ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -x -k "small_forward or decode" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_fwd.log
-echo "=== racecheck: radix select ==="
-timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "5000 or 4097 or 257" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine.log
+echo "=== memcheck: fused hook (rqae_hook_rmsnorm), small-unit instantiation, host pipeline modes ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -x -k "fused_hook or forward_host or invariance" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_hook.log
+echo "=== racecheck: radix select (lane-private counters: v2) ==="
+timeout 400 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "5000 or 4097 or 257 or specials or tiny or two_values" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine.log
+echo "=== memcheck: radix select v2, adversarial rows ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "adversarial and not long_2M" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_mine2.log
 echo "=== memcheck + racecheck: example search (table transpose, accumulate, per-position max) ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "golden or single_query or argument or int16" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_search.log
 timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "single_query" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_search.log
