@@ -507,7 +507,7 @@ def config3_9b_cpu_port(torch, tokens=32):
             "sample": f"{tokens} tokens, full depth (nq=2048), forward incl. reconstruction, torch CPU fp32, {dt:.1f} s"}
 
 
-def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_features=1024, group=128, top_k=100):
+def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_features=1024, group=256, top_k=100):
     """BASELINE configs[4] (scripts/3_make_rqae_features.py pattern) at its stated scale: every rank encodes its
     `tokens` tokens (2 Mi per GPU = 16 Mi on 8 GPUs), then for feature groups of `group`: intensities of the group over
     the rank's tokens at the 14 cuts of scripts/3:178 (tcgen05 GEMM), all_to_all so that every (feature, cut) row is
@@ -583,7 +583,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
            "select_gbs_per_gpu": rows_per_rank * n_total * 2 / ms_sel / 1e6,
            "exchange_gbs_per_gpu": (n_features * len(SCRIPT3_CUTS) * tokens * 2 * (world - 1) / world) / ms_x / 1e6 if world > 1 else None,
            "exchange_ms_per_group_rank0": ms_x_groups, "checksum_top_idx": checksum,
-           "timing": "host wall clock barrier -> last kernel done (encode + 8 feature groups x (GEMM, all_to_all, select)), "
+           "timing": "host wall clock barrier -> last kernel done (encode + feature groups x (GEMM, all_to_all, select)), "
                      "max over ranks"}
     del codes, buf
     torch.cuda.empty_cache()

@@ -79,6 +79,14 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
                      int code_dtype, int64_t code_stride, float* q_out, const int32_t* teacher,
                      float* z_out, void* stream);
 
+/* Kernel variant of rqae_forward_f32 (process-wide): 0 (default) = one CTA per unit of tokens; 1 = where built (hidden
+ * sizes 2305..3584), a cluster of two CTAs per unit, each owning half of the hidden dimension and exchanging its
+ * in-projection partials through distributed shared memory.  The variants sum the in-projection in different orders
+ * (both documented, both reproduced bit for bit by the C oracle), so codes can differ at near-ties; the variant is
+ * therefore never switched implicitly.  Returns the previous setting (a negative argument only queries), or -1 for an
+ * unknown variant.  Environment default: RQAE_CLUSTER=1. */
+int rqae_forward_variant(int variant);
+
 /* The body of RQAE.hook's hook_fn (rqae/model.py:276-289) for the Gemma-2 adapter (rqae/llm.py:60-73) in ONE launch:
  *     hs = hidden.float(); x = hs * rsqrt(mean(hs^2) + rms_eps) * (1 + rms_weight)          (llm.py:65-66)
  *     q, codes = forward(x)                                                                  (model.py:281)

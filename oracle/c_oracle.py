@@ -16,6 +16,10 @@ _lib = None
 # bias folded into the out-projection fma chain, reconstruction emitted as x - r_final.  With these switches the C oracle is
 # bit-identical to the kernel (codes AND reconstruction), which is what the GPU tests assert.
 KERNEL_ORDER = dict(order_nt=256, tree=1, gtree=1, fold_bias=True, recon="x_minus_r")
+# The opt-in D-split cluster variant of the kernel at Gemma-2-9B width (rqae_forward_variant(1), 2304 < D <= 3584): two
+# CTAs own 7 x 256 elements of the d axis each, every slice is summed in the order above, the two slice sums are added,
+# then the bias.
+KERNEL_ORDER_9B = dict(KERNEL_ORDER, seg_blocks=7)
 
 
 def lib():
@@ -63,7 +67,8 @@ def num_threads() -> int:
 
 
 def forward_f32(w: CWeights, x, max_layers: Optional[int] = None, order_nt: int = 0, fold_bias: bool = False,
-                recon: str = "accumulate", teacher=None, want_q: bool = True, tree: int = 0, gtree: int = 0):
+                recon: str = "accumulate", teacher=None, want_q: bool = True, tree: int = 0, gtree: int = 0,
+                seg_blocks: int = 0):
     x = _f32(x)
     lead = x.shape[:-1]
     x2 = x.reshape(-1, w.D)
@@ -75,7 +80,8 @@ def forward_f32(w: CWeights, x, max_layers: Optional[int] = None, order_nt: int 
     rc = lib().rqo_forward_f32(_p(w.w_in), _p(w.b_in), _p(w.w_out), _p(w.b_out), _p(w.codebook),
                                ctypes.c_int(int(w.shared)), ctypes.c_int(nq_run), ctypes.c_int(w.D),
                                ctypes.c_int(w.cd), ctypes.c_int(w.K), _p(x2), ctypes.c_long(n),
-                               ctypes.c_int(order_nt), ctypes.c_int(int(tree)), ctypes.c_int(int(gtree)), ctypes.c_int(int(fold_bias)),
+                               ctypes.c_int(order_nt), ctypes.c_int(int(tree)), ctypes.c_int(int(gtree)),
+                               ctypes.c_int(int(seg_blocks)), ctypes.c_int(int(fold_bias)),
                                ctypes.c_int({"accumulate": 0, "x_minus_r": 1}[recon]), _p(t), _p(codes), _p(q))
     if rc:
         raise RuntimeError(f"rqo_forward_f32 failed: {rc}")

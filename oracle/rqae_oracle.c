@@ -19,7 +19,9 @@
  * partial sums (lane t takes d = t, t+NT, ...), combines each aligned group of 32 lanes
  * with a pairwise tree (tree = 0: lanes paired by strides 16,8,4,2,1; tree = 1: strides
  * 1,2,16,8,4), then adds the groups sequentially (gtree = 0) or as a pairwise tree
- * ((g0+g1)+(g2+g3))+... (gtree = 1) -- the shapes a 32-wide SIMT machine produces.  Where the reference's fp32 arithmetic IS defined (the
+ * ((g0+g1)+(g2+g3))+... (gtree = 1) -- the shapes a 32-wide SIMT machine produces.  seg_blocks > 0 cuts
+ * the d axis into segments of seg_blocks * NT elements that are summed separately in that order and then
+ * added in segment order (a thread-block cluster whose CTAs own slices of the d axis).  Where the reference's fp32 arithmetic IS defined (the
  * K=4 contractions and the norm; probed against torch 2.11 CPU) this file
  * uses exactly that arithmetic:
  *   cos  = fmaf(z3,c3, fmaf(z2,c2, fmaf(z1,c1, z0*c0)))        (matmul, model.py:190)
@@ -59,8 +61,25 @@ int rqo_num_threads(void) {
 
 /* z[k] = sum_d w_in[k][d] * r[d] in the requested order (bias added by the caller). */
 static void inproj_f32(const float *w_in /*[cd][D]*/, const float *r, int D, int cd, int nt, int tree, int gtree,
-                       float *scratch /*[nt]*/, float *z) {
+                       int seg_blocks, float *scratch /*[nt]*/, float *z) {
   static const int strides[2][5] = {{16, 8, 4, 2, 1}, {1, 2, 16, 8, 4}};
+  if (nt > 0 && seg_blocks > 0 && (long)seg_blocks * nt < D) {
+    /* D-split order (the cluster variant of the CUDA kernel): the d axis is cut into segments of seg_blocks * nt
+     * elements, each segment is summed on its own in the order below, and the segment sums are added in order */
+    const int seg = seg_blocks * nt;
+    for (int k = 0; k < cd; k++) z[k] = 0.0f;
+    for (int s0 = 0, si = 0; s0 < D; s0 += seg, si++) {
+      const int len = (D - s0 < seg) ? (D - s0) : seg;
+      float zs[16];
+      /* recursion depth 1: the segment itself is not split again */
+      float *wseg = (float *)malloc(sizeof(float) * (size_t)cd * (size_t)len);
+      for (int k = 0; k < cd; k++) memcpy(wseg + (size_t)k * len, w_in + (size_t)k * D + s0, sizeof(float) * (size_t)len);
+      inproj_f32(wseg, r + s0, len, cd, nt, tree, gtree, 0, scratch, zs);
+      free(wseg);
+      for (int k = 0; k < cd; k++) z[k] = (si == 0) ? zs[k] : z[k] + zs[k];
+    }
+    return;
+  }
   for (int k = 0; k < cd; k++) {
     const float *w = w_in + (size_t)k * D;
     if (nt <= 0) {
@@ -114,9 +133,9 @@ static int argmax_cos_f32(const float *zn, const float *cb /*[K][cd]*/, int K, i
 
 int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
                     const float *codebook, int cb_shared, int nq_run, int D, int cd, int K,
-                    const float *x, long n_tokens, int order_nt, int tree, int gtree, int fold_bias, int recon_mode,
-                    const int32_t *teacher, int32_t *codes, float *q_out) {
-  if (D <= 0 || cd <= 0 || cd > 16 || K <= 0 || nq_run < 0 || n_tokens < 0 || order_nt < 0) return RQO_EINVAL;
+                    const float *x, long n_tokens, int order_nt, int tree, int gtree, int seg_blocks, int fold_bias,
+                    int recon_mode, const int32_t *teacher, int32_t *codes, float *q_out) {
+  if (D <= 0 || cd <= 0 || cd > 16 || K <= 0 || nq_run < 0 || n_tokens < 0 || order_nt < 0 || seg_blocks < 0) return RQO_EINVAL;
   if (tree < 0 || tree > 1 || (gtree && order_nt > 64 * 32)) return RQO_EINVAL;
   int err = 0;
 #pragma omp parallel
@@ -134,7 +153,7 @@ int rqo_forward_f32(const float *w_in, const float *b_in, const float *w_out, co
         memcpy(r, xt, sizeof(float) * (size_t)D);
         for (int l = 0; l < nq_run; l++) {
           float z[16], zn[16], c2[16];
-          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, tree, gtree, scr, z);
+          inproj_f32(w_in + (size_t)l * cd * D, r, D, cd, order_nt, tree, gtree, seg_blocks, scr, z);
           const float *bi = b_in + (size_t)l * cd;
           for (int k = 0; k < cd; k++) z[k] = z[k] + bi[k];
           float ss = z[0] * z[0];

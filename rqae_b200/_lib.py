@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.
 # every symbol include/rqae_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
-    "rqae_forward_f32", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_forward_host_mode", "rqae_widen_codes_host", "rqae_forward_host_release",
+    "rqae_forward_f32", "rqae_forward_variant", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_forward_host_mode", "rqae_widen_codes_host", "rqae_forward_host_release",
     "rqae_fp32_peak_probe",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
@@ -52,6 +52,8 @@ def load() -> ctypes.CDLL:
     lib.rqae_pack_weights.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz, vp]
     lib.rqae_forward_f32.restype = i
     lib.rqae_forward_f32.argtypes = [vp, vp, i, i, i, i, i, i, vp, i64, vp, i, i64, vp, vp, vp, vp]
+    lib.rqae_forward_variant.restype = i
+    lib.rqae_forward_variant.argtypes = [i]
     lib.rqae_hook_rmsnorm.restype = i
     lib.rqae_hook_rmsnorm.argtypes = [vp, vp, i, i, i, i, i, i, vp, i, i64, i, vp, c.c_float, i, i, vp, i, i64, vp]
     lib.rqae_decode_f32.restype = i

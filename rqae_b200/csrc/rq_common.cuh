@@ -112,6 +112,51 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- thread-block clusters: distributed shared memory and cluster-scope barriers -----------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA's window) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t caddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
+}
+// Asynchronous 4-byte store into another CTA's shared memory that, on completion, counts 4 bytes on a barrier of THAT
+// CTA (complete_tx): the receiver learns of the data through its own barrier, as with a bulk copy, and no fence is
+// needed on either side.  (A generic st.shared::cluster followed by a release.cluster arrive costs the sending warp a
+// cluster-scope memory barrier per hand-over: measured 6x slower on the forward kernel's critical path.)
+__device__ __forceinline__ void st_async_cluster_f32(uint32_t caddr, float v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(caddr),
+               "r"(__float_as_uint(v)), "r"(cbar)
+               : "memory");
+}
+// arrive on a barrier of another CTA of the cluster; release at cluster scope publishes the stores before it
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// wait that also acquires what other CTAs of the cluster stored before their (cluster-scope) arrives
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(RQ_WAIT_HINT_NS)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- bulk TMA (1-D): global -> shared, completion counted in bytes on an mbarrier --------
 // SASS: UBLKCP.  dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {

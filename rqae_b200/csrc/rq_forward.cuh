@@ -89,7 +89,14 @@ constexpr int kComputeWarps = 8;
 constexpr int kThreads = 384;
 constexpr int kCodeBuf = 16;  // layers buffered per token before a 128-byte code store
 
-template <int E, int EC, int CH, int NSLOT, int TG>
+// CS > 1: the D-split cluster variant.  A cluster of CS CTAs works on one unit; E, CH then describe ONE CTA's slice of
+// the D axis (elements d = (rank * E + j) * 256 + t) and of every stage (chunks rank * CH .. rank * CH + CH - 1).
+// Each compute warp hands its in-projection partials to the quantizer warps of EVERY CTA of the cluster (own shared
+// memory + st.async into the peers', whose completion counts bytes on the peer's own barrier); every CTA then sums the same CS * 8
+// partials in the same order, so all of them derive the same z, the same code and the same c' without exchanging
+// anything else.  The partial buffers alternate with the layer's parity: a fast CTA may already deliver layer l + 1
+// while a slow one still reads layer l (it cannot get two layers ahead: its layer l + 1 needs everybody's l).
+template <int E, int EC, int CH, int NSLOT, int TG, int CS = 1>
 struct FwdCfg {
   static constexpr int NP = TG / 2;              // token pairs per phase
   static constexpr int JC = E / CH;              // elements per thread per chunk
@@ -104,8 +111,10 @@ struct FwdCfg {
   static constexpr int SM_MAP = SM_CBT + RQ_SMEM_ROWS * 16;                 // uint16[RQ_SMEM_ROWS]
   static constexpr int SM_TP = SM_MAP + RQ_SMEM_ROWS * 2;                   // float4[24][RQ_CAN_MAX] canonical rows per order
   static constexpr int SM_MAP3 = SM_TP + RQ_NPERM * RQ_CAN_MAX * 16;        // uint16[16][24][RQ_CAN_MAX]
-  static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[2][8][32]
-  static constexpr int SM_CPR = SM_PART + 2 * kComputeWarps * 32 * 4;       // u64[2][4][4] (pairs padded to 4)
+  static constexpr int PART_WARPS = CS * kComputeWarps;                       // partial rows per (phase, parity)
+  static constexpr int PART_SETS = CS > 1 ? 4 : 2;                            // [phase] or [phase][layer parity]
+  static constexpr int SM_PART = SM_MAP3 + RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX * 2;  // float[PART_SETS][PART_WARPS][32]
+  static constexpr int SM_CPR = SM_PART + PART_SETS * PART_WARPS * 32 * 4;    // u64[2][4][4] (pairs padded to 4)
   static constexpr int SM_CODES = SM_CPR + 2 * 4 * 4 * 8;                   // uint16[2][8][kCodeBuf]
   static constexpr int SM_THR = SM_CODES + 2 * 8 * kCodeBuf * 2;            // float[4] search thresholds
   static constexpr int SM_HOOK = SM_THR + 16;                               // float[8][16] warp partials + float[2][16] scales (hook mode)
@@ -227,10 +236,12 @@ __device__ __forceinline__ void fwd_pass(u64 (&r2)[TG][E], u64 (&acc)[TG / 2][4]
 
 // Register budget: ptxas compiles the kernel for 384 threads/CTA at 168 registers, so the CTA owns a pool
 // of 384*168 = 64512 registers; setmaxnreg can only re-split THAT pool (an .inc beyond it spins forever).
-template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, bool HOOK = false, int REG_COMPUTE = RQ_REGC, int REG_HELPER = RQ_REGH>
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG = false, bool HOOK = false, int CS = 1, int REG_COMPUTE = RQ_REGC,
+          int REG_HELPER = RQ_REGH>
 __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams p) {
   static_assert(2 * 128 * REG_COMPUTE + 128 * REG_HELPER <= kThreads * 168, "register pool budget");
-  using C = FwdCfg<E, EC, CH, NSLOT, TG>;
+  static_assert(CS >= 1 && CS <= 4 && !(HOOK && CS > 1), "cluster variant: plain forward only");
+  using C = FwdCfg<E, EC, CH, NSLOT, TG, CS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,11 +254,15 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
   // work split: a unit is 2*TG consecutive tokens (phase A = first TG, phase B = next TG); CTA b handles
   // units b, b+grid, ...
   const long long n_units = (p.n_tokens + 2 * TG - 1) / (2 * TG);
-  const long long my_iters = (n_units > (long long)blockIdx.x) ? (n_units - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;      // this CTA's slice of the D axis
+  const long long cl_id = (long long)blockIdx.x / CS;          // unit stream of this CTA (cluster)
+  const long long n_cl = (long long)gridDim.x / CS;
+  const long long my_iters = (n_units > cl_id) ? (n_units - 1 - cl_id) / n_cl + 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kComputeWarps); }
-    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], kComputeWarps); mbar_init(&c_ready[g], 1); }
+    // cluster variant: 8 local warp arrivals + the quantizer's own expect_tx arrival; the peers' partials come as bytes
+    for (int g = 0; g < 2; g++) { mbar_init(&part_full[g], CS > 1 ? kComputeWarps + 1 : kComputeWarps); mbar_init(&c_ready[g], 1); }
     mbar_fence_init();
   }
   // search tables -> shared memory (shared-codebook mode): the de-duplicated table if it fits, and the
@@ -274,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     for (int i = threadIdx.x; i < RQ_NSIGN * RQ_NPERM * RQ_CAN_MAX / 2; i += kThreads) mdst[i] = msrc[i];
   }
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // the peers' barriers exist before anybody arrives on them
 
   if (warp < kComputeWarps) {
     // =============================== compute warps ===============================
@@ -281,11 +297,16 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
     const int ct = threadIdx.x;              // 0..255
     const uint32_t ring = smem_u32(smem + C::SM_RING);
     const uint32_t cpr = smem_u32(smem + C::SM_CPR);
-    const uint32_t part = smem_u32(smem + C::SM_PART) + warp * 32 * 4 + lane * 4;   // + phase * 1024
+    const uint32_t part = smem_u32(smem + C::SM_PART) + (crank * kComputeWarps + warp) * 32 * 4 + lane * 4;   // + set * PART_WARPS * 128
+    uint32_t part_r[CS > 1 ? CS : 1], pfull_r[CS > 1 ? CS : 1];   // the same slot / the phase barriers in every CTA of the cluster
+    if (CS > 1) {
+#pragma unroll
+      for (int r = 0; r < CS; r++) { part_r[r] = mapa_u32(part, r); pfull_r[r] = mapa_u32(smem_u32(&part_full[0]), r); }
+    }
     uint32_t slot = 0, full_par = 0, cr_par = 0;
 
     for (long long it = 0; it < my_iters; ++it) {
-      const long long tok0 = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG);
+      const long long tok0 = (cl_id + it * n_cl) * (2 * TG);
       // ---- load the unit's activations into registers (zeros outside [0,n_tokens) x [0,D)) ----
       u64 r2[TG][E];   // [phase * NP + pair][element]
       if constexpr (!HOOK) {
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           const float* xb = p.x + tb * (long long)p.D;
 #pragma unroll
           for (int j = 0; j < E; j++) {
-            const int d = j * RQ_GROUP_THREADS + ct;
+            const int d = ((int)crank * E + j) * RQ_GROUP_THREADS + ct;
             const float a = (ta < p.n_tokens && d < p.D) ? __ldcs(xa + d) : 0.0f;
             const float b = (tb < p.n_tokens && d < p.D) ? __ldcs(xb + d) : 0.0f;
             r2[pi][j] = pack2(a, b);
@@ -314,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           const long long ta = tok0 + 2 * pi, tb = ta + 1;
 #pragma unroll
           for (int j = 0; j < E; j++) {
-            const int d = j * RQ_GROUP_THREADS + ct;
+            const int d = ((int)crank * E + j) * RQ_GROUP_THREADS + ct;
             const float a = (ta < p.n_tokens && d < p.D) ? hook_load(p.hs, ta * (long long)p.D + d, p.hs_dtype) : 0.0f;
             const float b = (tb < p.n_tokens && d < p.D) ? hook_load(p.hs, tb * (long long)p.D + d, p.hs_dtype) : 0.0f;
             r2[pi][j] = pack2(a, b);
@@ -340,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
         named_bar_sync(1, RQ_GROUP_THREADS);
 #pragma unroll
         for (int j = 0; j < E; j++) {
-          const int d = j * RQ_GROUP_THREADS + ct;
+          const int d = ((int)crank * E + j) * RQ_GROUP_THREADS + ct;
           const float w1 = d < p.D ? __fadd_rn(1.0f, __ldg(p.rms_w + d)) : 0.0f;
 #pragma unroll
           for (int pi = 0; pi < TG; pi++) {
@@ -391,9 +412,20 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
 #pragma unroll
               for (int k = 0; k < 4; k++) unpack2(acc[pi][k], v[(2 * pi) * 4 + k], v[(2 * pi + 1) * 4 + k]);
             const float s = butterfly32(v, lane);
-            sts32(part + ph * (kComputeWarps * 32 * 4), s);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&part_full[ph]);
+            if (CS == 1) {
+              sts32(part + ph * (kComputeWarps * 32 * 4), s);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&part_full[ph]);
+            } else {
+              const uint32_t set = (uint32_t)(ph * 2 + (l & 1)) * (C::PART_WARPS * 32 * 4);
+#pragma unroll
+              for (int r = 0; r < CS; r++) {
+                if ((uint32_t)r != crank) st_async_cluster_f32(part_r[r] + set, s, pfull_r[r] + ph * 8);
+              }
+              sts32(part + set, s);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&part_full[ph]);
+            }
           }
         }
         if (l > 0) cr_par ^= 1;
@@ -410,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           const float* hk = reinterpret_cast<const float*>(smem + C::SM_HOOK) + kComputeWarps * 16;
 #pragma unroll
           for (int j = 0; j < E; j++) {
-            const int d = j * RQ_GROUP_THREADS + ct;
+            const int d = ((int)crank * E + j) * RQ_GROUP_THREADS + ct;
             const float w1 = d < p.D ? __fadd_rn(1.0f, __ldg(p.rms_w + d)) : 1.0f;
 #pragma unroll
             for (int pi = 0; pi < TG; pi++) {
@@ -438,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           const long long ta = tok0 + 2 * pi, tb = ta + 1;
 #pragma unroll
           for (int j = 0; j < E; j++) {
-            const int d = j * RQ_GROUP_THREADS + ct;
+            const int d = ((int)crank * E + j) * RQ_GROUP_THREADS + ct;
             float ra, rb;
             unpack2(r2[pi][j], ra, rb);
             if (d < p.D) {
@@ -458,7 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       // slot's `empty` barrier (hardware-suspended try_wait, no polling).
       if (lane == 0) {
         const uint32_t ring = smem_u32(smem + C::SM_RING);
-        const unsigned char* stages = p.packed + p.off_stage;
+        const unsigned char* stages = p.packed + p.off_stage + (size_t)crank * CH * (size_t)C::CHUNK_BYTES;
+        constexpr size_t kStageBytes = (size_t)CS * CH * (size_t)C::CHUNK_BYTES;
         const uint64_t pol = p.l2_hot >= 1.0f ? l2_policy_evict_last() : l2_policy_hot_fraction(p.l2_hot);
         uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on parity 1
         unsigned int target = 0;
@@ -470,8 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           // HBM.  In step, the stages in flight span a few layers and each stage is read from HBM about
           // once per unit.  Only this lane waits; the compute warps are throttled by the ring.
           if (it > 0 && p.sync_ctr != nullptr) {
-            const long long left = n_units - it * (long long)gridDim.x;
-            target += (unsigned int)(left < (long long)gridDim.x ? left : (long long)gridDim.x);
+            const long long left = n_units - it * n_cl;
+            target += (unsigned int)(left < n_cl ? left : n_cl) * CS;
             asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.sync_ctr) : "memory");
             unsigned int seen;
             do {
@@ -485,10 +518,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
               mbar_wait(&empty[slot], par);
               mbar_arrive_expect_tx(&full[slot], C::CHUNK_BYTES);
               if (p.l2_hot > 0.f)
-                tma_bulk_g2s_hint(ring + slot * C::CHUNK_BYTES, stages + ((size_t)l * CH + c) * (size_t)C::CHUNK_BYTES,
+                tma_bulk_g2s_hint(ring + slot * C::CHUNK_BYTES, stages + (size_t)l * kStageBytes + (size_t)c * C::CHUNK_BYTES,
                                   C::CHUNK_BYTES, &full[slot], pol);
               else
-                tma_bulk_g2s(ring + slot * C::CHUNK_BYTES, stages + ((size_t)l * CH + c) * (size_t)C::CHUNK_BYTES,
+                tma_bulk_g2s(ring + slot * C::CHUNK_BYTES, stages + (size_t)l * kStageBytes + (size_t)c * C::CHUNK_BYTES,
                              C::CHUNK_BYTES, &full[slot]);
               if (++slot == NSLOT) { slot = 0; par ^= 1; }
             }
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
       const uint32_t can_smem = smem_u32(smem + C::SM_TP);    // order 0 = canonical rows as stored
       const uint32_t map3_smem = smem_u32(smem + C::SM_MAP3);
       const uint32_t codes_s = smem_u32(smem + C::SM_CODES) + (ph * 8 + tok) * kCodeBuf * 2;
-      const uint32_t pa = smem_u32(smem + C::SM_PART) + (ph * kComputeWarps * 32 + lane) * 4;
+      const uint32_t pa0 = smem_u32(smem + C::SM_PART) + lane * 4;   // + set * PART_WARPS * 128
       const uint32_t cpr_t = smem_u32(smem + C::SM_CPR) + ph * 128 + (tok >> 1) * 32 + (tok & 1) * 4 + sub * 8;
       uint32_t pf_par = 0;
 
@@ -533,15 +566,25 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           const float bsub = __ldg(reinterpret_cast<const float*>(p.packed + p.off_bin) + l * 4 + sub);
           float4 c0, c1, c2, c3;   // canonical rows sub, sub+4, sub+8, sub+12 (zero rows beyond can_rows)
           lds128x4<64>(can_smem + sub * 16, c0, c1, c2, c3);
+          if (CS > 1 && lane == 0) mbar_arrive_expect_tx(&part_full[ph], (CS - 1) * kComputeWarps * 32 * 4);   // the peers' partials
           mbar_wait(&part_full[ph], pf_par);
           pf_par ^= 1;
-          // z_sub = ((P0 + P1) + (P2 + P3)) + ((P4 + P5) + (P6 + P7)) + b_in   (model.py:211)
+          // z_sub = ((P0 + P1) + (P2 + P3)) + ((P4 + P5) + (P6 + P7)) + b_in   (model.py:211); cluster variant: the
+          // same tree per CTA slice, the slices added in rank order, then the bias
           float zm;
           {
-            const float p0 = lds32(pa), p1 = lds32(pa + 128), p2 = lds32(pa + 256), p3 = lds32(pa + 384);
-            const float p4 = lds32(pa + 512), p5 = lds32(pa + 640), p6 = lds32(pa + 768), p7 = lds32(pa + 896);
-            zm = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)),
-                                     __fadd_rn(__fadd_rn(p4, p5), __fadd_rn(p6, p7))), bsub);
+            const uint32_t pa = pa0 + (uint32_t)(CS == 1 ? ph : ph * 2 + (l & 1)) * (C::PART_WARPS * 32 * 4);
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < CS; r++) {
+              const uint32_t q = pa + r * (kComputeWarps * 32 * 4);
+              const float p0 = lds32(q), p1 = lds32(q + 128), p2 = lds32(q + 256), p3 = lds32(q + 384);
+              const float p4 = lds32(q + 512), p5 = lds32(q + 640), p6 = lds32(q + 768), p7 = lds32(q + 896);
+              const float t = __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)),
+                                        __fadd_rn(__fadd_rn(p4, p5), __fadd_rn(p6, p7)));
+              acc = r == 0 ? t : __fadd_rn(acc, t);
+            }
+            zm = __fadd_rn(acc, bsub);
           }
           const int base = lane & ~3;
           const float z0 = __shfl_sync(0xffffffffu, zm, base), z1 = __shfl_sync(0xffffffffu, zm, base + 1);
@@ -624,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
           }
           if (DBG) {  // parity-test instantiation only: let given codes drive the recurrence
             if (p.teacher != nullptr) {
-              const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+              const long long token = (cl_id + it * n_cl) * (2 * TG) + ph * TG + tok;
               const int tc = (tok_live && token < p.n_tokens) ? p.teacher[token * p.nq_run + l] : 0;
               cwm = p.codebook[((p.cb_shared ? 0 : (size_t)l * p.K) + tc) * 4 + sub];
             }
@@ -644,17 +687,17 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
             code = (int)cs;
           }
           if (DBG) {
-            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
-            if (p.z_out != nullptr && sub == 0 && tok_live && token < p.n_tokens)
+            const long long token = (cl_id + it * n_cl) * (2 * TG) + ph * TG + tok;
+            if (p.z_out != nullptr && crank == 0 && sub == 0 && tok_live && token < p.n_tokens)
               reinterpret_cast<float4*>(p.z_out)[token * p.nq_run + l] = make_float4(z0, z1, z2, z3);
           }
           if (sub == 0 && tok_live)
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(codes_s + (l & (kCodeBuf - 1)) * 2), "h"((unsigned short)code) : "memory");
           // ---- flush buffered codes: 16 consecutive layers of one token = one 128-byte store ----
-          if (p.codes != nullptr && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
+          if (p.codes != nullptr && crank == 0 && ((l & (kCodeBuf - 1)) == kCodeBuf - 1 || l == p.nq_run - 1)) {
             __syncwarp();
             const int l0 = l & ~(kCodeBuf - 1);
-            const long long token = ((long long)blockIdx.x + it * gridDim.x) * (2 * TG) + ph * TG + tok;
+            const long long token = (cl_id + it * n_cl) * (2 * TG) + ph * TG + tok;
             const bool tok_valid = tok_live && token < p.n_tokens;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
@@ -673,6 +716,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_forward_kernel(const FwdParams
         }
       }
     }
+  }
+  if (CS > 1) {   // nobody leaves while a peer may still store into its shared memory or arrive on its barriers
+    __syncwarp();
+    cluster_sync_all();
   }
 }
 

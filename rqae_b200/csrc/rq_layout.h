@@ -54,6 +54,11 @@ static inline int rq_pick_shape(int D, struct RqShape* s) {
   return 1;
 }
 
+/* D-split cluster variant of the forward kernel (rq_forward.cuh, CS > 1): a cluster of CS CTAs works on ONE unit of
+ * 16 tokens, CTA c owning elements d = (c * E/CS + j) * 256 + t.  Its weights are a second copy of the stages cut into
+ * CS chunks, chunk c = CTA c's slice.  0 = the shape has no cluster variant. */
+static inline int rq_cluster_size(int E) { return E == 14 ? 2 : 0; }
+
 struct RqLayout {
   size_t off_bin;    /* float4[nq+1]          in-projection biases                    */
   size_t off_cbt;    /* float4[KT]            de-duplicated search table (shared mode) */
@@ -61,6 +66,7 @@ struct RqLayout {
   size_t off_tp;     /* float4[24][RQ_CAN_MAX] canonical rows, coordinates arranged per magnitude order */
   size_t off_map3;   /* uint16[16][24][RQ_CAN_MAX] (signs, order, canonical row) -> lowest original index */
   size_t off_stage;  /* (nq+1) stages                                                  */
+  size_t off_stage_cl; /* (nq+1) stages in the cluster variant's chunking (0 if none)  */
   size_t stage_bytes;
   size_t chunk_bytes;
   size_t total;
@@ -80,6 +86,11 @@ static inline void rq_layout(int nq, int K, const struct RqShape* s, struct RqLa
   L->stage_bytes = (size_t)s->E * RQ_GROUP_THREADS * RQ_BYTES_PER_ELEM;
   L->chunk_bytes = L->stage_bytes / s->CH;
   L->total = L->off_stage + (size_t)(nq + 1) * L->stage_bytes;
+  L->off_stage_cl = 0;
+  if (rq_cluster_size(s->E)) {
+    L->off_stage_cl = rq_align_up(L->total, 1024);
+    L->total = L->off_stage_cl + (size_t)(nq + 1) * L->stage_bytes;
+  }
 }
 
 /* Device-resident header at offset 0 of the packed buffer. */

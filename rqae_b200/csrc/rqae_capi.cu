@@ -36,6 +36,7 @@ namespace {
 constexpr int kSyncSlots = 64;
 __device__ unsigned int g_sync_ctr[kSyncSlots * 32];   // 128 bytes apart
 std::atomic<unsigned int> g_launch_seq{0};
+std::atomic<int> g_forward_variant{-1};   // -1: not initialised (RQAE_CLUSTER), 0: single-CTA units, 1: D-split clusters where built
 
 thread_local cudaError_t g_last_cuda = cudaSuccess;
 thread_local int64_t g_launches = 0;
@@ -368,6 +369,67 @@ int launch_forward_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   return RQAE_OK;
 }
 
+// D-split cluster variant: CS CTAs per unit, launched as clusters (co-scheduled on one GPC) and cooperatively (the
+// grid lock-step spins on a global counter, so every cluster must be resident).
+template <int E, int EC, int CH, int NSLOT, int TG, bool DBG, int CS>
+int launch_forward_cluster_t(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+  using C = rq::FwdCfg<E, EC, CH, NSLOT, TG, CS>;
+  auto kern = rq::rq_forward_kernel<E, EC, CH, NSLOT, TG, DBG, false, CS>;
+  RQ_CUDA(ensure_dynamic_smem((const void*)kern, C::SM_TOTAL));
+  static std::mutex mu;
+  static std::map<int, int> max_clusters;   // per device
+  int dev = 0;
+  RQ_CUDA(cudaGetDevice(&dev));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(rq::kThreads);
+  cfg.dynamicSmemBytes = C::SM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  int ncl = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = max_clusters.find(dev);
+    if (it == max_clusters.end()) {
+      cfg.gridDim = dim3((unsigned)(sms / CS * CS));
+      cfg.numAttrs = 1;
+      int n = 0;
+      RQ_CUDA(cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg));
+      if (n <= 0) return RQAE_EUNSUPPORTED;
+      it = max_clusters.emplace(dev, n).first;
+    }
+    ncl = it->second;
+  }
+  const long long n_units = (prm.n_tokens + 2 * TG - 1) / (2 * TG);
+  const int clusters = (int)(n_units < ncl ? n_units : ncl);
+  rq::FwdParams p2 = prm;
+  p2.sync_ctr = nullptr;
+  static const bool lockstep = [] { const char* e = getenv("RQAE_LOCKSTEP"); return e ? atoi(e) != 0 : true; }();
+  const bool coop = lockstep && n_units > clusters;
+  if (coop) {
+    unsigned int* base = nullptr;
+    RQ_CUDA(cudaGetSymbolAddress((void**)&base, g_sync_ctr));
+    p2.sync_ctr = base + (g_launch_seq.fetch_add(1) % kSyncSlots) * 32;
+    RQ_CUDA(cudaMemsetAsync(p2.sync_ctr, 0, sizeof(unsigned int), st));
+  }
+  cfg.gridDim = dim3((unsigned)(clusters * CS));
+  cfg.numAttrs = coop ? 2 : 1;
+  RQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p2));
+  g_launches++;
+  return RQAE_OK;
+}
+
+template <int E, int EC, int CH, int NSLOT, int TG, int CS>
+int launch_forward_cluster(const rq::FwdParams& prm, int sms, cudaStream_t st) {
+  if (prm.teacher != nullptr || prm.z_out != nullptr) return launch_forward_cluster_t<E, EC, CH, NSLOT, TG, true, CS>(prm, sms, st);
+  return launch_forward_cluster_t<E, EC, CH, NSLOT, TG, false, CS>(prm, sms, st);
+}
+
 template <int E, int EC, int CH, int NSLOT, int TG>
 int launch_forward(const rq::FwdParams& prm, int sms, cudaStream_t st) {
   if (prm.hs != nullptr) return launch_forward_t<E, EC, CH, NSLOT, TG, false, true>(prm, sms, st);
@@ -426,6 +488,13 @@ int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, 
                                                                       L.off_bin, L.off_stage, L.stage_bytes);
   g_launches++;
   RQ_CUDA(cudaGetLastError());
+  if (L.off_stage_cl) {   // second copy for the D-split cluster variant: one chunk per CTA of the cluster
+    pack_stages_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_in, b_in, w_out, b_out, nq, dim, s.E,
+                                                                        rq_cluster_size(s.E), pk, L.off_bin, L.off_stage_cl,
+                                                                        L.stage_bytes);
+    g_launches++;
+    RQ_CUDA(cudaGetLastError());
+  }
   if (codebook_shared) {
     // the table is tiny: fetch it, build the search tables on the host, upload (this entry point therefore
     // synchronises `stream`; it runs once per weight load, never on the hot path)
@@ -444,6 +513,13 @@ int rqae_pack_weights(const float* w_in, const float* b_in, const float* w_out, 
   return RQAE_OK;
 }
 
+static void forward_variant_init() {
+  if (g_forward_variant.load() < 0) {
+    const char* e = getenv("RQAE_CLUSTER");
+    g_forward_variant.store(e && atoi(e) != 0 ? 1 : 0);
+  }
+}
+
 static int forward_common(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,
                           int codebook_dim, int K, int64_t n_tokens, void* codes, int code_dtype, int64_t code_stride,
                           rq::FwdParams& prm, void* stream) {
@@ -453,6 +529,7 @@ static int forward_common(const void* packed, const float* codebook, int codeboo
   RqShape s;
   if (codebook_dim != 4 || K > 65535 || rq_pick_shape(dim, &s)) return RQAE_EUNSUPPORTED;
   if (n_tokens == 0) return RQAE_OK;
+  forward_variant_init();
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc) return rc;
@@ -485,9 +562,20 @@ static int forward_common(const void* packed, const float* codebook, int codeboo
     case 9:
       if (few) return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 4>(prm, sms, st);
       return launch_forward<9, 3, RQ_E9_CH, RQ_E9_NSLOT, 8>(prm, sms, st);
-    case 14:
+    case 14: {
+      // Gemma-2-9B width, opt-in (rqae_forward_variant(1) / RQAE_CLUSTER=1): the D-split cluster variant -- 2 CTAs x
+      // 7 elements per thread, 16 tokens per unit, whole half-stages double-buffered.  Measured (profiles/r2m_*):
+      // 302 k tokens/s against 310-318 k of the single-CTA kernel on large batches (the hand-over through the
+      // peer's shared memory lengthens the serial chain by what the shorter passes save), 13-43 % faster below
+      // ~2400 tokens.  Its summation order differs (c_oracle.KERNEL_ORDER_9B), so it is never chosen silently.
+      if (g_forward_variant.load() == 1 && prm.hs == nullptr && L.off_stage_cl) {
+        rq::FwdParams pc = prm;
+        pc.off_stage = L.off_stage_cl;
+        return launch_forward_cluster<7, 7, 1, 2, 8, 2>(pc, sms, st);
+      }
       if (few) return launch_forward<14, 2, 7, 10, 4>(prm, sms, st);
       return launch_forward<14, 2, 7, 10, 6>(prm, sms, st);
+    }
     default: return RQAE_EUNSUPPORTED;
   }
 }
@@ -501,6 +589,14 @@ int rqae_forward_f32(const void* packed, const float* codebook, int codebook_sha
   prm.x = x; prm.q_out = q_out; prm.teacher = teacher; prm.z_out = z_out;
   return forward_common(packed, codebook, codebook_shared, nq, nq_run, dim, codebook_dim, K, n_tokens, codes, code_dtype,
                         code_stride, prm, stream);
+}
+
+int rqae_forward_variant(int variant) {
+  forward_variant_init();
+  if (variant > 1) return -1;
+  const int old = g_forward_variant.load();
+  if (variant >= 0) g_forward_variant.store(variant);
+  return old;
 }
 
 int rqae_hook_rmsnorm(const void* packed, const float* codebook, int codebook_shared, int nq, int nq_run, int dim,

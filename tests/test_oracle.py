@@ -128,6 +128,10 @@ def test_9b_width_oracles_pinned_on_reference(golden_9b):
     qc, codes = c_oracle.forward_f32(cw, g["x"], **c_oracle.KERNEL_ORDER)
     rep = parity.compare_codes(codes, g["codes"], g["margins_fp64"])
     assert rep.failures == 0, str(rep)
+    # the opt-in D-split cluster variant sums in another order (two slices of 7 x 256 elements): pinned as well
+    _, codes_cl = c_oracle.forward_f32(cw, g["x"][:16], want_q=False, **c_oracle.KERNEL_ORDER_9B)
+    rep_cl = parity.compare_codes(codes_cl, g["codes"][:16], g["margins_fp64"][:16])
+    assert rep_cl.failures == 0, str(rep_cl)
     ok = parity.exact_token_mask(codes, g["codes"])
     assert ok.sum() >= len(ok) - 8
     assert np.abs(qc[ok] - g["q"][ok]).max() <= 2e-5 * np.abs(g["q"]).max()

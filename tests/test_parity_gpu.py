@@ -468,6 +468,45 @@ def test_gemma9b_width_bit_exact_vs_c_oracle():
     assert np.array_equal(dec.cpu().numpy(), c_oracle.decode_f32(cw, codes=co))
 
 
+def test_gemma9b_width_cluster_variant_bit_exact_in_its_own_order(golden_9b):
+    """Opt-in D-split cluster variant (rqae_forward_variant(1)): two CTAs per unit, each owning half of the hidden
+    dimension, partials exchanged through distributed shared memory.  Bit-exact against the C oracle evaluated in
+    THAT summation order (KERNEL_ORDER_9B), the reference's golden codes under the near-tie protocol, ragged and
+    multi-wave token counts, teacher forcing; and the default variant is restored."""
+    from rqae_b200 import RQAE, _lib
+    lib = _lib.load()
+    g = golden_9b
+    torch.manual_seed(0)
+    m = RQAE(dim=3584, num_quantizers=2048).eval()
+    cw = c_oracle.CWeights.from_stacked(util.stacked_from_module(m))
+    m = m.to(_cuda())
+    x = torch.from_numpy(g["x"])
+    n = x.shape[0]
+    assert lib.rqae_forward_variant(1) == 0
+    try:
+        q, idx = m(x.to(_cuda()).view(1, n, 3584))
+        codes = idx[0].cpu().numpy()
+        qo, co = c_oracle.forward_f32(cw, g["x"], **c_oracle.KERNEL_ORDER_9B)
+        assert np.array_equal(codes, co.astype(np.int64)) and np.array_equal(q[0].cpu().numpy(), qo)
+        rep = parity.compare_codes(codes, g["codes"], g["margins_fp64"])
+        print("9B-width KAT, cluster variant vs reference:", rep)
+        assert rep.failures == 0, str(rep)
+        # more units than clusters (lock-step path), ragged tail, shallow prefix
+        xb = torch.randn(1, 74 * 16 * 2 + 21, 3584, generator=torch.Generator().manual_seed(8))
+        ib = m.encode(xb.to(_cuda()), max_layers=12, out_dtype=torch.int32)[0].cpu().numpy()
+        _, cb = c_oracle.forward_f32(cw, xb[0].numpy(), max_layers=12, want_q=False, **c_oracle.KERNEL_ORDER_9B)
+        assert np.array_equal(ib, cb)
+        teacher = torch.from_numpy(g["codes"].astype(np.int32)).to(_cuda()).view(1, n, 2048)
+        _, tf, _ = m._run_forward(x.to(_cuda()).view(1, n, 3584), float("inf"), 0.0, False, torch.int32, teacher=teacher)
+        mism = tf[0].cpu().numpy() != g["codes"]
+        assert (g["margins_fp64"][mism] < parity.EPS).all()
+    finally:
+        assert lib.rqae_forward_variant(0) == 1
+    _, idx0 = m(x.to(_cuda()).view(1, n, 3584))
+    _, c0 = c_oracle.forward_f32(cw, g["x"], want_q=False, **KERNEL_ORDER)
+    assert np.array_equal(idx0[0].cpu().numpy(), c0.astype(np.int64))
+
+
 def test_cpu_tensors_are_rejected(model_2b):
     m, _ = model_2b
     with pytest.raises(RuntimeError):
