@@ -681,13 +681,13 @@ def run_b200(args, rank, local_rank, world):
         qh = torch.empty(Te, D, dtype=torch.float32, pin_memory=True)
         steps_e = args.e2e_steps or min(args.steps, 3)
 
-        def e2e_run(dt):
+        def e2e_run(dt, want_q=True):
             ch = torch.empty(Te, NQ, dtype=dt, pin_memory=True)
-            model.forward_host(xh[: 1 << 15], out=(qh[: 1 << 15], ch[: 1 << 15]), out_dtype=dt)  # warm-up of the host path
+            model.forward_host(xh[: 1 << 15], out=(qh[: 1 << 15], ch[: 1 << 15]), out_dtype=dt, want_q=want_q)  # warm-up of the host path
             barrier()
             t0 = time.perf_counter()
             for _ in range(steps_e):
-                model.forward_host(xh, out=(qh, ch), out_dtype=dt)
+                model.forward_host(xh, out=(qh, ch), out_dtype=dt, want_q=want_q)
             t_e = time.perf_counter() - t0    # forward_host returns after the last D2H copy completed
             barrier()
             if world > 1:
@@ -699,6 +699,7 @@ def run_b200(args, rank, local_rank, world):
         import ctypes
         v64, ck64 = e2e_run(torch.int64)
         v32, ck32 = e2e_run(torch.int32)
+        venc, ckenc = e2e_run(torch.int32, want_q=False)
         m_, t_ = ctypes.c_int(0), ctypes.c_int(0)
         lib.rqae_forward_host_mode(ctypes.byref(m_), ctypes.byref(t_))
         narrow = m_.value == 1
@@ -716,7 +717,13 @@ def run_b200(args, rank, local_rank, world):
                "int32_codes": {"value": v32, "unit": UNIT, "d2h_bytes_per_step": Te * ((NQ * 2 if narrow else NQ * 4) + D * 4),
                                "checksum_codes": ck32,
                                "note": "same call with out_dtype=int32, the dtype the reference's code store keeps "
-                                       "(scripts/1_create_activations.py:184-186)"}}
+                                       "(scripts/1_create_activations.py:184-186)"},
+               "encode_only_int32_codes": {"value": venc, "unit": UNIT, "d2h_bytes_per_step": Te * NQ * (2 if narrow else 4),
+                                           "checksum_codes": ckenc,
+                                           "note": "code extraction only (forward_host(want_q=False)): what scripts/1 keeps of the "
+                                                   "RQAE output; no reconstruction crosses PCIe, so the host link carries 9.2 KB in "
+                                                   "and 2 KB out per token -- the variant that shows the pipeline itself scales "
+                                                   "when the device->host bytes do not bind (DESIGN.md 7)"}}
         del xh, qh
 
     # ---- side measurements (outside the timed region) ----

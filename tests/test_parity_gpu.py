@@ -507,6 +507,31 @@ def test_gemma9b_width_cluster_variant_bit_exact_in_its_own_order(golden_9b):
     assert np.array_equal(idx0[0].cpu().numpy(), c0.astype(np.int64))
 
 
+def test_derived_tables_on_gpu_match_the_reference_formulas():
+    """SURVEY 8f-4 / model.py:133-178 on the device: ``subfeature_sims`` from the per-layer 5x5 Gram of [W_out | b_out]
+    (no (nq, K, D) intermediate) against the reference's own construction written out -- F.normalize(lin_out[l](codebook[l]))
+    and its Gram matrix in fp16 -- and ``layer_norms`` / ``codebook_sims`` against their formulas.  Load-time code on
+    cuBLAS, not a kernel of this library; the test pins its values on the GPU as the CPU tests do on the host."""
+    import torch.nn.functional as F
+    from rqae_b200 import RQAE
+    torch.manual_seed(3)
+    m = RQAE(dim=320, num_quantizers=9).eval().to(_cuda())
+    with torch.no_grad():
+        sims = m.subfeature_sims
+        assert sims.shape == (9, 625, 625) and sims.dtype == torch.float16 and sims.is_cuda
+        worst, differ = 0.0, 0.0
+        for l in range(9):
+            sub = F.normalize(m.layers[l][1](m.codebook[l]), dim=-1)                       # (K, D): model.py:145-167
+            ref = (sub @ sub.T).to(torch.float16)
+            worst = max(worst, float((ref.float() - sims[l].float()).abs().max()))
+            differ = max(differ, float((ref != sims[l]).float().mean()))
+        assert worst <= 2.0 ** -10 and differ < 0.01, (worst, differ)                    # one fp16 step, rare
+        ln = torch.stack([m.layers[l][1].weight.norm(dim=0).mean() for l in range(9)])
+        assert torch.allclose(m.layer_norms.to(ln.device), ln, rtol=1e-6, atol=0)
+        cb = F.normalize(m.codebook[0], dim=-1)
+        assert torch.equal(m.codebook_sims, (cb @ cb.T).to(torch.float16))
+
+
 def test_cpu_tensors_are_rejected(model_2b):
     m, _ = model_2b
     with pytest.raises(RuntimeError):
