@@ -259,6 +259,7 @@ def test_feature_helper_get_activations(top_k):
     helper = FeatureHelper(torch.zeros(N, S, dtype=torch.int64), list(range(N)), codes.to(dev).to(torch.int16))
     many = helper.get_activations_many(feats, top_k=top_k)
     inten = intensity_many(model, helper.indices, torch.from_numpy(kat["centers"]), layers, layer_weights=lw).cpu()
+    overlaps = []
     for fi, acts in enumerate(many):
         want = fo.get_activations(inten[fi].T.contiguous(), layers, top_k, S, stable=True)
         for l in layers:
@@ -270,10 +271,16 @@ def test_feature_helper_get_activations(top_k):
             gold_rows = kat[f"f{fi}/k{top_k}/{l}/activations"].astype(np.float32)
             pos = {s: i for i, s in enumerate(seqs)}
             common = [s for s in gold_seqs if s in pos]
+            overlaps.append(len(common) / len(gold_seqs))
+            # Mined sets are tolerance-equal, not identical: fp16 intensities tie
+            # heavily and sit one or two fp16 steps from the reference's, so tokens move across the window boundaries.
+            # The measured overlap is reported below; the floor only catches a broken selection.
             assert len(common) >= 0.5 * len(gold_seqs), (fi, l, len(common), len(gold_seqs))
             for s in common:
                 assert np.abs(got_rows[pos[s]].astype(np.float32) - gold_rows[gold_seqs.index(s)]).max() <= ATOL
             # the extreme values agree within the intensity tolerance whatever the tie order
             assert abs(float(got_rows.max()) - float(gold_rows.max())) <= ATOL and abs(float(got_rows.min()) - float(gold_rows.min())) <= ATOL
+    print(f"mined sequences shared with the unmodified scripts/3 output (top_k={top_k}): min {min(overlaps):.2f}, "
+          f"mean {sum(overlaps) / len(overlaps):.2f} over {len(overlaps)} (feature, layer) windows")
     one = helper.get_activations(feats[0], top_k=top_k)
     assert [a["text"] for a in one[layers[-1]]] == [a["text"] for a in many[0][layers[-1]]]
