@@ -16,15 +16,20 @@
 //
 // One CTA (448 threads, 1 per SM, persistent) computes units of 256 tokens x 256 features (two feature tiles
 // of 128 = two 128x256 fp32 accumulators = all 512 TMEM columns):
-//   warp 0      U producer : one lane, bulk-TMA copies of pre-swizzled 128x64 fp16 tiles (16 KB) from L2
+//   warp 0      U producer : one lane, bulk-TMA copies of pre-swizzled 128x64 fp16 tiles (16 KB) from L2, one ring
+//                            stage per tile
 //   warp 1      MMA issuer : one lane, tcgen05.mma M=128 (features) x N=256 (tokens) x K=16, 4 per tile and
 //                            K-block; owns the TMEM allocation
 //   warps 2-5   V builders : the token operand never exists in memory: each thread turns the codes of two tokens
 //                            (layer-major int16, coalesced) into 128-byte K-major rows through a 4 x fp16
 //                            lookup table in shared memory, written in the 128-byte swizzle the MMA expects
-//   warps 6-13  epilogue   : at every cut the MMA issuer pauses, the 8 warps read the running prefix from
-//                            TMEM (tcgen05.ld 32x32b.x32), release the accumulators, apply the reference's
-//                            fp16 roundings and store fp16 rows of out[f][cut][t]
+//   warps 6-13  epilogue   : four warps per accumulator.  At a cut the issuer commits that accumulator and goes on
+//                            with the other one; the warps pull the running prefix out of TMEM (tcgen05.ld
+//                            32x32b.x32) -- half of it as packed fp16 into registers, half through the reference's
+//                            fp16 roundings into a shared-memory row -- and release the accumulator as soon as the
+//                            last load has landed.  The rows of out[f][cut][t] then leave shared memory as bulk
+//                            TMA stores (each lane owns one feature row: no cross-thread hand-over) while the MMAs
+//                            of the next K-blocks run.
 // The K axis is cut into K-blocks of 16 layers (64 k = one 128-byte swizzle row); a segment between two cuts
 // that is not a multiple of 16 layers is padded with zero slots (schedule built by int_prep_kernel).
 #pragma once
@@ -38,15 +43,14 @@ constexpr int IT_TOK = 256;                     // tokens per unit = MMA N
 constexpr int IT_FT = 128;                      // features per tile = MMA M
 constexpr int IT_LPB = 16;                      // layers per K-block (64 k values, 128 bytes of fp16)
 constexpr int IT_VSTAGES = 2;                   // token operand: built locally, latency = the builders' own work
-constexpr int IT_USTAGES = 4;                   // feature operand: bulk copies from L2, deeper ring hides their latency
+constexpr int IT_USTAGES = 5;                   // feature operand: bulk copies from L2, one 16 KB tile per stage (2.5 K-blocks ahead)
 constexpr int IT_V_BYTES = IT_TOK * 128;        // 32 KB
 constexpr int IT_U_TILE = IT_FT * 128;          // 16 KB
-constexpr int IT_U_BYTES = 2 * IT_U_TILE;       // both feature tiles of the pair
 constexpr int IT_MAX_CUTS = 64;
 constexpr int IT_MAX_KB = 200;                  // nq = 1024 in three passes (decode, f16x3) is 192 K-blocks
 constexpr int IT_LUT_ROWS = 640;                // codebook rows + the zero row must fit (5^4 + 1); two tables
-constexpr int IT_STG_PITCH = 80;                // bytes per staged row: 32 tokens fp16 + 16 (conflict-free 128-bit access)
-constexpr int IT_STG_WARP = 32 * IT_STG_PITCH;  // per epilogue warp
+constexpr int IT_STG_PITCH = 272;               // bytes per staged row: 128 tokens fp16 + 16 (lane-strided 128-bit stores hit 8 distinct 16-byte slots)
+constexpr int IT_STG_ROWS = 2 * IT_FT;          // one row per TMEM lane of both accumulators
 constexpr int IT_THREADS = 448;
 constexpr int IT_EPI_WARPS = 8;
 constexpr int IT_BUILDERS = 128;
@@ -74,18 +78,18 @@ struct IntParams {
   const float* bias;
   long long T;
   int D;
-  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start, 64 no feature-operand copies
 };
 
 struct IntSmem {
   static constexpr int VRING = 0;
   static constexpr int URING = IT_VSTAGES * IT_V_BYTES;
-  static constexpr int LUT = URING + IT_USTAGES * IT_U_BYTES;
+  static constexpr int LUT = URING + IT_USTAGES * IT_U_TILE;
   static constexpr int SCHED = LUT + 2 * IT_LUT_ROWS * 8;
   static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
   static constexpr int STG = WCUM + 2 * IT_MAX_CUTS * 4;
-  static constexpr int BARS = STG + IT_EPI_WARPS * IT_STG_WARP;
-  static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 2) * 8;
+  static constexpr int BARS = STG + IT_STG_ROWS * IT_STG_PITCH;
+  static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 4) * 8;
   static constexpr int TOTAL = TMEM_PTR + 16;
 };
 static_assert(IntSmem::TOTAL <= 227 * 1024, "shared memory budget");
@@ -123,6 +127,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // The reference's post-sum arithmetic for a pair of values: prefix -> fp16, fp32 divide by the fp16 weight
@@ -133,6 +145,33 @@ __device__ __forceinline__ uint32_t finish2(float a, float b, float inv) {
   const float2 p = __half22float2(__floats2half2_rn(a, b));
   const __half2 h = __floats2half2_rn(p.x * inv, p.y * inv);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// The same arithmetic in two steps, so that the first rounding (the reference's own: prefix -> fp16) can be taken while
+// the accumulator is still held and the rest after it has been released.
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t finish_packed(uint32_t ph, float inv) {
+  const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&ph));
+  const __half2 h = __floats2half2_rn(p.x * inv, p.y * inv);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---- bulk TMA (1-D): shared -> global, tracked by the issuing thread's bulk async-group (SASS: UBLKCP) ----
+__device__ __forceinline__ void tma_bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem),
+               "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 
 // latency-critical waits (MMA issuer, producers): poll without the suspend hint
@@ -161,8 +200,8 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   uint64_t* v_empty = v_full + IT_VSTAGES;      // [VS] MMAs reading the stage have completed (tcgen05.commit)
   uint64_t* u_full = v_empty + IT_VSTAGES;      // [US] bulk copies landed
   uint64_t* u_empty = u_full + IT_USTAGES;      // [US] tcgen05.commit
-  uint64_t* acc_full = u_empty + IT_USTAGES;    // segment complete (tcgen05.commit)
-  uint64_t* acc_free = acc_full + 1;            // 8 epilogue warps have read the accumulators
+  uint64_t* acc_full = u_empty + IT_USTAGES;    // [2] segment complete in accumulator a (tcgen05.commit)
+  uint64_t* acc_free = acc_full + 2;            // [2] the 4 epilogue warps of accumulator a have read it
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + IntSmem::TMEM_PTR);
   const IntKBlock* sched = reinterpret_cast<const IntKBlock*>(smem + IntSmem::SCHED);
   const float* wcum_s = reinterpret_cast<const float*>(smem + IntSmem::WCUM);
@@ -179,8 +218,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   if (threadIdx.x == 0) {
     for (int s = 0; s < IT_VSTAGES; s++) { mbar_init(&v_full[s], IT_BUILDERS); mbar_init(&v_empty[s], 1); }
     for (int s = 0; s < IT_USTAGES; s++) { mbar_init(&u_full[s], 1); mbar_init(&u_empty[s], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_free, IT_EPI_WARPS);
+    for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_free[a], IT_EPI_WARPS / 2); }
     mbar_fence_init();
   }
   if (warp == 1) {   // TMEM: all 512 columns (1 CTA per SM)
@@ -212,12 +250,17 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
-          mbar_wait_spin(&u_empty[s], par);
-          mbar_arrive_expect_tx(&u_full[s], nft * IT_U_TILE);
-          for (int ft = 0; ft < nft; ft++)
-            tma_bulk_g2s(uring + s * IT_U_BYTES + ft * IT_U_TILE,
-                         p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE, &u_full[s]);
-          if (++s == IT_USTAGES) { s = 0; par ^= 1; }
+          for (int ft = 0; ft < nft; ft++) {
+            mbar_wait_spin(&u_empty[s], par);
+            if (p.dbg & 64) {   // timing experiment: no feature-operand traffic
+              mbar_arrive(&u_full[s]);
+            } else {
+              mbar_arrive_expect_tx(&u_full[s], IT_U_TILE);
+              tma_bulk_g2s(uring + s * IT_U_TILE, p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE,
+                           &u_full[s]);
+            }
+            if (++s == IT_USTAGES) { s = 0; par ^= 1; }
+          }
         }
       }
     }
@@ -226,33 +269,43 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(IT_FT, IT_TOK);
-      uint32_t vs = 0, vpar = 0, us = 0, upar = 0, free_par = 0;
+      uint32_t vs = 0, vpar = 0, us = 0, upar = 0;
+      uint32_t free_par0 = 0, free_par1 = 0;
+      bool pend0 = false, pend1 = false;   // accumulator a was handed to its epilogue warps and not yet taken back
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
-          mbar_wait_spin(&u_full[us], upar);
+          const bool is_cut = sched[kb].cut >= 0;
           mbar_wait_spin(&v_full[vs], vpar);
-          tc_fence_after();
-          for (int ft = 0; ft < ((p.dbg & 8) ? 0 : nft); ft++) {
-            const uint64_t ad = umma_desc_sw128(uring + us * IT_U_BYTES + ft * IT_U_TILE);
-            const uint64_t bd = umma_desc_sw128(vring + vs * IT_V_BYTES);
+          const uint64_t bd = umma_desc_sw128(vring + vs * IT_V_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
-              umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          }
-          tc_commit(&v_empty[vs]);
-          tc_commit(&u_empty[us]);
-          if (sched[kb].cut >= 0) {   // pause: the epilogue reads the running prefix
-            tc_commit(acc_full);
-            if (!(p.dbg & 4)) {
-              mbar_wait_spin(acc_free, free_par);
+          for (int ft = 0; ft < 2; ft++) {
+            if (ft >= nft) break;
+            mbar_wait_spin(&u_full[us], upar);
+            bool& pend = ft ? pend1 : pend0;
+            uint32_t& free_par = ft ? free_par1 : free_par0;
+            if (pend) {   // the epilogue of the previous cut (or of the previous unit's last cut) still owns this accumulator
+              if (!(p.dbg & 4)) mbar_wait_spin(&acc_free[ft], free_par);
               free_par ^= 1;
-              tc_fence_after();
+              pend = false;
+            }
+            tc_fence_after();
+            if (!(p.dbg & 8)) {
+              const uint64_t ad = umma_desc_sw128(uring + us * IT_U_TILE);
+#pragma unroll
+              for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
+                umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            }
+            tc_commit(&u_empty[us]);
+            if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
+            if (is_cut) {   // the running prefix of this accumulator goes to its epilogue warps; the other one carries on
+              tc_commit(&acc_full[ft]);
+              pend = true;
             }
           }
+          tc_commit(&v_empty[vs]);
           if (++vs == IT_VSTAGES) { vs = 0; vpar ^= 1; }
-          if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
         }
       }
     }
@@ -332,21 +385,25 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     // ======================= epilogue =======================
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int acc = (warp - 6) >> 2;   // accumulator (feature tile of the pair)
-    const uint32_t stg = smem_u32(smem + IntSmem::STG) + (warp - 6) * IT_STG_WARP;
+    uint64_t* const my_full = &acc_full[acc];
+    uint64_t* const my_free = &acc_free[acc];
+    // this lane's row of the staging area: 128 tokens of fp16 (one half of the unit's 256), written and read by nobody else
+    const uint32_t stg = smem_u32(smem + IntSmem::STG) + (uint32_t)(acc * IT_FT + q * 32 + lane) * IT_STG_PITCH;
+    const uint64_t pol = l2_policy_evict_first();   // the intensities are a stream: keep the U tiles and code rows in L2
     uint32_t full_par = 0;
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int pr = (int)(u % n_pairs);
       const long long tok0 = (u / n_pairs) * IT_TOK;
       const int nft = min(2, p.F_tiles - 2 * pr);
-      const bool live = acc < nft;
+      if (acc >= nft) continue;   // no such feature tile: the issuer does not signal this accumulator in this unit
       for (int kb = 0; kb < p.NKB; kb++) {
         const int cut = sched[kb].cut;
         if (cut < 0) continue;
-        mbar_wait(acc_full, full_par);
+        mbar_wait_spin(my_full, full_par);
         full_par ^= 1;
         tc_fence_after();
-        if (!live || (p.dbg & 16)) {
-          if (lane == 0) mbar_arrive(acc_free);
+        if (p.dbg & 16) {
+          if (lane == 0) mbar_arrive(my_free);
           continue;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * IT_TOK;
@@ -362,7 +419,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
             if (ch == IT_TOK / 32 - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(acc_free);
+              if (lane == 0) mbar_arrive(my_free);
             }
             float* o = p.q_out + (size_t)(tok0 + ch * 32) * p.D + d;
             if (d < p.D && !(p.dbg & 1)) {
@@ -374,45 +431,60 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           continue;
         }
         const float inv = wcum_s[p.n_cuts + cut];
-        // After the reference's roundings the warp's 32 features x 32 tokens go through a private staging
-        // tile so that a store instruction writes 8 rows x 64 contiguous bytes instead of 32 rows x 16.
-        const int frow0 = (2 * pr + acc) * IT_FT + q * 32;
-        const size_t row_stride = (size_t)p.n_cuts * (size_t)p.out_stride;
-        __half* obase = p.out + ((size_t)frow0 * p.n_cuts + cut) * (size_t)p.out_stride + tok0 + (lane & 3) * 8;
-#pragma unroll 1
-        for (int ch = 0; ch < IT_TOK / 32; ch++) {
+        const int frow = (2 * pr + acc) * IT_FT + q * 32 + lane;
+        const bool row_live = frow < p.F && !(p.dbg & 1);
+        __half* const orow = p.out + ((size_t)frow * p.n_cuts + cut) * (size_t)p.out_stride + tok0;
+        // (1) tokens 0..127 of the row: first rounding only (prefix -> fp16), kept packed in registers
+        uint32_t keep[64];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
           uint32_t v[32];
           tmem_ld32(taddr + ch * 32, v);
           tmem_ld_wait();
-          if (ch == IT_TOK / 32 - 1) {   // everything is in registers: let the MMA issuer go on
+#pragma unroll
+          for (int j = 0; j < 16; j++) keep[ch * 16 + j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        }
+        // (2) tokens 128..255: finished and staged; the staging row must have been read by the previous cut's stores
+        bulk_wait_read_all();
+#pragma unroll
+        for (int ch = 8; ch < 16; ch++) {   // 16 columns at a time: the kept half leaves few registers
+          uint32_t v[16];
+          tmem_ld16(taddr + ch * 16, v);
+          tmem_ld_wait();
+          if (ch == 15) {   // the whole prefix has left TMEM: the issuer may accumulate into it again
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_free);
+            if (lane == 0) mbar_arrive(my_free);
           }
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
+          for (int g = 0; g < 2; g++) {
             const uint32_t o0 = finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), inv);
             const uint32_t o1 = finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), inv);
             const uint32_t o2 = finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), inv);
             const uint32_t o3 = finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), inv);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * IT_STG_PITCH + g * 16), "r"(o0), "r"(o1),
-                         "r"(o2), "r"(o3)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (ch - 8) * 32 + g * 16), "r"(o0), "r"(o1), "r"(o2),
+                         "r"(o3)
                          : "memory");
           }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int r = i * 8 + (lane >> 2);
-            uint4 o;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                         : "r"(stg + r * IT_STG_PITCH + (lane & 3) * 16));
-            if (frow0 + r < p.F && !(p.dbg & 1)) __stcs(reinterpret_cast<uint4*>(obase + (size_t)r * row_stride + ch * 32), o);
-          }
-          __syncwarp();
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's generic-proxy writes -> visible to the bulk copy
+        if (row_live) tma_bulk_s2g(orow + 128, stg, 256, pol);
+        bulk_commit();
+        // (3) the kept half: remaining roundings in registers while the first store drains, then the same row again
+#pragma unroll
+        for (int j = 0; j < 64; j++) keep[j] = finish_packed(keep[j], inv);
+        bulk_wait_read_all();
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + j * 16), "r"(keep[4 * j]), "r"(keep[4 * j + 1]),
+                       "r"(keep[4 * j + 2]), "r"(keep[4 * j + 3])
+                       : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (row_live) tma_bulk_s2g(orow, stg, 256, pol);
+        bulk_commit();
       }
     }
+    bulk_wait_all();   // the staging rows are read, and the rows written, before the CTA retires
   }
 
   // ---- teardown ----
