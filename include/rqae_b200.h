@@ -240,6 +240,10 @@ int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* code
  * the FMA pipe deliver for the kernel's instruction mix. */
 int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, float* sink, void* stream);
 
+/* Measurement helper: per-CTA clock counters (16 x uint64 per CTA, meaning in rq_intensity.cuh) written by the last
+ * rqae_intensity_f16 launch that ran with the environment variable RQAE_INT_DBG having bit 1024 set; synchronises. */
+int rqae_intensity_profile(uint64_t* out_host, int n_ctas);
+
 /* Number of kernels this library has launched on this thread since the last reset
  * (bench.py reports it as gpu_launches). */
 int64_t rqae_launch_count(int reset);

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("RQAE_B200_LIB") or os.path.join(_HERE, "librqae_b200.
 SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
     "rqae_forward_f32", "rqae_forward_variant", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_forward_host_mode", "rqae_widen_codes_host", "rqae_forward_host_release",
-    "rqae_fp32_peak_probe",
+    "rqae_fp32_peak_probe", "rqae_intensity_profile",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
     "rqae_search_table_bytes", "rqae_search_build_table_f16", "rqae_search_accumulate_f16", "rqae_search_position_max_f16",
@@ -70,6 +70,8 @@ def load() -> ctypes.CDLL:
     lib.rqae_forward_host_release.argtypes = []
     lib.rqae_fp32_peak_probe.restype = i
     lib.rqae_fp32_peak_probe.argtypes = [i, i, c.POINTER(c.c_double), vp, vp]
+    lib.rqae_intensity_profile.restype = i
+    lib.rqae_intensity_profile.argtypes = [vp, i]
     lib.rqae_intensity_workspace_bytes.restype = sz
     lib.rqae_intensity_workspace_bytes.argtypes = [vp, i, i, i64]
     lib.rqae_intensity_f16.restype = i

@@ -14,25 +14,30 @@
 // numerators differ by rounding noise (tests state the tolerance); the roundings AFTER the sum -- prefix to
 // fp16, fp32 divide by the fp16 weight prefix, quotient to fp16 -- are the reference's own.
 //
-// One CTA (448 threads, 1 per SM, persistent) computes units of 256 tokens x 256 features (two feature tiles
-// of 128 = two 128x256 fp32 accumulators = all 512 TMEM columns):
+// One CTA (640 threads = 5 warpgroups, 1 per SM, persistent) computes units of 256 tokens x 256 features (two feature
+// tiles of 128 = two 128x256 fp32 accumulators = all 512 TMEM columns):
 //   warp 0      U producer : one lane, bulk-TMA copies of pre-swizzled 128x64 fp16 tiles (16 KB) from L2, one ring
 //                            stage per tile
-//   warp 1      MMA issuer : one lane, tcgen05.mma M=128 (features) x N=256 (tokens) x K=16, 4 per tile and
-//                            K-block; owns the TMEM allocation
-//   warps 2-5   V builders : the token operand never exists in memory: each thread turns the codes of two tokens
-//                            (layer-major int16, coalesced) into 128-byte K-major rows through a 4 x fp16
-//                            lookup table in shared memory, written in the 128-byte swizzle the MMA expects
-//   warps 6-13  epilogue   : four warps per accumulator.  At a cut the issuer commits that accumulator and goes on
+//   warp 1      MMA issuer : tcgen05.mma M=128 (features) x N=256 (tokens) x K=16, 4 per tile and K-block, issued by
+//                            one elected lane of a warp-uniform loop; owns the TMEM allocation (warps 2-3 idle)
+//   warps 4-11  V builders : the token operand never exists in memory: each thread turns the codes of ONE token
+//                            (layer-major int16, coalesced) into a 128-byte K-major row through a 4 x fp16 lookup
+//                            table in shared memory (four interleaved copies against bank conflicts), written in the
+//                            128-byte swizzle the MMA expects.  (Per-role clock counters: 4 builder warps with two
+//                            rows each needed 1.9 k clocks per K-block against 1.4 k for the MMAs; two groups of four
+//                            warps building alternate K-blocks into one stage each were slower still, 1.9 k, because
+//                            a group cannot build under its own stage's MMAs.)
+//   warps 12-19 epilogue   : four warps per accumulator.  At a cut the issuer commits that accumulator and goes on
 //                            with the other one; the warps pull the running prefix out of TMEM (tcgen05.ld
-//                            32x32b.x32) -- half of it as packed fp16 into registers, half through the reference's
-//                            fp16 roundings into a shared-memory row -- and release the accumulator as soon as the
-//                            last load has landed.  The rows of out[f][cut][t] then leave shared memory as bulk
-//                            TMA stores (each lane owns one feature row: no cross-thread hand-over) while the MMAs
-//                            of the next K-blocks run.
+//                            32x32b.x32) with only the reference's FIRST rounding applied (prefix -> fp16) -- half
+//                            into registers, half into shared memory -- and release the accumulator as soon as the
+//                            last load has landed.  The remaining roundings and the stores (TMA tensor stores of
+//                            [32 features][64 tokens] boxes of out[f][cut][t]) run while the MMAs of the next K-blocks do.
+// setmaxnreg gives the control warpgroup 40 registers, the builders 80 and the epilogue 136 per thread.
 // The K axis is cut into K-blocks of 16 layers (64 k = one 128-byte swizzle row); a segment between two cuts
 // that is not a multiple of 16 layers is padded with zero slots (schedule built by int_prep_kernel).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "rq_common.cuh"
@@ -43,17 +48,23 @@ constexpr int IT_TOK = 256;                     // tokens per unit = MMA N
 constexpr int IT_FT = 128;                      // features per tile = MMA M
 constexpr int IT_LPB = 16;                      // layers per K-block (64 k values, 128 bytes of fp16)
 constexpr int IT_VSTAGES = 2;                   // token operand: built locally, latency = the builders' own work
-constexpr int IT_USTAGES = 5;                   // feature operand: bulk copies from L2, one 16 KB tile per stage (2.5 K-blocks ahead)
+constexpr int IT_USTAGES = 4;                   // feature operand: bulk copies from L2, one 16 KB tile per stage (2 K-blocks ahead)
 constexpr int IT_V_BYTES = IT_TOK * 128;        // 32 KB
 constexpr int IT_U_TILE = IT_FT * 128;          // 16 KB
 constexpr int IT_MAX_CUTS = 64;
 constexpr int IT_MAX_KB = 200;                  // nq = 1024 in three passes (decode, f16x3) is 192 K-blocks
-constexpr int IT_LUT_ROWS = 640;                // codebook rows + the zero row must fit (5^4 + 1); two tables
-constexpr int IT_STG_PITCH = 272;               // bytes per staged row: 128 tokens fp16 + 16 (lane-strided 128-bit stores hit 8 distinct 16-byte slots)
-constexpr int IT_STG_ROWS = 2 * IT_FT;          // one row per TMEM lane of both accumulators
-constexpr int IT_THREADS = 448;
+constexpr int IT_LUT_ROWS = 640;                // codebook rows + the zero row must fit (5^4 + 1); two tables (decode f16x3: hi, lo)
+constexpr int IT_LUT_COPIES = 4;                // intensity kernel: interleaved copies of the one table it uses, copy = lane & 3 --
+                                                // entry (row, copy) sits in 8-byte bank pair (4 row + copy) & 15, so the 16 lanes of a
+                                                // half-warp collide 4-into-4 instead of 16-into-16 (2.1 against 3.1 wavefronts per load)
+constexpr int IT_STG_BOX = 32 * 128;            // staged box of a tensor-map store: 32 feature rows x 64 tokens fp16, 128-byte swizzle
+constexpr int IT_STG_WARP = 2 * IT_STG_BOX;     // per epilogue warp: its 32 rows x 128 tokens (half of the unit's 256)
+constexpr int IT_THREADS = 640;              // 5 warpgroups: control, builders x 2, epilogue x 2 (setmaxnreg re-splits the register file)
 constexpr int IT_EPI_WARPS = 8;
-constexpr int IT_BUILDERS = 128;
+// register pool: ptxas compiles for 640 threads at 96 registers = 61 440; setmaxnreg can only re-split that pool
+constexpr int IT_REG_CTRL = 40, IT_REG_BUILD = 80, IT_REG_EPI = 136;
+static_assert(128 * IT_REG_CTRL + 256 * IT_REG_BUILD + 256 * IT_REG_EPI <= IT_THREADS * 96, "register pool budget");
+constexpr int IT_BUILDERS = 256;             // one token row per builder thread
 
 struct IntKBlock {   // one K-block of the schedule: layers l0 .. l0+n-1 (n <= 16), the rest of the 16 slots zero
   int l0, n, cut, tab;   // cut >= 0: this block ends the segment of that cut (the epilogue emits it);
@@ -78,20 +89,22 @@ struct IntParams {
   const float* bias;
   long long T;
   int D;
-  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start, 64 no feature-operand copies
+  int stagger;   // clocks per start group with dbg bit 32
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start, 64 no feature-operand copies, 128 no code loads, 256 no proxy fence in the builders, 512 no L2 prefetch of code rows, 1024 per-role clock counters (g_int_prof)
 };
 
 struct IntSmem {
   static constexpr int VRING = 0;
   static constexpr int URING = IT_VSTAGES * IT_V_BYTES;
-  static constexpr int LUT = URING + IT_USTAGES * IT_U_TILE;
-  static constexpr int SCHED = LUT + 2 * IT_LUT_ROWS * 8;
+  static constexpr int STG = URING + IT_USTAGES * IT_U_TILE;   // 1024-byte aligned: the swizzle pattern of the store boxes
+  static constexpr int LUT = STG + IT_EPI_WARPS * IT_STG_WARP;
+  static constexpr int SCHED = LUT + IT_LUT_COPIES * IT_LUT_ROWS * 8;   // >= the decode kernel's two tables
   static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
-  static constexpr int STG = WCUM + 2 * IT_MAX_CUTS * 4;
-  static constexpr int BARS = STG + IT_STG_ROWS * IT_STG_PITCH;
+  static constexpr int BARS = WCUM + 2 * IT_MAX_CUTS * 4;
   static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 4) * 8;
   static constexpr int TOTAL = TMEM_PTR + 16;
 };
+static_assert(IntSmem::STG % 1024 == 0, "store boxes must be 1024-byte aligned");
 static_assert(IntSmem::TOTAL <= 227 * 1024, "shared memory budget");
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------------------
@@ -159,10 +172,12 @@ __device__ __forceinline__ uint32_t finish_packed(uint32_t ph, float inv) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// ---- bulk TMA (1-D): shared -> global, tracked by the issuing thread's bulk async-group (SASS: UBLKCP) ----
-__device__ __forceinline__ void tma_bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem),
-               "r"(bytes), "l"(policy)
+// ---- TMA tensor store: a [32 rows][64 tokens] fp16 box, shared -> global through a 3-D tensor map of out[f][cut][t]
+// (SASS: UTMASTG); tracked by the issuing thread's bulk async-group.  One instruction moves 4 KB; rows beyond the
+// tensor's extent (features >= F) are clipped by the hardware.
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, uint32_t src_smem, int tok, int cut, int frow, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(tmap),
+               "r"(tok), "r"(cut), "r"(frow), "r"(src_smem), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -172,6 +187,17 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+
+// one lane of a converged warp (the same one every time): tcgen05.commit tracks the MMAs of the thread that issues it
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // latency-critical waits (MMA issuer, producers): poll without the suspend hint
@@ -188,11 +214,19 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// Per-CTA clock counters of the last launch run with dbg bit 1024 (measurement only; read by rqae_intensity_profile):
+// [0] issuer: waiting for a token stage, [1] for a feature tile, [2] for an accumulator, [3] issuer total,
+// [4] builder: waiting for a free stage, [5] look-ups and stores, [6] builder total,
+// [7] epilogue warp: waiting for a cut, [8] holding the accumulator, [9] waiting for its stores to read, [10] epilogue total,
+// [11] feature-tile producer: waiting for a free stage, [12] producer total.
+constexpr int IT_PROF_SLOTS = 16;
+__device__ unsigned long long g_int_prof[256 * IT_PROF_SLOTS];
+
 // EPI = 0: feature intensities (fp16 out[f][cut][t] with the reference's roundings).
 // EPI = 1: tensor-core decode -- "features" are the D output dimensions, U holds W_out, one cut at the last layer,
 //          out is q_out[t][d] fp32 (+ the summed out-projection biases); opt-in, not bit-exact (rq_decode.cuh is).
 template <int EPI>
-__global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p) {
+__global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + IntSmem::BARS);
@@ -208,8 +242,14 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i <= p.K; i += IT_THREADS) {
-    reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
-    if (EPI == 1) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
+    if (EPI == 1) {
+      reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
+      reinterpret_cast<uint2*>(smem + IntSmem::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
+    } else {
+      const uint2 r = p.lut[i];
+#pragma unroll
+      for (int t = 0; t < IT_LUT_COPIES; t++) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i * IT_LUT_COPIES + t] = r;
+    }
   }
   for (int i = threadIdx.x; i < p.NKB * 4; i += IT_THREADS)
     reinterpret_cast<int*>(smem + IntSmem::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
@@ -232,9 +272,12 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 
   const int n_pairs = (p.F_tiles + 1) / 2;
   const long long n_units = p.n_tok_tiles * n_pairs;
+  const bool prof = (p.dbg & 1024) != 0 && blockIdx.x < 256;
+  unsigned long long* const pr_out = g_int_prof + (size_t)(blockIdx.x & 255) * IT_PROF_SLOTS;
+  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
   if (p.dbg & 32) {   // experiment: de-phase the CTAs so that their store-bound early cuts do not coincide
     const long long t0 = clock64();
-    const long long d = (long long)(blockIdx.x % 4) * 80000;
+    const long long d = (long long)(blockIdx.x % 4) * p.stagger;
     while (clock64() - t0 < d) {
     }
     __syncthreads();
@@ -242,16 +285,23 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   const uint32_t vring = smem_u32(smem + IntSmem::VRING), uring = smem_u32(smem + IntSmem::URING);
   if (vring & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
 
+  // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code it dominates)
+  if (warp < 4) {
+    reg_dec<IT_REG_CTRL>();
   if (warp == 0) {
     // ======================= U producer =======================
     if (lane == 0) {
       uint32_t s = 0, par = 1;   // a fresh barrier passes a wait on parity 1
+      long long w_e = 0;
+      const long long t_begin = tick();
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
           for (int ft = 0; ft < nft; ft++) {
+            const long long t0 = tick();
             mbar_wait_spin(&u_empty[s], par);
+            w_e += tick() - t0;
             if (p.dbg & 64) {   // timing experiment: no feature-operand traffic
               mbar_arrive(&u_full[s]);
             } else {
@@ -263,91 +313,119 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           }
         }
       }
+      if (prof) { pr_out[11] = (unsigned long long)w_e; pr_out[12] = (unsigned long long)(tick() - t_begin); }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow: descriptors, stage counters and barrier addresses stay in
+    // uniform registers) and ONE elected lane issues the MMAs and commits.  With the loop under `if (lane == 0)` the
+    // compiler moved every operand through ELECT / R2UR sequences: ~290 dependent instructions per K-block, more
+    // than the MMAs themselves take (ncu source view, profiles/r2r_intensity_stalls.txt).
+    {
       constexpr uint32_t idesc = umma_idesc_f16(IT_FT, IT_TOK);
       uint32_t vs = 0, vpar = 0, us = 0, upar = 0;
       uint32_t free_par0 = 0, free_par1 = 0;
       bool pend0 = false, pend1 = false;   // accumulator a was handed to its epilogue warps and not yet taken back
+      const bool no_mma = (p.dbg & 8) != 0, no_pause = (p.dbg & 4) != 0;
+      long long w_v = 0, w_u = 0, w_f = 0;
+      const long long t_begin = tick();
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int pr = (int)(u % n_pairs);
         const int nft = min(2, p.F_tiles - 2 * pr);
         for (int kb = 0; kb < p.NKB; kb++) {
           const bool is_cut = sched[kb].cut >= 0;
+          long long t0 = tick();
           mbar_wait_spin(&v_full[vs], vpar);
+          w_v += tick() - t0;
           const uint64_t bd = umma_desc_sw128(vring + vs * IT_V_BYTES);
 #pragma unroll
           for (int ft = 0; ft < 2; ft++) {
             if (ft >= nft) break;
+            t0 = tick();
             mbar_wait_spin(&u_full[us], upar);
+            w_u += tick() - t0;
             bool& pend = ft ? pend1 : pend0;
             uint32_t& free_par = ft ? free_par1 : free_par0;
             if (pend) {   // the epilogue of the previous cut (or of the previous unit's last cut) still owns this accumulator
-              if (!(p.dbg & 4)) mbar_wait_spin(&acc_free[ft], free_par);
+              t0 = tick();
+              if (!no_pause) mbar_wait_spin(&acc_free[ft], free_par);
+              w_f += tick() - t0;
               free_par ^= 1;
               pend = false;
             }
             tc_fence_after();
-            if (!(p.dbg & 8)) {
-              const uint64_t ad = umma_desc_sw128(uring + us * IT_U_TILE);
+            const uint64_t ad = umma_desc_sw128(uring + us * IT_U_TILE);
+            if (elect_one()) {
+              if (!no_mma) {
 #pragma unroll
-              for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
-                umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; k++)   // 16 k values = 32 bytes inside the swizzle row: start address += 2 (x16 B)
+                  umma_f16(tmem_base + ft * IT_TOK, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+              }
+              tc_commit(&u_empty[us]);
+              if (is_cut) tc_commit(&acc_full[ft]);   // the running prefix goes to its epilogue warps; the other accumulator carries on
             }
-            tc_commit(&u_empty[us]);
+            __syncwarp();
             if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
-            if (is_cut) {   // the running prefix of this accumulator goes to its epilogue warps; the other one carries on
-              tc_commit(&acc_full[ft]);
-              pend = true;
-            }
+            pend = is_cut;
           }
-          tc_commit(&v_empty[vs]);
+          if (elect_one()) tc_commit(&v_empty[vs]);
+          __syncwarp();
           if (++vs == IT_VSTAGES) { vs = 0; vpar ^= 1; }
         }
       }
+      if (prof && lane == 0) {
+        pr_out[0] = (unsigned long long)w_v; pr_out[1] = (unsigned long long)w_u; pr_out[2] = (unsigned long long)w_f;
+        pr_out[3] = (unsigned long long)(tick() - t_begin);
+      }
     }
-    __syncwarp();
-  } else if (warp < 6) {
+  }   // warps 2-3: spare warps of the control warpgroup
+  } else if (warp < 12) {
     // ======================= V builders =======================
-    const int b = threadIdx.x - 64;   // rows b and b + 128 of the token tile
-    const uint32_t lut = smem_u32(smem + IntSmem::LUT);
-    const uint32_t row_off0 = b * 128, row_off1 = (b + 128) * 128;
-    const uint32_t sw = (uint32_t)(b & 7);   // (b + 128) & 7 is the same
+    reg_dec<IT_REG_BUILD>();
+    const int b = threadIdx.x - 128;   // row b of the token tile
+    const uint32_t lut = smem_u32(smem + IntSmem::LUT) + (EPI == 0 ? (uint32_t)(lane & (IT_LUT_COPIES - 1)) * 8u : 0u);
+    constexpr uint32_t lut_pitch = EPI == 0 ? 8u * IT_LUT_COPIES : 8u;
+    const uint32_t row_off = b * 128;
+    const uint32_t sw = (uint32_t)(b & 7);
+    const uint32_t csh = (uint32_t)(b >> 7) * 16u;   // the code word holds token (b & 127) in its low and token (b & 127) + 128 in its high half
     uint32_t s = 0, par = 1;
-    // The codes of a K-block are 16 coalesced 128-byte warp loads (one word = the thread's two tokens).  They are
-    // requested TWO K-blocks ahead into registers, and the K-block IT_PF steps ahead is pulled into L2 with one
-    // bulk prefetch: the code rows stream from HBM and their latency must stay off the V hand-over path.
-    struct Pos { long long u; int kb; };
-    auto next = [&](Pos& q) { if (++q.kb == p.NKB) { q.kb = 0; q.u += gridDim.x; } };
+    long long bw_e = 0, bw_b = 0;
+    const long long bt_begin = tick();
+    // The codes of a K-block are 16 coalesced 128-byte warp loads.  They are requested TWO K-blocks ahead into
+    // registers, and the K-block IT_PF steps ahead is pulled into L2 with one bulk prefetch: the code rows stream
+    // from HBM and their latency must stay off the V hand-over path.
+    struct Pos { long long u; int kb; long long tile; };   // tile = u / n_pairs, divided once per unit (a 64-bit division per K-block showed up as ~400 clocks)
+    auto next = [&](Pos& q) { if (++q.kb == p.NKB) { q.kb = 0; q.u += gridDim.x; q.tile = q.u / n_pairs; } };
     auto fetch = [&](uint32_t (&c)[IT_LPB], const Pos& q) {
       const uint32_t padw = (uint32_t)p.K | ((uint32_t)p.K << 16);
-      if (q.u < n_units) {
+      if (q.u < n_units && !(p.dbg & 128)) {
         const int l0 = sched[q.kb].l0, n = sched[q.kb].n;
-        const uint32_t* src = p.codes_p + ((size_t)(q.u / n_pairs) * p.L + l0) * 128 + b;
+        const uint32_t* src = p.codes_p + ((size_t)q.tile * p.L + l0) * 128 + (b & 127);
 #pragma unroll
         for (int i = 0; i < IT_LPB; i++) c[i] = (i < n) ? __ldg(src + i * 128) : padw;
       }
     };
     auto l2_prefetch = [&](const Pos& q) {
-      if (b == 0 && q.u < n_units) {
+      if (b == 0 && q.u < n_units && !(p.dbg & 512)) {
         const int l0 = sched[q.kb].l0, n = sched[q.kb].n;
-        const uint32_t* src = p.codes_p + ((size_t)(q.u / n_pairs) * p.L + l0) * 128;
+        const uint32_t* src = p.codes_p + ((size_t)q.tile * p.L + l0) * 128;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * 512) : "memory");
       }
     };
     auto step = [&](uint32_t (&c)[IT_LPB], const Pos& now, Pos& fut, Pos& pf) {
-      uint32_t a0[IT_LPB], a1[IT_LPB];   // table byte offsets of this block's two rows
+      uint32_t a0[IT_LPB];   // table byte offsets of this block's row
       const uint32_t tsel = (EPI == 1) ? (uint32_t)(sched[now.kb].tab & 1) * (IT_LUT_ROWS * 8u) : 0u;
 #pragma unroll
-      for (int i = 0; i < IT_LPB; i++) { a0[i] = (c[i] & 0xFFFFu) * 8u + tsel; a1[i] = (c[i] >> 16) * 8u + tsel; }
+      for (int i = 0; i < IT_LPB; i++) a0[i] = ((c[i] >> csh) & 0xFFFFu) * lut_pitch + tsel;
       fetch(c, fut);
       next(fut);
       l2_prefetch(pf);
       next(pf);
+      const long long t0 = tick();
       mbar_wait_spin(&v_empty[s], par);
+      const long long t1 = tick();
+      bw_e += t1 - t0;
       const uint32_t vb = vring + s * IT_V_BYTES;
       if (!(p.dbg & 2))
 #pragma unroll
@@ -355,21 +433,17 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         uint32_t x0, x1, x2, x3;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a0[2 * cc]));
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a0[2 * cc + 1]));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off0 + (((uint32_t)cc ^ sw) << 4)), "r"(x0),
-                     "r"(x1), "r"(x2), "r"(x3)
-                     : "memory");
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(lut + a1[2 * cc]));
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(lut + a1[2 * cc + 1]));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off1 + (((uint32_t)cc ^ sw) << 4)), "r"(x0),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + row_off + (((uint32_t)cc ^ sw) << 4)), "r"(x0),
                      "r"(x1), "r"(x2), "r"(x3)
                      : "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      mbar_arrive(&v_full[s]);
+      if (!(p.dbg & 256)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      bw_b += tick() - t1;
+      mbar_arrive(&v_full[s]);   // (one poller and one arrival per warp instead of all threads was measured: slower, the __syncwarps sit on the hand-over path)
       if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
     };
     constexpr int IT_PF = 8;
-    Pos cur = {(long long)blockIdx.x, 0}, fut = cur, pf = cur;
+    Pos cur = {(long long)blockIdx.x, 0, (long long)blockIdx.x / n_pairs}, fut = cur, pf = cur;
     uint32_t cA[IT_LPB], cB[IT_LPB];
     fetch(cA, fut); next(fut);
     fetch(cB, fut); next(fut);
@@ -381,16 +455,29 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
       step(cB, cur, fut, pf);
       next(cur);
     }
+    if (prof && b == 0) {
+      pr_out[4] = (unsigned long long)bw_e; pr_out[5] = (unsigned long long)bw_b; pr_out[6] = (unsigned long long)(tick() - bt_begin);
+    }
   } else {
     // ======================= epilogue =======================
+    reg_inc<IT_REG_EPI>();
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int acc = (warp - 6) >> 2;   // accumulator (feature tile of the pair)
+    const int acc = (warp - 12) >> 2;   // accumulator (feature tile of the pair)
     uint64_t* const my_full = &acc_full[acc];
     uint64_t* const my_free = &acc_free[acc];
-    // this lane's row of the staging area: 128 tokens of fp16 (one half of the unit's 256), written and read by nobody else
-    const uint32_t stg = smem_u32(smem + IntSmem::STG) + (uint32_t)(acc * IT_FT + q * 32 + lane) * IT_STG_PITCH;
+    // The warp's staging area: two store boxes of [32 rows][64 tokens] fp16 (half of the unit's 256 tokens at a time).
+    // Lane = feature row; the 16-byte chunk index inside a 128-byte box row is XOR-ed with (row & 7): the 128-byte
+    // swizzle the tensor map names, and what keeps the lane-strided 128-bit stores free of bank conflicts.
+    const uint32_t wstg = smem_u32(smem + IntSmem::STG) + (uint32_t)(warp - 12) * IT_STG_WARP;
+    const uint32_t stg_row = wstg + (uint32_t)lane * 128u;
+    const uint32_t stg_x = (uint32_t)(lane & 7);
+    auto stg_addr = [&](int j) -> uint32_t {   // chunk j (0..15) of this lane's 128 staged tokens
+      return stg_row + (uint32_t)(j >> 3) * IT_STG_BOX + ((((uint32_t)j & 7u) ^ stg_x) << 4);
+    };
     const uint64_t pol = l2_policy_evict_first();   // the intensities are a stream: keep the U tiles and code rows in L2
     uint32_t full_par = 0;
+    long long ew_f = 0, ew_h = 0, ew_r = 0;
+    const long long et_begin = tick();
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int pr = (int)(u % n_pairs);
       const long long tok0 = (u / n_pairs) * IT_TOK;
@@ -399,7 +486,10 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
       for (int kb = 0; kb < p.NKB; kb++) {
         const int cut = sched[kb].cut;
         if (cut < 0) continue;
-        mbar_wait_spin(my_full, full_par);
+        const long long te0 = tick();
+        mbar_wait(my_full, full_par);   // idle most of the time: suspended wait, no polling traffic next to the builders
+        const long long te1 = tick();
+        ew_f += te1 - te0;
         full_par ^= 1;
         tc_fence_after();
         if (p.dbg & 16) {
@@ -431,10 +521,11 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           continue;
         }
         const float inv = wcum_s[p.n_cuts + cut];
-        const int frow = (2 * pr + acc) * IT_FT + q * 32 + lane;
-        const bool row_live = frow < p.F && !(p.dbg & 1);
-        __half* const orow = p.out + ((size_t)frow * p.n_cuts + cut) * (size_t)p.out_stride + tok0;
-        // (1) tokens 0..127 of the row: first rounding only (prefix -> fp16), kept packed in registers
+        const int frow0 = (2 * pr + acc) * IT_FT + q * 32;   // the warp's 32 feature rows; rows >= F are clipped by the tensor map
+        const bool do_store = lane == 0 && !(p.dbg & 1);
+        // (1) tokens 0..127 of the row: only the reference's FIRST rounding (prefix -> fp16), kept packed in registers;
+        // (2) tokens 128..255: finished and staged (the boxes have been read by the previous cut's stores: that wait
+        // sits at the bottom of this loop, not inside the hold).
         uint32_t keep[64];
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
@@ -444,47 +535,65 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 #pragma unroll
           for (int j = 0; j < 16; j++) keep[ch * 16 + j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         }
-        // (2) tokens 128..255: finished and staged; the staging row must have been read by the previous cut's stores
-        bulk_wait_read_all();
 #pragma unroll
-        for (int ch = 8; ch < 16; ch++) {   // 16 columns at a time: the kept half leaves few registers
-          uint32_t v[16];
-          tmem_ld16(taddr + ch * 16, v);
+        for (int ch = 4; ch < 8; ch++) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
           tmem_ld_wait();
-          if (ch == 15) {   // the whole prefix has left TMEM: the issuer may accumulate into it again
+          if (ch == 7) {   // the whole prefix has left TMEM: the issuer may accumulate into it again
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(my_free);
+            ew_h += tick() - te1;
           }
 #pragma unroll
-          for (int g = 0; g < 2; g++) {
-            const uint32_t o0 = finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), inv);
-            const uint32_t o1 = finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), inv);
-            const uint32_t o2 = finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), inv);
-            const uint32_t o3 = finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), inv);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (ch - 8) * 32 + g * 16), "r"(o0), "r"(o1), "r"(o2),
-                         "r"(o3)
+          for (int g = 0; g < 4; g++)   // all roundings at once: every trip through shared memory competes with the operand traffic
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr((ch - 4) * 4 + g)),
+                         "r"(finish2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), inv)),
+                         "r"(finish2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), inv)),
+                         "r"(finish2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), inv)),
+                         "r"(finish2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), inv))
                          : "memory");
-          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's generic-proxy writes -> visible to the bulk copy
-        if (row_live) tma_bulk_s2g(orow + 128, stg, 256, pol);
-        bulk_commit();
-        // (3) the kept half: remaining roundings in registers while the first store drains, then the same row again
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (do_store) {
+          tma_store_box(&out_map, wstg, (int)tok0 + 128, cut, frow0, pol);
+          tma_store_box(&out_map, wstg + IT_STG_BOX, (int)tok0 + 192, cut, frow0, pol);
+        }
+        if (lane == 0) bulk_commit();
+        // (4) the kept half: remaining roundings in registers while the first stores drain, then the same boxes again
 #pragma unroll
         for (int j = 0; j < 64; j++) keep[j] = finish_packed(keep[j], inv);
-        bulk_wait_read_all();
+        const long long te3 = tick();
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        ew_r += tick() - te3;
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + j * 16), "r"(keep[4 * j]), "r"(keep[4 * j + 1]),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr(j)), "r"(keep[4 * j]), "r"(keep[4 * j + 1]),
                        "r"(keep[4 * j + 2]), "r"(keep[4 * j + 3])
                        : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (row_live) tma_bulk_s2g(orow, stg, 256, pol);
-        bulk_commit();
+        __syncwarp();
+        if (do_store) {
+          tma_store_box(&out_map, wstg, (int)tok0, cut, frow0, pol);
+          tma_store_box(&out_map, wstg + IT_STG_BOX, (int)tok0 + 64, cut, frow0, pol);
+        }
+        if (lane == 0) bulk_commit();
+        // the boxes must have been read before the next cut's prefix is staged: wait here, not while holding TMEM
+        const long long te4 = tick();
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        ew_r += tick() - te4;
       }
     }
-    bulk_wait_all();   // the staging rows are read, and the rows written, before the CTA retires
+    if (lane == 0) bulk_wait_all();   // the boxes are read, and the rows written, before the CTA retires
+    __syncwarp();
+    if (prof && warp == 12 && lane == 0) {
+      pr_out[7] = (unsigned long long)ew_f; pr_out[8] = (unsigned long long)ew_h; pr_out[9] = (unsigned long long)ew_r;
+      pr_out[10] = (unsigned long long)(tick() - et_begin);
+    }
   }
 
   // ---- teardown ----

@@ -1,5 +1,6 @@
 // C ABI of librqae_b200.so (declared in include/rqae_b200.h): weight packing, kernel selection and
 // launch.  Host logic only; the kernels live in rq_forward.cuh / rq_decode.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -986,6 +987,31 @@ int rqae_forward_host_f32(const void* packed, const float* codebook, int codeboo
 // ---------------------------------------------------------------------------------------------
 // feature intensities (rq_intensity.cuh)
 // ---------------------------------------------------------------------------------------------
+// 3-D tensor map of the intensity output out[f][cut][t] (fp16) for the epilogue's TMA stores: box = 32 features x 1 cut
+// x 64 tokens, 128-byte swizzle.  cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime
+// so that the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_out_map(void* out, int64_t out_stride, int n_cuts, int n_features, CUtensorMap* map) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) { g_last_cuda = e != cudaSuccess ? e : cudaErrorSymbolNotFound; return RQAE_ECUDA; }
+    fn = (EncodeTiledFn)f;
+  }
+  const cuuint64_t gdim[3] = {(cuuint64_t)out_stride, (cuuint64_t)n_cuts, (cuuint64_t)n_features};
+  const cuuint64_t gstride[2] = {(cuuint64_t)out_stride * 2, (cuuint64_t)out_stride * 2 * (cuuint64_t)n_cuts};
+  const cuuint32_t box[3] = {64, 1, 32};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda = cudaErrorInvalidValue; return RQAE_ECUDA; }
+  return RQAE_OK;
+}
+
 struct IntLayout {
   int L, NKB, F_tiles;
   long long T_pad;
@@ -1013,6 +1039,12 @@ static int int_layout(const int32_t* cuts, int n_cuts, int F, int64_t n_tokens, 
   o->off_u = off;     off = up(off + (size_t)o->F_tiles * nkb * rq::IT_U_TILE);
   o->off_codes = off; off = up(off + (size_t)o->L * (size_t)o->T_pad * 2);
   o->total = off;
+  return RQAE_OK;
+}
+
+int rqae_intensity_profile(uint64_t* out_host, int n_ctas) {
+  if (!out_host || n_ctas <= 0 || n_ctas > 256) return RQAE_EINVAL;
+  RQ_CUDA(cudaMemcpyFromSymbol(out_host, rq::g_int_prof, (size_t)n_ctas * rq::IT_PROF_SLOTS * sizeof(unsigned long long)));
   return RQAE_OK;
 }
 
@@ -1073,11 +1105,15 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("RQAE_INT_STAGGER"); ip.stagger = e ? atoi(e) : 80000; }
   ip.q_out = nullptr; ip.bias = nullptr; ip.T = n_tokens; ip.D = 0;
   ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
   const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
-  rq::rq_intensity_kernel<0><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
+  CUtensorMap out_map;
+  rc = make_out_map(out, out_stride, n_cuts, n_features, &out_map);
+  if (rc) return rc;
+  rq::rq_intensity_kernel<0><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip, out_map);
   RQ_CUDA(cudaGetLastError());
   g_launches += 4;
   return RQAE_OK;
@@ -1276,9 +1312,12 @@ int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* code
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = 1; ip.F = dim; ip.F_tiles = L.F_tiles;
   ip.n_tok_tiles = L.T_pad / rq::IT_TOK; ip.q_out = q_out; ip.bias = (const float*)(ws + L.off_bias); ip.T = n_tokens; ip.D = dim;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
+  ip.stagger = 0;
   const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
-  rq::rq_intensity_kernel<1><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip);
+  CUtensorMap no_map;
+  memset(&no_map, 0, sizeof(no_map));   // the decode epilogue stores with plain instructions
+  rq::rq_intensity_kernel<1><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip, no_map);
   RQ_CUDA(cudaGetLastError());
   g_launches += 5;
   return RQAE_OK;
