@@ -240,6 +240,32 @@ int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* code
  * the FMA pipe deliver for the kernel's instruction mix. */
 int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, float* sink, void* stream);
 
+/* Tensor-core form of the search maxima (opt-in, NOT bit-exact; replaces the accumulate + per-position max of
+ * demo/server/server.py:204-267 for the RANKING only).  The engine's table is rank 5 per layer, so the accumulation is a
+ * GEMM over (layer, factor) with fp16 factor tables: vtab[l][c] = the dataset-side factor of codeword c at layer l,
+ * utab[l][c] = the same times the layer norm (query side), both [table_layers][640] rows of 8 fp16 (5 used; row K and
+ * the layers beyond the model's zero; table_layers a multiple of 8).
+ *   rqae_search_tc_pack_store   code store (n_seq, seq_len <= 128, code_stride) -> the 8-layer block-major copy the GEMM
+ *                               streams (once per store, not per query)
+ *   rqae_search_tc_maxima_f16   for every range end of `layers_host` (the `layers` list of find_examples):
+ *                               max_out[(c * 128 + q) * max_stride + n] = fp16(max_s sum_{l < layers[c]} table entry),
+ *                               rows = what rqae_select_top_middle_bottom_f16 ranks (row stride max_stride, n = n_seq)
+ *   rqae_search_rows_f16        rows_out[q][j][s] = intensity_accumulation[sel[q][j], s, q] after the first n_ranges
+ *                               ranges, with the reference's exact arithmetic (the rounding points of
+ *                               rqae_search_accumulate_f16), from the table of rqae_search_build_table_f16:
+ *                               server.py:290-305 for the selected sequences only. */
+size_t rqae_search_tc_store_bytes(int64_t n_seq, int nq_codes);
+int rqae_search_tc_pack_store(const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq, int seq_len,
+                              int nq_codes, int K, void* store_tc, size_t store_bytes, void* stream);
+size_t rqae_search_tc_workspace_bytes(const int32_t* layers_host, int n_layers_list);
+int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, int nq_codes, const void* vtab_f16,
+                              const void* utab_f16, int table_layers, int K, const int32_t* query, int64_t query_stride,
+                              int n_query, const int32_t* layers_host, int n_layers_list, void* max_out, int64_t max_stride,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq,
+                         int seq_len, const int32_t* sel, int n_query, int n_sel, const int32_t* layers_host,
+                         int n_ranges, void* rows_out, void* stream);
+
 /* Measurement helper: per-CTA clock counters (16 x uint64 per CTA, meaning in rq_intensity.cuh) written by the last
  * rqae_intensity_f16 launch that ran with the environment variable RQAE_INT_DBG having bit 1024 set; synchronises. */
 int rqae_intensity_profile(uint64_t* out_host, int n_ctas);

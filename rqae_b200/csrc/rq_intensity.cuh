@@ -89,8 +89,15 @@ struct IntParams {
   const float* bias;
   long long T;
   int D;
-  int stagger;   // clocks per start group with dbg bit 32
-  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 32 staggered CTA start, 64 no feature-operand copies, 128 no code loads, 256 no proxy fence in the builders, 512 no L2 prefetch of code rows, 1024 per-role clock counters (g_int_prof)
+  // example-search maxima (EPI = 2): the "features" are the query positions (one tile of 128), the tokens of a unit
+  // are two dataset sequences (128 columns each), the token operand is gathered per layer from a factor table
+  const uint4* s_codes;   // [n_units][L8][256] rows of 8 int16 codes (8-layer block-major copy of the code store)
+  const uint4* s_vtab;    // [L8 * 8][IT_LUT_ROWS] rows of 8 fp16: the dataset-side factors of the layer's table, row K and layers >= L zero
+  __half* s_max;          // [n_cuts][128][s_stride]: max over the positions of every sequence
+  long long s_stride;     // >= 2 * n_units, even
+  int s_len, L8;          // positions per sequence (<= 128), 8-layer blocks per token
+  int stagger;   // clocks between the four start groups of CTAs (0: all together)
+  int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 64 no feature-operand copies, 128 no code loads, 256 no proxy fence in the builders, 512 no L2 prefetch of code rows, 1024 per-role clock counters (g_int_prof)
 };
 
 struct IntSmem {
@@ -218,7 +225,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 // [0] issuer: waiting for a token stage, [1] for a feature tile, [2] for an accumulator, [3] issuer total,
 // [4] builder: waiting for a free stage, [5] look-ups and stores, [6] builder total,
 // [7] epilogue warp: waiting for a cut, [8] holding the accumulator, [9] waiting for its stores to read, [10] epilogue total,
-// [11] feature-tile producer: waiting for a free stage, [12] producer total.
+// [11] feature-tile producer: waiting for a free stage, [12] producer total,
+// [13] epilogue: cut signalled -> first stores issued (includes [8]), [14] roundings of the kept half, [15] first store-read wait + second staging + stores.
 constexpr int IT_PROF_SLOTS = 16;
 __device__ unsigned long long g_int_prof[256 * IT_PROF_SLOTS];
 
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   const float* wcum_s = reinterpret_cast<const float*>(smem + IntSmem::WCUM);
 
   // ---- one-time setup ----
-  for (int i = threadIdx.x; i <= p.K; i += IT_THREADS) {
+  for (int i = threadIdx.x; i <= p.K && EPI != 2; i += IT_THREADS) {
     if (EPI == 1) {
       reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
       reinterpret_cast<uint2*>(smem + IntSmem::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   }
   for (int i = threadIdx.x; i < p.NKB * 4; i += IT_THREADS)
     reinterpret_cast<int*>(smem + IntSmem::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
-  for (int i = threadIdx.x; i < 2 * p.n_cuts; i += IT_THREADS)
+  for (int i = threadIdx.x; i < 2 * p.n_cuts && EPI != 2; i += IT_THREADS)
     reinterpret_cast<float*>(smem + IntSmem::WCUM)[i] = p.wcum[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < IT_VSTAGES; s++) { mbar_init(&v_full[s], IT_BUILDERS); mbar_init(&v_empty[s], 1); }
@@ -275,7 +283,10 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   const bool prof = (p.dbg & 1024) != 0 && blockIdx.x < 256;
   unsigned long long* const pr_out = g_int_prof + (size_t)(blockIdx.x & 255) * IT_PROF_SLOTS;
   auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
-  if (p.dbg & 32) {   // experiment: de-phase the CTAs so that their store-bound early cuts do not coincide
+  if (p.stagger > 0) {
+    // De-phase the CTAs: the first ten cuts of scripts/3's list fall into the first ten K-blocks of a unit, so every
+    // unit begins with a burst of output (1.3 MB per SM) and, started together, all SMs burst together and wait on
+    // HBM writes.  Four start groups a fraction of a unit apart spread the bursts (measured: 1.73 -> 1.63 ms).
     const long long t0 = clock64();
     const long long d = (long long)(blockIdx.x % 4) * p.stagger;
     while (clock64() - t0 < d) {
@@ -383,6 +394,53 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   } else if (warp < 12) {
     // ======================= V builders =======================
     reg_dec<IT_REG_BUILD>();
+    if constexpr (EPI == 2) {
+      // Example search: row b of the tile is position (b & 127) of sequence 2 u + (b >> 7); a K-block is 8 layers x 8 fp16,
+      // one 16-byte factor row per (token, layer) gathered from the L2-resident table.  Per step: store the rows gathered
+      // during the previous step, hand the stage over, then request the next step's rows (their codes were loaded a step
+      // earlier) and the codes of the step after that.
+      const int b = threadIdx.x - 128;
+      const uint32_t row_off = b * 128;
+      const uint32_t sw = (uint32_t)(b & 7);
+      uint32_t s = 0, par = 1;
+      struct Pos { long long u; int kb; };
+      auto next = [&](Pos& q) { if (++q.kb == p.NKB) { q.kb = 0; q.u += gridDim.x; } };
+      auto load_codes = [&](const Pos& q) -> uint4 {
+        if (q.u >= n_units) return make_uint4(0u, 0u, 0u, 0u);
+        return __ldg(p.s_codes + ((size_t)q.u * p.L8 + sched[q.kb].l0) * IT_TOK + b);
+      };
+      auto gather = [&](uint4 (&g)[8], const uint4& c, const Pos& q) {
+        if (q.u >= n_units) return;
+        const uint4* tab = p.s_vtab + (size_t)sched[q.kb].l0 * 8 * IT_LUT_ROWS;
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = __ldg(tab + (size_t)i * IT_LUT_ROWS + ((w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu));
+      };
+      Pos cur = {(long long)blockIdx.x, 0}, p1 = cur, p2;
+      next(p1);
+      p2 = p1;
+      next(p2);
+      uint4 g[8];
+      gather(g, load_codes(cur), cur);
+      uint4 c1 = load_codes(p1);
+      while (cur.u < n_units) {
+        mbar_wait_spin(&v_empty[s], par);
+        const uint32_t vb = vring + s * IT_V_BYTES + row_off;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(vb + (((uint32_t)i ^ sw) << 4)), "r"(g[i].x), "r"(g[i].y),
+                       "r"(g[i].z), "r"(g[i].w)
+                       : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&v_full[s]);
+        if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
+        gather(g, c1, p1);
+        c1 = load_codes(p2);
+        cur = p1;
+        p1 = p2;
+        next(p2);
+      }
+    } else {
     const int b = threadIdx.x - 128;   // row b of the token tile
     const uint32_t lut = smem_u32(smem + IntSmem::LUT) + (EPI == 0 ? (uint32_t)(lane & (IT_LUT_COPIES - 1)) * 8u : 0u);
     constexpr uint32_t lut_pitch = EPI == 0 ? 8u * IT_LUT_COPIES : 8u;
@@ -458,6 +516,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     if (prof && b == 0) {
       pr_out[4] = (unsigned long long)bw_e; pr_out[5] = (unsigned long long)bw_b; pr_out[6] = (unsigned long long)(tick() - bt_begin);
     }
+    }   // EPI != 2
   } else {
     // ======================= epilogue =======================
     reg_inc<IT_REG_EPI>();
@@ -476,7 +535,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     };
     const uint64_t pol = l2_policy_evict_first();   // the intensities are a stream: keep the U tiles and code rows in L2
     uint32_t full_par = 0;
-    long long ew_f = 0, ew_h = 0, ew_r = 0;
+    long long ew_f = 0, ew_h = 0, ew_r = 0, ew_a = 0, ew_b = 0, ew_c = 0;
     const long long et_begin = tick();
     for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int pr = (int)(u % n_pairs);
@@ -497,6 +556,29 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           continue;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * IT_TOK;
+        if (EPI == 2) {
+          // example search: lane = query position, columns = the positions of two sequences; out = max over positions
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int ch = 0; ch < IT_TOK / 32; ch++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == IT_TOK / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(my_free);
+            }
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (((ch & 3) * 32 + j) < p.s_len) m = fmaxf(m, __uint_as_float(v[j]));
+            if (ch < 4) m0 = fmaxf(m0, m); else m1 = fmaxf(m1, m);
+          }
+          const __half2 r = __floats2half2_rn(m0, m1);
+          *reinterpret_cast<__half2*>(p.s_max + ((size_t)cut * IT_FT + q * 32 + lane) * (size_t)p.s_stride + 2 * u) = r;
+          continue;
+        }
         if (EPI == 1) {
           // decode: lane = output dimension d, columns = tokens; a store instruction covers 32 consecutive floats
           const int d = (2 * pr + acc) * IT_FT + q * 32 + lane;
@@ -562,10 +644,13 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
           tma_store_box(&out_map, wstg + IT_STG_BOX, (int)tok0 + 192, cut, frow0, pol);
         }
         if (lane == 0) bulk_commit();
+        const long long teA = tick();
+        ew_a += teA - te1;   // includes the hold
         // (4) the kept half: remaining roundings in registers while the first stores drain, then the same boxes again
 #pragma unroll
         for (int j = 0; j < 64; j++) keep[j] = finish_packed(keep[j], inv);
         const long long te3 = tick();
+        ew_b += te3 - teA;
         if (lane == 0) bulk_wait_read_all();
         __syncwarp();
         ew_r += tick() - te3;
@@ -583,6 +668,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         if (lane == 0) bulk_commit();
         // the boxes must have been read before the next cut's prefix is staged: wait here, not while holding TMEM
         const long long te4 = tick();
+        ew_c += te4 - te3;   // includes the first store-read wait
         if (lane == 0) bulk_wait_read_all();
         __syncwarp();
         ew_r += tick() - te4;
@@ -593,6 +679,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     if (prof && warp == 12 && lane == 0) {
       pr_out[7] = (unsigned long long)ew_f; pr_out[8] = (unsigned long long)ew_h; pr_out[9] = (unsigned long long)ew_r;
       pr_out[10] = (unsigned long long)(tick() - et_begin);
+      pr_out[13] = (unsigned long long)ew_a; pr_out[14] = (unsigned long long)ew_b; pr_out[15] = (unsigned long long)ew_c;
     }
   }
 

@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 
 #include "rq_common.cuh"
+#include "rq_intensity.cuh"
 
 namespace rq {
 
@@ -225,6 +226,140 @@ __global__ void __launch_bounds__(256) search_posmax_kernel(const SearchMaxParam
     const long long n = n0 + nl;
     if (n < p.out_stride)
       for (int q = qq; q < p.n_query; q += 8) p.out[(size_t)q * p.out_stride + n] = tile[nl][q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core form of the per-position maxima (opt-in, not bit-exact)
+// ---------------------------------------------------------------------------------------------------------
+// The engine's table is rank 5 per layer: subfeature_sims[l][a][b] is the cosine of the affine images of two codewords
+// (rqae/model.py:145-167), i.e. f_l(a) . f_l(b) with unit 5-vectors f_l(c), and server.py:104-115 scales it by the layer
+// norm.  Hence  acc[t][q] = sum_l  F_l[code_t[l]] . (norm_l F_l[qcode_q[l]])  is a dense contraction over k = (l, j):
+// rq_intensity_kernel<2> runs it on the tensor cores with the dataset operand gathered per (token, layer) as ONE
+// 16-byte row (5 values padded to 8) from a 10 MB table instead of the exact kernel's 256-byte row of table entries,
+// keeps the running fp32 prefix in TMEM, and at every cut writes only max over the positions of each sequence.
+// What differs from the reference: the products are not rounded to fp16 table entries and the prefix is not rounded
+// per chunk / range, so a maximum can sit a few fp16 steps from the reference's (tests state the bound); the rows
+// reported for the selected sequences are recomputed exactly by search_rows_kernel below.
+
+// code store (n_seq, seq_len, stride) -> [n_units][L8][256] rows of 8 int16 codes: unit u holds sequences 2u and 2u+1
+// in rows 0..127 / 128..255 (row = position); out-of-range codes, missing positions / sequences / layers -> K (zero row)
+template <typename CT>
+__global__ void __launch_bounds__(256) srch_pack_store_kernel(const CT* __restrict__ codes, long long stride, long long n_seq,
+                                                              int seq_len, int n_layers, int K, int L8, uint4* __restrict__ out) {
+  const long long u = blockIdx.x;
+  const int r = threadIdx.x;
+  const long long seq = 2 * u + (r >> 7);
+  const int pos = r & 127;
+  const bool live = seq < n_seq && pos < seq_len;
+  const CT* src = codes + (live ? (seq * seq_len + pos) * stride : 0);
+  for (int j = blockIdx.y; j < L8; j += gridDim.y) {
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      uint32_t pr[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int l = 8 * j + 2 * h + e;
+        uint32_t v = (uint32_t)K;
+        if (live && l < n_layers) {
+          const long long c = (long long)src[l];
+          if (c >= 0 && c < K) v = (uint32_t)c;
+        }
+        pr[e] = v;
+      }
+      w[h] = pr[0] | (pr[1] << 16);
+    }
+    out[((size_t)u * L8 + j) * 256 + r] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+struct SrchPrepParams {
+  int ends[IT_MAX_CUTS];   // the `layers` list: range c is [ends[c-1], ends[c])
+  int n_cuts;
+  IntKBlock* sched;        // entry: l0 = 8-layer block index, n = lo | hi << 8 (layers [lo, hi) of the block belong to the
+};                         // segment: the query operand is zero outside), cut >= 0 on the last entry of a segment
+
+__global__ void srch_prep_kernel(const SrchPrepParams p) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int kb = 0, a = 0;
+  for (int c = 0; c < p.n_cuts; c++) {
+    const int b = p.ends[c];
+    for (int j = a / 8; j <= (b - 1) / 8; j++) {
+      IntKBlock e;
+      const int lo = max(a, 8 * j) - 8 * j, hi = min(b, 8 * j + 8) - 8 * j;
+      e.l0 = j; e.n = lo | (hi << 8); e.cut = (j == (b - 1) / 8) ? c : -1; e.tab = 0;
+      p.sched[kb++] = e;
+    }
+    a = b;
+  }
+}
+
+// query operand tiles: [NKB] tiles of 128 query positions x 64 k fp16 (8 layers x 8), swizzled like the feature tiles;
+// row q, layer i of entry kb = utab[8 j + i][qcode[q][8 j + i]] inside the entry's layer window, else zero
+__global__ void srch_pack_u_kernel(const int* __restrict__ query, long long query_stride, int n_query, int n_layers, int K,
+                                   const uint4* __restrict__ utab, const IntKBlock* __restrict__ sched, int NKB,
+                                   unsigned char* __restrict__ u_tiles) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= NKB * IT_FT * 8) return;
+  const int i = gid & 7, q = (gid >> 3) & (IT_FT - 1), kb = gid >> 10;
+  const IntKBlock e = sched[kb];
+  const int lo = e.n & 0xFF, hi = e.n >> 8, l = 8 * e.l0 + i;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (q < n_query && i >= lo && i < hi && l < n_layers) {
+    const int c = query[(long long)q * query_stride + l];
+    if (c >= 0 && c < K) v = __ldg(utab + (size_t)l * IT_LUT_ROWS + c);
+  }
+  *reinterpret_cast<uint4*>(u_tiles + (size_t)kb * IT_U_TILE + q * 128 + ((i ^ (q & 7)) << 4)) = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rows[q][j][s] = intensity_accumulation[sel[q][j], s, q] after the ranges ends[0..n_ranges), recomputed with the
+// reference's arithmetic (the roundings of search_accumulate_kernel) for the selected sequences only
+// (server.py:290-305).  One warp per (query position, selected sequence); lanes take the positions.
+// ---------------------------------------------------------------------------------------------------------
+struct SearchRowsParams {
+  const __half* table;      // Qt [layers][K][SR_Q]
+  const void* codes;        // [n_seq][seq_len][code_stride]
+  long long code_stride, n_seq;
+  int seq_len, K, n_query, n_sel, n_ranges;
+  int ends[IT_MAX_CUTS];
+  const int* sel;           // [n_query][n_sel] sequence indices (< 0: skipped, the row is zero-filled)
+  __half* out;              // [n_query][n_sel][seq_len]
+};
+
+template <typename CodeT>
+__global__ void __launch_bounds__(256) search_rows_kernel(const SearchRowsParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)p.n_query * p.n_sel) return;
+  const int q = (int)(wid / p.n_sel);
+  const long long n = p.sel[wid];
+  __half* out = p.out + wid * p.seq_len;
+  const CodeT* __restrict__ codes = (const CodeT*)p.codes;
+  const __half* __restrict__ tab = p.table + q;
+  for (int s = lane; s < p.seq_len; s += 32) {
+    if (n < 0 || n >= p.n_seq) { out[s] = __float2half(0.f); continue; }
+    const CodeT* row = codes + (n * p.seq_len + s) * p.code_stride;
+    __half acc = __float2half(0.f);
+    int a = 0;
+    for (int r = 0; r < p.n_ranges; r++) {
+      const int b = p.ends[r];
+      __half rng = __float2half(0.f);
+      for (int c0 = a; c0 < b; c0 += SR_CHUNK) {
+        const int c1 = (c0 + SR_CHUNK < b) ? c0 + SR_CHUNK : b;
+        float cs = 0.f;
+        for (int l = c0; l < c1; l++) {                                     // fp32 sum, ascending layer order
+          const long long c = (long long)row[l];
+          if (c >= 0 && c < p.K) cs += __half2float(__ldg(tab + ((size_t)l * p.K + (size_t)c) * SR_Q));
+        }
+        const __half h = __float2half_rn(cs);                               // sum(dim=-1) of an fp16 tensor
+        rng = (c0 == a) ? h : __float2half_rn(__half2float(rng) + __half2float(h));    // intensities += chunk (fp16)
+      }
+      acc = (r == 0) ? rng : __float2half_rn(__half2float(acc) + __half2float(rng));   // accumulation += range (fp16)
+      a = b;
+    }
+    out[s] = acc;
   }
 }
 

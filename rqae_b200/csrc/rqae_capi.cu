@@ -1018,6 +1018,8 @@ struct IntLayout {
   size_t off_sched, off_wcum, off_lut, off_u, off_codes, total;
 };
 
+struct IntLayout;
+static long long ip_units(const IntLayout& L);
 static int int_layout(const int32_t* cuts, int n_cuts, int F, int64_t n_tokens, int nq, IntLayout* o) {
   if (!cuts || n_cuts <= 0 || n_cuts > rq::IT_MAX_CUTS || F <= 0 || n_tokens < 0) return RQAE_EINVAL;
   int prev = -1, nkb = 0;
@@ -1047,6 +1049,8 @@ int rqae_intensity_profile(uint64_t* out_host, int n_ctas) {
   RQ_CUDA(cudaMemcpyFromSymbol(out_host, rq::g_int_prof, (size_t)n_ctas * rq::IT_PROF_SLOTS * sizeof(unsigned long long)));
   return RQAE_OK;
 }
+
+static long long ip_units(const IntLayout& L) { return (L.T_pad / rq::IT_TOK) * (long long)((L.F_tiles + 1) / 2); }
 
 size_t rqae_intensity_workspace_bytes(const int32_t* cuts_host, int n_cuts, int n_features, int64_t n_tokens) {
   IntLayout L;
@@ -1105,10 +1109,11 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   ip.sched = (const rq::IntKBlock*)(ws + L.off_sched); ip.wcum = (const float*)(ws + L.off_wcum);
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = n_cuts; ip.F = n_features;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
-  { const char* e = getenv("RQAE_INT_STAGGER"); ip.stagger = e ? atoi(e) : 80000; }
+  const long long units = ip_units(L);
+  // start groups 20 k clocks apart when every CTA has several units to run (RQAE_INT_STAGGER overrides, for experiments)
+  { const char* e = getenv("RQAE_INT_STAGGER"); ip.stagger = e ? atoi(e) : (units >= 4LL * sms && n_cuts >= 4 ? 20000 : 0); }
   ip.q_out = nullptr; ip.bias = nullptr; ip.T = n_tokens; ip.D = 0;
   ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
-  const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
   CUtensorMap out_map;
   rc = make_out_map(out, out_stride, n_cuts, n_features, &out_map);
@@ -1226,6 +1231,132 @@ int rqae_search_position_max_f16(const void* acc, int64_t n_seq, int seq_len, in
   const long long blocks = (out_stride + 31) / 32;
   if (blocks >= (1LL << 31)) return RQAE_EUNSUPPORTED;
   rq::search_posmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mp);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core form of the search maxima (opt-in) and the exact rows of the selected sequences
+// ---------------------------------------------------------------------------------------------
+static int srch_tc_nkb(const int32_t* layers, int n_layers_list, int* nkb_out, int* last_out) {
+  if (!layers || n_layers_list <= 0 || n_layers_list > rq::IT_MAX_CUTS) return RQAE_EINVAL;
+  int a = 0, nkb = 0;
+  for (int c = 0; c < n_layers_list; c++) {
+    const int b = layers[c];
+    if (b <= a) return RQAE_EINVAL;                    // strictly ascending positive range ends
+    nkb += (b - 1) / 8 - a / 8 + 1;
+    a = b;
+  }
+  if (nkb > rq::IT_MAX_KB) return RQAE_EUNSUPPORTED;
+  *nkb_out = nkb;
+  *last_out = a;
+  return RQAE_OK;
+}
+
+size_t rqae_search_tc_store_bytes(int64_t n_seq, int nq_codes) {
+  if (n_seq <= 0 || nq_codes <= 0) return 0;
+  return (size_t)((n_seq + 1) / 2) * (size_t)((nq_codes + 7) / 8) * 256 * 16;
+}
+
+int rqae_search_tc_pack_store(const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq, int seq_len,
+                              int nq_codes, int K, void* store_tc, size_t store_bytes, void* stream) {
+  if (!codes || !store_tc || n_seq <= 0 || seq_len <= 0 || nq_codes <= 0 || K <= 0 || code_stride < nq_codes) return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2 || ((uintptr_t)store_tc & 15)) return RQAE_EINVAL;
+  if (seq_len > 128 || K + 1 > rq::IT_LUT_ROWS) return RQAE_EUNSUPPORTED;
+  if (store_bytes < rqae_search_tc_store_bytes(n_seq, nq_codes)) return RQAE_ESIZE;
+  const long long units = (n_seq + 1) / 2;
+  if (units >= (1LL << 31)) return RQAE_EUNSUPPORTED;
+  const int L8 = (nq_codes + 7) / 8;
+  dim3 grid((unsigned)units, (unsigned)(L8 < 8 ? L8 : 8));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (code_dtype == RQAE_CODE_I64) rq::srch_pack_store_kernel<long long><<<grid, 256, 0, st>>>((const long long*)codes, code_stride, n_seq, seq_len, nq_codes, K, L8, (uint4*)store_tc);
+  else if (code_dtype == RQAE_CODE_I32) rq::srch_pack_store_kernel<int><<<grid, 256, 0, st>>>((const int*)codes, code_stride, n_seq, seq_len, nq_codes, K, L8, (uint4*)store_tc);
+  else rq::srch_pack_store_kernel<short><<<grid, 256, 0, st>>>((const short*)codes, code_stride, n_seq, seq_len, nq_codes, K, L8, (uint4*)store_tc);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
+size_t rqae_search_tc_workspace_bytes(const int32_t* layers_host, int n_layers_list) {
+  int nkb = 0, last = 0;
+  if (srch_tc_nkb(layers_host, n_layers_list, &nkb, &last)) return 0;
+  return 4096 + (size_t)nkb * rq::IT_U_TILE;
+}
+
+int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, int nq_codes, const void* vtab_f16,
+                              const void* utab_f16, int table_layers, int K, const int32_t* query, int64_t query_stride,
+                              int n_query, const int32_t* layers_host, int n_layers_list, void* max_out, int64_t max_stride,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!store_tc || !vtab_f16 || !utab_f16 || !query || !max_out || !workspace || n_seq <= 0 || seq_len <= 0 || K <= 0)
+    return RQAE_EINVAL;
+  if (n_query <= 0 || n_query > rq::IT_FT || seq_len > 128 || K + 1 > rq::IT_LUT_ROWS) return RQAE_EUNSUPPORTED;
+  int nkb = 0, last = 0;
+  int rc = srch_tc_nkb(layers_host, n_layers_list, &nkb, &last);
+  if (rc) return rc;
+  const int L8 = (nq_codes + 7) / 8;
+  if (last > nq_codes || query_stride < last || table_layers < 8 * ((last + 7) / 8)) return RQAE_EINVAL;   // the tables are padded to whole blocks
+  const long long units = (n_seq + 1) / 2;
+  if (max_stride < 2 * units || (max_stride & 7) || ((uintptr_t)max_out & 15)) return RQAE_EINVAL;         // the layout the selection reads
+  if (((uintptr_t)workspace & 1023) || workspace_bytes < rqae_search_tc_workspace_bytes(layers_host, n_layers_list)) return RQAE_ESIZE;
+  if (((uintptr_t)store_tc & 15) || ((uintptr_t)vtab_f16 & 15) || ((uintptr_t)utab_f16 & 15)) return RQAE_EINVAL;
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  rq::SrchPrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int c = 0; c < n_layers_list; c++) pp.ends[c] = layers_host[c];
+  pp.n_cuts = n_layers_list; pp.sched = (rq::IntKBlock*)ws;
+  rq::srch_prep_kernel<<<1, 32, 0, st>>>(pp);
+  RQ_CUDA(cudaGetLastError());
+  {
+    const int total = nkb * rq::IT_FT * 8;
+    rq::srch_pack_u_kernel<<<(total + 255) / 256, 256, 0, st>>>(query, query_stride, n_query, last, K, (const uint4*)utab_f16,
+                                                               (const rq::IntKBlock*)ws, nkb, ws + 4096);
+    RQ_CUDA(cudaGetLastError());
+  }
+  RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_intensity_kernel<2>, rq::IntSmem::TOTAL));
+  rq::IntParams ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.u_tiles = ws + 4096; ip.sched = (const rq::IntKBlock*)ws; ip.K = K; ip.NKB = nkb; ip.n_cuts = n_layers_list;
+  ip.F = n_query; ip.F_tiles = 1; ip.n_tok_tiles = units; ip.L = last; ip.T_pad = units * rq::IT_TOK;
+  ip.s_codes = (const uint4*)store_tc; ip.s_vtab = (const uint4*)vtab_f16; ip.s_max = (__half*)max_out;
+  ip.s_stride = max_stride; ip.s_len = seq_len; ip.L8 = L8; ip.stagger = 0;
+  { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
+  const int grid = (int)(units < sms ? units : sms);
+  CUtensorMap no_map;
+  memset(&no_map, 0, sizeof(no_map));
+  rq::rq_intensity_kernel<2><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip, no_map);
+  RQ_CUDA(cudaGetLastError());
+  g_launches += 3;
+  return RQAE_OK;
+}
+
+int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq,
+                         int seq_len, const int32_t* sel, int n_query, int n_sel, const int32_t* layers_host,
+                         int n_ranges, void* rows_out, void* stream) {
+  if (!table || !codes || !sel || !rows_out || !layers_host || K <= 0 || n_seq <= 0 || seq_len <= 0) return RQAE_EINVAL;
+  if (code_dtype < 0 || code_dtype > 2 || n_query <= 0 || n_sel < 0 || n_ranges <= 0) return RQAE_EINVAL;
+  if (n_query > rq::SR_Q || n_ranges > rq::IT_MAX_CUTS) return RQAE_EUNSUPPORTED;
+  rq::SearchRowsParams rp;
+  memset(&rp, 0, sizeof(rp));
+  int a = 0;
+  for (int r = 0; r < n_ranges; r++) {
+    if (layers_host[r] <= a) return RQAE_EINVAL;
+    rp.ends[r] = a = layers_host[r];
+  }
+  if (code_stride < a) return RQAE_EINVAL;
+  if (n_sel == 0) return RQAE_OK;
+  rp.table = (const __half*)table; rp.codes = codes; rp.code_stride = code_stride; rp.n_seq = n_seq; rp.seq_len = seq_len;
+  rp.K = K; rp.n_query = n_query; rp.n_sel = n_sel; rp.n_ranges = n_ranges; rp.sel = sel; rp.out = (__half*)rows_out;
+  const long long warps = (long long)n_query * n_sel;
+  const unsigned blocks = (unsigned)((warps + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (code_dtype == RQAE_CODE_I64) rq::search_rows_kernel<long long><<<blocks, 256, 0, st>>>(rp);
+  else if (code_dtype == RQAE_CODE_I32) rq::search_rows_kernel<int><<<blocks, 256, 0, st>>>(rp);
+  else rq::search_rows_kernel<short><<<blocks, 256, 0, st>>>(rp);
   RQ_CUDA(cudaGetLastError());
   g_launches++;
   return RQAE_OK;

@@ -44,15 +44,55 @@ def engine_sims(model, mode: str = "projected") -> torch.Tensor:
     return sims.detach().contiguous()
 
 
+TC_ROWS = 640         # rq_intensity.cuh IT_LUT_ROWS: rows per layer of the factor tables (codebook rows + the zero row)
+
+
+def rank_factors(model, mode: str = "projected") -> torch.Tensor:
+    """Unit vectors f_l(c), (nq, K, R) float64, with  table_mode[l][a][b] = f_l(a) . f_l(b)  before the fp16 rounding and
+    the layer norm of server.py:104-115.  "projected" (rqae/model.py:145-167): a subfeature is the affine image
+    W_out[l] c + b_out[l], so its cosine with another one is that of R_l [c; 1] with R_l^T R_l the 5x5 Gram matrix of
+    [W_out[l] | b_out[l]] (R = 5).  "original" (model.py:140-142): the normalised codebook rows themselves (R = 4)."""
+    with torch.no_grad():
+        cb = model.codebook.detach().double()                                                # (nq or 1, K, cd)
+        if mode == "original":
+            f = torch.nn.functional.normalize(cb[0], dim=-1)
+            return f.unsqueeze(0).repeat(model.num_quantizers, 1, 1)
+        if mode != "projected":
+            raise ValueError(f"Invalid mode: {mode}")
+        w = torch.stack([l[1].weight.detach() for l in model.layers]).double()              # (nq, D, cd)
+        b = torch.stack([l[1].bias.detach() for l in model.layers]).double()                # (nq, D)
+        g = torch.cat([w, b.unsqueeze(-1)], dim=-1)
+        m = g.transpose(1, 2) @ g                                                            # (nq, cd+1, cd+1)
+        evals, evecs = torch.linalg.eigh(m)
+        r = evals.clamp_min(0).sqrt().unsqueeze(-1) * evecs.transpose(1, 2)                  # R^T R = M
+        if cb.shape[0] == 1:
+            cb = cb.expand(w.shape[0], -1, -1)
+        x = torch.cat([cb, torch.ones_like(cb[..., :1])], dim=-1)
+        u = x @ r.transpose(1, 2)
+        n = u.norm(dim=-1, keepdim=True)
+        return torch.where(n > 1e-12, u / n.clamp_min(1e-12), torch.zeros_like(u))
+
+
 class IntensityEngine:
     """server.py:71-325.  ``activations``: (N, S, nq) integer CUDA tensor, or a list of such shards (they are
-    concatenated once; the reference keeps the list).  ``sims``: the fp16 table, or ``model`` to build it."""
+    concatenated once; the reference keeps the list).  ``sims``: the fp16 table, or ``model`` to build it.
+
+    ``precision="tc"`` (opt-in, needs ``model``): the per-position maxima that RANK the sequences come from the
+    tensor-core form of the accumulation (``rqae_search_tc_maxima_f16``: the table is rank 5 per layer, fp16 factors,
+    fp32 running prefix, no per-chunk roundings) -- a few fp16 steps from the reference's values, so sequences whose
+    maxima are that close to a window boundary can swap; the ``intensities`` reported for the selected sequences are
+    recomputed with the reference's exact arithmetic (``rqae_search_rows_f16``).  Default ``"exact"``."""
 
     def __init__(self, model=None, activations: Union[torch.Tensor, Sequence[torch.Tensor], None] = None, *,
                  sims: Optional[torch.Tensor] = None, mode: str = "projected", dataset: str = "monology_pile",
-                 model_id: str = "rqae-rqae-round_fsq-cbd4-cbs5-nq1024"):
+                 model_id: str = "rqae-rqae-round_fsq-cbd4-cbs5-nq1024", precision: str = "exact"):
         self.dataset = dataset
         self.model_id = model_id
+        if precision not in ("exact", "tc"):
+            raise ValueError(f"precision must be 'exact' or 'tc', got {precision!r}")
+        if precision == "tc" and model is None:
+            raise ValueError("precision='tc' builds its factor tables from the model: pass model")
+        self.precision = precision
         if sims is None:
             if model is None:
                 raise ValueError("Must specify either model or sims")
@@ -73,6 +113,94 @@ class IntensityEngine:
         if activations.shape[0] == 0 or activations.shape[1] == 0:
             raise ValueError("the code store is empty")
         self.activations = activations.contiguous()
+        if precision == "tc":
+            self._setup_tc(model, mode)
+
+    def _setup_tc(self, model, mode: str) -> None:
+        """Factor tables (fp16, 8 values per row, layers padded to a multiple of 8) and the 8-layer block-major copy of
+        the code store that the GEMM streams; once per engine."""
+        dev = self.sims.device
+        N, S, nq_codes = self.activations.shape
+        nq, K = self.sims.shape[0], self.sims.shape[1]
+        if S > 128 or K + 1 > TC_ROWS:
+            raise NotImplementedError("precision='tc': at most 128 positions per sequence and 639 codebook rows")
+        f = rank_factors(model, mode).to(dev)                                                 # (nq, K, R) float64
+        norms = model.layer_norms.to(dev).double().reshape(-1, 1, 1)
+        lp = (nq + 7) // 8 * 8
+        self._vtab = torch.zeros(lp, TC_ROWS, 8, dtype=torch.float16, device=dev)
+        self._utab = torch.zeros(lp, TC_ROWS, 8, dtype=torch.float16, device=dev)
+        self._vtab[:nq, :K, :f.shape[-1]] = f.to(torch.float16)
+        self._utab[:nq, :K, :f.shape[-1]] = (f * norms).to(torch.float16)
+        lib = _lib.load()
+        nbytes = lib.rqae_search_tc_store_bytes(N, nq_codes)
+        self._store_tc = torch.empty(nbytes // 2, dtype=torch.int16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqae_search_tc_pack_store(self.activations.data_ptr(), _CODE_DTYPE[self.activations.dtype], nq_codes,
+                                                    N, S, nq_codes, K, self._store_tc.data_ptr(), nbytes,
+                                                    torch.cuda.current_stream(dev).cuda_stream), "rqae_search_tc_pack_store")
+
+    def maxima_tc(self, query: torch.Tensor, layers: Sequence[int]) -> torch.Tensor:
+        """(len(layers), Sq, N) fp16: max over the positions of every sequence of the running accumulation after each
+        range of ``layers`` -- ``max_values.T`` of server.py:267 for all cuts, from ONE tensor-core launch (a view of
+        a buffer whose rows are padded: what ``select_top_middle_bottom`` ranks)."""
+        if self.precision != "tc":
+            raise RuntimeError("maxima_tc needs an engine built with precision='tc'")
+        layers = [int(l) for l in layers]
+        if not layers or any(b <= a for a, b in zip([0] + layers[:-1], layers)):
+            raise ValueError("layers must be strictly ascending positive layer indices")
+        N, S, nq_codes = self.activations.shape
+        nq, K = self.sims.shape[0], self.sims.shape[1]
+        if layers[-1] > nq or layers[-1] > nq_codes:
+            raise ValueError(f"max(layers)={layers[-1]} exceeds the {min(nq, nq_codes)} layers of the table / code store")
+        dev = self.sims.device
+        Sq = query.shape[0]
+        lib = _lib.load()
+        lh = torch.tensor(layers, dtype=torch.int32)
+        wbytes = lib.rqae_search_tc_workspace_bytes(lh.data_ptr(), len(layers))
+        if wbytes == 0:
+            raise NotImplementedError("precision='tc': too many layer ranges for one launch")
+        ws = torch.empty(wbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 1024
+        stride = ((N + 1) // 2 * 2 + 7) // 8 * 8
+        out = torch.empty(len(layers), SQ_PAD, stride, dtype=torch.float16, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.rqae_search_tc_maxima_f16(self._store_tc.data_ptr(), N, S, nq_codes, self._vtab.data_ptr(),
+                                                    self._utab.data_ptr(), self._vtab.shape[0], K, query.data_ptr(),
+                                                    query.stride(0), Sq, lh.data_ptr(), len(layers), out.data_ptr(), stride,
+                                                    ws.data_ptr() + off, wbytes, st), "rqae_search_tc_maxima_f16")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return out[:, :Sq, :N]
+
+    def rows_exact(self, table: torch.Tensor, sel: torch.Tensor, layers: Sequence[int]) -> torch.Tensor:
+        """``intensity_accumulation[sel[q, j], :, q]`` after the ranges ``layers`` (server.py:290-305), (Sq, n_sel, S) fp16,
+        recomputed with the reference's arithmetic for the selected sequences only.  ``table``: the query's rows of the
+        engine table (``rqae_search_build_table_f16``); ``sel`` (Sq, n_sel) int32."""
+        N, S, nq_codes = self.activations.shape
+        K = self.sims.shape[1]
+        dev = self.sims.device
+        sel = sel.to(torch.int32).contiguous()
+        Sq, n_sel = sel.shape
+        out = torch.empty(Sq, n_sel, S, dtype=torch.float16, device=dev)
+        lh = torch.tensor([int(l) for l in layers], dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().rqae_search_rows_f16(table.data_ptr(), K, self.activations.data_ptr(),
+                                                       _CODE_DTYPE[self.activations.dtype], nq_codes, N, S, sel.data_ptr(), Sq,
+                                                       n_sel, lh.data_ptr(), len(layers), out.data_ptr(),
+                                                       torch.cuda.current_stream(dev).cuda_stream), "rqae_search_rows_f16")
+        return out
+
+    def _build_table(self, query: torch.Tensor, L: int) -> torch.Tensor:
+        lib = _lib.load()
+        K = self.sims.shape[1]
+        dev = self.sims.device
+        tbytes = lib.rqae_search_table_bytes(L, K)
+        table = torch.empty(tbytes // 2, dtype=torch.float16, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.rqae_search_build_table_f16(self.sims.data_ptr(), K, query.data_ptr(), query.stride(0), query.shape[0],
+                                                      L, table.data_ptr(), tbytes, st), "rqae_search_build_table_f16")
+        return table
 
     @classmethod
     def from_store(cls, model, folder: str, model_name: Optional[str] = None, dtype: torch.dtype = torch.int16, **kw):
@@ -154,6 +282,21 @@ class IntensityEngine:
         Sq = query.shape[0]
         k = window_k(top_examples, middle_examples, bottom_examples, N)
         from .feature import select_top_middle_bottom
+        if self.precision == "tc":
+            maxv_all = self.maxima_tc(query, layers)                         # every cut from one launch
+            table = self._build_table(query, max(layers))
+            for ci, layer in enumerate(layers):
+                sel, _ = select_top_middle_bottom(maxv_all[ci], k, n=N)      # (Sq, 3, k) int32
+                lists = window_lists(sel, top_examples, middle_examples, bottom_examples)
+                names = list(lists)
+                rows = self.rows_exact(table, torch.cat([lists[nm] for nm in names], dim=1), layers[:ci + 1])
+                out, o = {}, 0
+                for nm in names:
+                    w = lists[nm].shape[1]
+                    out[nm] = {"indices": lists[nm].cpu().int(), "intensities": rows[:, o:o + w].cpu().to(torch.float16)}
+                    o += w
+                yield out, layer
+            return
         qpos = torch.arange(Sq, device=self.sims.device).unsqueeze(-1)
         for layer, (acc, maxv) in zip(layers, self.accumulate(query, layers)):
             sel, _ = select_top_middle_bottom(maxv, k, n=N)                  # (Sq, 3, k) int32

@@ -181,3 +181,78 @@ def test_engine_from_model_and_store(tmp_path):
             assert res[part]["indices"].shape == ref[part]["indices"].shape
             same = (res[part]["indices"] == ref[part]["indices"]).all(dim=1)
             assert _ulps(res[part]["intensities"][same], ref[part]["intensities"][same]) <= ULPS
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# opt-in tensor-core ranking (precision="tc"): stated tolerance against the exact mode, exact rows for the selected
+# ---------------------------------------------------------------------------------------------------------------
+def _fp16_step(x: float) -> float:
+    import math
+    return 2.0 ** (max(math.floor(math.log2(max(abs(x), 6.2e-5))), -14) - 10)
+
+
+@pytest.mark.parametrize("mode", ["projected", "original"])
+@pytest.mark.parametrize("n_seq,S,Sq", [(9, 21, 13), (32, 127, 127)])
+def test_tensor_core_maxima_within_stated_tolerance_of_exact_mode(mode, n_seq, S, Sq):
+    """The tensor-core maxima (rank-5 factors in fp16, fp32 running prefix) against the exact mode's (fp16 table entries,
+    the reference's chunk / range roundings): at most TC_STEPS fp16 steps of the largest value of the cut -- the distance
+    is the reference's own rounding of its running value, not the factor rounding (oracle: test_search_oracle rank-5 test)."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import IntensityEngine
+    TC_STEPS = 4
+    dev = _dev()
+    torch.manual_seed(3)
+    nq = 150
+    model = RQAE(dim=256, num_quantizers=nq).eval().to(dev)
+    K = model.codebook.shape[1]
+    g = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, K, (n_seq, S, nq), generator=g, dtype=torch.int32)
+    codes[1, 2, 3] = -1                                                # contributes 0 in both modes
+    query = torch.randint(0, K, (Sq, nq), generator=g, dtype=torch.int32)
+    layers = [4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 150]
+    exact = IntensityEngine(model, codes.to(dev).to(torch.int16), mode=mode)
+    tc = IntensityEngine(model, codes.to(dev).to(torch.int16), mode=mode, precision="tc")
+    q = exact._query(None, query, max(layers))
+    got = tc.maxima_tc(q, layers).float().cpu()                        # (cuts, Sq, N)
+    worst = 0.0
+    for ci, (acc, maxv) in enumerate(exact.accumulate(q, layers)):
+        want = maxv.float().cpu()
+        step = _fp16_step(float(want.abs().max()))
+        d = float((got[ci] - want).abs().max())
+        worst = max(worst, d / step)
+        assert d <= TC_STEPS * step, (mode, layers[ci], d, step)
+    print(f"tensor-core maxima vs exact ({mode}, {n_seq} x {S}, {Sq} query positions): worst {worst:.2f} fp16 steps of the cut's largest value")
+
+
+def test_tensor_core_find_examples_reports_exact_rows_and_near_equal_ranks():
+    """precision="tc": the reported intensities are the exact accumulation rows of the reported sequences (bit for bit),
+    and at every rank the reported sequence's exact maximum is within the stated tolerance of the exact mode's value."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import IntensityEngine
+    dev = _dev()
+    torch.manual_seed(4)
+    nq, n_seq, S = 96, 41, 33
+    Sq = S                                                             # the query is sequence 5 of the store
+    model = RQAE(dim=256, num_quantizers=nq).eval().to(dev)
+    K = model.codebook.shape[1]
+    g = torch.Generator().manual_seed(12)
+    codes = torch.randint(0, K, (n_seq, S, nq), generator=g, dtype=torch.int32).to(dev)
+    layers = [4, 8, 16, 64, 96]
+    exact = IntensityEngine(model, codes)
+    tc = IntensityEngine(model, codes, precision="tc")
+    res_e = list(exact.find_examples(idx=5, top_examples=6, middle_examples=4, bottom_examples=3, layers=layers))
+    res_t = list(tc.find_examples(idx=5, top_examples=6, middle_examples=4, bottom_examples=3, layers=layers))
+    q = exact._query(5, None, max(layers))
+    accs = [(a.clone().cpu(), m.clone().cpu()) for a, m in exact.accumulate(q, layers)]
+    assert [l for _, l in res_t] == layers
+    qpos = torch.arange(Sq).unsqueeze(-1)
+    for (rt, _), (re_, _), (acc, maxv) in zip(res_t, res_e, accs):
+        step = _fp16_step(float(maxv.float().abs().max()))
+        for part in ("top", "middle", "bottom"):
+            it, ie = rt[part]["indices"].long(), re_[part]["indices"].long()
+            assert it.shape == ie.shape and rt[part]["intensities"].shape == re_[part]["intensities"].shape
+            assert torch.equal(rt[part]["intensities"].float(), acc[it, :, qpos].float()), part      # exact rows of ITS sequences
+            vt, ve = maxv.T[it, qpos].float(), maxv.T[ie, qpos].float()                              # exact maxima at every rank
+            assert float((vt - ve).abs().max()) <= 8 * step, part
+    # the query sequence itself tops every position at the last cut in both modes
+    assert bool((res_t[-1][0]["top"]["indices"][:, 0] == 5).all()) and bool((res_e[-1][0]["top"]["indices"][:, 0] == 5).all())

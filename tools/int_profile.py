@@ -26,7 +26,8 @@ _lib.check(_lib.load().rqae_intensity_profile(buf.ctypes.data, 148), "profile")
 a = buf.astype(np.float64).mean(0)
 kb = 70 * 2048 / 148
 names = ["issuer wait V", "issuer wait U", "issuer wait acc", "issuer total", "builder wait free", "builder build", "builder total",
-         "epilogue wait cut", "epilogue hold acc", "epilogue wait store-read", "epilogue total", "producer wait free", "producer total"]
+         "epilogue wait cut", "epilogue hold acc", "epilogue wait store-read", "epilogue total", "producer wait free", "producer total",
+         "epi: cut -> stores 1 issued", "epi: kept-half roundings", "epi: wait + stage 2 + stores 2"]
 print(f"dbg={dbg}: mean clocks per CTA, and per K-block ({kb:.0f} K-blocks per CTA)")
 for n, v in zip(names, a):
     print(f"  {n:26s} {v:12.0f}  {v / kb:8.1f}")
