@@ -331,8 +331,34 @@ def search_extras(torch, model, dev, sequences=36864, positions=127):
         cpu = search_cpu_port(torch, eng.sims.cpu())
     except Exception as e:
         cpu = {"error": repr(e)}
+    # opt-in tensor-core ranking (precision="tc"): one GEMM launch for the maxima of all cuts + exact rows of the selected
+    tc = {}
+    try:
+        del eng
+        eng_tc = IntensityEngine(model, codes, precision="tc")
+        query = eng_tc._query(idx, None, L)
+
+        def one_tc():
+            last = None
+            for r, layer in eng_tc.find_examples(idx=idx):
+                last = r
+            return last
+        res_tc, ms_tc = _event_ms(torch, dev, one_tc, reps=2)
+        _, ms_max = _event_ms(torch, dev, lambda: eng_tc.maxima_tc(query, SERVER_LAYERS), reps=2)
+        # algorithmic: the code store once (2 B per token-layer); on-chip, one 16-byte factor row per token-layer from L2
+        tc = {"find_examples_ms": ms_tc, "sequences_per_s": sequences / ms_tc * 1e3, "maxima_gemm_ms": ms_max,
+              "gemm_tflops": 2.0 * rows * 8 * 128 / ms_max / 1e9, "factor_row_tbps": rows * 16 / ms_max / 1e9,
+              "hbm_gbs": rows * 2 / ms_max / 1e6, "hbm_frac_of_peak": rows * 2 / ms_max / 1e6 / hbm_peak,
+              "self_match_top1": bool((res_tc["top"]["indices"][:, 0] == idx).all().item()),
+              "top_overlap_with_exact_last_cut": float((res_tc["top"]["indices"].unsqueeze(2) == res["top"]["indices"].unsqueeze(1))
+                                                       .any(dim=2).float().mean().item()),
+              "note": "ranking from the rank-5 tensor-core GEMM (maxima within a few fp16 steps of the exact mode, "
+                      "tests/test_search_gpu.py); reported intensities recomputed exactly for the selected sequences"}
+        del eng_tc
+    except Exception as e:
+        tc = {"error": repr(e)}
     return {
-        "cpu_port": cpu,
+        "cpu_port": cpu, "tensor_core_ranking_opt_in": tc,
         "sequences": sequences, "positions": positions, "layers": L, "query_positions": positions, "cuts": len(SERVER_LAYERS),
         "find_examples_ms": ms, "sequences_per_s": sequences / ms * 1e3, "launches_per_query": launches,
         "table_row_tbps": rows * 256 / ms / 1e9, "hbm_gbs": hbm / ms / 1e6, "hbm_frac_of_peak": hbm / ms / 1e6 / hbm_peak,

@@ -250,8 +250,9 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
  *   rqae_search_tc_maxima_f16   for every range end of `layers_host` (the `layers` list of find_examples):
  *                               max_out[(c * 128 + q) * max_stride + n] = fp16(max_s sum_{l < layers[c]} table entry),
  *                               rows = what rqae_select_top_middle_bottom_f16 ranks (row stride max_stride, n = n_seq)
- *   rqae_search_rows_f16        rows_out[q][j][s] = intensity_accumulation[sel[q][j], s, q] after the first n_ranges
- *                               ranges, with the reference's exact arithmetic (the rounding points of
+ *   rqae_search_rows_f16        rows_out[c][q][j][s] = intensity_accumulation[sel[c][q][j], s, q] after the ranges
+ *                               0 .. first_range + c of layers_host, c < n_cuts (one launch serves the selections of
+ *                               several consecutive cuts), with the reference's exact arithmetic (the rounding points of
  *                               rqae_search_accumulate_f16), from the table of rqae_search_build_table_f16:
  *                               server.py:290-305 for the selected sequences only. */
 size_t rqae_search_tc_store_bytes(int64_t n_seq, int nq_codes);
@@ -264,7 +265,7 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
                               void* workspace, size_t workspace_bytes, void* stream);
 int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq,
                          int seq_len, const int32_t* sel, int n_query, int n_sel, const int32_t* layers_host,
-                         int n_ranges, void* rows_out, void* stream);
+                         int first_range, int n_cuts, void* rows_out, void* stream);
 
 /* Measurement helper: per-CTA clock counters (16 x uint64 per CTA, meaning in rq_intensity.cuh) written by the last
  * rqae_intensity_f16 launch that ran with the environment variable RQAE_INT_DBG having bit 1024 set; synchronises. */

@@ -100,7 +100,7 @@ def load() -> ctypes.CDLL:
     lib.rqae_search_tc_maxima_f16.restype = i
     lib.rqae_search_tc_maxima_f16.argtypes = [vp, i64, i, i, vp, vp, i, i, vp, i64, i, vp, i, vp, i64, vp, sz, vp]
     lib.rqae_search_rows_f16.restype = i
-    lib.rqae_search_rows_f16.argtypes = [vp, i, vp, i, i64, i64, i, vp, i, i, vp, i, vp, vp]
+    lib.rqae_search_rows_f16.argtypes = [vp, i, vp, i, i64, i64, i, vp, i, i, vp, i, i, vp, vp]
     lib.rqae_launch_count.restype = i64
     lib.rqae_launch_count.argtypes = [i]
     _lib = lib

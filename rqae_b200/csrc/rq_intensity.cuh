@@ -64,6 +64,8 @@ constexpr int IT_EPI_WARPS = 8;
 // register pool: ptxas compiles for 640 threads at 96 registers = 61 440; setmaxnreg can only re-split that pool
 constexpr int IT_REG_CTRL = 40, IT_REG_BUILD = 80, IT_REG_EPI = 136;
 static_assert(128 * IT_REG_CTRL + 256 * IT_REG_BUILD + 256 * IT_REG_EPI <= IT_THREADS * 96, "register pool budget");
+constexpr int IT_REG_BUILD_S = 112, IT_REG_EPI_S = 104;   // example search: the builders hold two batches of gathered rows, the epilogue only reduces
+static_assert(128 * IT_REG_CTRL + 256 * IT_REG_BUILD_S + 256 * IT_REG_EPI_S <= IT_THREADS * 96, "register pool budget");
 constexpr int IT_BUILDERS = 256;             // one token row per builder thread
 
 struct IntKBlock {   // one K-block of the schedule: layers l0 .. l0+n-1 (n <= 16), the rest of the 16 slots zero
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
   }   // warps 2-3: spare warps of the control warpgroup
   } else if (warp < 12) {
     // ======================= V builders =======================
-    reg_dec<IT_REG_BUILD>();
+    if constexpr (EPI == 2) reg_inc<IT_REG_BUILD_S>(); else reg_dec<IT_REG_BUILD>();
     if constexpr (EPI == 2) {
       // Example search: row b of the tile is position (b & 127) of sequence 2 u + (b >> 7); a K-block is 8 layers x 8 fp16,
       // one 16-byte factor row per (token, layer) gathered from the L2-resident table.  Per step: store the rows gathered
@@ -416,14 +418,18 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
 #pragma unroll
         for (int i = 0; i < 8; i++) g[i] = __ldg(tab + (size_t)i * IT_LUT_ROWS + ((w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu));
       };
-      Pos cur = {(long long)blockIdx.x, 0}, p1 = cur, p2;
+      // two batches of gathers in flight: the rows stored in step k were requested in step k - 2
+      Pos cur = {(long long)blockIdx.x, 0}, p1 = cur, p2, p3;
       next(p1);
       p2 = p1;
       next(p2);
-      uint4 g[8];
-      gather(g, load_codes(cur), cur);
-      uint4 c1 = load_codes(p1);
-      while (cur.u < n_units) {
+      p3 = p2;
+      next(p3);
+      uint4 gA[8], gB[8];
+      gather(gA, load_codes(cur), cur);
+      gather(gB, load_codes(p1), p1);
+      uint4 cn = load_codes(p2);
+      auto do_step = [&](uint4 (&g)[8]) {
         mbar_wait_spin(&v_empty[s], par);
         const uint32_t vb = vring + s * IT_V_BYTES + row_off;
 #pragma unroll
@@ -434,11 +440,17 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&v_full[s]);
         if (++s == IT_VSTAGES) { s = 0; par ^= 1; }
-        gather(g, c1, p1);
-        c1 = load_codes(p2);
+        gather(g, cn, p2);
+        cn = load_codes(p3);
         cur = p1;
         p1 = p2;
-        next(p2);
+        p2 = p3;
+        next(p3);
+      };
+      while (cur.u < n_units) {
+        do_step(gA);
+        if (cur.u >= n_units) break;
+        do_step(gB);
       }
     } else {
     const int b = threadIdx.x - 128;   // row b of the token tile
@@ -519,7 +531,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     }   // EPI != 2
   } else {
     // ======================= epilogue =======================
-    reg_inc<IT_REG_EPI>();
+    reg_inc<(EPI == 2 ? IT_REG_EPI_S : IT_REG_EPI)>();
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int acc = (warp - 12) >> 2;   // accumulator (feature tile of the pair)
     uint64_t* const my_full = &acc_full[acc];

@@ -322,36 +322,55 @@ struct SearchRowsParams {
   const __half* table;      // Qt [layers][K][SR_Q]
   const void* codes;        // [n_seq][seq_len][code_stride]
   long long code_stride, n_seq;
-  int seq_len, K, n_query, n_sel, n_ranges;
+  int seq_len, K, n_query, n_sel, n_cuts;   // n_cuts selections of [n_query][n_sel] sequences; selection c uses ranges 0 .. first_range + c
+  int first_range;
   int ends[IT_MAX_CUTS];
-  const int* sel;           // [n_query][n_sel] sequence indices (< 0: skipped, the row is zero-filled)
-  __half* out;              // [n_query][n_sel][seq_len]
+  const int* sel;           // [n_cuts][n_query][n_sel] sequence indices (< 0: skipped, the row is zero-filled)
+  __half* out;              // [n_cuts][n_query][n_sel][seq_len]
 };
 
 template <typename CodeT>
 __global__ void __launch_bounds__(256) search_rows_kernel(const SearchRowsParams p) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wid >= (long long)p.n_query * p.n_sel) return;
-  const int q = (int)(wid / p.n_sel);
+  const long long per_cut = (long long)p.n_query * p.n_sel;
+  if (wid >= per_cut * p.n_cuts) return;
+  const int cut = (int)(wid / per_cut);
+  const int q = (int)((wid - cut * per_cut) / p.n_sel);
+  const int n_ranges = p.first_range + cut + 1;
   const long long n = p.sel[wid];
   __half* out = p.out + wid * p.seq_len;
   const CodeT* __restrict__ codes = (const CodeT*)p.codes;
   const __half* __restrict__ tab = p.table + q;
+  const int K = p.K;
   for (int s = lane; s < p.seq_len; s += 32) {
     if (n < 0 || n >= p.n_seq) { out[s] = __float2half(0.f); continue; }
     const CodeT* row = codes + (n * p.seq_len + s) * p.code_stride;
     __half acc = __float2half(0.f);
     int a = 0;
-    for (int r = 0; r < p.n_ranges; r++) {
+    for (int r = 0; r < n_ranges; r++) {
       const int b = p.ends[r];
       __half rng = __float2half(0.f);
       for (int c0 = a; c0 < b; c0 += SR_CHUNK) {
         const int c1 = (c0 + SR_CHUNK < b) ? c0 + SR_CHUNK : b;
         float cs = 0.f;
-        for (int l = c0; l < c1; l++) {                                     // fp32 sum, ascending layer order
+        int l = c0;
+        for (; l + 8 <= c1; l += 8) {                                       // eight independent gathers in flight
+          long long c[8];
+          __half v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) c[i] = (long long)row[l + i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const bool ok = c[i] >= 0 && c[i] < K;
+            v[i] = ok ? __ldg(tab + ((size_t)(l + i) * K + (size_t)c[i]) * SR_Q) : __float2half(0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) cs += __half2float(v[i]);             // fp32 sum, ascending layer order (+0 for a skipped code)
+        }
+        for (; l < c1; l++) {
           const long long c = (long long)row[l];
-          if (c >= 0 && c < p.K) cs += __half2float(__ldg(tab + ((size_t)l * p.K + (size_t)c) * SR_Q));
+          if (c >= 0 && c < K) cs += __half2float(__ldg(tab + ((size_t)l * K + (size_t)c) * SR_Q));
         }
         const __half h = __float2half_rn(cs);                               // sum(dim=-1) of an fp16 tensor
         rng = (c0 == a) ? h : __float2half_rn(__half2float(rng) + __half2float(h));    // intensities += chunk (fp16)

@@ -1336,22 +1336,24 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
 
 int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq,
                          int seq_len, const int32_t* sel, int n_query, int n_sel, const int32_t* layers_host,
-                         int n_ranges, void* rows_out, void* stream) {
+                         int first_range, int n_cuts, void* rows_out, void* stream) {
   if (!table || !codes || !sel || !rows_out || !layers_host || K <= 0 || n_seq <= 0 || seq_len <= 0) return RQAE_EINVAL;
-  if (code_dtype < 0 || code_dtype > 2 || n_query <= 0 || n_sel < 0 || n_ranges <= 0) return RQAE_EINVAL;
-  if (n_query > rq::SR_Q || n_ranges > rq::IT_MAX_CUTS) return RQAE_EUNSUPPORTED;
+  if (code_dtype < 0 || code_dtype > 2 || n_query <= 0 || n_sel < 0 || first_range < 0 || n_cuts <= 0) return RQAE_EINVAL;
+  if (n_query > rq::SR_Q || first_range + n_cuts > rq::IT_MAX_CUTS) return RQAE_EUNSUPPORTED;
   rq::SearchRowsParams rp;
   memset(&rp, 0, sizeof(rp));
   int a = 0;
-  for (int r = 0; r < n_ranges; r++) {
+  for (int r = 0; r < first_range + n_cuts; r++) {
     if (layers_host[r] <= a) return RQAE_EINVAL;
     rp.ends[r] = a = layers_host[r];
   }
   if (code_stride < a) return RQAE_EINVAL;
   if (n_sel == 0) return RQAE_OK;
   rp.table = (const __half*)table; rp.codes = codes; rp.code_stride = code_stride; rp.n_seq = n_seq; rp.seq_len = seq_len;
-  rp.K = K; rp.n_query = n_query; rp.n_sel = n_sel; rp.n_ranges = n_ranges; rp.sel = sel; rp.out = (__half*)rows_out;
-  const long long warps = (long long)n_query * n_sel;
+  rp.K = K; rp.n_query = n_query; rp.n_sel = n_sel; rp.n_cuts = n_cuts; rp.first_range = first_range; rp.sel = sel;
+  rp.out = (__half*)rows_out;
+  const long long warps = (long long)n_query * n_sel * n_cuts;
+  if ((warps + 7) / 8 >= (1LL << 31)) return RQAE_EUNSUPPORTED;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (code_dtype == RQAE_CODE_I64) rq::search_rows_kernel<long long><<<blocks, 256, 0, st>>>(rp);

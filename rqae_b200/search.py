@@ -139,7 +139,7 @@ class IntensityEngine:
                                                     N, S, nq_codes, K, self._store_tc.data_ptr(), nbytes,
                                                     torch.cuda.current_stream(dev).cuda_stream), "rqae_search_tc_pack_store")
 
-    def maxima_tc(self, query: torch.Tensor, layers: Sequence[int]) -> torch.Tensor:
+    def maxima_tc(self, query: torch.Tensor, layers: Sequence[int], padded: bool = False) -> torch.Tensor:
         """(len(layers), Sq, N) fp16: max over the positions of every sequence of the running accumulation after each
         range of ``layers`` -- ``max_values.T`` of server.py:267 for all cuts, from ONE tensor-core launch (a view of
         a buffer whose rows are padded: what ``select_top_middle_bottom`` ranks)."""
@@ -170,25 +170,41 @@ class IntensityEngine:
                                                     query.stride(0), Sq, lh.data_ptr(), len(layers), out.data_ptr(), stride,
                                                     ws.data_ptr() + off, wbytes, st), "rqae_search_tc_maxima_f16")
         ws.record_stream(torch.cuda.current_stream(dev))
-        return out[:, :Sq, :N]
+        return out[:, :, :N] if padded else out[:, :Sq, :N]     # padded: all 128 rows per cut (rows >= Sq are zero)
 
-    def rows_exact(self, table: torch.Tensor, sel: torch.Tensor, layers: Sequence[int]) -> torch.Tensor:
-        """``intensity_accumulation[sel[q, j], :, q]`` after the ranges ``layers`` (server.py:290-305), (Sq, n_sel, S) fp16,
-        recomputed with the reference's arithmetic for the selected sequences only.  ``table``: the query's rows of the
-        engine table (``rqae_search_build_table_f16``); ``sel`` (Sq, n_sel) int32."""
+    def rows_exact(self, table: torch.Tensor, sel: torch.Tensor, layers: Sequence[int], first_range: Optional[int] = None) -> torch.Tensor:
+        """``intensity_accumulation[sel[..., q, j], :, q]`` (server.py:290-305) recomputed with the reference's arithmetic
+        for the selected sequences only.  ``table``: the query's rows of the engine table (``rqae_search_build_table_f16``).
+        ``sel`` (Sq, n_sel): after all ranges of ``layers`` -> (Sq, n_sel, S) fp16.  ``sel`` (C, Sq, n_sel) with
+        ``first_range``: selection c after the ranges 0 .. first_range + c -> (C, Sq, n_sel, S), one launch."""
         N, S, nq_codes = self.activations.shape
         K = self.sims.shape[1]
         dev = self.sims.device
         sel = sel.to(torch.int32).contiguous()
-        Sq, n_sel = sel.shape
-        out = torch.empty(Sq, n_sel, S, dtype=torch.float16, device=dev)
+        single = sel.dim() == 2
+        if single:
+            sel = sel.unsqueeze(0)
+            first_range = len(layers) - 1
+        C, Sq, n_sel = sel.shape
+        out = torch.empty(C, Sq, n_sel, S, dtype=torch.float16, device=dev)
         lh = torch.tensor([int(l) for l in layers], dtype=torch.int32)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().rqae_search_rows_f16(table.data_ptr(), K, self.activations.data_ptr(),
                                                        _CODE_DTYPE[self.activations.dtype], nq_codes, N, S, sel.data_ptr(), Sq,
-                                                       n_sel, lh.data_ptr(), len(layers), out.data_ptr(),
+                                                       n_sel, lh.data_ptr(), int(first_range), C, out.data_ptr(),
                                                        torch.cuda.current_stream(dev).cuda_stream), "rqae_search_rows_f16")
-        return out
+        return out[0] if single else out
+
+    def _pinned(self, name: str, shape, dtype) -> torch.Tensor:
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        t = cache.get(name)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(n, dtype=dtype, pin_memory=True)
+            cache[name] = t
+        return t[:n].view(*shape)
 
     def _build_table(self, query: torch.Tensor, L: int) -> torch.Tensor:
         lib = _lib.load()
@@ -283,17 +299,29 @@ class IntensityEngine:
         k = window_k(top_examples, middle_examples, bottom_examples, N)
         from .feature import select_top_middle_bottom
         if self.precision == "tc":
-            maxv_all = self.maxima_tc(query, layers)                         # every cut from one launch
+            # every cut at once: one GEMM launch for the maxima, one selection launch over (cut, position) rows, one launch
+            # for the exact rows of everything selected, two device->host copies; the generator then yields cut by cut
+            maxv_all = self.maxima_tc(query, layers, padded=True)                      # (C, 128, N), rows >= Sq zero
             table = self._build_table(query, max(layers))
+            sel, _ = select_top_middle_bottom(maxv_all, k, n=N)                        # (C, 128, 3, k) int32
+            sel = sel[:, :Sq].contiguous()
+            C = len(layers)
+            lists = window_lists(sel.reshape(C * Sq, 3, k), top_examples, middle_examples, bottom_examples)
+            names = list(lists)
+            cat = torch.cat([lists[nm] for nm in names], dim=1).reshape(C, Sq, -1)     # (C, Sq, n_sel)
+            rows_d = self.rows_exact(table, cat, layers, first_range=0)                # (C, Sq, n_sel, S)
+            # one copy each through cached pinned buffers (a pageable .cpu() of the 21 MB of rows costs 10 ms)
+            rows = self._pinned("rows", rows_d.shape, torch.float16)
+            idxs = self._pinned("sel", cat.shape, torch.int32)
+            rows.copy_(rows_d, non_blocking=True)
+            idxs.copy_(cat, non_blocking=True)
+            torch.cuda.current_stream(self.sims.device).synchronize()
+            rows, cat = rows.clone(), idxs.clone()                                     # the caller owns what it is handed
             for ci, layer in enumerate(layers):
-                sel, _ = select_top_middle_bottom(maxv_all[ci], k, n=N)      # (Sq, 3, k) int32
-                lists = window_lists(sel, top_examples, middle_examples, bottom_examples)
-                names = list(lists)
-                rows = self.rows_exact(table, torch.cat([lists[nm] for nm in names], dim=1), layers[:ci + 1])
                 out, o = {}, 0
                 for nm in names:
                     w = lists[nm].shape[1]
-                    out[nm] = {"indices": lists[nm].cpu().int(), "intensities": rows[:, o:o + w].cpu().to(torch.float16)}
+                    out[nm] = {"indices": cat[ci, :, o:o + w].contiguous(), "intensities": rows[ci, :, o:o + w].contiguous()}
                     o += w
                 yield out, layer
             return
