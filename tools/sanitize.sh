@@ -19,3 +19,5 @@ timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_f
 echo "=== memcheck + racecheck: example search (table transpose, accumulate, per-position max) ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "golden or single_query or argument or int16" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_search.log
 timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "single_query" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_search.log
+echo "=== memcheck: tensor-core search (store pack, factor gathers, maxima epilogue, exact rows) and tensor-core decode ==="
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py tests/test_parity_gpu.py -q -x -k "tensor_core and not 127" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_tc.log
