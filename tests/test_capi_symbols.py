@@ -82,6 +82,34 @@ def test_search_entry_points_validate_before_touching_the_gpu():
     assert lib.rqae_search_position_max_f16(one, 24, 7, 200, one, 24, None) == 2               # more than 128 query positions
 
 
+def test_tensor_core_search_entry_points_validate_before_touching_the_gpu():
+    import ctypes
+    import numpy as np
+    lib = _lib.load()
+    # the block-major store copy: ceil(n_seq / 2) units x ceil(layers / 8) blocks x 256 rows x 16 bytes
+    assert lib.rqae_search_tc_store_bytes(36864, 1024) == 18432 * 128 * 256 * 16
+    assert lib.rqae_search_tc_store_bytes(9, 150) == 5 * 19 * 256 * 16
+    assert lib.rqae_search_tc_store_bytes(0, 1024) == 0
+    cuts = np.array([4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1023], dtype=np.int32)    # server.py:167
+    # 131 K-blocks of 8 layers: a range end inside a block costs a K-block of its own
+    assert lib.rqae_search_tc_workspace_bytes(cuts.ctypes.data, 13) == 4096 + 131 * 16384
+    bad = np.array([8, 8], dtype=np.int32)
+    assert lib.rqae_search_tc_workspace_bytes(bad.ctypes.data, 2) == 0                         # not strictly ascending
+    one = ctypes.c_void_p(4096)
+    wb = lib.rqae_search_tc_workspace_bytes(cuts.ctypes.data, 13)
+    assert lib.rqae_search_tc_pack_store(one, 0, 1024, 10, 200, 1024, 625, one, 1 << 40, None) == 2    # more than 128 positions
+    assert lib.rqae_search_tc_pack_store(one, 0, 512, 10, 127, 1024, 625, one, 1 << 40, None) == 1     # code rows shorter than the layers
+    assert lib.rqae_search_tc_pack_store(one, 0, 1024, 10, 127, 1024, 625, one, 16, None) == 5         # store copy too small
+    args = (one, 10, 127, 1024, one, one, 1024, 625, one, 1024, 127, cuts.ctypes.data, 13, one)
+    assert lib.rqae_search_tc_maxima_f16(*args[:10], 200, *args[11:], 16, one, wb, None) == 2          # more than 128 query positions
+    assert lib.rqae_search_tc_maxima_f16(*args, 8, one, wb, None) == 1                                 # rows shorter than the 10 sequences
+    assert lib.rqae_search_tc_maxima_f16(*args, 16, one, 64, None) == 5                                # workspace too small
+    assert lib.rqae_search_tc_maxima_f16(*args[:6], 512, *args[7:], 16, one, wb, None) == 1            # factor tables shorter than the layers
+    assert lib.rqae_search_rows_f16(one, 625, one, 0, 1024, 10, 127, one, 127, 50, cuts.ctypes.data, 60, 10, one, None) == 2  # more than 64 ranges
+    assert lib.rqae_search_rows_f16(one, 625, one, 0, 512, 10, 127, one, 127, 50, cuts.ctypes.data, 0, 13, one, None) == 1    # code rows shorter than the last range
+    assert lib.rqae_search_rows_f16(one, 625, one, 0, 1024, 10, 127, one, 127, 0, cuts.ctypes.data, 0, 13, one, None) == 0    # nothing selected
+
+
 def test_host_widening_pool_matches_numpy():
     """The widening step of the narrow host pipeline (int16 -> int32 / int64, AVX2 streaming stores, persistent worker
     pool) on its own: every thread count, unaligned destinations, sizes around the split and vector widths."""
