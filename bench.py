@@ -545,9 +545,16 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
     ev = lambda: torch.cuda.Event(enable_timing=True)
     codes = torch.empty(tokens, NQ, dtype=torch.int16, device=dev)
     lw = layer_weights_f16(model).to(dev)
-    if world > 1:   # bring up NCCL's point-to-point channels (lazy, seconds on first use) outside the timed region
-        wu = torch.zeros(world * 1024, dtype=torch.uint8, device=dev)
-        dist.all_to_all_single(torch.empty_like(wu), wu)
+    buf = torch.empty(group, len(SCRIPT3_CUTS), (tokens + 255) // 256 * 256, dtype=torch.float16, device=dev)
+    # One untimed pass of a feature group over whatever the buffers hold (the warm-up of this extra): NCCL brings up its
+    # point-to-point channels lazily and per message size, and the caching allocator has to obtain the 15 GB receive and
+    # repack buffers once; both cost 100-200 ms on first use and belong to a cold process, not to the path.
+    codes.zero_()
+    wu = intensity_many(model, codes, codes[:group].to(torch.int32), SCRIPT3_CUTS, layer_weights=lw, out=buf)
+    if world > 1:
+        wu, _ = shard.exchange_to_feature_shards(wu, world * tokens)
+    select_top_middle_bottom(wu, top_k)
+    del wu
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -572,7 +579,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
     ms_int = ms_x = ms_sel = 0.0
     ms_x_groups = []
     checksum = 0
-    buf = torch.empty(group, len(SCRIPT3_CUTS), (tokens + 255) // 256 * 256, dtype=torch.float16, device=dev)
+    ms_int_groups = []
     for f0 in range(0, n_features, group):
         a, b, c, d = ev(), ev(), ev(), ev()
         a.record()
@@ -588,6 +595,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
         torch.cuda.synchronize(dev)
         ms_int += a.elapsed_time(b); ms_x += b.elapsed_time(c); ms_sel += c.elapsed_time(d)
         ms_x_groups.append(round(b.elapsed_time(c), 2))
+        ms_int_groups.append(round(a.elapsed_time(b), 2))
         checksum += int(idx[:, :, 0, 0].sum().item())
         del rows, idx, val
     t_wall = time.perf_counter() - t_wall0
@@ -608,7 +616,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
                                             / (peaks["bf16_tflops"] if peaks else 1590.0),
            "select_gbs_per_gpu": rows_per_rank * n_total * 2 / ms_sel / 1e6,
            "exchange_gbs_per_gpu": (n_features * len(SCRIPT3_CUTS) * tokens * 2 * (world - 1) / world) / ms_x / 1e6 if world > 1 else None,
-           "exchange_ms_per_group_rank0": ms_x_groups, "checksum_top_idx": checksum,
+           "exchange_ms_per_group_rank0": ms_x_groups, "intensity_ms_per_group_rank0": ms_int_groups, "checksum_top_idx": checksum,
            "timing": "host wall clock barrier -> last kernel done (encode + feature groups x (GEMM, all_to_all, select)), "
                      "max over ranks"}
     del codes, buf
