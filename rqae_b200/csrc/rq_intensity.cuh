@@ -98,7 +98,7 @@ struct IntParams {
   __half* s_max;          // [n_cuts][128][s_stride]: max over the positions of every sequence
   long long s_stride;     // >= 2 * n_units, even
   int s_len, L8;          // positions per sequence (<= 128), 8-layer blocks per token
-  int stagger;   // clocks between the four start groups of CTAs (0: all together)
+  int stagger, stagger_groups;   // clocks between the start groups of CTAs (0: all together), number of groups
   int dbg;   // timing experiments only (RQAE_INT_DBG): 1 no output stores, 2 no table look-ups, 4 no pause at cuts, 8 no MMA, 16 no epilogue work, 64 no feature-operand copies, 128 no code loads, 256 no proxy fence in the builders, 512 no L2 prefetch of code rows, 1024 per-role clock counters (g_int_prof)
 };
 
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     // unit begins with a burst of output (1.3 MB per SM) and, started together, all SMs burst together and wait on
     // HBM writes.  Four start groups a fraction of a unit apart spread the bursts (measured: 1.73 -> 1.63 ms).
     const long long t0 = clock64();
-    const long long d = (long long)(blockIdx.x % 4) * p.stagger;
+    const long long d = (long long)(blockIdx.x % p.stagger_groups) * p.stagger;
     while (clock64() - t0 < d) {
     }
     __syncthreads();

@@ -1112,6 +1112,7 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   const long long units = ip_units(L);
   // start groups 20 k clocks apart when every CTA has several units to run (RQAE_INT_STAGGER overrides, for experiments)
   { const char* e = getenv("RQAE_INT_STAGGER"); ip.stagger = e ? atoi(e) : (units >= 4LL * sms && n_cuts >= 4 ? 20000 : 0); }
+  { const char* e = getenv("RQAE_INT_GROUPS"); ip.stagger_groups = e && atoi(e) > 0 ? atoi(e) : 4; }
   ip.q_out = nullptr; ip.bias = nullptr; ip.T = n_tokens; ip.D = 0;
   ip.F_tiles = L.F_tiles; ip.out = (__half*)out; ip.out_stride = out_stride; ip.n_tok_tiles = L.T_pad / rq::IT_TOK;
   const int grid = (int)(units < sms ? units : sms);
@@ -1323,7 +1324,7 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
   ip.u_tiles = ws + 4096; ip.sched = (const rq::IntKBlock*)ws; ip.K = K; ip.NKB = nkb; ip.n_cuts = n_layers_list;
   ip.F = n_query; ip.F_tiles = 1; ip.n_tok_tiles = units; ip.L = last; ip.T_pad = units * rq::IT_TOK;
   ip.s_codes = (const uint4*)store_tc; ip.s_vtab = (const uint4*)vtab_f16; ip.s_max = (__half*)max_out;
-  ip.s_stride = max_stride; ip.s_len = seq_len; ip.L8 = L8; ip.stagger = 0;
+  ip.s_stride = max_stride; ip.s_len = seq_len; ip.L8 = L8; ip.stagger = 0; ip.stagger_groups = 1;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
   const int grid = (int)(units < sms ? units : sms);
   CUtensorMap no_map;
@@ -1445,7 +1446,7 @@ int rqae_decode_tc_f32(const float* w_out, const float* b_out, const float* code
   ip.lut = (const uint2*)(ws + L.off_lut); ip.K = K; ip.NKB = L.NKB; ip.n_cuts = 1; ip.F = dim; ip.F_tiles = L.F_tiles;
   ip.n_tok_tiles = L.T_pad / rq::IT_TOK; ip.q_out = q_out; ip.bias = (const float*)(ws + L.off_bias); ip.T = n_tokens; ip.D = dim;
   { const char* e = getenv("RQAE_INT_DBG"); ip.dbg = e ? atoi(e) : 0; }
-  ip.stagger = 0;
+  ip.stagger = 0; ip.stagger_groups = 1;
   const long long units = ip.n_tok_tiles * ((L.F_tiles + 1) / 2);
   const int grid = (int)(units < sms ? units : sms);
   CUtensorMap no_map;
