@@ -113,6 +113,22 @@ struct IntSmem {
   static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 4) * 8;
   static constexpr int TOTAL = TMEM_PTR + 16;
 };
+// Example search (EPI = 2): no staging boxes and no lookup table, three feature-tile stages -- 119 KB, so that the SM keeps
+// ~120 KB of L1 for the factor-row gathers (two rows share a 32-byte sector and 8 layers x 640 rows are 80 KB per K-block).
+constexpr int IT_USTAGES_S = 3;
+struct IntSmemS {
+  static constexpr int VRING = 0;
+  static constexpr int URING = IT_VSTAGES * IT_V_BYTES;
+  static constexpr int STG = 0, LUT = 0;   // unused
+  static constexpr int SCHED = URING + IT_USTAGES_S * IT_U_TILE;
+  static constexpr int WCUM = SCHED + IT_MAX_KB * 16;
+  static constexpr int BARS = WCUM + 2 * IT_MAX_CUTS * 4;
+  static constexpr int TMEM_PTR = BARS + (2 * IT_VSTAGES + 2 * IT_USTAGES + 4) * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+static_assert(IntSmemS::TOTAL <= 131 * 1024, "example search: fits the 132 KB carve-out");
+template <int EPI> struct IntSmemOf { using type = IntSmem; };
+template <> struct IntSmemOf<2> { using type = IntSmemS; };
 static_assert(IntSmem::STG % 1024 == 0, "store boxes must be 1024-byte aligned");
 static_assert(IntSmem::TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -238,33 +254,35 @@ __device__ unsigned long long g_int_prof[256 * IT_PROF_SLOTS];
 template <int EPI>
 __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntParams p, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  using SM = typename IntSmemOf<EPI>::type;
+  constexpr int USTAGES = EPI == 2 ? IT_USTAGES_S : IT_USTAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + IntSmem::BARS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* v_full = bars;                      // [VS] 128 builder arrivals
   uint64_t* v_empty = v_full + IT_VSTAGES;      // [VS] MMAs reading the stage have completed (tcgen05.commit)
   uint64_t* u_full = v_empty + IT_VSTAGES;      // [US] bulk copies landed
   uint64_t* u_empty = u_full + IT_USTAGES;      // [US] tcgen05.commit
   uint64_t* acc_full = u_empty + IT_USTAGES;    // [2] segment complete in accumulator a (tcgen05.commit)
   uint64_t* acc_free = acc_full + 2;            // [2] the 4 epilogue warps of accumulator a have read it
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + IntSmem::TMEM_PTR);
-  const IntKBlock* sched = reinterpret_cast<const IntKBlock*>(smem + IntSmem::SCHED);
-  const float* wcum_s = reinterpret_cast<const float*>(smem + IntSmem::WCUM);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEM_PTR);
+  const IntKBlock* sched = reinterpret_cast<const IntKBlock*>(smem + SM::SCHED);
+  const float* wcum_s = reinterpret_cast<const float*>(smem + SM::WCUM);
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i <= p.K && EPI != 2; i += IT_THREADS) {
     if (EPI == 1) {
-      reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i] = p.lut[i];
-      reinterpret_cast<uint2*>(smem + IntSmem::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
+      reinterpret_cast<uint2*>(smem + SM::LUT)[i] = p.lut[i];
+      reinterpret_cast<uint2*>(smem + SM::LUT)[IT_LUT_ROWS + i] = p.lut[IT_LUT_ROWS + i];
     } else {
       const uint2 r = p.lut[i];
 #pragma unroll
-      for (int t = 0; t < IT_LUT_COPIES; t++) reinterpret_cast<uint2*>(smem + IntSmem::LUT)[i * IT_LUT_COPIES + t] = r;
+      for (int t = 0; t < IT_LUT_COPIES; t++) reinterpret_cast<uint2*>(smem + SM::LUT)[i * IT_LUT_COPIES + t] = r;
     }
   }
   for (int i = threadIdx.x; i < p.NKB * 4; i += IT_THREADS)
-    reinterpret_cast<int*>(smem + IntSmem::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
+    reinterpret_cast<int*>(smem + SM::SCHED)[i] = reinterpret_cast<const int*>(p.sched)[i];
   for (int i = threadIdx.x; i < 2 * p.n_cuts && EPI != 2; i += IT_THREADS)
-    reinterpret_cast<float*>(smem + IntSmem::WCUM)[i] = p.wcum[i];
+    reinterpret_cast<float*>(smem + SM::WCUM)[i] = p.wcum[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < IT_VSTAGES; s++) { mbar_init(&v_full[s], IT_BUILDERS); mbar_init(&v_empty[s], 1); }
     for (int s = 0; s < IT_USTAGES; s++) { mbar_init(&u_full[s], 1); mbar_init(&u_empty[s], 1); }
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     }
     __syncthreads();
   }
-  const uint32_t vring = smem_u32(smem + IntSmem::VRING), uring = smem_u32(smem + IntSmem::URING);
+  const uint32_t vring = smem_u32(smem + SM::VRING), uring = smem_u32(smem + SM::URING);
   if (vring & 1023u) __trap();   // the hand-written swizzle assumes 1024-byte aligned tiles
 
   // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code it dominates)
@@ -322,7 +340,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
               tma_bulk_g2s(uring + s * IT_U_TILE, p.u_tiles + ((size_t)(2 * pr + ft) * p.NKB + kb) * (size_t)IT_U_TILE, IT_U_TILE,
                            &u_full[s]);
             }
-            if (++s == IT_USTAGES) { s = 0; par ^= 1; }
+            if (++s == USTAGES) { s = 0; par ^= 1; }
           }
         }
       }
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
               if (is_cut) tc_commit(&acc_full[ft]);   // the running prefix goes to its epilogue warps; the other accumulator carries on
             }
             __syncwarp();
-            if (++us == IT_USTAGES) { us = 0; upar ^= 1; }
+            if (++us == USTAGES) { us = 0; upar ^= 1; }
             pend = is_cut;
           }
           if (elect_one()) tc_commit(&v_empty[vs]);
@@ -454,7 +472,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
       }
     } else {
     const int b = threadIdx.x - 128;   // row b of the token tile
-    const uint32_t lut = smem_u32(smem + IntSmem::LUT) + (EPI == 0 ? (uint32_t)(lane & (IT_LUT_COPIES - 1)) * 8u : 0u);
+    const uint32_t lut = smem_u32(smem + SM::LUT) + (EPI == 0 ? (uint32_t)(lane & (IT_LUT_COPIES - 1)) * 8u : 0u);
     constexpr uint32_t lut_pitch = EPI == 0 ? 8u * IT_LUT_COPIES : 8u;
     const uint32_t row_off = b * 128;
     const uint32_t sw = (uint32_t)(b & 7);
@@ -539,7 +557,7 @@ __global__ void __launch_bounds__(IT_THREADS, 1) rq_intensity_kernel(const IntPa
     // The warp's staging area: two store boxes of [32 rows][64 tokens] fp16 (half of the unit's 256 tokens at a time).
     // Lane = feature row; the 16-byte chunk index inside a 128-byte box row is XOR-ed with (row & 7): the 128-byte
     // swizzle the tensor map names, and what keeps the lane-strided 128-bit stores free of bank conflicts.
-    const uint32_t wstg = smem_u32(smem + IntSmem::STG) + (uint32_t)(warp - 12) * IT_STG_WARP;
+    const uint32_t wstg = smem_u32(smem + SM::STG) + (uint32_t)(warp - 12) * IT_STG_WARP;
     const uint32_t stg_row = wstg + (uint32_t)lane * 128u;
     const uint32_t stg_x = (uint32_t)(lane & 7);
     auto stg_addr = [&](int j) -> uint32_t {   // chunk j (0..15) of this lane's 128 staged tokens

@@ -1318,7 +1318,17 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
                                                                (const rq::IntKBlock*)ws, nkb, ws + 4096);
     RQ_CUDA(cudaGetLastError());
   }
-  RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_intensity_kernel<2>, rq::IntSmem::TOTAL));
+  RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_intensity_kernel<2>, rq::IntSmemS::TOTAL));
+  {   // leave the rest of the SM's 256 KB to L1: the factor gathers re-use sectors within a K-block
+    static std::mutex mu;
+    static std::map<int, cudaError_t> done;
+    int dev = 0;
+    RQ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done.count(dev))
+      done[dev] = cudaFuncSetAttribute((const void*)rq::rq_intensity_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+    RQ_CUDA(done[dev]);
+  }
   rq::IntParams ip;
   memset(&ip, 0, sizeof(ip));
   ip.u_tiles = ws + 4096; ip.sched = (const rq::IntKBlock*)ws; ip.K = K; ip.NKB = nkb; ip.n_cuts = n_layers_list;
@@ -1329,7 +1339,7 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
   const int grid = (int)(units < sms ? units : sms);
   CUtensorMap no_map;
   memset(&no_map, 0, sizeof(no_map));
-  rq::rq_intensity_kernel<2><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip, no_map);
+  rq::rq_intensity_kernel<2><<<grid, rq::IT_THREADS, rq::IntSmemS::TOTAL, st>>>(ip, no_map);
   RQ_CUDA(cudaGetLastError());
   g_launches += 3;
   return RQAE_OK;
