@@ -253,9 +253,13 @@ int rqae_fp32_peak_probe(int packed_f32x2, int iters, double* flops_per_launch, 
  *   rqae_search_rows_f16        rows_out[c][q][j][s] = intensity_accumulation[sel[c][q][j], s, q] after the ranges
  *                               0 .. first_range + c of layers_host, c < n_cuts (one launch serves the selections of
  *                               several consecutive cuts), with the reference's exact arithmetic (the rounding points of
- *                               rqae_search_accumulate_f16), from the table of rqae_search_build_table_f16:
- *                               server.py:290-305 for the selected sequences only. */
+ *                               rqae_search_accumulate_f16), from `table` = the query's rows of the engine table as
+ *                               they lie, Qr[l][q][c] = sims[l][query[q][l]][c] (rqae_search_build_qrows_f16;
+ *                               server.py:183-196's query_sims): server.py:290-305 for the selected sequences only. */
 size_t rqae_search_tc_store_bytes(int64_t n_seq, int nq_codes);
+size_t rqae_search_qrows_bytes(int n_layers, int n_query, int K);
+int rqae_search_build_qrows_f16(const void* sims_f16, int K, const int32_t* query, int64_t query_stride, int n_query,
+                                int n_layers, void* qrows, size_t qrows_bytes, void* stream);
 int rqae_search_tc_pack_store(const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq, int seq_len,
                               int nq_codes, int K, void* store_tc, size_t store_bytes, void* stream);
 size_t rqae_search_tc_workspace_bytes(const int32_t* layers_host, int n_layers_list);

@@ -18,7 +18,8 @@ SYMBOLS = [
     "rqae_version", "rqae_strerror", "rqae_last_cuda_error", "rqae_packed_bytes", "rqae_pack_weights",
     "rqae_forward_f32", "rqae_forward_variant", "rqae_hook_rmsnorm", "rqae_decode_f32", "rqae_forward_host_f32", "rqae_forward_host_config", "rqae_forward_host_mode", "rqae_widen_codes_host", "rqae_forward_host_release",
     "rqae_fp32_peak_probe", "rqae_intensity_profile", "rqae_search_tc_store_bytes", "rqae_search_tc_pack_store",
-    "rqae_search_tc_workspace_bytes", "rqae_search_tc_maxima_f16", "rqae_search_rows_f16",
+    "rqae_search_tc_workspace_bytes", "rqae_search_tc_maxima_f16", "rqae_search_rows_f16", "rqae_search_qrows_bytes",
+    "rqae_search_build_qrows_f16",
     "rqae_launch_count", "rqae_intensity_workspace_bytes", "rqae_intensity_f16",
     "rqae_select_top_middle_bottom_f16", "rqae_decode_tc_workspace_bytes", "rqae_decode_tc_f32",
     "rqae_search_table_bytes", "rqae_search_build_table_f16", "rqae_search_accumulate_f16", "rqae_search_position_max_f16",
@@ -99,6 +100,10 @@ def load() -> ctypes.CDLL:
     lib.rqae_search_tc_workspace_bytes.argtypes = [vp, i]
     lib.rqae_search_tc_maxima_f16.restype = i
     lib.rqae_search_tc_maxima_f16.argtypes = [vp, i64, i, i, vp, vp, i, i, vp, i64, i, vp, i, vp, i64, vp, sz, vp]
+    lib.rqae_search_qrows_bytes.restype = sz
+    lib.rqae_search_qrows_bytes.argtypes = [i, i, i]
+    lib.rqae_search_build_qrows_f16.restype = i
+    lib.rqae_search_build_qrows_f16.argtypes = [vp, i, vp, i64, i, i, vp, sz, vp]
     lib.rqae_search_rows_f16.restype = i
     lib.rqae_search_rows_f16.argtypes = [vp, i, vp, i, i64, i64, i, vp, i, i, vp, i, i, vp, vp]
     lib.rqae_launch_count.restype = i64

@@ -318,8 +318,24 @@ __global__ void srch_pack_u_kernel(const int* __restrict__ query, long long quer
 // reference's arithmetic (the roundings of search_accumulate_kernel) for the selected sequences only
 // (server.py:290-305).  One warp per (query position, selected sequence); lanes take the positions.
 // ---------------------------------------------------------------------------------------------------------
+// Qr[l][q][c] = sims[l][qcode[q][l]][c]: the query's rows of the table as they lie (server.py:183-196's `query_sims`).
+// The rows kernel below gathers from THIS layout: for one (layer, query position) all K entries are 1 250 contiguous
+// bytes, so the warps that work on the same query position (a block holds eight selected sequences of one position) find
+// each other's sectors in L1; from the code-major table of the accumulate kernel every gather was a sector of its own.
+__global__ void __launch_bounds__(256) search_qrows_kernel(const __half* __restrict__ sims, const int* __restrict__ query,
+                                                           long long query_stride, int n_query, int n_layers, int K,
+                                                           __half* __restrict__ out) {
+  const int l = blockIdx.y, q = blockIdx.x;
+  if (l >= n_layers || q >= n_query) return;
+  const int qc = query[(long long)q * query_stride + l];
+  __half* dst = out + ((size_t)l * n_query + q) * K;
+  const __half* src = sims + ((size_t)l * K + (qc >= 0 && qc < K ? qc : 0)) * K;
+  const bool ok = qc >= 0 && qc < K;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) dst[c] = ok ? src[c] : __float2half(0.f);
+}
+
 struct SearchRowsParams {
-  const __half* table;      // Qt [layers][K][SR_Q]
+  const __half* table;      // Qr [layers][n_query][K]
   const void* codes;        // [n_seq][seq_len][code_stride]
   long long code_stride, n_seq;
   int seq_len, K, n_query, n_sel, n_cuts;   // n_cuts selections of [n_query][n_sel] sequences; selection c uses ranges 0 .. first_range + c
@@ -341,7 +357,8 @@ __global__ void __launch_bounds__(256) search_rows_kernel(const SearchRowsParams
   const long long n = p.sel[wid];
   __half* out = p.out + wid * p.seq_len;
   const CodeT* __restrict__ codes = (const CodeT*)p.codes;
-  const __half* __restrict__ tab = p.table + q;
+  const __half* __restrict__ tab = p.table + (size_t)q * p.K;
+  const size_t lstride = (size_t)p.n_query * p.K;
   const int K = p.K;
   for (int s = lane; s < p.seq_len; s += 32) {
     if (n < 0 || n >= p.n_seq) { out[s] = __float2half(0.f); continue; }
@@ -363,14 +380,14 @@ __global__ void __launch_bounds__(256) search_rows_kernel(const SearchRowsParams
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const bool ok = c[i] >= 0 && c[i] < K;
-            v[i] = ok ? __ldg(tab + ((size_t)(l + i) * K + (size_t)c[i]) * SR_Q) : __float2half(0.f);
+            v[i] = ok ? __ldg(tab + (size_t)(l + i) * lstride + (size_t)c[i]) : __float2half(0.f);
           }
 #pragma unroll
           for (int i = 0; i < 8; i++) cs += __half2float(v[i]);             // fp32 sum, ascending layer order (+0 for a skipped code)
         }
         for (; l < c1; l++) {
           const long long c = (long long)row[l];
-          if (c >= 0 && c < K) cs += __half2float(__ldg(tab + ((size_t)l * K + (size_t)c) * SR_Q));
+          if (c >= 0 && c < K) cs += __half2float(__ldg(tab + (size_t)l * lstride + (size_t)c));
         }
         const __half h = __float2half_rn(cs);                               // sum(dim=-1) of an fp16 tensor
         rng = (c0 == a) ? h : __float2half_rn(__half2float(rng) + __half2float(h));    // intensities += chunk (fp16)

@@ -1345,6 +1345,24 @@ int rqae_search_tc_maxima_f16(const void* store_tc, int64_t n_seq, int seq_len, 
   return RQAE_OK;
 }
 
+size_t rqae_search_qrows_bytes(int n_layers, int n_query, int K) {
+  if (n_layers <= 0 || n_query <= 0 || K <= 0) return 0;
+  return (size_t)n_layers * (size_t)n_query * (size_t)K * sizeof(__half);
+}
+
+int rqae_search_build_qrows_f16(const void* sims_f16, int K, const int32_t* query, int64_t query_stride, int n_query,
+                                int n_layers, void* qrows, size_t qrows_bytes, void* stream) {
+  if (!sims_f16 || !query || !qrows || K <= 0 || n_layers <= 0 || n_query <= 0 || query_stride < n_layers) return RQAE_EINVAL;
+  if (n_query > rq::SR_Q || n_layers > 65535) return RQAE_EUNSUPPORTED;
+  if (qrows_bytes < rqae_search_qrows_bytes(n_layers, n_query, K)) return RQAE_ESIZE;
+  dim3 grid((unsigned)n_query, (unsigned)n_layers);
+  rq::search_qrows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)sims_f16, query, query_stride, n_query, n_layers, K,
+                                                                  (__half*)qrows);
+  RQ_CUDA(cudaGetLastError());
+  g_launches++;
+  return RQAE_OK;
+}
+
 int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_dtype, int64_t code_stride, int64_t n_seq,
                          int seq_len, const int32_t* sel, int n_query, int n_sel, const int32_t* layers_host,
                          int first_range, int n_cuts, void* rows_out, void* stream) {

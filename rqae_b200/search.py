@@ -174,7 +174,7 @@ class IntensityEngine:
 
     def rows_exact(self, table: torch.Tensor, sel: torch.Tensor, layers: Sequence[int], first_range: Optional[int] = None) -> torch.Tensor:
         """``intensity_accumulation[sel[..., q, j], :, q]`` (server.py:290-305) recomputed with the reference's arithmetic
-        for the selected sequences only.  ``table``: the query's rows of the engine table (``rqae_search_build_table_f16``).
+        for the selected sequences only.  ``table``: the query's rows of the engine table as they lie (``_build_qrows``).
         ``sel`` (Sq, n_sel): after all ranges of ``layers`` -> (Sq, n_sel, S) fp16.  ``sel`` (C, Sq, n_sel) with
         ``first_range``: selection c after the ranges 0 .. first_range + c -> (C, Sq, n_sel, S), one launch."""
         N, S, nq_codes = self.activations.shape
@@ -206,17 +206,18 @@ class IntensityEngine:
             cache[name] = t
         return t[:n].view(*shape)
 
-    def _build_table(self, query: torch.Tensor, L: int) -> torch.Tensor:
+    def _build_qrows(self, query: torch.Tensor, L: int) -> torch.Tensor:
+        """server.py:183-196: ``query_sims[l, q] = sims[l, query[q, l]]`` as one (L, Sq, K) fp16 tensor -- what ``rows_exact`` gathers from."""
         lib = _lib.load()
         K = self.sims.shape[1]
         dev = self.sims.device
-        tbytes = lib.rqae_search_table_bytes(L, K)
-        table = torch.empty(tbytes // 2, dtype=torch.float16, device=dev)
+        Sq = query.shape[0]
+        out = torch.empty(L, Sq, K, dtype=torch.float16, device=dev)
         with torch.cuda.device(dev):
-            st = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.rqae_search_build_table_f16(self.sims.data_ptr(), K, query.data_ptr(), query.stride(0), query.shape[0],
-                                                      L, table.data_ptr(), tbytes, st), "rqae_search_build_table_f16")
-        return table
+            _lib.check(lib.rqae_search_build_qrows_f16(self.sims.data_ptr(), K, query.data_ptr(), query.stride(0), Sq, L,
+                                                      out.data_ptr(), out.numel() * 2, torch.cuda.current_stream(dev).cuda_stream),
+                       "rqae_search_build_qrows_f16")
+        return out
 
     @classmethod
     def from_store(cls, model, folder: str, model_name: Optional[str] = None, dtype: torch.dtype = torch.int16, **kw):
@@ -302,7 +303,7 @@ class IntensityEngine:
             # every cut at once: one GEMM launch for the maxima, one selection launch over (cut, position) rows, one launch
             # for the exact rows of everything selected, two device->host copies; the generator then yields cut by cut
             maxv_all = self.maxima_tc(query, layers, padded=True)                      # (C, 128, N), rows >= Sq zero
-            table = self._build_table(query, max(layers))
+            table = self._build_qrows(query, max(layers))
             sel, _ = select_top_middle_bottom(maxv_all, k, n=N)                        # (C, 128, 3, k) int32
             sel = sel[:, :Sq].contiguous()
             C = len(layers)

@@ -30,7 +30,7 @@ def timed(fn, reps=3):
 
 
 maxv, t_max = timed(lambda: eng.maxima_tc(query, layers, padded=True))
-table, t_tab = timed(lambda: eng._build_table(query, max(layers)))
+table, t_tab = timed(lambda: eng._build_qrows(query, max(layers)))
 (sel, _), t_sel = timed(lambda: select_top_middle_bottom(maxv, k, n=N))
 sel = sel[:, :127].contiguous()
 lists = window_lists(sel.reshape(len(layers) * 127, 3, k), 30, 10, 10)
