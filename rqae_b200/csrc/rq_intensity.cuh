@@ -29,10 +29,11 @@
 //                            a group cannot build under its own stage's MMAs.)
 //   warps 12-19 epilogue   : four warps per accumulator.  At a cut the issuer commits that accumulator and goes on
 //                            with the other one; the warps pull the running prefix out of TMEM (tcgen05.ld
-//                            32x32b.x32) with only the reference's FIRST rounding applied (prefix -> fp16) -- half
-//                            into registers, half into shared memory -- and release the accumulator as soon as the
-//                            last load has landed.  The remaining roundings and the stores (TMA tensor stores of
-//                            [32 features][64 tokens] boxes of out[f][cut][t]) run while the MMAs of the next K-blocks do.
+//                            32x32b.x32) -- tokens 0..127 of a row with only the reference's FIRST rounding (prefix ->
+//                            fp16) as packed registers, tokens 128..255 finished into swizzled staging boxes -- and
+//                            release the accumulator as soon as the last load has landed.  The stores (TMA tensor stores
+//                            of [32 features][64 tokens] boxes of out[f][cut][t]), the remaining roundings of the kept
+//                            half and its trip through the same boxes run while the MMAs of the next K-blocks do.
 // setmaxnreg gives the control warpgroup 40 registers, the builders 80 and the epilogue 136 per thread.
 // The K axis is cut into K-blocks of 16 layers (64 k = one 128-byte swizzle row); a segment between two cuts
 // that is not a multiple of 16 layers is padded with zero slots (schedule built by int_prep_kernel).
