@@ -129,3 +129,27 @@ def test_engine_table_modes_follow_the_server_setup():
     assert torch.equal(orig, want)
     with pytest.raises(ValueError, match="Invalid mode"):
         engine_sims(m, "other")
+
+
+@pytest.mark.parametrize("mode", ["projected", "original"])
+def test_product_rank_factors_reproduce_the_engine_table(mode):
+    """rqae_b200.search.rank_factors (what the tensor-core ranking builds its fp16 tables from) against the engine
+    table of the same mode (server.py:103-115) and, for 'projected', against the oracle's factorisation: the Gram
+    matrices agree (the factors themselves are only defined up to a rotation)."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import engine_sims, rank_factors
+    torch.manual_seed(7)
+    m = RQAE(dim=80, num_quantizers=12).eval()
+    f = rank_factors(m, mode)                                         # (nq, K, R) float64
+    assert f.dtype == torch.float64 and f.shape[:2] == (12, 625) and f.shape[2] == (5 if mode == "projected" else 4)
+    gram = f @ f.transpose(1, 2)
+    table = engine_sims(m, mode).double()
+    scaled = gram * m.layer_norms.double().reshape(-1, 1, 1)
+    assert float((scaled - table).abs().max()) <= 2 ** -9 * float(m.layer_norms.max())      # the table's own fp16 roundings
+    if mode == "projected":
+        w = torch.stack([l[1].weight.detach() for l in m.layers])
+        b = torch.stack([l[1].bias.detach() for l in m.layers])
+        fo_ = so.rank5_factors(w, b, m.codebook.detach())
+        assert float((gram - fo_ @ fo_.transpose(1, 2)).abs().max()) <= 1e-12
+    with pytest.raises(ValueError, match="Invalid mode"):
+        rank_factors(m, "other")
