@@ -163,6 +163,8 @@ class IntensityEngine:
         off = (-ws.data_ptr()) % 1024
         stride = ((N + 1) // 2 * 2 + 7) // 8 * 8
         out = torch.empty(len(layers), SQ_PAD, stride, dtype=torch.float16, device=dev)
+        if stride > (N + 1) // 2 * 2:     # the kernel writes two columns per unit; the selection's 16-byte loads touch the padding
+            out[:, :, (N + 1) // 2 * 2:].zero_()
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.rqae_search_tc_maxima_f16(self._store_tc.data_ptr(), N, S, nq_codes, self._vtab.data_ptr(),
