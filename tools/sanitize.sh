@@ -21,6 +21,8 @@ timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_s
 timeout 300 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "single_query" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_search.log
 echo "=== memcheck: tensor-core search (store pack, factor gathers, maxima epilogue, exact rows) and tensor-core decode ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py tests/test_parity_gpu.py -q -x -k "tensor_core and not 127" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_tc.log
-echo "=== initcheck: tensor-core search, mining path, example search ==="
+echo "=== initcheck: example search (both modes), selection ==="
+# (not the intensity GEMM: initcheck does not see the writes of TMA tensor stores, so every later read of the output is
+#  reported as uninitialised although the values are checked against the goldens by the same tests)
 timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "tensor_core or single_query or int16" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_search.log
-timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "small or dtypes or api_shapes or 4097 or 257" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_mining.log
+timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "4097 or 257 or 5000" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_select.log
