@@ -539,8 +539,9 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
     the rank's tokens at the 14 cuts of scripts/3:178 (tcgen05 GEMM), all_to_all so that every (feature, cut) row is
     whole on one rank (shard.exchange_to_feature_shards), top / middle / bottom-100 of every row over ALL tokens
     (radix select).  Wall clock from a barrier to the last kernel, max over ranks; stage times are CUDA events."""
-    from rqae_b200.feature import intensity_many, select_top_middle_bottom, layer_weights_f16
+    from rqae_b200.feature import intensity_many, select_top_middle_bottom, layer_weights_f16, IntensityWorkspace
     from rqae_b200 import shard
+    iws = IntensityWorkspace()     # feature groups run over the same codes: their tile-major copy is made once
     T_x = x.shape[1]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     codes = torch.empty(tokens, NQ, dtype=torch.int16, device=dev)
@@ -583,7 +584,7 @@ def config4_mining_extra(torch, dist, model, x, dev, rank, world, tokens, n_feat
     for f0 in range(0, n_features, group):
         a, b, c, d = ev(), ev(), ev(), ev()
         a.record()
-        inten = intensity_many(model, codes, centers[f0:f0 + group], SCRIPT3_CUTS, layer_weights=lw, out=buf)
+        inten = intensity_many(model, codes, centers[f0:f0 + group], SCRIPT3_CUTS, layer_weights=lw, out=buf, workspace=iws)
         b.record()
         if world > 1:
             rows, _ = shard.exchange_to_feature_shards(inten, n_total)

@@ -170,6 +170,13 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
                        int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
                        const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
                        int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for another set of features over the SAME code tensor, cuts and codebook as the previous rqae_intensity_f16 call on
+ * this workspace (scripts/3_make_rqae_features.py:164-196 mines its features group by group over one code store): the
+ * tile-major copy of the codes is still in the workspace and is not rebuilt; the workspace must be large enough for this
+ * call's n_features (rqae_intensity_workspace_bytes). */
+int rqae_intensity_again_f16(const float* cb_norm, int K, int64_t n_tokens, const int32_t* centers, int64_t center_stride,
+                             int n_features, const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                             int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The selection step of the mining loop, scripts/3_make_rqae_features.py:116-128: for every row
  * (one feature at one cut) of `vals`, the positions of the top_k largest values, of the 2*(top_k/2)

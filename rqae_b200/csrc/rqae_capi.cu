@@ -1038,8 +1038,8 @@ static int int_layout(const int32_t* cuts, int n_cuts, int F, int64_t n_tokens, 
   o->off_sched = off; off = up(off + (size_t)rq::IT_MAX_KB * sizeof(rq::IntKBlock));
   o->off_wcum = off;  off = up(off + 2 * (size_t)rq::IT_MAX_CUTS * 4);
   o->off_lut = off;   off = up(off + 2 * (size_t)rq::IT_LUT_ROWS * 8);
+  o->off_codes = off; off = up(off + (size_t)o->L * (size_t)o->T_pad * 2);   // before the feature tiles: its place does not depend on F
   o->off_u = off;     off = up(off + (size_t)o->F_tiles * nkb * rq::IT_U_TILE);
-  o->off_codes = off; off = up(off + (size_t)o->L * (size_t)o->T_pad * 2);
   o->total = off;
   return RQAE_OK;
 }
@@ -1058,11 +1058,32 @@ size_t rqae_intensity_workspace_bytes(const int32_t* cuts_host, int n_cuts, int 
   return L.total;
 }
 
+static int intensity_impl(const float* cb_norm, int K, const void* codes, int code_dtype, int64_t code_stride,
+                          int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
+                          const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                          int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream, bool reuse_codes);
+
 int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_dtype, int64_t code_stride,
                        int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
                        const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
                        int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!cb_norm || !codes || !centers || !layer_weights_f16 || !out || !workspace || K <= 0) return RQAE_EINVAL;
+  if (!codes) return RQAE_EINVAL;
+  return intensity_impl(cb_norm, K, codes, code_dtype, code_stride, n_tokens, centers, center_stride, n_features, layer_weights_f16,
+                        cuts_host, n_cuts, out, out_stride, workspace, workspace_bytes, stream, false);
+}
+
+int rqae_intensity_again_f16(const float* cb_norm, int K, int64_t n_tokens, const int32_t* centers, int64_t center_stride,
+                             int n_features, const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                             int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  return intensity_impl(cb_norm, K, nullptr, 0, 1 << 30, n_tokens, centers, center_stride, n_features, layer_weights_f16, cuts_host,
+                        n_cuts, out, out_stride, workspace, workspace_bytes, stream, true);
+}
+
+static int intensity_impl(const float* cb_norm, int K, const void* codes, int code_dtype, int64_t code_stride,
+                          int64_t n_tokens, const int32_t* centers, int64_t center_stride, int n_features,
+                          const void* layer_weights_f16, const int32_t* cuts_host, int n_cuts, void* out,
+                          int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream, bool reuse_codes) {
+  if (!cb_norm || (!codes && !reuse_codes) || !centers || !layer_weights_f16 || !out || !workspace || K <= 0) return RQAE_EINVAL;
   if (code_dtype < 0 || code_dtype > 2) return RQAE_EINVAL;
   if (K + 1 > rq::IT_LUT_ROWS) return RQAE_EUNSUPPORTED;
   IntLayout L;
@@ -1085,8 +1106,8 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   pp.sched = (rq::IntKBlock*)(ws + L.off_sched); pp.wcum = (float*)(ws + L.off_wcum); pp.lut = (uint2*)(ws + L.off_lut);
   rq::int_prep_kernel<<<4, 256, 0, st>>>(pp);
   RQ_CUDA(cudaGetLastError());
-  // 2. codes -> layer-major int16
-  {
+  // 2. codes -> layer-major int16 (kept from the previous call on this workspace when the caller says they are the same)
+  if (!reuse_codes) {
     dim3 grid((unsigned)(L.T_pad / rq::IT_TOK), (unsigned)((L.L + 31) / 32)), block(256);
     uint32_t* ct = (uint32_t*)(ws + L.off_codes);
     if (code_dtype == 2) rq::int_transpose_kernel<long long><<<grid, block, 0, st>>>((const long long*)codes, code_stride, n_tokens, L.L, K, ct);
@@ -1121,7 +1142,7 @@ int rqae_intensity_f16(const float* cb_norm, int K, const void* codes, int code_
   if (rc) return rc;
   rq::rq_intensity_kernel<0><<<grid, rq::IT_THREADS, rq::IntSmem::TOTAL, st>>>(ip, out_map);
   RQ_CUDA(cudaGetLastError());
-  g_launches += 4;
+  g_launches += reuse_codes ? 3 : 4;
   return RQAE_OK;
 }
 

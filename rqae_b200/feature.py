@@ -60,8 +60,20 @@ def _cuts(layers: Sequence[int]):
     return cuts, [pos[int(l)] for l in layers]
 
 
+class IntensityWorkspace:
+    """Caller-owned scratch of ``intensity_many``.  It keeps the tile-major copy of the code tensor between calls: a later
+    call with the same code tensor (same storage, shape and version), the same cuts and codebook size only rebuilds the
+    feature operand (``rqae_intensity_again_f16``) -- scripts/3_make_rqae_features.py:164-196 mines its features group by
+    group over one code store."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.key = None
+
+
 def intensity_many(rqae, token_indices: torch.Tensor, centers: torch.Tensor, layers: Sequence[int],
-                   layer_weights: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   layer_weights: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   workspace: Optional[IntensityWorkspace] = None) -> torch.Tensor:
     """Intensities of F features over T tokens at the given layer cuts.
 
     token_indices (..., nq) integer codes on the GPU (int16 / int32 / int64); centers (F, nq) integer;
@@ -104,15 +116,32 @@ def intensity_many(rqae, token_indices: torch.Tensor, centers: torch.Tensor, lay
         nbytes = lib.rqae_intensity_workspace_bytes(cuts_arr.ctypes.data, len(cuts), Fn, T)
         if nbytes == 0:
             raise NotImplementedError("unsupported intensity shape (at most 64 distinct cuts / 256 K-blocks)")
-        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        key = (codes.data_ptr(), codes._version, tuple(codes.shape), codes.stride(0), codes.dtype, tuple(cuts), K, str(dev))
+        again = workspace is not None and workspace.key == key and workspace.buf is not None \
+            and workspace.buf.numel() >= nbytes + 1024
+        if workspace is None:
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        else:
+            if not again:
+                if workspace.buf is None or workspace.buf.numel() < nbytes + 1024 or workspace.buf.device != dev:
+                    workspace.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                workspace.key = None          # set below, once the codes are in place
+            ws = workspace.buf
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
         with torch.cuda.device(dev):
-            rc = lib.rqae_intensity_f16(
-                cb_norm.data_ptr(), K, codes.data_ptr(), _lib.CODE_DTYPE[str(codes.dtype).split(".")[-1]],
-                codes.stride(0) if T > 1 else nq_codes, T, centers.data_ptr(), centers.shape[1], Fn, w.data_ptr(),
-                cuts_arr.ctypes.data, len(cuts), out.data_ptr(), out.shape[2], ws_ptr, nbytes,
-                torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(rc, "rqae_intensity_f16")
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if again:
+                rc = lib.rqae_intensity_again_f16(cb_norm.data_ptr(), K, T, centers.data_ptr(), centers.shape[1], Fn, w.data_ptr(),
+                                                  cuts_arr.ctypes.data, len(cuts), out.data_ptr(), out.shape[2], ws_ptr, ws_bytes, st)
+            else:
+                rc = lib.rqae_intensity_f16(
+                    cb_norm.data_ptr(), K, codes.data_ptr(), _lib.CODE_DTYPE[str(codes.dtype).split(".")[-1]],
+                    codes.stride(0) if T > 1 else nq_codes, T, centers.data_ptr(), centers.shape[1], Fn, w.data_ptr(),
+                    cuts_arr.ctypes.data, len(cuts), out.data_ptr(), out.shape[2], ws_ptr, ws_bytes, st)
+        _lib.check(rc, "rqae_intensity_again_f16" if again else "rqae_intensity_f16")
+        if workspace is not None:
+            workspace.key = key
         for t in (ws, cb_norm, w, centers, codes):
             t.record_stream(torch.cuda.current_stream(dev))
     res = out[:, :, :T]
@@ -305,7 +334,10 @@ class FeatureHelper:
             raise ValueError("Model not loaded. Needed for intensity calculation.")
         n_seq, seq_len = self.indices.shape[:2]
         centers = torch.stack([f.center.reshape(-1) for f in features])
-        inten = intensity_many(rqae, self.indices, centers, layers, layer_weights=features[0].layer_weights)   # (F, C, T)
+        if "_workspace" not in self.__dict__:
+            self._workspace = IntensityWorkspace()       # the code store's tile-major copy survives from one feature group to the next
+        inten = intensity_many(rqae, self.indices, centers, layers, layer_weights=features[0].layer_weights,
+                               workspace=self._workspace)                                                      # (F, C, T)
         sel, _ = select_top_middle_bottom(inten, top_k)                                                        # (F, C, 3, k)
         sel = sel.cpu()
         mid = 2 * (top_k // 2)

@@ -96,6 +96,34 @@ def test_many_features_many_tokens_against_exact_value():
     assert float((out[7, :, 123].float() - 1.0).abs().max()) <= ATOL
 
 
+def test_workspace_reuse_skips_the_code_copy_and_changes_nothing():
+    """intensity_many(workspace=...) on the same code tensor with other features (rqae_intensity_again_f16): identical to
+    independent calls, also after the code tensor was modified in place (the copy is rebuilt) and with more features than
+    the first call had (the workspace grows)."""
+    from rqae_b200 import RQAE, _lib
+    from rqae_b200.feature import intensity_many, IntensityWorkspace
+    dev = _dev()
+    torch.manual_seed(0)
+    m = RQAE(dim=64, num_quantizers=96).eval().to(dev)
+    g = torch.Generator().manual_seed(21)
+    codes = torch.randint(0, 625, (700, 96), generator=g).to(dev).to(torch.int16)
+    cA = torch.randint(0, 625, (40, 96), generator=g)
+    cB = torch.randint(0, 625, (300, 96), generator=g)
+    layers = [2, 7, 16, 40, 95]
+    ws = IntensityWorkspace()
+    lib = _lib.load()
+    a1 = intensity_many(m, codes, cA, layers, workspace=ws).clone()
+    n0 = int(lib.rqae_launch_count(0))
+    a2 = intensity_many(m, codes, cA[:7], layers, workspace=ws).clone()
+    assert int(lib.rqae_launch_count(0)) - n0 == 3                      # schedule, feature operand, GEMM: no code copy
+    b1 = intensity_many(m, codes, cB, layers, workspace=ws).clone()     # more features: the workspace is re-made
+    assert torch.equal(a1, intensity_many(m, codes, cA, layers)) and torch.equal(a2, a1[:7])
+    assert torch.equal(b1, intensity_many(m, codes, cB, layers))
+    codes[5, 3] = (int(codes[5, 3]) + 1) % 625                          # in place: the version changes, the copy is rebuilt
+    c1 = intensity_many(m, codes, cA, layers, workspace=ws)
+    assert torch.equal(c1, intensity_many(m, codes, cA, layers)) and not torch.equal(c1, a1)
+
+
 def test_rqae_feature_api_shapes(kat):
     """RQAEFeature.intensity keeps the reference's (..., nq) -> (..., len(layers)) contract."""
     from rqae_b200 import RQAE, RQAEFeature
