@@ -345,57 +345,109 @@ struct SearchRowsParams {
   __half* out;              // [n_cuts][n_query][n_sel][seq_len]
 };
 
+// One block per (cut, query position): its selected sequences all read the same table rows Qr[l][q][:], so the block
+// stages the rows of 16 layers (20 KB) in shared memory and every thread advances its items -- (selected sequence,
+// position) pairs, up to SRW_ITEMS per thread -- through them; fp32 chunk sums and the fp16 range / accumulation values
+// of the items stay in registers.  (A warp per pair gathering two-byte entries straight from L1 was bound by the L1
+// data pipe: 7.7 ms for the 82 550 pairs of a query; 13 ms from the code-major table.)
+constexpr int SRW_THREADS = 256;
+constexpr int SRW_ITEMS = 26;                        // items per thread and pass: 6 656 per block (50 selections x 127 positions = 6 350)
+constexpr int SRW_PASS = SRW_THREADS * SRW_ITEMS;
+constexpr int SRW_KMAX = 640;                        // table row length the staging buffer holds
+constexpr int SRW_LB = 16;                           // layers per stage: an item's codes of a stage are one whole 32-byte sector (static shared memory: 47 KB)
+
 template <typename CodeT>
-__global__ void __launch_bounds__(256) search_rows_kernel(const SearchRowsParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long per_cut = (long long)p.n_query * p.n_sel;
-  if (wid >= per_cut * p.n_cuts) return;
-  const int cut = (int)(wid / per_cut);
-  const int q = (int)((wid - cut * per_cut) / p.n_sel);
+__global__ void __launch_bounds__(SRW_THREADS) search_rows_kernel(const SearchRowsParams p) {
+  __shared__ __align__(16) __half tab[SRW_LB][SRW_KMAX];
+  __shared__ uint32_t tok[SRW_PASS];                 // token index (sequence * seq_len + position) of every item, 0xFFFFFFFF: skipped
+  const int tid = threadIdx.x;
+  const int cut = p.n_cuts - 1 - blockIdx.x / p.n_query, q = blockIdx.x % p.n_query;   // deepest cuts first: their blocks run longest
   const int n_ranges = p.first_range + cut + 1;
-  const long long n = p.sel[wid];
-  __half* out = p.out + wid * p.seq_len;
-  const CodeT* __restrict__ codes = (const CodeT*)p.codes;
-  const __half* __restrict__ tab = p.table + (size_t)q * p.K;
-  const size_t lstride = (size_t)p.n_query * p.K;
   const int K = p.K;
-  for (int s = lane; s < p.seq_len; s += 32) {
-    if (n < 0 || n >= p.n_seq) { out[s] = __float2half(0.f); continue; }
-    const CodeT* row = codes + (n * p.seq_len + s) * p.code_stride;
-    __half acc = __float2half(0.f);
+  const long long per = (long long)p.n_sel * p.seq_len;
+  const int* sel = p.sel + ((size_t)cut * p.n_query + q) * p.n_sel;
+  __half* out = p.out + ((size_t)cut * p.n_query + q) * (size_t)per;
+  const CodeT* __restrict__ codes = (const CodeT*)p.codes;
+  const __half* __restrict__ qr = p.table + (size_t)q * K;
+  const size_t lstride = (size_t)p.n_query * K;
+  // int16 code rows that start on 16-byte boundaries: the 8 codes of an aligned layer block are one vector load
+  const bool vec16 = sizeof(CodeT) == 2 && (p.code_stride % SRW_LB) == 0 && ((uintptr_t)p.codes % 32) == 0;
+  for (long long base = 0; base < per; base += SRW_PASS) {
+    for (int i = tid; i < SRW_PASS; i += SRW_THREADS) {
+      const long long it = base + i;
+      uint32_t t = 0xFFFFFFFFu;
+      if (it < per) {
+        const int j = (int)(it / p.seq_len), s = (int)(it - (long long)j * p.seq_len);
+        const long long n = sel[j];
+        if (n >= 0 && n < p.n_seq) t = (uint32_t)(n * p.seq_len + s);
+      }
+      tok[i] = t;
+    }
+    __syncthreads();
+    float cs[SRW_ITEMS];
+    __half rng[SRW_ITEMS], acc[SRW_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SRW_ITEMS; k++) { cs[k] = 0.f; rng[k] = __float2half(0.f); acc[k] = __float2half(0.f); }
     int a = 0;
     for (int r = 0; r < n_ranges; r++) {
       const int b = p.ends[r];
-      __half rng = __float2half(0.f);
       for (int c0 = a; c0 < b; c0 += SR_CHUNK) {
         const int c1 = (c0 + SR_CHUNK < b) ? c0 + SR_CHUNK : b;
-        float cs = 0.f;
-        int l = c0;
-        for (; l + 8 <= c1; l += 8) {                                       // eight independent gathers in flight
-          long long c[8];
-          __half v[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) c[i] = (long long)row[l + i];
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const bool ok = c[i] >= 0 && c[i] < K;
-            v[i] = ok ? __ldg(tab + (size_t)(l + i) * lstride + (size_t)c[i]) : __float2half(0.f);
+        for (int jb = c0 / SRW_LB; jb <= (c1 - 1) / SRW_LB; jb++) {            // aligned blocks of SRW_LB layers: the codes of an item are whole 32-byte sectors
+          const int l0 = SRW_LB * jb;
+          const int lo = (c0 > l0 ? c0 : l0) - l0, hi = (c1 < l0 + SRW_LB ? c1 : l0 + SRW_LB) - l0;
+          __syncthreads();                                                    // the previous stage has been consumed
+          for (int i = tid; i < (hi - lo) * K; i += SRW_THREADS) {
+            const int li = i / K, c = i - li * K;
+            tab[lo + li][c] = qr[(size_t)(l0 + lo + li) * lstride + c];
           }
+          __syncthreads();
 #pragma unroll
-          for (int i = 0; i < 8; i++) cs += __half2float(v[i]);             // fp32 sum, ascending layer order (+0 for a skipped code)
+          for (int k = 0; k < SRW_ITEMS; k++) {
+            const uint32_t t = tok[tid + k * SRW_THREADS];
+            if (t != 0xFFFFFFFFu) {
+              const CodeT* row = codes + (size_t)t * p.code_stride + l0;
+              float sum = cs[k];
+              if (vec16) {
+                uint32_t ww[SRW_LB / 2];
+#pragma unroll
+                for (int v = 0; v < SRW_LB / 8; v++) {
+                  const uint4 w = __ldg(reinterpret_cast<const uint4*>(row) + v);
+                  ww[4 * v] = w.x; ww[4 * v + 1] = w.y; ww[4 * v + 2] = w.z; ww[4 * v + 3] = w.w;
+                }
+#pragma unroll
+                for (int li = 0; li < SRW_LB; li++) {                         // fp32 sum, ascending layer order (+0 for a skipped code)
+                  const int c = (int)(short)((ww[li >> 1] >> ((li & 1) * 16)) & 0xFFFFu);
+                  if (li >= lo && li < hi && c >= 0 && c < K) sum += __half2float(tab[li][c]);
+                }
+              } else {
+                for (int li = lo; li < hi; li++) {
+                  const long long c = (long long)row[li];
+                  if (c >= 0 && c < K) sum += __half2float(tab[li][c]);
+                }
+              }
+              cs[k] = sum;
+            }
+          }
         }
-        for (; l < c1; l++) {
-          const long long c = (long long)row[l];
-          if (c >= 0 && c < K) cs += __half2float(__ldg(tab + (size_t)l * lstride + (size_t)c));
+#pragma unroll
+        for (int k = 0; k < SRW_ITEMS; k++) {
+          const __half h = __float2half_rn(cs[k]);                            // sum(dim=-1) of an fp16 tensor
+          rng[k] = (c0 == a) ? h : __float2half_rn(__half2float(rng[k]) + __half2float(h));   // intensities += chunk (fp16)
+          cs[k] = 0.f;
         }
-        const __half h = __float2half_rn(cs);                               // sum(dim=-1) of an fp16 tensor
-        rng = (c0 == a) ? h : __float2half_rn(__half2float(rng) + __half2float(h));    // intensities += chunk (fp16)
       }
-      acc = (r == 0) ? rng : __float2half_rn(__half2float(acc) + __half2float(rng));   // accumulation += range (fp16)
+#pragma unroll
+      for (int k = 0; k < SRW_ITEMS; k++)
+        acc[k] = (r == 0) ? rng[k] : __float2half_rn(__half2float(acc[k]) + __half2float(rng[k]));   // accumulation += range (fp16)
       a = b;
     }
-    out[s] = acc;
+#pragma unroll
+    for (int k = 0; k < SRW_ITEMS; k++) {
+      const long long it = base + tid + (long long)k * SRW_THREADS;
+      if (it < per) out[it] = (tok[tid + k * SRW_THREADS] != 0xFFFFFFFFu) ? acc[k] : __float2half(0.f);
+    }
+    __syncthreads();                                                          // tok is rewritten by the next pass
   }
 }
 

@@ -1402,13 +1402,12 @@ int rqae_search_rows_f16(const void* table, int K, const void* codes, int code_d
   rp.table = (const __half*)table; rp.codes = codes; rp.code_stride = code_stride; rp.n_seq = n_seq; rp.seq_len = seq_len;
   rp.K = K; rp.n_query = n_query; rp.n_sel = n_sel; rp.n_cuts = n_cuts; rp.first_range = first_range; rp.sel = sel;
   rp.out = (__half*)rows_out;
-  const long long warps = (long long)n_query * n_sel * n_cuts;
-  if ((warps + 7) / 8 >= (1LL << 31)) return RQAE_EUNSUPPORTED;
-  const unsigned blocks = (unsigned)((warps + 7) / 8);
+  if (K > rq::SRW_KMAX || n_seq * (int64_t)seq_len >= 0xFFFFFFFFLL) return RQAE_EUNSUPPORTED;
+  const unsigned blocks = (unsigned)(n_query * n_cuts);                      // one block per (cut, query position)
   cudaStream_t st = (cudaStream_t)stream;
-  if (code_dtype == RQAE_CODE_I64) rq::search_rows_kernel<long long><<<blocks, 256, 0, st>>>(rp);
-  else if (code_dtype == RQAE_CODE_I32) rq::search_rows_kernel<int><<<blocks, 256, 0, st>>>(rp);
-  else rq::search_rows_kernel<short><<<blocks, 256, 0, st>>>(rp);
+  if (code_dtype == RQAE_CODE_I64) rq::search_rows_kernel<long long><<<blocks, rq::SRW_THREADS, 0, st>>>(rp);
+  else if (code_dtype == RQAE_CODE_I32) rq::search_rows_kernel<int><<<blocks, rq::SRW_THREADS, 0, st>>>(rp);
+  else rq::search_rows_kernel<short><<<blocks, rq::SRW_THREADS, 0, st>>>(rp);
   RQ_CUDA(cudaGetLastError());
   g_launches++;
   return RQAE_OK;
