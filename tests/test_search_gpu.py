@@ -224,7 +224,8 @@ def test_tensor_core_maxima_within_stated_tolerance_of_exact_mode(mode, n_seq, S
     print(f"tensor-core maxima vs exact ({mode}, {n_seq} x {S}, {Sq} query positions): worst {worst:.2f} fp16 steps of the cut's largest value")
 
 
-def test_tensor_core_find_examples_reports_exact_rows_and_near_equal_ranks():
+@pytest.mark.parametrize("dtype", [torch.int16, torch.int32, torch.int64])
+def test_tensor_core_find_examples_reports_exact_rows_and_near_equal_ranks(dtype):
     """precision="tc": the reported intensities are the exact accumulation rows of the reported sequences (bit for bit),
     and at every rank the reported sequence's exact maximum is within the stated tolerance of the exact mode's value."""
     from rqae_b200 import RQAE
@@ -236,7 +237,8 @@ def test_tensor_core_find_examples_reports_exact_rows_and_near_equal_ranks():
     model = RQAE(dim=256, num_quantizers=nq).eval().to(dev)
     K = model.codebook.shape[1]
     g = torch.Generator().manual_seed(12)
-    codes = torch.randint(0, K, (n_seq, S, nq), generator=g, dtype=torch.int32).to(dev)
+    codes = torch.randint(0, K, (n_seq, S, nq), generator=g, dtype=torch.int32).to(dev).to(dtype)   # int16: vector code loads in the rows kernel
+    codes[3, 2, 5] = -1                                                # contributes 0 in both modes and in the exact rows
     layers = [4, 8, 16, 64, 96]
     exact = IntensityEngine(model, codes)
     tc = IntensityEngine(model, codes, precision="tc")
