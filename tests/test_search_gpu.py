@@ -258,3 +258,32 @@ def test_tensor_core_find_examples_reports_exact_rows_and_near_equal_ranks(dtype
             assert float((vt - ve).abs().max()) <= 8 * step, part
     # the query sequence itself tops every position at the last cut in both modes
     assert bool((res_t[-1][0]["top"]["indices"][:, 0] == 5).all()) and bool((res_e[-1][0]["top"]["indices"][:, 0] == 5).all())
+
+
+@pytest.mark.parametrize("n_seq,S,Sq,layers", [(1, 5, 3, [3]), (2, 128, 1, [9, 10]), (5, 1, 128, [1, 2, 40])])
+def test_tensor_core_ranking_edge_shapes(n_seq, S, Sq, layers):
+    """One sequence / one position / 128 positions per sequence (no padding column) / 128 query positions / ranges that
+    start and end inside an 8-layer block: maxima within the stated tolerance of the exact mode, rows bit-equal."""
+    from rqae_b200 import RQAE
+    from rqae_b200.search import IntensityEngine
+    dev = _dev()
+    torch.manual_seed(9)
+    nq = 48
+    model = RQAE(dim=128, num_quantizers=nq).eval().to(dev)
+    K = model.codebook.shape[1]
+    g = torch.Generator().manual_seed(13)
+    codes = torch.randint(0, K, (n_seq, S, nq), generator=g, dtype=torch.int32).to(dev).to(torch.int16)
+    query = torch.randint(0, K, (Sq, nq), generator=g, dtype=torch.int32)
+    exact = IntensityEngine(model, codes)
+    tc = IntensityEngine(model, codes, precision="tc")
+    q = exact._query(None, query, max(layers))
+    got = tc.maxima_tc(q, layers).float().cpu()
+    accs = [(a.clone(), m.clone()) for a, m in exact.accumulate(q, layers)]
+    for ci, (acc, maxv) in enumerate(accs):
+        want = maxv.float().cpu()
+        assert got[ci].shape == want.shape
+        assert float((got[ci] - want).abs().max()) <= 4 * _fp16_step(float(want.abs().max()))
+    sel = torch.arange(n_seq, dtype=torch.int32, device=dev).repeat(Sq, 1)               # every sequence for every position
+    rows = tc.rows_exact(tc._build_qrows(q, max(layers)), sel, layers).cpu()                # (Sq, n_seq, S) after the last range
+    acc = accs[-1][0].cpu()                                                                  # (N, S, Sq)
+    assert torch.equal(rows.float(), acc.permute(2, 0, 1).float())
