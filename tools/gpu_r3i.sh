@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 second evidence visit: whole -m gpu suite, sanitizer, bench line, launch list, ncu of the intensity GEMM and the search GEMM
 set -u
-TAG=${1:-r3z}
+TAG=${1:-r4a}
 OUT=gpurun_out
 mkdir -p $OUT
 echo "=== pytest -m gpu ==="
