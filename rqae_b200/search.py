@@ -197,6 +197,17 @@ class IntensityEngine:
                                                        torch.cuda.current_stream(dev).cuda_stream), "rqae_search_rows_f16")
         return out[0] if single else out
 
+    def _pinned(self, name: str, shape, dtype) -> torch.Tensor:
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        t = cache.get(name)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(n, dtype=dtype, pin_memory=True)
+            cache[name] = t
+        return t[:n].view(*shape)
+
     def _build_qrows(self, query: torch.Tensor, L: int) -> torch.Tensor:
         """server.py:183-196: ``query_sims[l, q] = sims[l, query[q, l]]`` as one (L, Sq, K) fp16 tensor -- what ``rows_exact`` gathers from."""
         lib = _lib.load()
@@ -302,20 +313,20 @@ class IntensityEngine:
             names = list(lists)
             cat = torch.cat([lists[nm] for nm in names], dim=1).reshape(C, Sq, -1)     # (C, Sq, n_sel)
             rows_d = self.rows_exact(table, cat, layers, first_range=0)                # (C, Sq, n_sel, S)
-            # per window one contiguous device tensor and one copy into a fresh pinned tensor (torch's caching host allocator
-            # hands back the blocks of earlier queries; a pageable .cpu() of the 21 MB of rows costs 10 ms): what a cut
-            # yields is a contiguous view of those, owned by the caller
-            host, o = {}, 0
+            # per window one contiguous device tensor, one copy through a pinned staging buffer the engine keeps (a pageable
+            # .cpu() of the 21 MB of rows costs 10 ms; allocating pinned memory per query costs as much on a cold process),
+            # and one host copy out of it: what a cut yields is a contiguous view of that copy, owned by the caller
+            stage, o = {}, 0
             for nm in names:
                 w = lists[nm].shape[1]
                 r_d, i_d = rows_d[:, :, o:o + w].contiguous(), cat[:, :, o:o + w].contiguous()
-                r_h = torch.empty(r_d.shape, dtype=torch.float16, pin_memory=True)
-                i_h = torch.empty(i_d.shape, dtype=torch.int32, pin_memory=True)
+                r_h, i_h = self._pinned("rows_" + nm, r_d.shape, torch.float16), self._pinned("sel_" + nm, i_d.shape, torch.int32)
                 r_h.copy_(r_d, non_blocking=True)
                 i_h.copy_(i_d, non_blocking=True)
-                host[nm] = (i_h, r_h)
+                stage[nm] = (i_h, r_h)
                 o += w
             torch.cuda.current_stream(self.sims.device).synchronize()
+            host = {nm: (stage[nm][0].clone(), stage[nm][1].clone()) for nm in names}
             for ci, layer in enumerate(layers):
                 out = {nm: {"indices": host[nm][0][ci], "intensities": host[nm][1][ci]} for nm in names}
                 yield out, layer
