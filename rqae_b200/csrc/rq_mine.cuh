@@ -29,6 +29,15 @@ struct MineParams {
   int k;                  // top_k; the middle window holds 2 * (k / 2) values
   int* idx_out;           // [rows][3][k]   (top, middle, bottom), -1 in unused middle slots
   __half* val_out;        // [rows][3][k]   nullable
+  // list mode (rq_mine2_kernel as the fallback of rq_mine3_kernel): the rows to process are row_list[0 .. *row_count)
+  const int* row_list = nullptr;
+  const int* row_count = nullptr;
+  // rq_mine3_kernel: rows it cannot finish are appended to fb_list (counter fb_count) for the list-mode launch
+  int* fb_list = nullptr;
+  int* fb_count = nullptr;
+  int sample_log2 = 4;    // one 32-byte sector out of 2^sample_log2 is sampled
+  int c_top = 24;         // sample count that brackets the top / bottom window
+  int c_hi = 0, c_lo = 0; // sample ranks that bracket the middle window
 };
 
 // key that sorts ascending when the value sorts descending (+0 just before -0)
@@ -358,7 +367,9 @@ __global__ void __launch_bounds__(M2_THREADS, 16 / M2_WARPS) rq_mine2_kernel(con
     for (int i = tid; i < M2_LP_BYTES / 16; i += M2_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
 
-  for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+  const long long n_rows = p.row_count ? (long long)*p.row_count : p.rows;
+  for (long long ri = blockIdx.x; ri < n_rows; ri += gridDim.x) {
+    const long long row = p.row_list ? (long long)p.row_list[ri] : ri;
     const uint4* src = reinterpret_cast<const uint4*>(p.vals + row * p.row_stride);
     for (int i = tid; i < M2_WARPS * 256; i += M2_THREADS) (&sm.wtot[0][0])[i] = 0;
     for (int i = tid; i < 3 * M2_WARPS * 256; i += M2_THREADS) (&sm.ah[0][0][0])[i] = 0;

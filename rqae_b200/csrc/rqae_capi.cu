@@ -24,6 +24,7 @@
 #include "rq_forward.cuh"
 #include "rq_intensity.cuh"
 #include "rq_mine.cuh"
+#include "rq_mine3.cuh"
 #include "rq_search.cuh"
 #include "rq_layout.h"
 
@@ -1155,17 +1156,59 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
   rq::MineParams mp;
   mp.vals = (const __half*)vals; mp.rows = rows; mp.row_stride = row_stride; mp.n = n; mp.k = top_k;
   mp.idx_out = idx_out; mp.val_out = (__half*)val_out;
   // RQAE_MINE_V1=1 selects the first version of the kernel (shared-memory atomics per element; A/B timing)
   static const bool v1 = [] { const char* e = getenv("RQAE_MINE_V1"); return e && atoi(e) != 0; }();
+  // RQAE_MINE_V2=1 keeps the three-pass kernel for every row (A/B timing against the sample-bracketed one)
+  static const bool v2 = [] { const char* e = getenv("RQAE_MINE_V2"); return e && atoi(e) != 0; }();
+  constexpr int smem2 = rq::M2_SMEM_BYTES_PAD + rq::M2_LP_BYTES + (int)sizeof(rq::Mine2Smem);
+  constexpr int per_sm2 = 16 / rq::M2_WARPS;
+  if (!v1 && !v2 && n >= 16384 && n <= 262144 && rows < ((int64_t)1 << 31)) {
+    // rq_mine3_kernel: brackets from a sample, one streaming pass, exact selection among the candidates; rows whose
+    // brackets miss are finished by rq_mine2_kernel in list mode
+    const int slog = n <= 131072 ? 4 : 3;
+    const double ms = (double)(((n / 16) >> slog) * 16), s = (double)n / ms, sig = 0.5 * sqrt(ms), z = 4.5;
+    const long long kh = top_k / 2, m0 = n / 2 - kh, m1 = n / 2 + kh;
+    mp.sample_log2 = slog;
+    mp.c_top = (int)ceil(top_k / s + 6.0 * sqrt(top_k / s) + 3.0);
+    mp.c_hi = (int)floor((double)m0 / s - z * sig) - 1;
+    mp.c_lo = (int)ceil((double)m1 / s + z * sig) + 1;
+    int* fb = nullptr;
+    RQ_CUDA(cudaMallocAsync((void**)&fb, (size_t)(rows + 1) * sizeof(int), st));
+    cudaError_t e = cudaMemsetAsync(fb, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+      mp.fb_count = fb; mp.fb_list = fb + 1;
+      constexpr int smem3 = (int)sizeof(rq::Mine3Smem);
+      static_assert(2 * (smem3 + 1024) <= 227 * 1024, "two CTAs per SM");
+      e = ensure_dynamic_smem((const void*)rq::rq_mine3_kernel, smem3);
+      if (e == cudaSuccess) {
+        const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
+        rq::rq_mine3_kernel<<<grid, rq::M3_THREADS, smem3, st>>>(mp);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)rq::rq_mine2_kernel, smem2);
+      if (e == cudaSuccess) {
+        rq::MineParams fp = mp;
+        fp.row_count = fb; fp.row_list = fb + 1;
+        const long long cap = (long long)sms * per_sm2;
+        rq::rq_mine2_kernel<<<(int)(rows < cap ? rows : cap), rq::M2_THREADS, smem2, st>>>(fp);
+        e = cudaGetLastError();
+      }
+    }
+    cudaFreeAsync(fb, st);
+    RQ_CUDA(e);
+    g_launches += 2;
+    return RQAE_OK;
+  }
   if (v1) {
     const int grid = (int)(rows < 2LL * sms ? rows : 2LL * sms);
     rq::rq_mine_kernel<<<grid, rq::MN_THREADS, 0, (cudaStream_t)stream>>>(mp);
   } else {
-    constexpr int smem = rq::M2_SMEM_BYTES_PAD + rq::M2_LP_BYTES + (int)sizeof(rq::Mine2Smem);
-    constexpr int per_sm = 16 / rq::M2_WARPS;
+    constexpr int smem = smem2;
+    constexpr int per_sm = per_sm2;
     static_assert(smem <= (228 * 1024 - per_sm * 1024) / per_sm, "shared memory budget");
     RQ_CUDA(ensure_dynamic_smem((const void*)rq::rq_mine2_kernel, smem));
     const int grid = (int)(rows < (long long)sms * per_sm ? rows : (long long)sms * per_sm);

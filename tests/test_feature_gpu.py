@@ -194,9 +194,11 @@ def _key_windows(bits: np.ndarray, k: int):
 
 
 @pytest.mark.parametrize("case", ["constant_131072", "two_values", "one_bin", "straddle", "specials", "ragged_131077",
-                                  "long_2M", "tiny"])
+                                  "long_2M", "tiny", "zero_centered_131072", "few_values_131072", "skewed_262144",
+                                  "heavy_median_tie", "short_16384"])
 def test_select_adversarial_rows_against_key_order(case):
-    """Rows built to hit the corners of the lane-private-counter kernel: 8-bit counters that wrap (a lane sees 256
+    """Rows built to hit the corners of the sample-bracketed kernel (16 384 <= n <= 262 144: brackets that miss or
+    overflow fall back to the three-pass kernel row by row) and of the lane-private-counter kernel: 8-bit counters that wrap (a lane sees 256
     equal high bytes), every boundary inside one histogram bin, the median window straddling two bins, dense tail
     bins (the atomics path), inf / -0 / NaN bit patterns, partial last vectors, several fold blocks per lane."""
     from rqae_b200.feature import select_top_middle_bottom
@@ -224,6 +226,21 @@ def test_select_adversarial_rows_against_key_order(case):
             r[rng.integers(0, 40000, 20)] = 0xFE01      # NaN, sign set
     elif case == "ragged_131077":
         rows = (rng.normal(0.02, 0.05, size=(3, 131077))).astype(np.float16).view(np.uint16)
+    elif case == "zero_centered_131072":   # the median bracket spans every small exponent, +0 and -0 included
+        rows = (rng.normal(0.0, 0.05, size=(6, 131072))).astype(np.float16).view(np.uint16)
+        rows[:, ::97] = 0x8000
+        rows[:, 5::89] = 0x0000
+    elif case == "few_values_131072":      # like the first layer cut: a few hundred distinct values, every boundary inside a tie
+        vals = rng.normal(0.01, 0.06, size=625).astype(np.float16).view(np.uint16)
+        rows = vals[rng.integers(0, 625, size=(4, 131072))].astype(np.uint16)
+    elif case == "skewed_262144":
+        rows = (rng.gamma(2.0, 0.03, size=(3, 262144)) - 0.02).astype(np.float16).view(np.uint16)
+    elif case == "heavy_median_tie":       # 40 % of the row is one value around the median: the bracket overflows
+        rows = (rng.normal(0.0, 0.05, size=(3, 131072))).astype(np.float16)
+        rows[rng.random((3, 131072)) < 0.4] = np.float16(0.0)
+        rows = rows.view(np.uint16)
+    elif case == "short_16384":
+        rows = (rng.normal(0.02, 0.05, size=(5, 16384))).astype(np.float16).view(np.uint16)
     elif case == "long_2M":
         rows = (rng.normal(0.0, 0.04, size=(1, (1 << 21) + 3))).astype(np.float16).view(np.uint16)
     else:
