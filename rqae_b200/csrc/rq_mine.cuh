@@ -38,6 +38,7 @@ struct MineParams {
   int sample_log2 = 4;    // one 32-byte sector out of 2^sample_log2 is sampled
   int c_top = 24;         // sample count that brackets the top / bottom window
   int c_hi = 0, c_lo = 0; // sample ranks that bracket the middle window
+  unsigned long long* prof = nullptr;   // RQAE_M3_PROF: clocks of steps A / B / C, rows, fallback rows, candidates
 };
 
 // key that sorts ascending when the value sorts descending (+0 just before -0)

@@ -29,21 +29,21 @@ namespace rq {
 constexpr int M3_THREADS = 512;
 constexpr int M3_WARPS = M3_THREADS / 32;
 constexpr int M3_CAP = 12288;      // candidates per row
-constexpr int M3_LIST = 1024;      // members of one class that enter a rank sort
+constexpr int M3_LIST = 512;       // members of one class that enter its rank sort (the window and the ties at its ends)
 constexpr int M3_BINS = 2048;
+constexpr int M3_SORT_THREADS = 160;   // threads per class in the rank sort (five warps each)
 
 struct Mine3Smem {
-  uint32_t hist[M3_BINS];
+  uint32_t hist[3][M3_BINS];         // [0] also holds the sample histogram of step A
   uint32_t candi[M3_CAP];
   unsigned short candk[M3_CAP];
-  uint32_t lk[M3_LIST];
-  uint32_t li[M3_LIST];
-  uint32_t h2[2][32];
-  uint32_t scan[M3_WARPS];
-  uint32_t ccount, G, nan, lcount;
+  uint32_t lk[3][M3_LIST];           // (key - klo) << 18 | index
+  uint32_t h2[3][2][32];
+  uint32_t scan[3][M3_WARPS];
+  uint32_t ccount, G, nan, lcount[3];
   uint32_t pt, pb, ps, pe;           // bin positions (descending-value order) of the four thresholds
-  uint32_t binA, exA, binB, exB;     // level-1 bins of the two middle-window ranks and their exclusive prefixes
-  uint32_t klo, khi, less_lo;
+  uint32_t binA[3], exA[3], binB[3], exB[3];   // level-1 bins of a window's first / last rank and their exclusive prefixes
+  uint32_t klo[3], khi[3], less_lo[3];
 };
 
 __device__ __forceinline__ uint32_t m3_hash(uint32_t g, uint32_t row) {
@@ -52,146 +52,23 @@ __device__ __forceinline__ uint32_t m3_hash(uint32_t g, uint32_t row) {
   return h;
 }
 
-// slot for every lane with pred set: one atomic per warp
-__device__ __forceinline__ uint32_t m3_warp_slot(bool pred, uint32_t* counter, int lane) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-  if (mask == 0) return 0;
-  uint32_t base = 0;
-  const int leader = __ffs(mask) - 1;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return base + __popc(mask & ((1u << lane) - 1u));
+__device__ __forceinline__ uint32_t m3_atoms_add(uint32_t* addr, uint32_t v) {   // plain ATOMS.ADD with a return value
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
 }
+__device__ __forceinline__ void m3_prefetch_l2(const void* ptr, uint32_t bytes) {   // 16-byte aligned, multiple of 16
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t m3_sel3(int c, uint32_t a0, uint32_t a1, uint32_t a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
-__device__ __forceinline__ uint32_t m3_block_exclusive(uint32_t v, uint32_t* scan, int warp, int lane, uint32_t* total) {
-  uint32_t x = v;
+__device__ __forceinline__ uint32_t m3_warp_inclusive(uint32_t v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
+    const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += y;
   }
-  if (lane == 31) scan[warp] = x;
-  __syncthreads();
-  uint32_t before = 0, all = 0;
-#pragma unroll
-  for (int w = 0; w < M3_WARPS; w++) {
-    const uint32_t s = scan[w];
-    before += w < warp ? s : 0u;
-    all += s;
-  }
-  __syncthreads();
-  if (total) *total = all;
-  return before + x - v;
-}
-
-struct M3Thr { __half stop, sbot, smhi, smlo; };
-__device__ __forceinline__ bool m3_in_class(int cls, __half h, const M3Thr& t) {
-  return cls == 0 ? __hge(h, t.stop) : (cls == 2 ? __hle(h, t.sbot) : (__hge(h, t.smlo) && !__hgt(h, t.smhi)));
-}
-
-// One window out of one class of the candidate buffer (0: values >= T_top, window = its first k; 1: the bracket of the
-// median, window = ranks m0 - G .. m1 - 1 - G; 2: values <= T_bot, window = its last k), by a two-level radix select
-// over the class's key range [kbase, kend] and a rank sort of the keys that remain.  Whole block; returns false
-// (uniformly) when the class does not hold the window.
-__device__ bool m3_select(Mine3Smem& sm, const int cls, const M3Thr thr, const uint32_t ncand, const uint32_t kbase,
-                          const uint32_t kend, const uint32_t G, const long long m0, const long long m1, const int k,
-                          const long long row, const MineParams& p) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int shift = 0;
-  while (((kend - kbase) >> shift) >= (uint32_t)M3_BINS) shift++;
-  const uint32_t lowmask = (1u << shift) - 1u;
-  for (int i = tid; i < M3_BINS; i += M3_THREADS) sm.hist[i] = 0;
-  if (tid < 64) (&sm.h2[0][0])[tid] = 0;
-  if (tid == 0) sm.lcount = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < ncand; i += M3_THREADS) {
-    const uint32_t bits = sm.candk[i];
-    if (m3_in_class(cls, __ushort_as_half((unsigned short)bits), thr)) atomicAdd(&sm.hist[(mn_dkey(bits) - kbase) >> shift], 1u);
-  }
-  __syncthreads();
-  uint32_t c[4], tot = 0, total = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) { c[i] = sm.hist[tid * 4 + i]; tot += c[i]; }
-  uint32_t ex = m3_block_exclusive(tot, sm.scan, warp, lane, &total);
-  uint32_t r_lo, r_hi;
-  if (cls == 1) {
-    if ((long long)G > m0 || (long long)G + (long long)total < m1) return false;
-    r_lo = (uint32_t)(m0 - (long long)G); r_hi = (uint32_t)(m1 - 1 - (long long)G);
-  } else {
-    if (total < (uint32_t)k) return false;
-    r_lo = cls == 0 ? 0u : total - (uint32_t)k; r_hi = r_lo + (uint32_t)k - 1u;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t in = ex + c[i];
-    if (ex <= r_lo && r_lo < in) { sm.binA = (uint32_t)tid * 4 + i; sm.exA = ex; }
-    if (ex <= r_hi && r_hi < in) { sm.binB = (uint32_t)tid * 4 + i; sm.exB = ex; }
-    ex = in;
-  }
-  __syncthreads();
-  const uint32_t binA = sm.binA, binB = sm.binB;
-  if (shift > 0) {   // level 2: the low key bits inside the two boundary bins
-    for (uint32_t i = tid; i < ncand; i += M3_THREADS) {
-      const uint32_t bits = sm.candk[i];
-      if (m3_in_class(cls, __ushort_as_half((unsigned short)bits), thr)) {
-        const uint32_t d = mn_dkey(bits) - kbase;
-        if ((d >> shift) == binA) atomicAdd(&sm.h2[0][d & lowmask], 1u);
-        if ((d >> shift) == binB) atomicAdd(&sm.h2[1][d & lowmask], 1u);
-      }
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    uint32_t run = sm.exA, klo = kbase + (binA << shift);
-    for (uint32_t j = 0; shift > 0 && j <= lowmask; j++) {
-      if (r_lo < run + sm.h2[0][j]) { klo += j; break; }
-      run += sm.h2[0][j];
-    }
-    sm.klo = klo; sm.less_lo = run;
-    uint32_t run2 = sm.exB, khi = kbase + (binB << shift);
-    for (uint32_t j = 0; shift > 0 && j <= lowmask; j++) {
-      if (r_hi < run2 + sm.h2[1][j]) { khi += j; break; }
-      run2 += sm.h2[1][j];
-    }
-    sm.khi = khi;
-  }
-  __syncthreads();
-  const uint32_t klo = sm.klo, khi = sm.khi;
-  for (uint32_t i0 = 0; i0 < ncand; i0 += M3_THREADS) {
-    const uint32_t i = i0 + tid;
-    bool take = false;
-    uint32_t d = 0;
-    if (i < ncand) {
-      const uint32_t bits = sm.candk[i];
-      d = mn_dkey(bits);
-      take = m3_in_class(cls, __ushort_as_half((unsigned short)bits), thr) && d >= klo && d <= khi;
-    }
-    const uint32_t s = m3_warp_slot(take, &sm.lcount, lane);
-    if (take && s < M3_LIST) { sm.lk[s] = d; sm.li[s] = sm.candi[i]; }
-  }
-  __syncthreads();
-  const int cnt = (int)sm.lcount;
-  if (cnt > M3_LIST) return false;
-  // rank sort: (key, index) ascending = value descending, index ascending
-  const int first = (int)(r_lo - sm.less_lo), size = (int)(r_hi - r_lo + 1u);
-  int* io = p.idx_out + (row * 3 + cls) * (long long)k;
-  __half* vo = p.val_out ? p.val_out + (row * 3 + cls) * (long long)k : nullptr;
-  for (int t = tid; t < cnt; t += M3_THREADS) {
-    const uint32_t dk = sm.lk[t], di = sm.li[t];
-    int r = 0;
-    for (int o = 0; o < cnt; o++) {
-      const uint32_t ok = sm.lk[o], oi = sm.li[o];
-      r += (ok < dk) || (ok == dk && oi < di);
-    }
-    r -= first;
-    if (r >= 0 && r < size) {
-      io[r] = (int)di;
-      if (vo) vo[r] = __ushort_as_half((unsigned short)mn_bits(dk));
-    }
-  }
-  if (tid >= size && tid < k) { io[tid] = -1; if (vo) vo[tid] = __ushort_as_half((unsigned short)0); }
-  __syncthreads();
-  return true;
+  return v;
 }
 
 __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParams p) {
@@ -209,7 +86,8 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
   for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
     const uint4* src = reinterpret_cast<const uint4*>(p.vals + row * p.row_stride);
     const unsigned short* src16 = reinterpret_cast<const unsigned short*>(p.vals + row * p.row_stride);
-    for (int i = tid; i < M3_BINS; i += M3_THREADS) sm.hist[i] = 0;
+    const long long t0 = clock64();
+    for (int i = tid; i < M3_BINS; i += M3_THREADS) sm.hist[0][i] = 0;
     if (tid == 0) {
       sm.ccount = 0; sm.G = 0; sm.nan = 0;
       sm.pt = 0; sm.pb = M3_BINS - 1; sm.ps = 0; sm.pe = M3_BINS - 1;
@@ -225,16 +103,21 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       for (int e = 0; e < 8; e++) {
         const uint32_t w = w8[e];
         const uint32_t d2 = w ^ ((((w >> 15) & 0x00010001u) * 0x7FFFu) ^ 0x7FFF7FFFu);   // packed descending keys
-        atomicAdd(&sm.hist[(d2 & 0xFFFFu) >> 5], 1u);
-        atomicAdd(&sm.hist[d2 >> 21], 1u);
+        atomicAdd(&sm.hist[0][(d2 & 0xFFFFu) >> 5], 1u);
+        atomicAdd(&sm.hist[0][d2 >> 21], 1u);
       }
     }
     __syncthreads();
     {
       uint32_t c[4], tot = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++) { c[i] = sm.hist[tid * 4 + i]; tot += c[i]; }
-      uint32_t ex = m3_block_exclusive(tot, sm.scan, warp, lane, nullptr);
+      for (int i = 0; i < 4; i++) { c[i] = sm.hist[0][tid * 4 + i]; tot += c[i]; }
+      const uint32_t inc = m3_warp_inclusive(tot, lane);
+      if (lane == 31) sm.scan[0][warp] = inc;
+      __syncthreads();
+      uint32_t ex = inc - tot;
+#pragma unroll
+      for (int w = 0; w < M3_WARPS; w++) ex += w < warp ? sm.scan[0][w] : 0u;
       const uint32_t ct = (uint32_t)p.c_top;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -258,11 +141,22 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const __half2 hmhi = *reinterpret_cast<const __half2*>(&mhi2), hmlo = *reinterpret_cast<const __half2*>(&mlo2);
     const __half stop = __ushort_as_half((unsigned short)Ttop), sbot = __ushort_as_half((unsigned short)Tbot);
     const __half smhi = __ushort_as_half((unsigned short)Mhi), smlo = __ushort_as_half((unsigned short)Mlo);
+    // zero what step C accumulates into (hist[0] is free again after the barrier above)
+    for (int i = tid; i < 3 * M3_BINS; i += M3_THREADS) (&sm.hist[0][0])[i] = 0;
+    if (tid < 192) (&sm.h2[0][0][0])[tid] = 0;
+    if (tid < 3) sm.lcount[tid] = 0;
 
     // ---- B: one pass over the row ----
+    // A NaN compares "greater or unordered" to T_top, so it becomes a candidate; step C sees its bit pattern and sends
+    // the row to the fallback (no separate NaN test per value).
+    const long long t1 = clock64();
     {
-      uint32_t gcount = 0, nanacc = 0;
-      for (long long v0 = 0; v0 < nv; v0 += 4LL * M3_THREADS) {      // warp-uniform trip count
+      uint32_t gcount = 0;
+      for (long long v0 = 0; v0 < nv; v0 += 4LL * M3_THREADS) {      // block-uniform trip count
+        if (tid == 0) {   // the chunk three iterations ahead goes to L2 now (32 KB per iteration)
+          const long long pv = v0 + 12LL * M3_THREADS;
+          if (pv < nv) m3_prefetch_l2(src + pv, (uint32_t)((nv - pv < 4LL * M3_THREADS ? nv - pv : 4LL * M3_THREADS) * 16));
+        }
         uint4 q[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -271,44 +165,51 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           if (v < nv) q[u] = __ldg(src + v);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const long long v = v0 + (long long)u * M3_THREADS + tid;
-          const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-          uint32_t cm[4], gm[4];
+        for (int u2 = 0; u2 < 4; u2 += 2) {
+          uint32_t m8[2];
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const __half2 h = *reinterpret_cast<const __half2*>(&w4[e]);
-            gm[e] = __hgt2_mask(h, hmhi);
-            cm[e] = __hge2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
-            nanacc |= __hneu2_mask(h, h);
-          }
-          uint32_t m8 = 0;
-          if (v < nv) {
-            gcount += __popc((gm[0] & 0x00010001u) | (gm[1] & 0x00020002u) | (gm[2] & 0x00040004u) | (gm[3] & 0x00080008u));
-            m8 = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
-            m8 = (m8 | (m8 >> 16)) & 0xFFu;
-          }   // lanes beyond the row hold zeros: no NaN, no candidate
-          const uint32_t cnt = __popc(m8);
-          uint32_t x = cnt;
+          for (int h2i = 0; h2i < 2; h2i++) {
+            const int u = u2 + h2i;
+            const long long v = v0 + (long long)u * M3_THREADS + tid;
+            const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            uint32_t cm[4], gm[4];
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            for (int e = 0; e < 4; e++) {
+              const __half2 h = *reinterpret_cast<const __half2*>(&w4[e]);
+              gm[e] = __hgt2_mask(h, hmhi);
+              cm[e] = __hgeu2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
+            }
+            uint32_t m = 0;
+            if (v < nv) {   // lanes beyond the row hold zeros and must stay out
+              gcount += __popc((gm[0] & 0x00010001u) | (gm[1] & 0x00020002u) | (gm[2] & 0x00040004u) | (gm[3] & 0x00080008u));
+              m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
+              m = (m | (m >> 16)) & 0xFFu;
+            }
+            m8[h2i] = m;
           }
+          const uint32_t cnt = __popc(m8[0] | (m8[1] << 8));
+          const uint32_t x = m3_warp_inclusive(cnt, lane);
           const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
           if (total == 0) continue;
           uint32_t base = 0;
-          if (lane == 31) base = atomicAdd(&sm.ccount, total);
+          if (lane == 31) base = m3_atoms_add(&sm.ccount, total);
           uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + x - cnt;
-          while (m8) {
-            const int e = __ffs(m8) - 1;
-            m8 &= m8 - 1;
-            const uint32_t lohi = e < 4 ? (e < 2 ? w4[0] : w4[1]) : (e < 6 ? w4[2] : w4[3]);
-            if (pos < M3_CAP) {
-              sm.candk[pos] = (unsigned short)((e & 1) ? (lohi >> 16) : (lohi & 0xFFFFu));
-              sm.candi[pos] = (uint32_t)(v * 8 + e);
+#pragma unroll
+          for (int h2i = 0; h2i < 2; h2i++) {
+            const int u = u2 + h2i;
+            const long long v = v0 + (long long)u * M3_THREADS + tid;
+            const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            uint32_t m = m8[h2i];
+            while (m) {
+              const int e = __ffs(m) - 1;
+              m &= m - 1;
+              const uint32_t lohi = e < 4 ? (e < 2 ? w4[0] : w4[1]) : (e < 6 ? w4[2] : w4[3]);
+              if (pos < M3_CAP) {
+                sm.candk[pos] = (unsigned short)((e & 1) ? (lohi >> 16) : (lohi & 0xFFFFu));
+                sm.candi[pos] = (uint32_t)(v * 8 + e);
+              }
+              pos++;
             }
-            pos++;
           }
         }
       }
@@ -317,49 +218,233 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         for (long long i = nv * 8; i < n; i++) {
           const unsigned short bits = src16[i];
           const __half h = __ushort_as_half(bits);
-          if (__hisnan(h)) nanacc = 1;
           if (__hgt(h, smhi)) gcount++;
-          if (__hge(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
+          if (__hgeu(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
             const uint32_t pos = atomicAdd(&sm.ccount, 1u);
             if (pos < M3_CAP) { sm.candk[pos] = bits; sm.candi[pos] = (uint32_t)i; }
           }
         }
       }
-      // block totals
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        gcount += __shfl_xor_sync(0xffffffffu, gcount, o);
-        nanacc |= __shfl_xor_sync(0xffffffffu, nanacc, o);
-      }
-      if (lane == 0) {
-        atomicAdd(&sm.G, gcount);
-        if (nanacc) atomicOr(&sm.nan, 1u);
-      }
+      for (int o = 16; o > 0; o >>= 1) gcount += __shfl_xor_sync(0xffffffffu, gcount, o);
+      if (lane == 0) atomicAdd(&sm.G, gcount);
     }
     __syncthreads();
 
-    // ---- C: exact selection among the candidates ----
-    const uint32_t ncand = sm.ccount;
-    bool ok = sm.nan == 0 && ncand <= (uint32_t)M3_CAP;
-    M3Thr thr;
-    thr.stop = stop; thr.sbot = sbot; thr.smhi = smhi; thr.smlo = smlo;
-    // key ranges of the classes (+0 / -0 compare equal: a range that ends at one of them is widened over both)
-    const uint32_t top_end = Ttop == 0x0000u ? 0x8000u : mn_dkey(Ttop);
-    const uint32_t bot_base = Tbot == 0x8000u ? 0x7FFFu : mn_dkey(Tbot);
-    const uint32_t mid_base = Mhi == 0x8000u ? 0x7FFFu : mn_dkey(Mhi);
-    const uint32_t mid_end = Mlo == 0x0000u ? 0x8000u : mn_dkey(Mlo);
-    ok = ok && m3_select(sm, 0, thr, ncand, 0u, top_end, sm.G, m0, m1, k, row, p);
-    ok = ok && (kh == 0 || m3_select(sm, 1, thr, ncand, mid_base, mid_end, sm.G, m0, m1, k, row, p));
-    ok = ok && m3_select(sm, 2, thr, ncand, bot_base, 0xFFFFu, sm.G, m0, m1, k, row, p);
-    if (ok && kh == 0 && tid < k) {
-      p.idx_out[(row * 3 + 1) * (long long)k + tid] = -1;
-      if (p.val_out) p.val_out[(row * 3 + 1) * (long long)k + tid] = __ushort_as_half((unsigned short)0);
+    // ---- C: exact selection among the candidates, the three classes side by side ----
+    // class 0: values >= T_top, window = its first k;  class 1: the bracket of the median, window = ranks m0 - G ..
+    // m1 - 1 - G;  class 2: values <= T_bot, window = its last k.  Per class a two-level radix select over the key
+    // range [kbase, kend] (+0 / -0 compare equal: a range that ends at one of them is widened over both), then a rank
+    // sort of the keys that remain.
+    const long long t2 = clock64();
+    if (row + gridDim.x < p.rows) {   // the next row of this CTA: sample sectors and the first chunks on their way to L2
+      const long long nrow = row + gridDim.x;
+      const uint4* nsrc = reinterpret_cast<const uint4*>(p.vals + nrow * p.row_stride);
+      if (tid == 0) {
+        const long long first = nv < 12LL * M3_THREADS ? nv : 12LL * M3_THREADS;
+        for (long long pv = 0; pv < first; pv += 4LL * M3_THREADS)
+          m3_prefetch_l2(nsrc + pv, (uint32_t)((first - pv < 4LL * M3_THREADS ? first - pv : 4LL * M3_THREADS) * 16));
+      }
+      for (long long g = tid; g < ngroups; g += M3_THREADS) {
+        const long long sector = (g << slog) + (m3_hash((uint32_t)g, (uint32_t)nrow) >> (32 - slog));
+        if (sector * 2 >= 12LL * M3_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + sector * 2));
+      }
+    }
+    const uint32_t ncand = sm.ccount, G = sm.G;
+    bool ok = ncand <= (uint32_t)M3_CAP;
+    const uint32_t nc = ok ? ncand : 0u;
+    const uint32_t kb0 = 0u, kb1 = Mhi == 0x8000u ? 0x7FFFu : mn_dkey(Mhi), kb2 = Tbot == 0x8000u ? 0x7FFFu : mn_dkey(Tbot);
+    const uint32_t ke0 = Ttop == 0x0000u ? 0x8000u : mn_dkey(Ttop), ke1 = Mlo == 0x0000u ? 0x8000u : mn_dkey(Mlo), ke2 = 0xFFFFu;
+    int sh0 = 0, sh1 = 0, sh2 = 0;
+    while (((ke0 - kb0) >> sh0) >= (uint32_t)M3_BINS) sh0++;
+    while (((ke1 - kb1) >> sh1) >= (uint32_t)M3_BINS) sh1++;
+    while (((ke2 - kb2) >> sh2) >= (uint32_t)M3_BINS) sh2++;
+    // C1: class bits of every candidate (kept in bits 18..20 of its index word), level-1 histograms
+    for (uint32_t i = tid; i < nc; i += M3_THREADS) {
+      const uint32_t bits = sm.candk[i];
+      const __half h = __ushort_as_half((unsigned short)bits);
+      const uint32_t d = mn_dkey(bits);
+      const bool c0 = __hge(h, stop), c2 = __hle(h, sbot), c1 = kh > 0 && __hge(h, smlo) && !__hgt(h, smhi);
+      if ((bits & 0x7FFFu) > 0x7C00u) sm.nan = 1u;
+      sm.candi[i] |= (c0 ? 1u << 18 : 0u) | (c1 ? 2u << 18 : 0u) | (c2 ? 4u << 18 : 0u);
+      if (c1) atomicAdd(&sm.hist[1][(d - kb1) >> sh1], 1u);
+      if (c0) atomicAdd(&sm.hist[0][(d - kb0) >> sh0], 1u);
+      if (c2) atomicAdd(&sm.hist[2][(d - kb2) >> sh2], 1u);
+    }
+    __syncthreads();
+    ok = ok && sm.nan == 0;
+    const long long tc1 = clock64();
+    // C2: prefix sums, the bins of each window's first and last rank
+    uint32_t rl0 = 0, rl1 = 0, rl2 = 0, rh0 = 0, rh1 = 0, rh2 = 0;
+    {
+      uint32_t cb[3][4], tot[3], inc[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        tot[c] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { cb[c][i] = sm.hist[c][tid * 4 + i]; tot[c] += cb[c][i]; }
+        inc[c] = m3_warp_inclusive(tot[c], lane);
+        if (lane == 31) sm.scan[c][warp] = inc[c];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        uint32_t ex = inc[c] - tot[c], total = 0;
+#pragma unroll
+        for (int w = 0; w < M3_WARPS; w++) {
+          const uint32_t sw = sm.scan[c][w];
+          ex += w < warp ? sw : 0u;
+          total += sw;
+        }
+        uint32_t rl, rh;
+        if (c == 1) {
+          if (kh == 0) continue;
+          if ((long long)G > m0 || (long long)G + (long long)total < m1) { ok = false; continue; }
+          rl = (uint32_t)(m0 - (long long)G); rh = (uint32_t)(m1 - 1 - (long long)G);
+          rl1 = rl; rh1 = rh;
+        } else {
+          if (total < (uint32_t)k) { ok = false; continue; }
+          rl = c == 0 ? 0u : total - (uint32_t)k; rh = rl + (uint32_t)k - 1u;
+          if (c == 0) { rl0 = rl; rh0 = rh; } else { rl2 = rl; rh2 = rh; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t in = ex + cb[c][i];
+          if (ex <= rl && rl < in) { sm.binA[c] = (uint32_t)tid * 4 + i; sm.exA[c] = ex; }
+          if (ex <= rh && rh < in) { sm.binB[c] = (uint32_t)tid * 4 + i; sm.exB[c] = ex; }
+          ex = in;
+        }
+      }
+    }
+    __syncthreads();
+    const long long tc2 = clock64();
+    long long tc3 = tc2, tc4 = tc2, tc5 = tc2;
+    if (ok) {   // block-uniform
+      // C3: the low key bits inside the boundary bins (first key of bin A / B of each class)
+      const uint32_t fa0 = kb0 + (sm.binA[0] << sh0), fb0 = kb0 + (sm.binB[0] << sh0);
+      const uint32_t fa1 = kb1 + (sm.binA[1] << sh1), fb1 = kb1 + (sm.binB[1] << sh1);
+      const uint32_t fa2 = kb2 + (sm.binA[2] << sh2), fb2 = kb2 + (sm.binB[2] << sh2);
+      if (sh0 | sh1 | sh2) {
+        const uint32_t w0 = 1u << sh0, w1 = 1u << sh1, w2 = 1u << sh2;
+        for (uint32_t i = tid; i < nc; i += M3_THREADS) {
+          const uint32_t d = mn_dkey(sm.candk[i]), cl = sm.candi[i] >> 18;
+          if ((cl & 2u) && sh1 > 0) {
+            if (d - fa1 < w1) atomicAdd(&sm.h2[1][0][d - fa1], 1u);
+            if (d - fb1 < w1) atomicAdd(&sm.h2[1][1][d - fb1], 1u);
+          }
+          if ((cl & 1u) && sh0 > 0) {
+            if (d - fa0 < w0) atomicAdd(&sm.h2[0][0][d - fa0], 1u);
+            if (d - fb0 < w0) atomicAdd(&sm.h2[0][1][d - fb0], 1u);
+          }
+          if ((cl & 4u) && sh2 > 0) {
+            if (d - fa2 < w2) atomicAdd(&sm.h2[2][0][d - fa2], 1u);
+            if (d - fb2 < w2) atomicAdd(&sm.h2[2][1][d - fb2], 1u);
+          }
+        }
+        __syncthreads();
+      }
+      tc3 = clock64();
+      // C4: warp 2 c + b resolves boundary b of class c
+      if (warp < 6) {
+        const int c = warp >> 1, b = warp & 1;
+        const int sh = (int)m3_sel3(c, sh0, sh1, sh2);
+        const uint32_t exb = b ? sm.exB[c] : sm.exA[c];
+        const uint32_t r = b ? m3_sel3(c, rh0, rh1, rh2) : m3_sel3(c, rl0, rl1, rl2);
+        uint32_t key = b ? m3_sel3(c, fb0, fb1, fb2) : m3_sel3(c, fa0, fa1, fa2), less = exb;
+        if (sh > 0) {
+          const uint32_t cnt = lane < (1 << sh) ? sm.h2[c][b][lane] : 0u;
+          const uint32_t inc = m3_warp_inclusive(cnt, lane);
+          const bool mine = exb + inc - cnt <= r && r < exb + inc;
+          const uint32_t sel = __ballot_sync(0xffffffffu, mine);
+          const int j = sel ? __ffs(sel) - 1 : 0;
+          key += (uint32_t)j;
+          less = exb + __shfl_sync(0xffffffffu, inc - cnt, j);
+        }
+        if (lane == 0) {
+          if (b == 0) { sm.klo[c] = key; sm.less_lo[c] = less; } else sm.khi[c] = key;
+        }
+      }
+      __syncthreads();
+      tc4 = clock64();
+      // C5: the keys between the two boundary keys
+      const uint32_t kl0 = sm.klo[0], kl1 = sm.klo[1], kl2 = sm.klo[2];
+      const uint32_t sp0 = sm.khi[0] - kl0, sp1 = kh > 0 ? sm.khi[1] - kl1 : 0u, sp2 = sm.khi[2] - kl2;
+      for (uint32_t i = tid; i < nc; i += M3_THREADS) {
+        const uint32_t d = mn_dkey(sm.candk[i]), ci = sm.candi[i];
+        if ((ci & (2u << 18)) && d - kl1 <= sp1) {
+          const uint32_t s1 = atomicAdd(&sm.lcount[1], 1u);
+          if (s1 < (uint32_t)M3_LIST) sm.lk[1][s1] = ((d - kl1) << 18) | (ci & 0x3FFFFu);
+        }
+        if ((ci & (1u << 18)) && d - kl0 <= sp0) {
+          const uint32_t s0 = atomicAdd(&sm.lcount[0], 1u);
+          if (s0 < (uint32_t)M3_LIST) sm.lk[0][s0] = ((d - kl0) << 18) | (ci & 0x3FFFFu);
+        }
+        if ((ci & (4u << 18)) && d - kl2 <= sp2) {
+          const uint32_t s2 = atomicAdd(&sm.lcount[2], 1u);
+          if (s2 < (uint32_t)M3_LIST) sm.lk[2][s2] = ((d - kl2) << 18) | (ci & 0x3FFFFu);
+        }
+      }
+      __syncthreads();
+      if (sm.lcount[0] > (uint32_t)M3_LIST || sm.lcount[2] > (uint32_t)M3_LIST || sp0 >= 16384u || sp2 >= 16384u) ok = false;
+      if (kh > 0 && (sm.lcount[1] > (uint32_t)M3_LIST || sp1 >= 16384u)) ok = false;
+      tc5 = clock64();
+      if (ok) {
+        // C6: rank sorts, five warps per class: packed (key, index) ascending = value descending, index ascending
+        const int c = tid / M3_SORT_THREADS;
+        if (c < 3 && (c != 1 || kh > 0)) {
+          const int cnt = (int)sm.lcount[c];
+          const uint32_t rl = m3_sel3(c, rl0, rl1, rl2), rh = m3_sel3(c, rh0, rh1, rh2), kl = m3_sel3(c, kl0, kl1, kl2);
+          const int first = (int)(rl - sm.less_lo[c]), size = (int)(rh - rl + 1u);
+          int* io = p.idx_out + (row * 3 + c) * (long long)k;
+          __half* vo = p.val_out ? p.val_out + (row * 3 + c) * (long long)k : nullptr;
+          const uint32_t* list = sm.lk[c];
+          for (int t = tid - c * M3_SORT_THREADS; t < cnt; t += M3_SORT_THREADS) {
+            const uint32_t mine = list[t];
+            int r = 0;
+            int o = 0;
+#pragma unroll 4
+            for (; o + 4 <= cnt; o += 4) {
+              const uint4 ot = *reinterpret_cast<const uint4*>(list + o);
+              r += (ot.x < mine) + (ot.y < mine) + (ot.z < mine) + (ot.w < mine);
+            }
+            for (; o < cnt; o++) r += list[o] < mine;
+            r -= first;
+            if (r >= 0 && r < size) {
+              io[r] = (int)(mine & 0x3FFFFu);
+              if (vo) vo[r] = __ushort_as_half((unsigned short)mn_bits(kl + (mine >> 18)));
+            }
+          }
+          for (int t = size + tid - c * M3_SORT_THREADS; t < k; t += M3_SORT_THREADS) {
+            io[t] = -1;
+            if (vo) vo[t] = __ushort_as_half((unsigned short)0);
+          }
+        }
+        if (kh == 0 && tid < k) {
+          p.idx_out[(row * 3 + 1) * (long long)k + tid] = -1;
+          if (p.val_out) p.val_out[(row * 3 + 1) * (long long)k + tid] = __ushort_as_half((unsigned short)0);
+        }
+      }
     }
     if (!ok && tid == 0) {
       const int slot = atomicAdd(p.fb_count, 1);
       p.fb_list[slot] = (int)row;
     }
     __syncthreads();
+    if (p.prof && tid == 0) {
+      const long long t3 = clock64();
+      atomicAdd(p.prof + 0, (unsigned long long)(t1 - t0));
+      atomicAdd(p.prof + 1, (unsigned long long)(t2 - t1));
+      atomicAdd(p.prof + 2, (unsigned long long)(t3 - t2));
+      atomicAdd(p.prof + 3, 1ull);
+      atomicAdd(p.prof + 4, ok ? 0ull : 1ull);
+      atomicAdd(p.prof + 5, (unsigned long long)ncand);
+      atomicAdd(p.prof + 6, (unsigned long long)(tc1 - t2));
+      atomicAdd(p.prof + 7, (unsigned long long)(tc2 - tc1));
+      atomicAdd(p.prof + 8, (unsigned long long)(tc3 - tc2));
+      atomicAdd(p.prof + 9, (unsigned long long)(tc4 - tc3));
+      atomicAdd(p.prof + 10, (unsigned long long)(tc5 - tc4));
+      atomicAdd(p.prof + 11, (unsigned long long)(t3 - tc5));
+    }
   }
 }
 
