@@ -22,13 +22,16 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "rq_mine.cuh"
 
 namespace rq {
 
 constexpr int M3_THREADS = 512;
 constexpr int M3_WARPS = M3_THREADS / 32;
-constexpr int M3_CAP = 12288;      // candidates per row
+constexpr int M3_WCAP = 768;       // candidates per warp and row: every warp appends to its own region (no atomics)
+constexpr int M3_CAP = M3_WCAP * M3_WARPS;
 constexpr int M3_LIST = 512;       // members of one class that enter its rank sort (the window and the ties at its ends)
 constexpr int M3_BINS = 2048;
 constexpr int M3_SORT_THREADS = 160;   // threads per class in the rank sort (five warps each)
@@ -40,7 +43,8 @@ struct Mine3Smem {
   uint32_t lk[3][M3_LIST];           // (key - klo) << 18 | index
   uint32_t h2[3][2][32];
   uint32_t scan[3][M3_WARPS];
-  uint32_t ccount, G, nan, lcount[3];
+  uint32_t wcount[M3_WARPS];         // candidates of each warp
+  uint32_t G, nan, lcount[3];
   uint32_t pt, pb, ps, pe;           // bin positions (descending-value order) of the four thresholds
   uint32_t binA[3], exA[3], binB[3], exB[3];   // level-1 bins of a window's first / last rank and their exclusive prefixes
   uint32_t klo[3], khi[3], less_lo[3];
@@ -52,11 +56,6 @@ __device__ __forceinline__ uint32_t m3_hash(uint32_t g, uint32_t row) {
   return h;
 }
 
-__device__ __forceinline__ uint32_t m3_atoms_add(uint32_t* addr, uint32_t v) {   // plain ATOMS.ADD with a return value
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
-  return old;
-}
 __device__ __forceinline__ void m3_prefetch_l2(const void* ptr, uint32_t bytes) {   // 16-byte aligned, multiple of 16
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const long long t0 = clock64();
     for (int i = tid; i < M3_BINS; i += M3_THREADS) sm.hist[0][i] = 0;
     if (tid == 0) {
-      sm.ccount = 0; sm.G = 0; sm.nan = 0;
+      sm.G = 0; sm.nan = 0;
       sm.pt = 0; sm.pb = M3_BINS - 1; sm.ps = 0; sm.pe = M3_BINS - 1;
     }
     __syncthreads();
@@ -141,10 +140,20 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const __half2 hmhi = *reinterpret_cast<const __half2*>(&mhi2), hmlo = *reinterpret_cast<const __half2*>(&mlo2);
     const __half stop = __ushort_as_half((unsigned short)Ttop), sbot = __ushort_as_half((unsigned short)Tbot);
     const __half smhi = __ushort_as_half((unsigned short)Mhi), smlo = __ushort_as_half((unsigned short)Mlo);
-    // zero what step C accumulates into (hist[0] is free again after the barrier above)
+    // key ranges [kb, ke] of the three classes (0: values >= T_top, 1: the bracket of the median, 2: values <= T_bot) and
+    // the bin widths of their level-1 histograms.  +0 / -0 compare equal: a range that ends at one of them is widened
+    // over both.
+    const uint32_t kb0 = 0u, kb1 = Mhi == 0x8000u ? 0x7FFFu : mn_dkey(Mhi), kb2 = Tbot == 0x8000u ? 0x7FFFu : mn_dkey(Tbot);
+    const uint32_t ke0 = Ttop == 0x0000u ? 0x8000u : mn_dkey(Ttop), ke1 = Mlo == 0x0000u ? 0x8000u : mn_dkey(Mlo), ke2 = 0xFFFFu;
+    int sh0 = 0, sh1 = 0, sh2 = 0;
+    while (((ke0 - kb0) >> sh0) >= (uint32_t)M3_BINS) sh0++;
+    while (((ke1 - kb1) >> sh1) >= (uint32_t)M3_BINS) sh1++;
+    while (((ke2 - kb2) >> sh2) >= (uint32_t)M3_BINS) sh2++;
+    // zero what steps B and C accumulate into (hist[0] is free again after the barrier above)
     for (int i = tid; i < 3 * M3_BINS; i += M3_THREADS) (&sm.hist[0][0])[i] = 0;
     if (tid < 192) (&sm.h2[0][0][0])[tid] = 0;
     if (tid < 3) sm.lcount[tid] = 0;
+    __syncthreads();
 
     // ---- B: one pass over the row ----
     // A NaN compares "greater or unordered" to T_top, so it becomes a candidate; step C sees its bit pattern and sends
@@ -152,8 +161,15 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const long long t1 = clock64();
     {
       uint32_t gcount = 0;
-      for (long long v0 = 0; v0 < nv; v0 += 4LL * M3_THREADS) {      // block-uniform trip count
-        if (tid == 0) {   // the chunk three iterations ahead goes to L2 now (32 KB per iteration)
+      uint32_t wcnt = 0;                                              // candidates of this warp so far (warp-uniform)
+      const uint32_t ka = smem_u32(sm.candk) + (uint32_t)warp * (M3_WCAP * 2u);
+      const uint32_t ia = smem_u32(sm.candi) + (uint32_t)warp * (M3_WCAP * 4u);
+      const uint32_t ltmask = (1u << lane) - 1u;
+      const uint32_t kb1m = kh > 0 ? kb1 : 0x10000u, span1 = ke1 - kb1, h1a = smem_u32(&sm.hist[1][0]);   // kh == 0: no bracket
+      // one iteration = 4 x 512 vectors (32 KB); FULL: every thread's four vectors lie inside the row
+      auto chunk = [&](const long long v0, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        if (tid == 0) {   // the chunk three iterations ahead goes to L2 now
           const long long pv = v0 + 12LL * M3_THREADS;
           if (pv < nv) m3_prefetch_l2(src + pv, (uint32_t)((nv - pv < 4LL * M3_THREADS ? nv - pv : 4LL * M3_THREADS) * 16));
         }
@@ -162,56 +178,57 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         for (int u = 0; u < 4; u++) {
           const long long v = v0 + (long long)u * M3_THREADS + tid;
           q[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (v < nv) q[u] = __ldg(src + v);
+          if (FULL || v < nv) q[u] = __ldg(src + v);
         }
 #pragma unroll
-        for (int u2 = 0; u2 < 4; u2 += 2) {
-          uint32_t m8[2];
+        for (int u = 0; u < 4; u++) {
+          const long long v = v0 + (long long)u * M3_THREADS + tid;
+          const uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
+          const uint32_t w4[4] = {w0, w1, w2, w3};
+          uint32_t cm[4], gm[4];
 #pragma unroll
-          for (int h2i = 0; h2i < 2; h2i++) {
-            const int u = u2 + h2i;
-            const long long v = v0 + (long long)u * M3_THREADS + tid;
-            const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-            uint32_t cm[4], gm[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const __half2 h = *reinterpret_cast<const __half2*>(&w4[e]);
-              gm[e] = __hgt2_mask(h, hmhi);
-              cm[e] = __hgeu2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
-            }
-            uint32_t m = 0;
-            if (v < nv) {   // lanes beyond the row hold zeros and must stay out
-              gcount += __popc((gm[0] & 0x00010001u) | (gm[1] & 0x00020002u) | (gm[2] & 0x00040004u) | (gm[3] & 0x00080008u));
-              m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
-              m = (m | (m >> 16)) & 0xFFu;
-            }
-            m8[h2i] = m;
+          for (int e = 0; e < 4; e++) {
+            const __half2 h = *reinterpret_cast<const __half2*>(&w4[e]);
+            gm[e] = __hgt2_mask(h, hmhi);
+            cm[e] = __hgeu2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
           }
-          const uint32_t cnt = __popc(m8[0] | (m8[1] << 8));
-          const uint32_t x = m3_warp_inclusive(cnt, lane);
-          const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
-          if (total == 0) continue;
-          uint32_t base = 0;
-          if (lane == 31) base = m3_atoms_add(&sm.ccount, total);
-          uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + x - cnt;
-#pragma unroll
-          for (int h2i = 0; h2i < 2; h2i++) {
-            const int u = u2 + h2i;
-            const long long v = v0 + (long long)u * M3_THREADS + tid;
-            const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-            uint32_t m = m8[h2i];
-            while (m) {
-              const int e = __ffs(m) - 1;
-              m &= m - 1;
-              const uint32_t lohi = e < 4 ? (e < 2 ? w4[0] : w4[1]) : (e < 6 ? w4[2] : w4[3]);
-              if (pos < M3_CAP) {
-                sm.candk[pos] = (unsigned short)((e & 1) ? (lohi >> 16) : (lohi & 0xFFFFu));
-                sm.candi[pos] = (uint32_t)(v * 8 + e);
-              }
-              pos++;
-            }
+          uint32_t m = 0;
+          if (FULL || v < nv) {   // lanes beyond the row hold zeros and must stay out
+            gcount += __popc((gm[0] & 0x00010001u) | (gm[1] & 0x00020002u) | (gm[2] & 0x00040004u) | (gm[3] & 0x00080008u));
+            // bit 2 j + half of the mask = value `half` of word j
+            m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
+            m = (m | (m >> 16)) & 0xFFu;
+          }
+          const uint32_t idx0 = (uint32_t)v * 8u;
+          // every round appends one candidate of every lane that still has one; the slots come from a ballot
+          for (;;) {
+            const uint32_t act = __ballot_sync(0xffffffffu, m != 0);
+            if (act == 0) break;
+            const uint32_t mo = m;
+            const int e = __ffs(mo) - 1;                                                      // -1 in a lane without one
+            m = mo & (mo - 1u);
+            const bool upper = (e & 4) != 0;
+            const uint32_t a = upper ? w2 : w0, bsel = upper ? w3 : w1;
+            const uint32_t val = __byte_perm(a, bsel, (uint32_t)(e & 3) * 0x22u + 0x10u) & 0xFFFFu;   // value e
+            const uint32_t d = mn_dkey(val);
+            uint32_t pos = wcnt + __popc(act & ltmask);
+            pos = pos < (uint32_t)M3_WCAP ? pos : (uint32_t)M3_WCAP - 1u;                     // a warp that overflows is caught below
+            // the key and the index go to the warp's region; a member of the median bracket is counted in its level-1
+            // histogram right here (the shared-memory atomics hide under the stream instead of piling up in step C)
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %4, 0;\n\tsetp.le.and.u32 q, %5, %6, p;\n\t"
+                "@p st.shared.u16 [%0], %1;\n\t@p st.shared.u32 [%2], %3;\n\t@q red.shared.add.u32 [%7], 1;\n\t}" ::"r"(ka + pos * 2u),
+                "h"((unsigned short)d), "r"(ia + pos * 4u), "r"(idx0 + (uint32_t)e), "r"(mo), "r"(d - kb1m), "r"(span1),
+                "r"(h1a + (((d - kb1m) >> sh1) << 2))
+                : "memory");
+            wcnt += __popc(act);
           }
         }
+      };
+      {
+        long long v0 = 0;
+        for (; v0 + 4LL * M3_THREADS <= nv; v0 += 4LL * M3_THREADS) chunk(v0, std::true_type{});
+        if (v0 < nv) chunk(v0, std::false_type{});
       }
       // the last n % 8 values
       if (tid == 0) {
@@ -220,14 +237,21 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           const __half h = __ushort_as_half(bits);
           if (__hgt(h, smhi)) gcount++;
           if (__hgeu(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
-            const uint32_t pos = atomicAdd(&sm.ccount, 1u);
-            if (pos < M3_CAP) { sm.candk[pos] = bits; sm.candi[pos] = (uint32_t)i; }
+            const uint32_t pos = wcnt < (uint32_t)M3_WCAP ? wcnt : (uint32_t)M3_WCAP - 1u;
+            const uint32_t d = mn_dkey(bits);
+            sm.candk[pos] = (unsigned short)d; sm.candi[pos] = (uint32_t)i;
+            if (d - kb1m <= span1) atomicAdd(&sm.hist[1][(d - kb1m) >> sh1], 1u);
+            wcnt++;
           }
         }
       }
+      wcnt = __shfl_sync(0xffffffffu, wcnt, 0);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gcount += __shfl_xor_sync(0xffffffffu, gcount, o);
-      if (lane == 0) atomicAdd(&sm.G, gcount);
+      if (lane == 0) {
+        atomicAdd(&sm.G, gcount);
+        sm.wcount[warp] = wcnt;
+      }
     }
     __syncthreads();
 
@@ -250,26 +274,30 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         if (sector * 2 >= 12LL * M3_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + sector * 2));
       }
     }
-    const uint32_t ncand = sm.ccount, G = sm.G;
-    bool ok = ncand <= (uint32_t)M3_CAP;
-    const uint32_t nc = ok ? ncand : 0u;
-    const uint32_t kb0 = 0u, kb1 = Mhi == 0x8000u ? 0x7FFFu : mn_dkey(Mhi), kb2 = Tbot == 0x8000u ? 0x7FFFu : mn_dkey(Tbot);
-    const uint32_t ke0 = Ttop == 0x0000u ? 0x8000u : mn_dkey(Ttop), ke1 = Mlo == 0x0000u ? 0x8000u : mn_dkey(Mlo), ke2 = 0xFFFFu;
-    int sh0 = 0, sh1 = 0, sh2 = 0;
-    while (((ke0 - kb0) >> sh0) >= (uint32_t)M3_BINS) sh0++;
-    while (((ke1 - kb1) >> sh1) >= (uint32_t)M3_BINS) sh1++;
-    while (((ke2 - kb2) >> sh2) >= (uint32_t)M3_BINS) sh2++;
-    // C1: class bits of every candidate (kept in bits 18..20 of its index word), level-1 histograms
-    for (uint32_t i = tid; i < nc; i += M3_THREADS) {
-      const uint32_t bits = sm.candk[i];
-      const __half h = __ushort_as_half((unsigned short)bits);
-      const uint32_t d = mn_dkey(bits);
-      const bool c0 = __hge(h, stop), c2 = __hle(h, sbot), c1 = kh > 0 && __hge(h, smlo) && !__hgt(h, smhi);
-      if ((bits & 0x7FFFu) > 0x7C00u) sm.nan = 1u;
-      sm.candi[i] |= (c0 ? 1u << 18 : 0u) | (c1 ? 2u << 18 : 0u) | (c2 ? 4u << 18 : 0u);
-      if (c1) atomicAdd(&sm.hist[1][(d - kb1) >> sh1], 1u);
-      if (c0) atomicAdd(&sm.hist[0][(d - kb0) >> sh0], 1u);
-      if (c2) atomicAdd(&sm.hist[2][(d - kb2) >> sh2], 1u);
+    const uint32_t G = sm.G;
+    uint32_t ncand = 0;
+    bool ok = true;
+#pragma unroll
+    for (int w = 0; w < M3_WARPS; w++) {
+      const uint32_t cw = sm.wcount[w];
+      ncand += cw;
+      ok = ok && cw <= (uint32_t)M3_WCAP;
+    }
+    // this warp's candidates: slots wb .. wb + wn
+    const uint32_t wb = (uint32_t)warp * M3_WCAP, wn = ok ? sm.wcount[warp] : 0u;
+    // C1: level-1 histograms of the two tail classes (the buffer holds keys; NaN keys lie beyond the two infinities)
+    const uint32_t wend = wb + wn;
+    for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
+      uint32_t d[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0x8000u;   // -0: in no tail class
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool live = i0 + 32 * j < wend;
+        if (d[j] < 0x3FFu || d[j] > 0xFC00u) sm.nan = 1u;
+        if (live && d[j] <= ke0) atomicAdd(&sm.hist[0][(d[j] - kb0) >> sh0], 1u);
+        if (live && d[j] >= kb2) atomicAdd(&sm.hist[2][(d[j] - kb2) >> sh2], 1u);
+      }
     }
     __syncthreads();
     ok = ok && sm.nan == 0;
@@ -326,19 +354,26 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       const uint32_t fa2 = kb2 + (sm.binA[2] << sh2), fb2 = kb2 + (sm.binB[2] << sh2);
       if (sh0 | sh1 | sh2) {
         const uint32_t w0 = 1u << sh0, w1 = 1u << sh1, w2 = 1u << sh2;
-        for (uint32_t i = tid; i < nc; i += M3_THREADS) {
-          const uint32_t d = mn_dkey(sm.candk[i]), cl = sm.candi[i] >> 18;
-          if ((cl & 2u) && sh1 > 0) {
-            if (d - fa1 < w1) atomicAdd(&sm.h2[1][0][d - fa1], 1u);
-            if (d - fb1 < w1) atomicAdd(&sm.h2[1][1][d - fb1], 1u);
-          }
-          if ((cl & 1u) && sh0 > 0) {
-            if (d - fa0 < w0) atomicAdd(&sm.h2[0][0][d - fa0], 1u);
-            if (d - fb0 < w0) atomicAdd(&sm.h2[0][1][d - fb0], 1u);
-          }
-          if ((cl & 4u) && sh2 > 0) {
-            if (d - fa2 < w2) atomicAdd(&sm.h2[2][0][d - fa2], 1u);
-            if (d - fb2 < w2) atomicAdd(&sm.h2[2][1][d - fb2], 1u);
+        const bool l1 = sh1 > 0 && kh > 0, l0 = sh0 > 0, l2 = sh2 > 0;
+        for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
+          uint32_t d[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (i0 + 32 * j >= wend) continue;
+            if (l1) {
+              if (d[j] - fa1 < w1) atomicAdd(&sm.h2[1][0][d[j] - fa1], 1u);
+              if (d[j] - fb1 < w1) atomicAdd(&sm.h2[1][1][d[j] - fb1], 1u);
+            }
+            if (l0) {
+              if (d[j] - fa0 < w0) atomicAdd(&sm.h2[0][0][d[j] - fa0], 1u);
+              if (d[j] - fb0 < w0) atomicAdd(&sm.h2[0][1][d[j] - fb0], 1u);
+            }
+            if (l2) {
+              if (d[j] - fa2 < w2) atomicAdd(&sm.h2[2][0][d[j] - fa2], 1u);
+              if (d[j] - fb2 < w2) atomicAdd(&sm.h2[2][1][d[j] - fb2], 1u);
+            }
           }
         }
         __syncthreads();
@@ -369,19 +404,28 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       // C5: the keys between the two boundary keys
       const uint32_t kl0 = sm.klo[0], kl1 = sm.klo[1], kl2 = sm.klo[2];
       const uint32_t sp0 = sm.khi[0] - kl0, sp1 = kh > 0 ? sm.khi[1] - kl1 : 0u, sp2 = sm.khi[2] - kl2;
-      for (uint32_t i = tid; i < nc; i += M3_THREADS) {
-        const uint32_t d = mn_dkey(sm.candk[i]), ci = sm.candi[i];
-        if ((ci & (2u << 18)) && d - kl1 <= sp1) {
-          const uint32_t s1 = atomicAdd(&sm.lcount[1], 1u);
-          if (s1 < (uint32_t)M3_LIST) sm.lk[1][s1] = ((d - kl1) << 18) | (ci & 0x3FFFFu);
-        }
-        if ((ci & (1u << 18)) && d - kl0 <= sp0) {
-          const uint32_t s0 = atomicAdd(&sm.lcount[0], 1u);
-          if (s0 < (uint32_t)M3_LIST) sm.lk[0][s0] = ((d - kl0) << 18) | (ci & 0x3FFFFu);
-        }
-        if ((ci & (4u << 18)) && d - kl2 <= sp2) {
-          const uint32_t s2 = atomicAdd(&sm.lcount[2], 1u);
-          if (s2 < (uint32_t)M3_LIST) sm.lk[2][s2] = ((d - kl2) << 18) | (ci & 0x3FFFFu);
+      for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
+        uint32_t d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const bool live = i0 + 32 * j < wend;
+          const bool in1 = live && kh > 0 && d[j] - kl1 <= sp1, in0 = live && d[j] - kl0 <= sp0, in2 = live && d[j] - kl2 <= sp2;
+          if (!(in0 | in1 | in2)) continue;
+          const uint32_t ci = sm.candi[i0 + 32 * j];
+          if (in1) {
+            const uint32_t s1 = atomicAdd(&sm.lcount[1], 1u);
+            if (s1 < (uint32_t)M3_LIST) sm.lk[1][s1] = ((d[j] - kl1) << 18) | ci;
+          }
+          if (in0) {
+            const uint32_t s0 = atomicAdd(&sm.lcount[0], 1u);
+            if (s0 < (uint32_t)M3_LIST) sm.lk[0][s0] = ((d[j] - kl0) << 18) | ci;
+          }
+          if (in2) {
+            const uint32_t s2 = atomicAdd(&sm.lcount[2], 1u);
+            if (s2 < (uint32_t)M3_LIST) sm.lk[2][s2] = ((d[j] - kl2) << 18) | ci;
+          }
         }
       }
       __syncthreads();
