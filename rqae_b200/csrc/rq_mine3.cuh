@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const long long t1 = clock64();
     {
       uint32_t gcount = 0;
+      __half2 gacc = __float2half2_rn(0.f);
       uint32_t wcnt = 0;                                              // candidates of this warp so far (warp-uniform)
       const uint32_t ka = smem_u32(sm.candk) + (uint32_t)warp * (M3_WCAP * 2u);
       const uint32_t ia = smem_u32(sm.candi) + (uint32_t)warp * (M3_WCAP * 4u);
-      const uint32_t ltmask = (1u << lane) - 1u;
       const uint32_t kb1m = kh > 0 ? kb1 : 0x10000u, span1 = ke1 - kb1, h1a = smem_u32(&sm.hist[1][0]);   // kh == 0: no bracket
       // one iteration = 4 x 512 vectors (32 KB); FULL: every thread's four vectors lie inside the row
       auto chunk = [&](const long long v0, auto full_tag) {
@@ -180,11 +180,12 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           q[u] = make_uint4(0u, 0u, 0u, 0u);
           if (FULL || v < nv) q[u] = __ldg(src + v);
         }
+        // candidate masks of the four vectors: bit 2 j + half of mv[u] = value `half` of word j of vector u
+        uint32_t mv[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const long long v = v0 + (long long)u * M3_THREADS + tid;
-          const uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
-          const uint32_t w4[4] = {w0, w1, w2, w3};
+          const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
           uint32_t cm[4], gm[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) {
@@ -192,36 +193,45 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
             gm[e] = __hgt2_mask(h, hmhi);
             cm[e] = __hgeu2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
           }
-          uint32_t m = 0;
+          mv[u] = 0;
           if (FULL || v < nv) {   // lanes beyond the row hold zeros and must stay out
-            gcount += __popc((gm[0] & 0x00010001u) | (gm[1] & 0x00020002u) | (gm[2] & 0x00040004u) | (gm[3] & 0x00080008u));
-            // bit 2 j + half of the mask = value `half` of word j
-            m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
-            m = (m | (m >> 16)) & 0xFFu;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {   // the count above the bracket accumulates as packed fp16 ones (fma pipe; <= 256 per half and row)
+              const uint32_t one = gm[e] & 0x3C003C00u;
+              gacc = __hadd2(gacc, *reinterpret_cast<const __half2*>(&one));
+            }
+            uint32_t m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
+            mv[u] = (m | (m >> 16)) & 0xFFu;
           }
-          const uint32_t idx0 = (uint32_t)v * 8u;
-          // every round appends one candidate of every lane that still has one; the slots come from a ballot
-          for (;;) {
-            const uint32_t act = __ballot_sync(0xffffffffu, m != 0);
-            if (act == 0) break;
-            const uint32_t mo = m;
-            const int e = __ffs(mo) - 1;                                                      // -1 in a lane without one
-            m = mo & (mo - 1u);
-            const bool upper = (e & 4) != 0;
-            const uint32_t a = upper ? w2 : w0, bsel = upper ? w3 : w1;
-            const uint32_t val = __byte_perm(a, bsel, (uint32_t)(e & 3) * 0x22u + 0x10u) & 0xFFFFu;   // value e
+        }
+        // slots: the lane's candidates of all four vectors lie side by side, lanes in order (one scan per chunk)
+        const uint32_t cnt = __popc(mv[0] | (mv[1] << 8) | (mv[2] << 16) | (mv[3] << 24));
+        const uint32_t inc = m3_warp_inclusive(cnt, lane);
+        uint32_t pos = wcnt + inc - cnt;
+        wcnt += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
+          const uint32_t vtag = (uint32_t)(v0 + (long long)u * M3_THREADS + tid) << 8;
+          uint32_t m = mv[u];
+          while (m) {   // no index arithmetic on the way: the candidate is named by its one-hot bit
+            const uint32_t b = m & (0u - m);
+            m ^= b;
+            const bool upper = (b & 0xF0u) != 0;
+            const uint32_t a = upper ? w2 : w0, c = upper ? w3 : w1;
+            const uint32_t w = (b & 0xCCu) ? c : a;
+            const uint32_t val = (b & 0xAAu) ? (w >> 16) : (w & 0xFFFFu);
             const uint32_t d = mn_dkey(val);
-            uint32_t pos = wcnt + __popc(act & ltmask);
-            pos = pos < (uint32_t)M3_WCAP ? pos : (uint32_t)M3_WCAP - 1u;                     // a warp that overflows is caught below
-            // the key and the index go to the warp's region; a member of the median bracket is counted in its level-1
-            // histogram right here (the shared-memory atomics hide under the stream instead of piling up in step C)
+            const uint32_t ps = pos < (uint32_t)M3_WCAP ? pos : (uint32_t)M3_WCAP - 1u;   // a warp that overflows is caught below
+            const uint32_t t = d - kb1m;
+            // the key and (vector << 8 | bit) go to the warp's region; a member of the median bracket is counted in its
+            // level-1 histogram right here (the shared-memory atomics hide under the stream instead of piling up in step C)
             asm volatile(
-                "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %4, 0;\n\tsetp.le.and.u32 q, %5, %6, p;\n\t"
-                "@p st.shared.u16 [%0], %1;\n\t@p st.shared.u32 [%2], %3;\n\t@q red.shared.add.u32 [%7], 1;\n\t}" ::"r"(ka + pos * 2u),
-                "h"((unsigned short)d), "r"(ia + pos * 4u), "r"(idx0 + (uint32_t)e), "r"(mo), "r"(d - kb1m), "r"(span1),
-                "r"(h1a + (((d - kb1m) >> sh1) << 2))
+                "{\n\t.reg .pred q;\n\tsetp.le.u32 q, %4, %5;\n\t"
+                "st.shared.u16 [%0], %1;\n\tst.shared.u32 [%2], %3;\n\t@q red.shared.add.u32 [%6], 1;\n\t}" ::"r"(ka + ps * 2u),
+                "h"((unsigned short)d), "r"(ia + ps * 4u), "r"(vtag | b), "r"(t), "r"(span1), "r"(h1a + ((t >> sh1) << 2))
                 : "memory");
-            wcnt += __popc(act);
+            pos++;
           }
         }
       };
@@ -239,13 +249,14 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           if (__hgeu(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
             const uint32_t pos = wcnt < (uint32_t)M3_WCAP ? wcnt : (uint32_t)M3_WCAP - 1u;
             const uint32_t d = mn_dkey(bits);
-            sm.candk[pos] = (unsigned short)d; sm.candi[pos] = (uint32_t)i;
+            sm.candk[pos] = (unsigned short)d; sm.candi[pos] = ((uint32_t)(i >> 3) << 8) | (1u << (i & 7));
             if (d - kb1m <= span1) atomicAdd(&sm.hist[1][(d - kb1m) >> sh1], 1u);
             wcnt++;
           }
         }
       }
       wcnt = __shfl_sync(0xffffffffu, wcnt, 0);
+      gcount += (uint32_t)(__low2float(gacc) + __high2float(gacc) + 0.5f);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gcount += __shfl_xor_sync(0xffffffffu, gcount, o);
       if (lane == 0) {
@@ -413,7 +424,8 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           const bool live = i0 + 32 * j < wend;
           const bool in1 = live && kh > 0 && d[j] - kl1 <= sp1, in0 = live && d[j] - kl0 <= sp0, in2 = live && d[j] - kl2 <= sp2;
           if (!(in0 | in1 | in2)) continue;
-          const uint32_t ci = sm.candi[i0 + 32 * j];
+          const uint32_t cw = sm.candi[i0 + 32 * j];
+          const uint32_t ci = (cw >> 8) * 8u + (uint32_t)(__ffs(cw & 0xFFu) - 1);   // vector << 8 | one-hot bit -> index
           if (in1) {
             const uint32_t s1 = atomicAdd(&sm.lcount[1], 1u);
             if (s1 < (uint32_t)M3_LIST) sm.lk[1][s1] = ((d[j] - kl1) << 18) | ci;
