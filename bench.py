@@ -239,6 +239,13 @@ def mining_extras(torch, model, codes, dev):
     buf = torch.empty(Fn, len(SCRIPT3_CUTS), (T + 255) // 256 * 256, dtype=torch.float16, device=dev)
     out, ms_int = _event_ms(torch, dev, lambda: intensity_many(model, codes, centers, SCRIPT3_CUTS, layer_weights=lw, out=buf))
     (idx, val), ms_sel = _event_ms(torch, dev, lambda: select_top_middle_bottom(out, 100))
+    # the same rows through the three-pass kernel (the sample-bracketed kernel's fallback), for the A/B
+    os.environ["RQAE_MINE_V2"] = "1"
+    try:
+        (idx2, _), ms_sel2 = _event_ms(torch, dev, lambda: select_top_middle_bottom(out, 100))
+    finally:
+        os.environ.pop("RQAE_MINE_V2", None)
+    assert torch.equal(idx, idx2), "selection: the single-pass kernel and the three-pass kernel disagree"
     peaks = measured_peaks()
     tensor_peak = peaks["bf16_tflops"] if peaks else 1590.0
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
@@ -251,7 +258,9 @@ def mining_extras(torch, model, codes, dev):
         "intensity_out_gbs": out_bytes / ms_int / 1e6, "intensity_frac_of_hbm_peak": out_bytes / ms_int / 1e6 / hbm_peak,
         "tensor_peak_source": "MEASURED_PEAKS.json (burst)" if peaks else "fallback 1.59 PFLOP/s (B200_PROFILING.md)",
         "select_ms": ms_sel, "select_rows_per_s": Fn * len(SCRIPT3_CUTS) / ms_sel * 1e3,
-        "select_gbs": out_bytes / ms_sel / 1e6,
+        "select_gbs": out_bytes / ms_sel / 1e6, "select_frac_of_hbm_peak": out_bytes / ms_sel / 1e6 / hbm_peak,
+        "select_kernel": "rq_mine3 (brackets from a 1/16 sample, one streaming pass; rows whose brackets miss go to rq_mine2)",
+        "select_ms_three_pass_kernel": ms_sel2, "select_equal_to_three_pass_kernel": True,
         "checksum_top_idx": int(idx[:, :, 0].sum().item()),
     }
     # the reference's CPU path for the same step (one feature at a time, rqae/feature.py:102-129), bounded sample

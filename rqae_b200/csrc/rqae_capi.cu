@@ -1163,7 +1163,7 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
   // RQAE_MINE_V1=1 selects the first version of the kernel (shared-memory atomics per element; A/B timing)
   static const bool v1 = [] { const char* e = getenv("RQAE_MINE_V1"); return e && atoi(e) != 0; }();
   // RQAE_MINE_V2=1 keeps the three-pass kernel for every row (A/B timing against the sample-bracketed one)
-  static const bool v2 = [] { const char* e = getenv("RQAE_MINE_V2"); return e && atoi(e) != 0; }();
+  const bool v2 = [] { const char* e = getenv("RQAE_MINE_V2"); return e && atoi(e) != 0; }();   // read per call: A/B in one process
   constexpr int smem2 = rq::M2_SMEM_BYTES_PAD + rq::M2_LP_BYTES + (int)sizeof(rq::Mine2Smem);
   constexpr int per_sm2 = 16 / rq::M2_WARPS;
   if (!v1 && !v2 && n >= 16384 && n <= 262144 && rows < ((int64_t)1 << 31)) {

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 last evidence visit (1 GPU): whole -m gpu suite, smoke, bench line, ncu --set full of the sample-bracketed selection
+set -u
+TAG=${1:-r5k}
+OUT=gpurun_out
+mkdir -p $OUT
+echo "=== pytest -m gpu ==="
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee $OUT/pytest_gpu_$TAG.log
+echo "=== smoke ==="
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee $OUT/smoke_$TAG.log
+echo "=== selection A/B (normal rows) ==="
+{ RQAE_M3_PROF=1 timeout 120 python tools/bench_select.py --reps 1 2>&1 | tail -3
+  for v in 0 1; do RQAE_MINE_V2=$v timeout 120 python tools/bench_select.py 2>&1 | tail -1; done; } | tee $OUT/select_ab_$TAG.log
+echo "=== bench ==="
+timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit=$?"
+tail -3 $OUT/bench_$TAG.err
+echo "=== ncu full: selection v3 ==="
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_mine3 -s 1 -c 1 -f \
+  -o $OUT/prof_mine3_$TAG python tools/bench_select.py --rows 2368 --reps 1 > $OUT/ncu_mine3_$TAG.log 2>&1
+tail -2 $OUT/ncu_mine3_$TAG.log

@@ -14,7 +14,9 @@ echo "=== memcheck: fused hook (rqae_hook_rmsnorm), small-unit instantiation, ho
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -x -k "fused_hook or forward_host or invariance" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_hook.log
 echo "=== racecheck: radix select (lane-private counters: v2) ==="
 timeout 400 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "5000 or 4097 or 257 or specials or tiny or two_values" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine.log
-echo "=== memcheck: radix select v2, adversarial rows ==="
+echo "=== racecheck: sample-bracketed selection (v3: per-warp candidate regions, shared-memory histograms, fallback list) ==="
+timeout 400 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "65536 or short_16384 or heavy_median_tie or few_values" 2>&1 | tail -6 | tee $OUT/sanitize_racecheck_mine3.log
+echo "=== memcheck: selection v2 / v3, adversarial rows ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "adversarial and not long_2M" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_mine2.log
 echo "=== memcheck + racecheck: example search (table transpose, accumulate, per-position max) ==="
 timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "golden or single_query or argument or int16" 2>&1 | tail -6 | tee $OUT/sanitize_memcheck_search.log
@@ -25,4 +27,4 @@ echo "=== initcheck: example search (both modes), selection ==="
 # (not the intensity GEMM: initcheck does not see the writes of TMA tensor stores, so every later read of the output is
 #  reported as uninitialised although the values are checked against the goldens by the same tests)
 timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_search_gpu.py -q -x -k "tensor_core or single_query or int16" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_search.log
-timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "4097 or 257 or 5000" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_select.log
+timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "4097 or 257 or 5000 or short_16384 or zero_centered or specials" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_select.log
