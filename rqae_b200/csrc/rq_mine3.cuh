@@ -45,7 +45,7 @@ struct Mine3Smem {
   uint32_t scan[3][M3_WARPS];
   uint32_t wcount[M3_WARPS];         // candidates of each warp
   uint32_t G, nan, lcount[3];
-  uint32_t pt, pb, ps, pe;           // bin positions (descending-value order) of the four thresholds
+  uint32_t tbin[4], tex[4], tkey[4]; // level-1 bin, its exclusive prefix and the key of the four thresholds (T_top, T_bot, M_hi, M_lo)
   uint32_t binA[3], exA[3], binB[3], exB[3];   // level-1 bins of a window's first / last rank and their exclusive prefixes
   uint32_t klo[3], khi[3], less_lo[3];
 };
@@ -87,13 +87,18 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const unsigned short* src16 = reinterpret_cast<const unsigned short*>(p.vals + row * p.row_stride);
     const long long t0 = clock64();
     for (int i = tid; i < M3_BINS; i += M3_THREADS) sm.hist[0][i] = 0;
+    if (tid < 128) (&sm.h2[0][0][0])[tid] = 0;
     if (tid == 0) {
       sm.G = 0; sm.nan = 0;
-      sm.pt = 0; sm.pb = M3_BINS - 1; sm.ps = 0; sm.pe = M3_BINS - 1;
+      for (int j = 0; j < 4; j++) { sm.tbin[j] = 0; sm.tex[j] = 0; }
     }
     __syncthreads();
 
-    // ---- A: histogram of the sample, thresholds at bin edges ----
+    // ---- A: two-level radix select over the sample: the keys at four sample ranks are the thresholds ----
+    // 0-based ranks in descending-value order: T_top = rank c_top - 1, T_bot = rank ms - c_top, M_hi = rank c_hi,
+    // M_lo = rank c_lo - 1
+    const uint32_t rk[4] = {(uint32_t)p.c_top - 1u, ms - (uint32_t)p.c_top, (uint32_t)(p.c_hi > 0 ? p.c_hi : 0),
+                            (uint32_t)p.c_lo - 1u < ms ? (uint32_t)p.c_lo - 1u : ms - 1u};
     for (long long g = tid; g < ngroups; g += M3_THREADS) {
       const long long sector = (g << slog) + (m3_hash((uint32_t)g, (uint32_t)row) >> (32 - slog));
       const uint4 a = __ldg(src + sector * 2), b = __ldg(src + sector * 2 + 1);
@@ -117,24 +122,49 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       uint32_t ex = inc - tot;
 #pragma unroll
       for (int w = 0; w < M3_WARPS; w++) ex += w < warp ? sm.scan[0][w] : 0u;
-      const uint32_t ct = (uint32_t)p.c_top;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint32_t in = ex + c[i], pos = (uint32_t)tid * 4 + i;
-        if (c[i] != 0) {
-          if (ex < ct && ct <= in) sm.pt = pos;
-          if (ms - in < ct && ct <= ms - ex) sm.pb = pos;
-          if (p.c_hi >= 0 && ex <= (uint32_t)p.c_hi && (uint32_t)p.c_hi < in) sm.ps = pos;
-          if ((uint32_t)p.c_lo <= ms && ex < (uint32_t)p.c_lo && (uint32_t)p.c_lo <= in) sm.pe = pos;
-        }
+        const uint32_t in = ex + c[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (ex <= rk[j] && rk[j] < in) { sm.tbin[j] = (uint32_t)tid * 4 + i; sm.tex[j] = ex; }
         ex = in;
       }
     }
     __syncthreads();
-    // bit patterns: lowest value of the top bin, highest of the bottom bin, highest of the first / lowest of the last
-    // bracket bin
-    const uint32_t Ttop = mn_bits((sm.pt << 5) | 31u), Tbot = mn_bits(sm.pb << 5);
-    const uint32_t Mhi = mn_bits(sm.ps << 5), Mlo = mn_bits((sm.pe << 5) | 31u);
+    {   // level 2: the low five key bits inside the four bins (the sample is read again: it sits in L1 / L2)
+      const uint32_t b0 = sm.tbin[0], b1 = sm.tbin[1], b2 = sm.tbin[2], b3 = sm.tbin[3];
+      for (long long g = tid; g < ngroups; g += M3_THREADS) {
+        const long long sector = (g << slog) + (m3_hash((uint32_t)g, (uint32_t)row) >> (32 - slog));
+        const uint4 a = __ldg(src + sector * 2), b = __ldg(src + sector * 2 + 1);
+        const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const uint32_t w = w8[e];
+          const uint32_t d2 = w ^ ((((w >> 15) & 0x00010001u) * 0x7FFFu) ^ 0x7FFF7FFFu);
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const uint32_t d = hh ? d2 >> 16 : d2 & 0xFFFFu, bin = d >> 5;
+            if (bin == b0) atomicAdd(&sm.h2[0][0][d & 31u], 1u);
+            if (bin == b1) atomicAdd(&sm.h2[0][1][d & 31u], 1u);
+            if (bin == b2) atomicAdd(&sm.h2[1][0][d & 31u], 1u);
+            if (bin == b3) atomicAdd(&sm.h2[1][1][d & 31u], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      if (warp < 4) {
+        const uint32_t cnt = (&sm.h2[0][0][0])[warp * 32 + lane];
+        const uint32_t inc = m3_warp_inclusive(cnt, lane);
+        const uint32_t target = rk[warp] - sm.tex[warp];
+        const uint32_t sel = __ballot_sync(0xffffffffu, inc - cnt <= target && target < inc);
+        if (lane == 0) sm.tkey[warp] = (sm.tbin[warp] << 5) | (sel ? (uint32_t)__ffs(sel) - 1u : 0u);
+      }
+      __syncthreads();
+    }
+    // bit patterns of the thresholds (rank c_hi < 0: the bracket starts at the very top, key 0)
+    const uint32_t Ttop = mn_bits(sm.tkey[0]), Tbot = mn_bits(sm.tkey[1]);
+    const uint32_t Mhi = mn_bits(p.c_hi >= 0 ? sm.tkey[2] : 0u), Mlo = mn_bits(sm.tkey[3]);
     const uint32_t ttop2 = Ttop * 0x10001u, tbot2 = Tbot * 0x10001u, mhi2 = Mhi * 0x10001u, mlo2 = Mlo * 0x10001u;
     const __half2 htop = *reinterpret_cast<const __half2*>(&ttop2), hbot = *reinterpret_cast<const __half2*>(&tbot2);
     const __half2 hmhi = *reinterpret_cast<const __half2*>(&mhi2), hmlo = *reinterpret_cast<const __half2*>(&mlo2);
