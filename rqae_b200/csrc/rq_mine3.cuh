@@ -32,7 +32,7 @@ constexpr int M3_THREADS = 512;
 constexpr int M3_WARPS = M3_THREADS / 32;
 constexpr int M3_WCAP = 768;       // candidates per warp and row: every warp appends to its own region (no atomics)
 constexpr int M3_CAP = M3_WCAP * M3_WARPS;
-constexpr int M3_LIST = 512;       // members of one class that enter its rank sort (the window and the ties at its ends)
+constexpr int M3_LIST = MN_KMAX;   // members of one window
 constexpr int M3_BINS = 2048;
 constexpr int M3_SORT_THREADS = 160;   // threads per class in the rank sort (five warps each)
 
@@ -40,14 +40,15 @@ struct Mine3Smem {
   uint32_t hist[3][M3_BINS];         // [0] also holds the sample histogram of step A
   uint32_t candi[M3_CAP];
   unsigned short candk[M3_CAP];
-  uint32_t lk[3][M3_LIST];           // (key - klo) << 18 | index
+  unsigned long long lk[3][M3_LIST]; // key << 32 | index of the members of each window
   uint32_t h2[3][2][32];
   uint32_t scan[3][M3_WARPS];
   uint32_t wcount[M3_WARPS];         // candidates of each warp
   uint32_t G, nan, lcount[3];
   uint32_t tbin[4], tex[4], tkey[4]; // level-1 bin, its exclusive prefix and the key of the four thresholds (T_top, T_bot, M_hi, M_lo)
   uint32_t binA[3], exA[3], binB[3], exB[3];   // level-1 bins of a window's first / last rank and their exclusive prefixes
-  uint32_t klo[3], khi[3], less_lo[3];
+  uint32_t klo[3], khi[3], less_lo[3], less_hi[3];
+  uint32_t tie[6][M3_WARPS];         // per warp: candidates equal to klo / khi of each class
 };
 
 __device__ __forceinline__ uint32_t m3_hash(uint32_t g, uint32_t row) {
@@ -196,25 +197,29 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       const uint32_t ka = smem_u32(sm.candk) + (uint32_t)warp * (M3_WCAP * 2u);
       const uint32_t ia = smem_u32(sm.candi) + (uint32_t)warp * (M3_WCAP * 4u);
       const uint32_t kb1m = kh > 0 ? kb1 : 0x10000u, span1 = ke1 - kb1, h1a = smem_u32(&sm.hist[1][0]);   // kh == 0: no bracket
-      // one iteration = 4 x 512 vectors (32 KB); FULL: every thread's four vectors lie inside the row
+      // Warp w streams the contiguous slice [ws, we) of the row's vectors, 4 x 32 vectors (2 KB) per step, so that its
+      // region of the candidate buffer is in ascending index order and regions follow each other in index order: the rank
+      // of a value among equal values (index ascending) is a count over earlier regions plus a running count.
+      // FULL: all four vectors of every lane lie inside the slice.
+      const long long per = (nv + M3_WARPS - 1) / M3_WARPS, ws = warp * per < nv ? warp * per : nv, we = ws + per < nv ? ws + per : nv;
       auto chunk = [&](const long long v0, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        if (tid == 0) {   // the chunk three iterations ahead goes to L2 now
-          const long long pv = v0 + 12LL * M3_THREADS;
-          if (pv < nv) m3_prefetch_l2(src + pv, (uint32_t)((nv - pv < 4LL * M3_THREADS ? nv - pv : 4LL * M3_THREADS) * 16));
+        if (lane == 0) {   // the step three ahead goes to L2 now
+          const long long pv = v0 + 3 * 128;
+          if (pv < we) m3_prefetch_l2(src + pv, (uint32_t)((we - pv < 128 ? we - pv : 128) * 16));
         }
         uint4 q[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const long long v = v0 + (long long)u * M3_THREADS + tid;
+          const long long v = v0 + u * 32 + lane;
           q[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (FULL || v < nv) q[u] = __ldg(src + v);
+          if (FULL || v < we) q[u] = __ldg(src + v);
         }
         // candidate masks of the four vectors: bit 2 j + half of mv[u] = value `half` of word j of vector u
         uint32_t mv[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const long long v = v0 + (long long)u * M3_THREADS + tid;
+          const long long v = v0 + u * 32 + lane;
           const uint32_t w4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
           uint32_t cm[4], gm[4];
 #pragma unroll
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
             cm[e] = __hgeu2_mask(h, htop) | __hle2_mask(h, hbot) | (__hge2_mask(h, hmlo) & ~gm[e]);
           }
           mv[u] = 0;
-          if (FULL || v < nv) {   // lanes beyond the row hold zeros and must stay out
+          if (FULL || v < we) {   // lanes beyond the slice hold zeros and must stay out
 #pragma unroll
             for (int e = 0; e < 4; e++) {   // the count above the bracket accumulates as packed fp16 ones (fma pipe; <= 256 per half and row)
               const uint32_t one = gm[e] & 0x3C003C00u;
@@ -234,16 +239,22 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
             mv[u] = (m | (m >> 16)) & 0xFFu;
           }
         }
-        // slots: the lane's candidates of all four vectors lie side by side, lanes in order (one scan per chunk)
-        const uint32_t cnt = __popc(mv[0] | (mv[1] << 8) | (mv[2] << 16) | (mv[3] << 24));
-        const uint32_t inc = m3_warp_inclusive(cnt, lane);
-        uint32_t pos = wcnt + inc - cnt;
-        wcnt += __shfl_sync(0xffffffffu, inc, 31);
+        // slots in index order: vector u of every lane before vector u + 1 of any lane; two packed scans per step
+        const uint32_t c0 = __popc(mv[0]), c1 = __popc(mv[1]), c2 = __popc(mv[2]), c3 = __popc(mv[3]);
+        const uint32_t i01 = m3_warp_inclusive(c0 | (c1 << 16), lane), i23 = m3_warp_inclusive(c2 | (c3 << 16), lane);
+        const uint32_t t01 = __shfl_sync(0xffffffffu, i01, 31), t23 = __shfl_sync(0xffffffffu, i23, 31);
+        uint32_t posv[4];
+        posv[0] = wcnt + (i01 & 0xFFFFu) - c0;
+        posv[1] = wcnt + (t01 & 0xFFFFu) + (i01 >> 16) - c1;
+        posv[2] = wcnt + (t01 & 0xFFFFu) + (t01 >> 16) + (i23 & 0xFFFFu) - c2;
+        posv[3] = wcnt + (t01 & 0xFFFFu) + (t01 >> 16) + (t23 & 0xFFFFu) + (i23 >> 16) - c3;
+        wcnt += (t01 & 0xFFFFu) + (t01 >> 16) + (t23 & 0xFFFFu) + (t23 >> 16);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
-          const uint32_t vtag = (uint32_t)(v0 + (long long)u * M3_THREADS + tid) << 8;
+          const uint32_t vtag = (uint32_t)(v0 + u * 32 + lane) << 8;
           uint32_t m = mv[u];
+          uint32_t pos = posv[u];
           while (m) {   // no index arithmetic on the way: the candidate is named by its one-hot bit
             const uint32_t b = m & (0u - m);
             m ^= b;
@@ -266,12 +277,12 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         }
       };
       {
-        long long v0 = 0;
-        for (; v0 + 4LL * M3_THREADS <= nv; v0 += 4LL * M3_THREADS) chunk(v0, std::true_type{});
-        if (v0 < nv) chunk(v0, std::false_type{});
+        long long v0 = ws;
+        for (; v0 + 128 <= we; v0 += 128) chunk(v0, std::true_type{});
+        if (v0 < we) chunk(v0, std::false_type{});
       }
-      // the last n % 8 values
-      if (tid == 0) {
+      // the last n % 8 values: the end of the last warp's slice
+      if (tid == (M3_WARPS - 1) * 32) {
         for (long long i = nv * 8; i < n; i++) {
           const unsigned short bits = src16[i];
           const __half h = __ushort_as_half(bits);
@@ -279,7 +290,8 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           if (__hgeu(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
             const uint32_t pos = wcnt < (uint32_t)M3_WCAP ? wcnt : (uint32_t)M3_WCAP - 1u;
             const uint32_t d = mn_dkey(bits);
-            sm.candk[pos] = (unsigned short)d; sm.candi[pos] = ((uint32_t)(i >> 3) << 8) | (1u << (i & 7));
+            sm.candk[(M3_WARPS - 1) * M3_WCAP + pos] = (unsigned short)d;
+            sm.candi[(M3_WARPS - 1) * M3_WCAP + pos] = ((uint32_t)(i >> 3) << 8) | (1u << (i & 7));
             if (d - kb1m <= span1) atomicAdd(&sm.hist[1][(d - kb1m) >> sh1], 1u);
             wcnt++;
           }
@@ -305,14 +317,13 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     if (row + gridDim.x < p.rows) {   // the next row of this CTA: sample sectors and the first chunks on their way to L2
       const long long nrow = row + gridDim.x;
       const uint4* nsrc = reinterpret_cast<const uint4*>(p.vals + nrow * p.row_stride);
-      if (tid == 0) {
-        const long long first = nv < 12LL * M3_THREADS ? nv : 12LL * M3_THREADS;
-        for (long long pv = 0; pv < first; pv += 4LL * M3_THREADS)
-          m3_prefetch_l2(nsrc + pv, (uint32_t)((first - pv < 4LL * M3_THREADS ? first - pv : 4LL * M3_THREADS) * 16));
+      if (lane == 0) {   // the first three steps of this warp's slice
+        const long long per = (nv + M3_WARPS - 1) / M3_WARPS, ws = warp * per < nv ? warp * per : nv, we = ws + per < nv ? ws + per : nv;
+        if (ws < we) m3_prefetch_l2(nsrc + ws, (uint32_t)((we - ws < 384 ? we - ws : 384) * 16));
       }
       for (long long g = tid; g < ngroups; g += M3_THREADS) {
         const long long sector = (g << slog) + (m3_hash((uint32_t)g, (uint32_t)nrow) >> (32 - slog));
-        if (sector * 2 >= 12LL * M3_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + sector * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + sector * 2));
       }
     }
     const uint32_t G = sm.G;
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       ncand += cw;
       ok = ok && cw <= (uint32_t)M3_WCAP;
     }
+    uint32_t why = ok ? 0u : 1u;   // RQAE_M3_PROF: 1 region overflow, 2 NaN, 4 bracket missed, 8 tail class short, 16 key span / list
     // this warp's candidates: slots wb .. wb + wn
     const uint32_t wb = (uint32_t)warp * M3_WCAP, wn = ok ? sm.wcount[warp] : 0u;
     // C1: level-1 histograms of the two tail classes (the buffer holds keys; NaN keys lie beyond the two infinities)
@@ -341,6 +353,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       }
     }
     __syncthreads();
+    if (sm.nan != 0) why |= 2u;
     ok = ok && sm.nan == 0;
     const long long tc1 = clock64();
     // C2: prefix sums, the bins of each window's first and last rank
@@ -368,11 +381,11 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         uint32_t rl, rh;
         if (c == 1) {
           if (kh == 0) continue;
-          if ((long long)G > m0 || (long long)G + (long long)total < m1) { ok = false; continue; }
+          if ((long long)G > m0 || (long long)G + (long long)total < m1) { ok = false; why |= 4u; continue; }
           rl = (uint32_t)(m0 - (long long)G); rh = (uint32_t)(m1 - 1 - (long long)G);
           rl1 = rl; rh1 = rh;
         } else {
-          if (total < (uint32_t)k) { ok = false; continue; }
+          if (total < (uint32_t)k) { ok = false; why |= 8u; continue; }
           rl = c == 0 ? 0u : total - (uint32_t)k; rh = rl + (uint32_t)k - 1u;
           if (c == 0) { rl0 = rl; rh0 = rh; } else { rl2 = rl; rh2 = rh; }
         }
@@ -437,67 +450,114 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           less = exb + __shfl_sync(0xffffffffu, inc - cnt, j);
         }
         if (lane == 0) {
-          if (b == 0) { sm.klo[c] = key; sm.less_lo[c] = less; } else sm.khi[c] = key;
+          if (b == 0) { sm.klo[c] = key; sm.less_lo[c] = less; } else { sm.khi[c] = key; sm.less_hi[c] = less; }
         }
       }
       __syncthreads();
       tc4 = clock64();
-      // C5: the keys between the two boundary keys
+      // C5: the members of the three windows.  A key strictly between the boundary keys is in; a key EQUAL to a boundary
+      // key is in according to its rank among the equal values in index order: regions are in index order (step B), so
+      // that rank is (equal values in earlier warps' regions) + (equal values earlier in this region).
       const uint32_t kl0 = sm.klo[0], kl1 = sm.klo[1], kl2 = sm.klo[2];
-      const uint32_t sp0 = sm.khi[0] - kl0, sp1 = kh > 0 ? sm.khi[1] - kl1 : 0u, sp2 = sm.khi[2] - kl2;
-      for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
+      const uint32_t kh0 = sm.khi[0], kh1 = sm.khi[1], kh2 = sm.khi[2];
+      const uint32_t sp0 = kh0 - kl0, sp1 = kh > 0 ? kh1 - kl1 : 0u, sp2 = kh2 - kl2;
+      const uint32_t K[6] = {kl0, kh0, kl1, kh1, kl2, kh2};
+      {   // per-warp counts of the six boundary keys
+        uint32_t cn[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t i = wb + lane; i < wend; i += 32) {
+          const uint32_t d = sm.candk[i];
+          if (d - kl0 <= sp0 || d - kl1 <= sp1 || d - kl2 <= sp2) {   // a few per cent of the region
+#pragma unroll
+            for (int q = 0; q < 6; q++) cn[q] += d == K[q];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cn[q] += __shfl_xor_sync(0xffffffffu, cn[q], o);
+          if (lane == 0) sm.tie[q][warp] = cn[q];
+        }
+      }
+      __syncthreads();
+      uint32_t run[6];                                  // equal values before the current position (warp-uniform)
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        run[q] = 0;
+#pragma unroll
+        for (int w = 0; w < M3_WARPS; w++) run[q] += w < warp ? sm.tie[q][w] : 0u;
+      }
+      // tie ranks [lo_from, lo_to) of klo and [0, hi_to) of khi belong to the window (klo == khi: one group holds both ends)
+      const uint32_t s0 = rl0 - sm.less_lo[0], s1 = rl1 - sm.less_lo[1], s2 = rl2 - sm.less_lo[2];
+      const uint32_t lo_from[3] = {s0, s1, s2};
+      const uint32_t lo_to[3] = {kl0 == kh0 ? s0 + (rh0 - rl0 + 1u) : 0xFFFFFFFFu, kl1 == kh1 ? s1 + (rh1 - rl1 + 1u) : 0xFFFFFFFFu,
+                                 kl2 == kh2 ? s2 + (rh2 - rl2 + 1u) : 0xFFFFFFFFu};
+      const uint32_t hi_to[3] = {rh0 - sm.less_hi[0] + 1u, rh1 - sm.less_hi[1] + 1u, rh2 - sm.less_hi[2] + 1u};
+      const uint32_t ltm = (1u << lane) - 1u;
+      for (uint32_t i0 = wb + lane; i0 - lane < wend; i0 += 128) {   // warp-uniform trip count, region order
         uint32_t d[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const bool live = i0 + 32 * j < wend;
-          const bool in1 = live && kh > 0 && d[j] - kl1 <= sp1, in0 = live && d[j] - kl0 <= sp0, in2 = live && d[j] - kl2 <= sp2;
-          if (!(in0 | in1 | in2)) continue;
+          const bool r0 = live && d[j] - kl0 <= sp0, r1 = live && kh > 0 && d[j] - kl1 <= sp1, r2 = live && d[j] - kl2 <= sp2;
+          if (!__any_sync(0xffffffffu, r0 | r1 | r2)) continue;
+          bool in[3] = {r0, r1, r2};
+          const bool eq = d[j] == K[0] || d[j] == K[1] || d[j] == K[2] || d[j] == K[3] || d[j] == K[4] || d[j] == K[5];
+          if (__any_sync(0xffffffffu, eq))   // rare on rows without heavy ties
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const bool elo = in[c] && d[j] == K[2 * c], ehi = in[c] && d[j] == K[2 * c + 1] && K[2 * c] != K[2 * c + 1];
+            const uint32_t blo = __ballot_sync(0xffffffffu, elo), bhi = __ballot_sync(0xffffffffu, ehi);
+            if (elo) { const uint32_t t = run[2 * c] + __popc(blo & ltm); in[c] = t >= lo_from[c] && t < lo_to[c]; }
+            if (ehi) { const uint32_t t = run[2 * c + 1] + __popc(bhi & ltm); in[c] = t < hi_to[c]; }
+            run[2 * c] += __popc(blo); run[2 * c + 1] += __popc(bhi);
+          }
+          if (!(in[0] | in[1] | in[2])) continue;
           const uint32_t cw = sm.candi[i0 + 32 * j];
           const uint32_t ci = (cw >> 8) * 8u + (uint32_t)(__ffs(cw & 0xFFu) - 1);   // vector << 8 | one-hot bit -> index
-          if (in1) {
-            const uint32_t s1 = atomicAdd(&sm.lcount[1], 1u);
-            if (s1 < (uint32_t)M3_LIST) sm.lk[1][s1] = ((d[j] - kl1) << 18) | ci;
+          if (in[1]) {
+            const uint32_t sl = atomicAdd(&sm.lcount[1], 1u);
+            if (sl < (uint32_t)M3_LIST) sm.lk[1][sl] = ((unsigned long long)d[j] << 32) | ci;
           }
-          if (in0) {
-            const uint32_t s0 = atomicAdd(&sm.lcount[0], 1u);
-            if (s0 < (uint32_t)M3_LIST) sm.lk[0][s0] = ((d[j] - kl0) << 18) | ci;
+          if (in[0]) {
+            const uint32_t sl = atomicAdd(&sm.lcount[0], 1u);
+            if (sl < (uint32_t)M3_LIST) sm.lk[0][sl] = ((unsigned long long)d[j] << 32) | ci;
           }
-          if (in2) {
-            const uint32_t s2 = atomicAdd(&sm.lcount[2], 1u);
-            if (s2 < (uint32_t)M3_LIST) sm.lk[2][s2] = ((d[j] - kl2) << 18) | ci;
+          if (in[2]) {
+            const uint32_t sl = atomicAdd(&sm.lcount[2], 1u);
+            if (sl < (uint32_t)M3_LIST) sm.lk[2][sl] = ((unsigned long long)d[j] << 32) | ci;
           }
         }
       }
       __syncthreads();
-      if (sm.lcount[0] > (uint32_t)M3_LIST || sm.lcount[2] > (uint32_t)M3_LIST || sp0 >= 16384u || sp2 >= 16384u) ok = false;
-      if (kh > 0 && (sm.lcount[1] > (uint32_t)M3_LIST || sp1 >= 16384u)) ok = false;
+      if (sm.lcount[0] > (uint32_t)M3_LIST || sm.lcount[2] > (uint32_t)M3_LIST || (kh > 0 && sm.lcount[1] > (uint32_t)M3_LIST)) {
+        ok = false; why |= 16u;   // cannot happen: a list holds exactly its window
+      }
       tc5 = clock64();
       if (ok) {
         // C6: rank sorts, five warps per class: packed (key, index) ascending = value descending, index ascending
         const int c = tid / M3_SORT_THREADS;
         if (c < 3 && (c != 1 || kh > 0)) {
           const int cnt = (int)sm.lcount[c];
-          const uint32_t rl = m3_sel3(c, rl0, rl1, rl2), rh = m3_sel3(c, rh0, rh1, rh2), kl = m3_sel3(c, kl0, kl1, kl2);
-          const int first = (int)(rl - sm.less_lo[c]), size = (int)(rh - rl + 1u);
+          const uint32_t rl = m3_sel3(c, rl0, rl1, rl2), rh = m3_sel3(c, rh0, rh1, rh2);
+          const int size = (int)(rh - rl + 1u);   // the list holds exactly the window (step C5)
           int* io = p.idx_out + (row * 3 + c) * (long long)k;
           __half* vo = p.val_out ? p.val_out + (row * 3 + c) * (long long)k : nullptr;
-          const uint32_t* list = sm.lk[c];
+          const unsigned long long* list = sm.lk[c];
           for (int t = tid - c * M3_SORT_THREADS; t < cnt; t += M3_SORT_THREADS) {
-            const uint32_t mine = list[t];
+            const unsigned long long mine = list[t];
             int r = 0;
             int o = 0;
 #pragma unroll 4
-            for (; o + 4 <= cnt; o += 4) {
-              const uint4 ot = *reinterpret_cast<const uint4*>(list + o);
-              r += (ot.x < mine) + (ot.y < mine) + (ot.z < mine) + (ot.w < mine);
+            for (; o + 2 <= cnt; o += 2) {
+              const ulonglong2 ot = *reinterpret_cast<const ulonglong2*>(list + o);
+              r += (ot.x < mine) + (ot.y < mine);
             }
             for (; o < cnt; o++) r += list[o] < mine;
-            r -= first;
-            if (r >= 0 && r < size) {
-              io[r] = (int)(mine & 0x3FFFFu);
-              if (vo) vo[r] = __ushort_as_half((unsigned short)mn_bits(kl + (mine >> 18)));
+            if (r < size) {
+              io[r] = (int)(uint32_t)mine;
+              if (vo) vo[r] = __ushort_as_half((unsigned short)mn_bits((uint32_t)(mine >> 32)));
             }
           }
           for (int t = size + tid - c * M3_SORT_THREADS; t < k; t += M3_SORT_THREADS) {
@@ -530,6 +590,8 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       atomicAdd(p.prof + 9, (unsigned long long)(tc4 - tc3));
       atomicAdd(p.prof + 10, (unsigned long long)(tc5 - tc4));
       atomicAdd(p.prof + 11, (unsigned long long)(t3 - tc5));
+      for (int bit = 0; bit < 5; bit++)
+        if (why & (1u << bit)) atomicAdd(p.prof + 12 + bit, 1ull);
     }
   }
 }

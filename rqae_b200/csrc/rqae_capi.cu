@@ -1183,7 +1183,7 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
       mp.fb_count = fb; mp.fb_list = fb + 1;
       static const bool prof = [] { const char* pe = getenv("RQAE_M3_PROF"); return pe && atoi(pe) != 0; }();
       unsigned long long* dprof = nullptr;
-      if (prof && cudaMalloc((void**)&dprof, 128) == cudaSuccess) { cudaMemset(dprof, 0, 128); mp.prof = dprof; }
+      if (prof && cudaMalloc((void**)&dprof, 256) == cudaSuccess) { cudaMemset(dprof, 0, 256); mp.prof = dprof; }
       constexpr int smem3 = (int)sizeof(rq::Mine3Smem);
       static_assert(2 * (smem3 + 1024) <= 227 * 1024, "two CTAs per SM");
       e = ensure_dynamic_smem((const void*)rq::rq_mine3_kernel, smem3);
@@ -1192,9 +1192,9 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
         rq::rq_mine3_kernel<<<grid, rq::M3_THREADS, smem3, st>>>(mp);
         e = cudaGetLastError();
         if (dprof) {   // timing experiment only: synchronises
-          unsigned long long h[16] = {0};
+          unsigned long long h[32] = {0};
           cudaStreamSynchronize(st);
-          cudaMemcpy(h, dprof, 128, cudaMemcpyDeviceToHost);
+          cudaMemcpy(h, dprof, 256, cudaMemcpyDeviceToHost);
           cudaFree(dprof);
           mp.prof = nullptr;
           const double r = h[3] ? (double)h[3] : 1.0;
@@ -1202,6 +1202,8 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
                   h[0] / r, h[1] / r, h[2] / r, h[3], h[4], h[5] / r);
           fprintf(stderr, "  select steps: histogram %.0f, prefix %.0f, low bits %.0f, resolve %.0f, collect %.0f, rank sort %.0f\n",
                   h[6] / r, h[7] / r, h[8] / r, h[9] / r, h[10] / r, h[11] / r);
+          if (h[4]) fprintf(stderr, "  fallback reasons: region overflow %llu, NaN %llu, bracket missed %llu, tail class short %llu, key span / list %llu\n",
+                            h[12], h[13], h[14], h[15], h[16]);
         }
       }
       if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)rq::rq_mine2_kernel, smem2);
