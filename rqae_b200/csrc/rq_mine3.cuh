@@ -4,21 +4,31 @@
 // rq_mine2_kernel is exact but instruction-bound (49 thread-instructions per value over its three passes; an
 // HBM-bound pass affords about 11).  Here the four window boundaries are BRACKETED from a 1/16 sample of the row
 // before the row is streamed:
-//   A  sample   one 32-byte sector out of every 16 (the sector inside a group is picked by a hash, so that a
-//               period in the token order cannot alias with the sample), histogram of the high 11 key bits, and from
-//               its prefix sums four thresholds at bin edges: T_top (at least c_top sample values lie above it), T_bot,
-//               and [M_lo, M_hi] around the median ranks (4.5 sigma of the sample's rank error on either side)
+//   A  sample   one 32-byte sector out of every 16 (the sector inside a group is picked by a hash, so that a period
+//               in the token order cannot alias with the sample); a two-level radix select over the sample yields the
+//               keys at four sample ranks: T_top (c_top sample values lie at or above it), T_bot, and [M_lo, M_hi]
+//               around the median ranks (4.5 sigma of the sample's rank error on either side).  Exact sample order
+//               statistics, not bin edges: the bracket's size does not depend on the magnitude of the row.
 //   B  stream   every value is compared against the thresholds with packed fp16 compares (two values per
-//               instruction): values above M_hi are COUNTED (G), values >= T_top, <= T_bot or inside [M_lo, M_hi]
-//               (about 6 % of a row) are appended, bit pattern and index, to a shared-memory candidate buffer
-//   C  select   exact selection among the candidates: top-k / bottom-k by a rank sort of their class, the middle
-//               window by a two-level radix select over the candidates of the bracket (ranks m0 - G .. m1 - 1 - G)
+//               instruction): values above M_hi are COUNTED (G, as packed fp16 ones on the fma pipe), values >= T_top,
+//               <= T_bot or inside [M_lo, M_hi] (about 6 % of a row) are appended, key and position, to the warp's own
+//               region of a shared-memory candidate buffer.  Warp w streams the contiguous slice w of the row and
+//               appends in index order (slots from two packed warp scans per 2 KB step, no atomics), so the buffer as a
+//               whole is in index order.  Bracket members are counted in their level-1 histogram on the way.
+//   C  select   exact selection among the candidates, the three windows side by side: a two-level radix select over
+//               each class's key range finds the keys at the window's first and last rank; keys strictly between them
+//               are members, a key EQUAL to a boundary key is a member according to its rank among the equal values in
+//               index order (= equal values in earlier regions + equal values earlier in the region: tie groups are
+//               never listed, however large); the <= 256 members of a window are ordered by a 64-bit (key, index)
+//               rank sort.
 // The brackets are VERIFIED, not trusted: G <= m0, G + |bracket| >= m1, at least k values in either tail class, no
-// NaN in the row, no buffer overflow.  A row that fails any of it is appended to a fallback list and finished by
-// rq_mine2_kernel in list mode (same stream, no host round trip), so the result is the exact selection in the same total
-// order (value descending, index ascending; +0 before -0) whatever the data looks like -- heavily tied rows, constant
-// rows and rows with NaN simply take the old path.  fp compares treat +0 and -0 as equal; both then fall into the
-// same class and are ordered by their exact keys in step C.
+// NaN in the row (a NaN becomes a candidate through an unordered compare and is seen in step C), no region overflow.
+// A row that fails any of it is appended to a fallback list and finished by rq_mine2_kernel in list mode (same stream,
+// no host round trip), so the result is the exact selection in the same total order (value descending, index ascending;
+// +0 before -0) whatever the data looks like -- constant rows, rows whose bracket holds more than 768 candidates per
+// warp and rows with NaN simply take the old path.  fp compares treat +0 and -0 as equal; both then fall into the same
+// class and are told apart by their keys in step C.  16 384 <= n <= 262 144 (the sample statistics and the 18-bit
+// position); other sizes go to rq_mine2_kernel directly.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -263,14 +273,15 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
             const uint32_t w = (b & 0xCCu) ? c : a;
             const uint32_t val = (b & 0xAAu) ? (w >> 16) : (w & 0xFFFFu);
             const uint32_t d = mn_dkey(val);
-            const uint32_t ps = pos < (uint32_t)M3_WCAP ? pos : (uint32_t)M3_WCAP - 1u;   // a warp that overflows is caught below
             const uint32_t t = d - kb1m;
-            // the key and (vector << 8 | bit) go to the warp's region; a member of the median bracket is counted in its
-            // level-1 histogram right here (the shared-memory atomics hide under the stream instead of piling up in step C)
+            // the key and (vector << 8 | bit) go to the warp's region (nothing is stored beyond its end: a warp that
+            // overflows is caught below); a member of the median bracket is counted in its level-1 histogram right
+            // here (the shared-memory atomics hide under the stream instead of piling up in step C)
             asm volatile(
-                "{\n\t.reg .pred q;\n\tsetp.le.u32 q, %4, %5;\n\t"
-                "st.shared.u16 [%0], %1;\n\tst.shared.u32 [%2], %3;\n\t@q red.shared.add.u32 [%6], 1;\n\t}" ::"r"(ka + ps * 2u),
-                "h"((unsigned short)d), "r"(ia + ps * 4u), "r"(vtag | b), "r"(t), "r"(span1), "r"(h1a + ((t >> sh1) << 2))
+                "{\n\t.reg .pred p, q;\n\tsetp.lt.u32 p, %7, %8;\n\tsetp.le.u32 q, %4, %5;\n\t"
+                "@p st.shared.u16 [%0], %1;\n\t@p st.shared.u32 [%2], %3;\n\t@q red.shared.add.u32 [%6], 1;\n\t}" ::"r"(ka + pos * 2u),
+                "h"((unsigned short)d), "r"(ia + pos * 4u), "r"(vtag | b), "r"(t), "r"(span1), "r"(h1a + ((t >> sh1) << 2)),
+                "r"(pos), "r"((uint32_t)M3_WCAP)
                 : "memory");
             pos++;
           }
@@ -288,10 +299,12 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           const __half h = __ushort_as_half(bits);
           if (__hgt(h, smhi)) gcount++;
           if (__hgeu(h, stop) || __hle(h, sbot) || (__hge(h, smlo) && !__hgt(h, smhi))) {
-            const uint32_t pos = wcnt < (uint32_t)M3_WCAP ? wcnt : (uint32_t)M3_WCAP - 1u;
+            const uint32_t pos = wcnt;
             const uint32_t d = mn_dkey(bits);
-            sm.candk[(M3_WARPS - 1) * M3_WCAP + pos] = (unsigned short)d;
-            sm.candi[(M3_WARPS - 1) * M3_WCAP + pos] = ((uint32_t)(i >> 3) << 8) | (1u << (i & 7));
+            if (pos < (uint32_t)M3_WCAP) {
+              sm.candk[(M3_WARPS - 1) * M3_WCAP + pos] = (unsigned short)d;
+              sm.candi[(M3_WARPS - 1) * M3_WCAP + pos] = ((uint32_t)(i >> 3) << 8) | (1u << (i & 7));
+            }
             if (d - kb1m <= span1) atomicAdd(&sm.hist[1][(d - kb1m) >> sh1], 1u);
             wcnt++;
           }

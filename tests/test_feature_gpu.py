@@ -155,7 +155,8 @@ def _stable_windows(v: torch.Tensor, k: int):
 
 
 @pytest.mark.parametrize("T,k,quant", [(5000, 100, None), (5000, 100, 0.05), (4097, 7, 0.25), (300003, 100, 0.01),
-                                       (100, 100, None), (257, 1, 0.5), (65536, 256, 0.002)])
+                                       (100, 100, None), (257, 1, 0.5), (65536, 256, 0.002),
+                                       (20000, 1, None), (16384, 7, 0.25), (40003, 255, None), (262144, 100, 0.05)])
 def test_select_top_middle_bottom_matches_stable_argsort(T, k, quant):
     from rqae_b200.feature import select_top_middle_bottom
     dev = _dev()

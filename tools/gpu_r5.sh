@@ -1,9 +1,11 @@
 #!/bin/bash
-# Round-2 last evidence visit (1 GPU): whole -m gpu suite, smoke, bench line, ncu --set full of the sample-bracketed selection
+# Round-2 last evidence visit (1 GPU): whole -m gpu suite, smoke, selection A/B, bench line, sanitizer over the new
+# selection kernel, ncu --set full of it
 set -u
-TAG=${1:-r5k}
+TAG=${1:-r5p}
 OUT=gpurun_out
 mkdir -p $OUT
+CS=/usr/local/cuda/bin/compute-sanitizer
 echo "=== pytest -m gpu ==="
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee $OUT/pytest_gpu_$TAG.log
 echo "=== smoke ==="
@@ -14,6 +16,10 @@ echo "=== selection A/B (normal rows) ==="
 echo "=== bench ==="
 timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit=$?"
 tail -3 $OUT/bench_$TAG.err
+echo "=== sanitizer: selection v3 (racecheck, memcheck on the adversarial rows, initcheck) ==="
+timeout 400 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "65536 or short_16384 or heavy_median_tie or few_values or 20000" 2>&1 | tail -4 | tee $OUT/sanitize_racecheck_mine3_$TAG.log
+timeout 400 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "(adversarial and not long_2M) or 16384 or 40003" 2>&1 | tail -4 | tee $OUT/sanitize_memcheck_mine3_$TAG.log
+timeout 400 $CS --tool initcheck --error-exitcode 9 python -m pytest tests/test_feature_gpu.py -q -x -k "short_16384 or zero_centered or specials or 20000" 2>&1 | tail -4 | tee $OUT/sanitize_initcheck_mine3_$TAG.log
 echo "=== ncu full: selection v3 ==="
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_mine3 -s 1 -c 1 -f \
   -o $OUT/prof_mine3_$TAG python tools/bench_select.py --rows 2368 --reps 1 > $OUT/ncu_mine3_$TAG.log 2>&1
