@@ -70,6 +70,11 @@ __device__ __forceinline__ uint32_t m3_hash(uint32_t g, uint32_t row) {
 __device__ __forceinline__ void m3_prefetch_l2(const void* ptr, uint32_t bytes) {   // 16-byte aligned, multiple of 16
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ int m3_dp4a_su(uint32_t a_signed_bytes, uint32_t b_unsigned_bytes, int c) {
+  int d;
+  asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed_bytes), "r"(b_unsigned_bytes), "r"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t m3_sel3(int c, uint32_t a0, uint32_t a1, uint32_t a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
 
 __device__ __forceinline__ uint32_t m3_warp_inclusive(uint32_t v, int lane) {
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
     const long long t1 = clock64();
     {
       uint32_t gcount = 0;
-      __half2 gacc = __float2half2_rn(0.f);
+      uint32_t gacc = 0;                                              // 510 x (values above the bracket)
       uint32_t wcnt = 0;                                              // candidates of this warp so far (warp-uniform)
       const uint32_t ka = smem_u32(sm.candk) + (uint32_t)warp * (M3_WCAP * 2u);
       const uint32_t ia = smem_u32(sm.candi) + (uint32_t)warp * (M3_WCAP * 4u);
@@ -240,13 +245,12 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
           }
           mv[u] = 0;
           if (FULL || v < we) {   // lanes beyond the slice hold zeros and must stay out
+            // count above the bracket: every true half of a compare mask is two 0xFF bytes, dp4a adds 2 x 255 (no alu op)
 #pragma unroll
-            for (int e = 0; e < 4; e++) {   // the count above the bracket accumulates as packed fp16 ones (fma pipe; <= 256 per half and row)
-              const uint32_t one = gm[e] & 0x3C003C00u;
-              gacc = __hadd2(gacc, *reinterpret_cast<const __half2*>(&one));
-            }
-            uint32_t m = (cm[0] & 0x00020001u) | (cm[1] & 0x00080004u) | (cm[2] & 0x00200010u) | (cm[3] & 0x00800040u);
-            mv[u] = (m | (m >> 16)) & 0xFFu;
+            for (int e = 0; e < 4; e++) gacc = __dp4a(gm[e], 0x01010101u, gacc);
+            // the eight candidate flags as bits: byte 0 / 2 of each mask word are -1 or 0, dp4a weighs them 1, 2, 4, ...
+            mv[u] = (uint32_t)(-m3_dp4a_su(__byte_perm(cm[0], cm[1], 0x6420u), 0x08040201u,
+                                           m3_dp4a_su(__byte_perm(cm[2], cm[3], 0x6420u), 0x80402010u, 0)));
           }
         }
         // slots in index order: vector u of every lane before vector u + 1 of any lane; two packed scans per step
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
         }
       }
       wcnt = __shfl_sync(0xffffffffu, wcnt, 0);
-      gcount += (uint32_t)(__low2float(gacc) + __high2float(gacc) + 0.5f);
+      gcount += gacc / 510u;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gcount += __shfl_xor_sync(0xffffffffu, gcount, o);
       if (lane == 0) {
@@ -359,10 +363,11 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0x8000u;   // -0: in no tail class
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const bool live = i0 + 32 * j < wend;
-        if (d[j] < 0x3FFu || d[j] > 0xFC00u) sm.nan = 1u;
-        if (live && d[j] <= ke0) atomicAdd(&sm.hist[0][(d[j] - kb0) >> sh0], 1u);
-        if (live && d[j] >= kb2) atomicAdd(&sm.hist[2][(d[j] - kb2) >> sh2], 1u);
+        if (i0 + 32 * j < wend && (d[j] <= ke0 || d[j] >= kb2)) {   // one candidate in eight; NaN keys are tail keys
+          if (d[j] < 0x3FFu || d[j] > 0xFC00u) sm.nan = 1u;
+          if (d[j] <= ke0) atomicAdd(&sm.hist[0][(d[j] - kb0) >> sh0], 1u);
+          if (d[j] >= kb2) atomicAdd(&sm.hist[2][(d[j] - kb2) >> sh2], 1u);
+        }
       }
     }
     __syncthreads();
@@ -477,11 +482,16 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       const uint32_t K[6] = {kl0, kh0, kl1, kh1, kl2, kh2};
       {   // per-warp counts of the six boundary keys
         uint32_t cn[6] = {0, 0, 0, 0, 0, 0};
-        for (uint32_t i = wb + lane; i < wend; i += 32) {
-          const uint32_t d = sm.candk[i];
-          if (d - kl0 <= sp0 || d - kl1 <= sp1 || d - kl2 <= sp2) {   // a few per cent of the region
+        for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
+          uint32_t d[4];
 #pragma unroll
-            for (int q = 0; q < 6; q++) cn[q] += d == K[q];
+          for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (d[j] - kl0 <= sp0 || d[j] - kl1 <= sp1 || d[j] - kl2 <= sp2) {   // a few per cent of the region
+#pragma unroll
+              for (int q = 0; q < 6; q++) cn[q] += d[j] == K[q];
+            }
           }
         }
 #pragma unroll
@@ -493,11 +503,16 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       }
       __syncthreads();
       uint32_t run[6];                                  // equal values before the current position (warp-uniform)
+      {   // lane w holds the counts of warp w, two keys per word (a count is < 2^14); the warps before this one are summed
+        uint32_t pk[3];
 #pragma unroll
-      for (int q = 0; q < 6; q++) {
-        run[q] = 0;
+        for (int h = 0; h < 3; h++) {
+          pk[h] = lane < warp ? (sm.tie[2 * h][lane & (M3_WARPS - 1)] | (sm.tie[2 * h + 1][lane & (M3_WARPS - 1)] << 16)) : 0u;
 #pragma unroll
-        for (int w = 0; w < M3_WARPS; w++) run[q] += w < warp ? sm.tie[q][w] : 0u;
+          for (int o = 8; o > 0; o >>= 1) pk[h] += __shfl_xor_sync(0xffffffffu, pk[h], o);
+          pk[h] = __shfl_sync(0xffffffffu, pk[h], 0);
+          run[2 * h] = pk[h] & 0xFFFFu; run[2 * h + 1] = pk[h] >> 16;
+        }
       }
       // tie ranks [lo_from, lo_to) of klo and [0, hi_to) of khi belong to the window (klo == khi: one group holds both ends)
       const uint32_t s0 = rl0 - sm.less_lo[0], s1 = rl1 - sm.less_lo[1], s2 = rl2 - sm.less_lo[2];
