@@ -480,30 +480,49 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       const uint32_t kh0 = sm.khi[0], kh1 = sm.khi[1], kh2 = sm.khi[2];
       const uint32_t sp0 = kh0 - kl0, sp1 = kh > 0 ? kh1 - kl1 : 0u, sp2 = kh2 - kl2;
       const uint32_t K[6] = {kl0, kh0, kl1, kh1, kl2, kh2};
-      {   // per-warp counts of the six boundary keys
-        uint32_t cn[6] = {0, 0, 0, 0, 0, 0};
-        for (uint32_t i0 = wb + lane; i0 < wend; i0 += 128) {
-          uint32_t d[4];
+      // First the few per cent of the region whose keys lie inside a window's key range are compacted, in order, into a
+      // short list per warp (the level-1 histograms are free by now and hold the lists): the tie counts and the member
+      // pass then run over ~20-150 entries per warp instead of ~470.
+      constexpr uint32_t SL = 256;                                   // short-list entries per warp: key << 16 | position in the region
+      uint32_t* const sl = &sm.hist[0][0] + (uint32_t)warp * SL;     // 16 x 256 words = hist[0] and hist[1]
+      const uint32_t ltm = (1u << lane) - 1u;
+      uint32_t nsl = 0;                                              // warp-uniform
+      for (uint32_t i0 = wb + lane; i0 - lane < wend; i0 += 128) {   // warp-uniform trip count, region order
+        uint32_t d[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
+        for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (d[j] - kl0 <= sp0 || d[j] - kl1 <= sp1 || d[j] - kl2 <= sp2) {   // a few per cent of the region
-#pragma unroll
-              for (int q = 0; q < 6; q++) cn[q] += d[j] == K[q];
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) cn[q] += __shfl_xor_sync(0xffffffffu, cn[q], o);
-          if (lane == 0) sm.tie[q][warp] = cn[q];
+        for (int j = 0; j < 4; j++) {
+          const bool inr = i0 + 32 * j < wend && (d[j] - kl0 <= sp0 || (kh > 0 && d[j] - kl1 <= sp1) || d[j] - kl2 <= sp2);
+          const uint32_t bal = __ballot_sync(0xffffffffu, inr);
+          if (bal == 0) continue;
+          const uint32_t slot = nsl + __popc(bal & ltm);
+          if (inr && slot < SL) sl[slot] = (d[j] << 16) | (i0 + 32 * j - wb);
+          nsl += __popc(bal);
         }
       }
+      __syncwarp();
+      const uint32_t nslc = nsl < SL ? nsl : SL;
+      {   // per-warp counts of the six boundary keys
+        uint32_t cn[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t t = lane; t < nslc; t += 32) {
+          const uint32_t d = sl[t] >> 16;
+#pragma unroll
+          for (int q = 0; q < 6; q++) cn[q] += d == K[q];
+        }
+#pragma unroll
+        for (int h = 0; h < 3; h++) {   // two counts per word (a count is < 2^14)
+          uint32_t pk = cn[2 * h] | (cn[2 * h + 1] << 16);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pk += __shfl_xor_sync(0xffffffffu, pk, o);
+          if (lane == 0) { sm.tie[2 * h][warp] = pk & 0xFFFFu; sm.tie[2 * h + 1][warp] = pk >> 16; }
+        }
+        if (lane == 0 && nsl > SL) sm.nan = 2u;   // the short list overflowed (a tie group of thousands): the row falls back
+      }
       __syncthreads();
+      if (sm.nan != 0) { ok = false; why |= 16u; }
       uint32_t run[6];                                  // equal values before the current position (warp-uniform)
-      {   // lane w holds the counts of warp w, two keys per word (a count is < 2^14); the warps before this one are summed
+      {   // lane w holds the counts of warp w, two keys per word; the warps before this one are summed
         uint32_t pk[3];
 #pragma unroll
         for (int h = 0; h < 3; h++) {
@@ -520,42 +539,36 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       const uint32_t lo_to[3] = {kl0 == kh0 ? s0 + (rh0 - rl0 + 1u) : 0xFFFFFFFFu, kl1 == kh1 ? s1 + (rh1 - rl1 + 1u) : 0xFFFFFFFFu,
                                  kl2 == kh2 ? s2 + (rh2 - rl2 + 1u) : 0xFFFFFFFFu};
       const uint32_t hi_to[3] = {rh0 - sm.less_hi[0] + 1u, rh1 - sm.less_hi[1] + 1u, rh2 - sm.less_hi[2] + 1u};
-      const uint32_t ltm = (1u << lane) - 1u;
-      for (uint32_t i0 = wb + lane; i0 - lane < wend; i0 += 128) {   // warp-uniform trip count, region order
-        uint32_t d[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) d[j] = i0 + 32 * j < wend ? (uint32_t)sm.candk[i0 + 32 * j] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const bool live = i0 + 32 * j < wend;
-          const bool r0 = live && d[j] - kl0 <= sp0, r1 = live && kh > 0 && d[j] - kl1 <= sp1, r2 = live && d[j] - kl2 <= sp2;
-          if (!__any_sync(0xffffffffu, r0 | r1 | r2)) continue;
-          bool in[3] = {r0, r1, r2};
-          const bool eq = d[j] == K[0] || d[j] == K[1] || d[j] == K[2] || d[j] == K[3] || d[j] == K[4] || d[j] == K[5];
-          if (__any_sync(0xffffffffu, eq))   // rare on rows without heavy ties
+      for (uint32_t t0 = 0; ok && t0 < nslc; t0 += 32) {   // warp-uniform trip count, region order
+        const bool live = t0 + lane < nslc;
+        const uint32_t ent = live ? sl[t0 + lane] : 0xFFFFFFFFu;
+        const uint32_t d = live ? ent >> 16 : 0xFFFFFFFFu;
+        bool in[3] = {live && d - kl0 <= sp0, live && kh > 0 && d - kl1 <= sp1, live && d - kl2 <= sp2};
+        const bool eq = d == K[0] || d == K[1] || d == K[2] || d == K[3] || d == K[4] || d == K[5];
+        if (__any_sync(0xffffffffu, eq)) {
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            const bool elo = in[c] && d[j] == K[2 * c], ehi = in[c] && d[j] == K[2 * c + 1] && K[2 * c] != K[2 * c + 1];
+            const bool elo = in[c] && d == K[2 * c], ehi = in[c] && d == K[2 * c + 1] && K[2 * c] != K[2 * c + 1];
             const uint32_t blo = __ballot_sync(0xffffffffu, elo), bhi = __ballot_sync(0xffffffffu, ehi);
             if (elo) { const uint32_t t = run[2 * c] + __popc(blo & ltm); in[c] = t >= lo_from[c] && t < lo_to[c]; }
             if (ehi) { const uint32_t t = run[2 * c + 1] + __popc(bhi & ltm); in[c] = t < hi_to[c]; }
             run[2 * c] += __popc(blo); run[2 * c + 1] += __popc(bhi);
           }
-          if (!(in[0] | in[1] | in[2])) continue;
-          const uint32_t cw = sm.candi[i0 + 32 * j];
-          const uint32_t ci = (cw >> 8) * 8u + (uint32_t)(__ffs(cw & 0xFFu) - 1);   // vector << 8 | one-hot bit -> index
-          if (in[1]) {
-            const uint32_t sl = atomicAdd(&sm.lcount[1], 1u);
-            if (sl < (uint32_t)M3_LIST) sm.lk[1][sl] = ((unsigned long long)d[j] << 32) | ci;
-          }
-          if (in[0]) {
-            const uint32_t sl = atomicAdd(&sm.lcount[0], 1u);
-            if (sl < (uint32_t)M3_LIST) sm.lk[0][sl] = ((unsigned long long)d[j] << 32) | ci;
-          }
-          if (in[2]) {
-            const uint32_t sl = atomicAdd(&sm.lcount[2], 1u);
-            if (sl < (uint32_t)M3_LIST) sm.lk[2][sl] = ((unsigned long long)d[j] << 32) | ci;
-          }
+        }
+        if (!(in[0] | in[1] | in[2])) continue;
+        const uint32_t cw = sm.candi[wb + (ent & 0xFFFFu)];
+        const uint32_t ci = (cw >> 8) * 8u + (uint32_t)(__ffs(cw & 0xFFu) - 1);   // vector << 8 | one-hot bit -> index
+        if (in[1]) {
+          const uint32_t slt = atomicAdd(&sm.lcount[1], 1u);
+          if (slt < (uint32_t)M3_LIST) sm.lk[1][slt] = ((unsigned long long)d << 32) | ci;
+        }
+        if (in[0]) {
+          const uint32_t slt = atomicAdd(&sm.lcount[0], 1u);
+          if (slt < (uint32_t)M3_LIST) sm.lk[0][slt] = ((unsigned long long)d << 32) | ci;
+        }
+        if (in[2]) {
+          const uint32_t slt = atomicAdd(&sm.lcount[2], 1u);
+          if (slt < (uint32_t)M3_LIST) sm.lk[2][slt] = ((unsigned long long)d << 32) | ci;
         }
       }
       __syncthreads();
