@@ -190,7 +190,7 @@ int rqae_intensity_again_f16(const float* cb_norm, int K, int64_t n_tokens, cons
  * top_k <= 256, top_k <= n < 2^31.
  * Rows of 16 384 .. 262 144 values go through the sample-bracketed single-pass kernel (rq_mine3.cuh); a row whose
  * brackets miss, and every other row length, through the three-pass kernel (rq_mine.cuh) -- same result, same order.
- * The call takes a few bytes per row from the device's stream-ordered pool (cudaMallocAsync on `stream`) for the
+ * The call takes a few bytes per row from a stream-ordered pool of the library (cudaMallocFromPoolAsync on `stream`) for the
  * fallback list.  Environment, read per call: RQAE_MINE_V2=1 three-pass kernel only, RQAE_MINE_V1=1 the first version
  * (both for A/B timing), RQAE_M3_PROF=1 per-step clocks on stderr (synchronises). */
 int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t row_stride, int64_t n, int top_k,

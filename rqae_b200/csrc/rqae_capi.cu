@@ -68,6 +68,35 @@ cudaError_t ensure_dynamic_smem(const void* kern, int bytes) {
   return e;
 }
 
+// A stream-ordered pool of this library's own per device, for the few bytes per row of the selection's fallback list.
+// The default pool gives unused memory back at every synchronisation (release threshold 0), so the first call after
+// a sync would pay an allocation from the driver; this pool keeps what it has.
+cudaError_t scratch_pool(cudaMemPool_t* out) {
+  static std::mutex mu;
+  static std::map<int, cudaMemPool_t> pools;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = pools.find(dev);
+  if (it == pools.end()) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return e;
+    it = pools.emplace(dev, pool).first;
+  }
+  *out = it->second;
+  return cudaSuccess;
+}
+
 int device_sm_count(int* sms) {
   int dev = 0;
   RQ_CUDA(cudaGetDevice(&dev));
@@ -1177,7 +1206,9 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
     mp.c_hi = (int)floor((double)m0 / s - z * sig) - 1;
     mp.c_lo = (int)ceil((double)m1 / s + z * sig) + 1;
     int* fb = nullptr;
-    RQ_CUDA(cudaMallocAsync((void**)&fb, (size_t)(rows + 1) * sizeof(int), st));
+    cudaMemPool_t pool;
+    RQ_CUDA(scratch_pool(&pool));
+    RQ_CUDA(cudaMallocFromPoolAsync((void**)&fb, (size_t)(rows + 1) * sizeof(int), pool, st));
     cudaError_t e = cudaMemsetAsync(fb, 0, sizeof(int), st);
     if (e == cudaSuccess) {
       mp.fb_count = fb; mp.fb_list = fb + 1;
