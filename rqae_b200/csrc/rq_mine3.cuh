@@ -10,7 +10,7 @@
 //               around the median ranks (4.5 sigma of the sample's rank error on either side).  Exact sample order
 //               statistics, not bin edges: the bracket's size does not depend on the magnitude of the row.
 //   B  stream   every value is compared against the thresholds with packed fp16 compares (two values per
-//               instruction): values above M_hi are COUNTED (G, as packed fp16 ones on the fma pipe), values >= T_top,
+//               instruction): values above M_hi are COUNTED (G, dp4a over the compare masks), values >= T_top,
 //               <= T_bot or inside [M_lo, M_hi] (about 6 % of a row) are appended, key and position, to the warp's own
 //               region of a shared-memory candidate buffer.  Warp w streams the contiguous slice w of the row and
 //               appends in index order (slots from two packed warp scans per 2 KB step, no atomics), so the buffer as a
@@ -18,8 +18,8 @@
 //   C  select   exact selection among the candidates, the three windows side by side: a two-level radix select over
 //               each class's key range finds the keys at the window's first and last rank; keys strictly between them
 //               are members, a key EQUAL to a boundary key is a member according to its rank among the equal values in
-//               index order (= equal values in earlier regions + equal values earlier in the region: tie groups are
-//               never listed, however large); the <= 256 members of a window are ordered by a 64-bit (key, index)
+//               index order (= equal values in earlier regions + equal values earlier in the region; computed over a
+//               short per-warp list of the keys inside the windows' key ranges: tie groups are never sorted); the <= 256 members of a window are ordered by a 64-bit (key, index)
 //               rank sort.
 // The brackets are VERIFIED, not trusted: G <= m0, G + |bracket| >= m1, at least k values in either tail class, no
 // NaN in the row (a NaN becomes a candidate through an unordered compare and is seen in step C), no region overflow.
