@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) rq_mine3_kernel(const MineParam
       ncand += cw;
       ok = ok && cw <= (uint32_t)M3_WCAP;
     }
-    uint32_t why = ok ? 0u : 1u;   // RQAE_M3_PROF: 1 region overflow, 2 NaN, 4 bracket missed, 8 tail class short, 16 key span / list
+    uint32_t why = ok ? 0u : 1u;   // RQAE_M3_PROF: 1 region overflow, 2 NaN, 4 bracket missed, 8 tail class short, 16 a warp's short list of window-range keys overflowed
     // this warp's candidates: slots wb .. wb + wn
     const uint32_t wb = (uint32_t)warp * M3_WCAP, wn = ok ? sm.wcount[warp] : 0u;
     // C1: level-1 histograms of the two tail classes (the buffer holds keys; NaN keys lie beyond the two infinities)

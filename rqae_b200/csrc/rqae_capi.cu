@@ -1233,7 +1233,7 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
                   h[0] / r, h[1] / r, h[2] / r, h[3], h[4], h[5] / r);
           fprintf(stderr, "  select steps: histogram %.0f, prefix %.0f, low bits %.0f, resolve %.0f, collect %.0f, rank sort %.0f\n",
                   h[6] / r, h[7] / r, h[8] / r, h[9] / r, h[10] / r, h[11] / r);
-          if (h[4]) fprintf(stderr, "  fallback reasons: region overflow %llu, NaN %llu, bracket missed %llu, tail class short %llu, key span / list %llu\n",
+          if (h[4]) fprintf(stderr, "  fallback reasons: region overflow %llu, NaN %llu, bracket missed %llu, tail class short %llu, short list overflow %llu\n",
                             h[12], h[13], h[14], h[15], h[16]);
         }
       }

@@ -196,7 +196,8 @@ def _key_windows(bits: np.ndarray, k: int):
 
 @pytest.mark.parametrize("case", ["constant_131072", "two_values", "one_bin", "straddle", "specials", "ragged_131077",
                                   "long_2M", "tiny", "zero_centered_131072", "few_values_131072", "skewed_262144",
-                                  "heavy_median_tie", "short_16384"])
+                                  "heavy_median_tie", "short_16384", "median_tie_1pct", "median_tie_4pct",
+                                  "top_tie_group"])
 def test_select_adversarial_rows_against_key_order(case):
     """Rows built to hit the corners of the sample-bracketed kernel (16 384 <= n <= 262 144: brackets that miss or
     overflow fall back to the three-pass kernel row by row) and of the lane-private-counter kernel: 8-bit counters that wrap (a lane sees 256
@@ -239,6 +240,20 @@ def test_select_adversarial_rows_against_key_order(case):
     elif case == "heavy_median_tie":       # 40 % of the row is one value around the median: the bracket overflows
         rows = (rng.normal(0.0, 0.05, size=(3, 131072))).astype(np.float16)
         rows[rng.random((3, 131072)) < 0.4] = np.float16(0.0)
+        rows = rows.view(np.uint16)
+    elif case in ("median_tie_1pct", "median_tie_4pct"):   # one key at the median holds 1 % / 4 % of the row: tie ranks over
+        # a group of ~1 300 (ranked in the kernel) / ~5 200 values (the per-warp short lists overflow: fallback)
+        frac = 0.01 if case == "median_tie_1pct" else 0.04
+        rows = (rng.normal(0.02, 0.05, size=(4, 131072))).astype(np.float16)
+        for r in rows:
+            r[rng.random(131072) < frac] = np.float16(np.median(r.astype(np.float32)))
+        rows = rows.view(np.uint16)
+    elif case == "top_tie_group":          # the k-th largest and the k-th smallest value sit inside groups of equal values
+        rows = (rng.normal(0.0, 0.05, size=(3, 100003))).astype(np.float16)
+        for r in rows:
+            srt = np.sort(r.astype(np.float32))
+            r[rng.integers(0, 100003, 700)] = np.float16(srt[-60])
+            r[rng.integers(0, 100003, 700)] = np.float16(srt[60])
         rows = rows.view(np.uint16)
     elif case == "short_16384":
         rows = (rng.normal(0.02, 0.05, size=(5, 16384))).astype(np.float16).view(np.uint16)
