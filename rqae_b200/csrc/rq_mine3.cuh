@@ -7,7 +7,7 @@
 //   A  sample   one 32-byte sector out of every 16 (the sector inside a group is picked by a hash, so that a period
 //               in the token order cannot alias with the sample); a two-level radix select over the sample yields the
 //               keys at four sample ranks: T_top (c_top sample values lie at or above it), T_bot, and [M_lo, M_hi]
-//               around the median ranks (4.5 sigma of the sample's rank error on either side).  Exact sample order
+//               around the median ranks (4 sigma of the sample's rank error on either side).  Exact sample order
 //               statistics, not bin edges: the bracket's size does not depend on the magnitude of the row.
 //   B  stream   every value is compared against the thresholds with packed fp16 compares (two values per
 //               instruction): values above M_hi are COUNTED (G, dp4a over the compare masks), values >= T_top,

@@ -1199,7 +1199,9 @@ int rqae_select_top_middle_bottom_f16(const void* vals, int64_t rows, int64_t ro
     // rq_mine3_kernel: brackets from a sample, one streaming pass, exact selection among the candidates; rows whose
     // brackets miss are finished by rq_mine2_kernel in list mode
     const int slog = n <= 131072 ? 4 : 3;
-    const double ms = (double)(((n / 16) >> slog) * 16), s = (double)n / ms, sig = 0.5 * sqrt(ms), z = 4.5;
+    const double ms = (double)(((n / 16) >> slog) * 16), s = (double)n / ms, sig = 0.5 * sqrt(ms);
+    // half-width of the median bracket in sigmas of the sample's rank error (RQAE_M3_Z overrides, for experiments)
+    const double z = [] { const char* e = getenv("RQAE_M3_Z"); const double v = e ? atof(e) : 0.0; return v >= 1.0 && v <= 8.0 ? v : 4.0; }();
     const long long kh = top_k / 2, m0 = n / 2 - kh, m1 = n / 2 + kh;
     mp.sample_log2 = slog;
     mp.c_top = (int)ceil(top_k / s + 6.0 * sqrt(top_k / s) + 3.0);
